@@ -105,7 +105,13 @@ def tangent_vectors(x1d, y1d, R=1.0):
 class LeanGrid:
     """Duck-typed stand-in for `cubed_sphere` holding only what the path reads."""
 
-    def __init__(self, N, with_conversion=True):
+    @classmethod
+    def centres_only(cls, N):
+        """Grid with only pc coordinates -- enough for the Lagrange tables and
+        the halo fill at sizes where the full grid is not needed (N=3072)."""
+        return cls(N, positions=("pc",), with_conversion=False, with_metric=False)
+
+    def __init__(self, N, with_conversion=True, positions=("pc", "pu", "pv"), with_metric=True):
         self.N = N
         self.R = 1.0
         self.projection = "gnomonic_equiangular"
@@ -129,8 +135,12 @@ class LeanGrid:
         self._axes = {"pc": (x_c, y_c), "pu": (x_e, y_c), "pv": (x_c, y_e)}
 
         for pos, (xs, ys) in self._axes.items():
+            if pos not in positions:
+                continue
             pts = gnomonic_points(xs, ys)
             setattr(self, pos, pts)
+            if not with_metric:
+                continue
             ex, ey = tangent_vectors(xs, ys, self.R)
             # sqrt(g) on panel 0, copied to all panels (src/cs_datastruct.py:407-446)
             e0 = [c[:, :, 0] for c in ex]

@@ -98,6 +98,20 @@ def qexact_adv(lon, lat, t, sim):
     return 1.0 - f * f
 
 
+def q_scalar_field(lon, lat, ic):
+    """Analytic fields of the ghost-cell interpolation test (src/interpolation_test.py:55-71)."""
+    if ic == 1:
+        X0, Y0, Z0 = sph2cart(np.pi / 4.0, np.pi / 6.0)
+        X, Y, Z = sph2cart(lon, lat)
+        return np.exp(-10.0 * ((X - X0) ** 2 + (Y - Y0) ** 2 + (Z - Z0) ** 2))
+    m = n = 1
+    return (-np.cos(lon) * np.sin(m * lon) * m * np.cos(n * lat) ** 4 / np.cos(lat)
+            - np.sin(lon) * np.cos(m * lon) * m ** 2 * np.cos(n * lat) ** 4 / np.cos(lat)
+            + 12.0 * np.sin(lon) * np.cos(m * lon) * np.cos(n * lat) ** 2 * np.sin(n * lat) ** 2 * n ** 2 * np.cos(lat)
+            - 4.0 * np.sin(lon) * np.cos(m * lon) * np.cos(n * lat) ** 4 * n ** 2 * np.cos(lat)
+            + 4.0 * np.sin(lon) * np.cos(m * lon) * np.cos(n * lat) ** 3 * np.sin(n * lat) * n * np.sin(lat)) / np.cos(lat)
+
+
 def init_vars_adv(g, sim):
     """src/advection_vars.py:19-107."""
     i0, iend, j0, jend = g.i0, g.iend, g.j0, g.jend

@@ -1,0 +1,260 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/ from the UNMODIFIED reference.
+
+Runs only in the build container (needs /root/reference; see _refshim.py).
+Usage:  python tests/golden/make_golden.py small|kmin|norms|big384|big768|big1536|all
+
+  small    N=16 step / operator / halo-fill / grid fixtures (seconds)
+  kmin     Lagrange stencil tables (index maps) for N = 16 ... 3072 (bit-exact pin)
+  norms    full-period error norms at N=16, 32, 48
+  big384   config 2: N=384 default scheme, full period, sub-sampled Q + norms (~50 min)
+  big768   config 3: N=768 vf=2 RK2, first 50 steps, sub-sampled Q
+  big1536  config 4: N=1536 vf=3, first 20 steps, sub-sampled Q (needs ~15 GB RAM)
+"""
+import json
+import os
+import sys
+import time
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import _refshim as R  # noqa: E402
+
+R.install()
+cs = R.ref("cs_datastruct")
+rtr = R.ref("cs_transform")
+ric = R.ref("advection_ic")
+rav = R.ref("advection_vars")
+rts = R.ref("advection_timestep")
+rlag = R.ref("lagrange")
+rint = R.ref("interpolation")
+rhalo = R.ref("halo_data")
+rerr = R.ref("errors")
+rdiag = R.ref("diagnostics")
+rtest = R.ref("interpolation_test")
+
+# (recon, dp, split, et, mt, mf); the first five are the reference's own
+# tuples (par default + src/advection_error.py:61-66), the rest widen coverage.
+TUPLES = {
+    "default": (3, 1, 1, 3, 1, 3),
+    "PL07-RK1": (3, 1, 3, 2, 2, 1),
+    "PL07-RK1-DG-PR": (3, 1, 3, 3, 2, 3),
+    "AVLT-RK2-DG-AF": (3, 2, 1, 3, 1, 2),
+    "AVLT-RK2-DG-PR": (3, 2, 1, 3, 1, 3),
+    "PPM0-S72": (1, 1, 1, 1, 1, 1),
+    "CW84-L04-S72-AF": (2, 2, 2, 1, 1, 2),
+    "L04-L04-PL07-PR": (4, 2, 2, 2, 1, 3),
+    "CW84-PL07-PL07": (2, 1, 3, 2, 2, 1),
+    "L04-AVLT-DG-PR": (4, 1, 1, 3, 1, 3),
+    "PPM0-RK2-PL07sp-S72-AF": (1, 2, 3, 1, 2, 2),
+}
+DT16 = {1: 0.025, 2: 0.0125, 3: 0.00625, 4: 0.0125}   # src/advection_error.py:43-50
+
+
+def grid(N):
+    return cs.cubed_sphere(N, "gnomonic_equiangular", False, False)
+
+
+def new_sim(g, vf, tup, ic=2, dt=None):
+    recon, dp, split, et, mt, mf = tup
+    dt = DT16[vf] * 16 / g.N if dt is None else dt
+    sim = ric.adv_simulation_par(g, dt, 5, ic, vf, 1, recon, dp, split, et, mt, mf)
+    rav.init_vars_adv(g, sim)
+    return sim
+
+
+def advance(g, sim, k0, k1):
+    for k in range(k0 + 1, k1 + 1):
+        t = k * sim.dt
+        rts.adv_time_step(g, sim, k, t)
+        rts.update_adv(g, sim, t)
+
+
+def errors(g, sim, k):
+    I = np.s_[g.i0:g.iend, g.j0:g.jend, :]
+    qe = ric.qexact_adv(g.pc.lon[I], g.pc.lat[I], k * sim.dt, sim)
+    return [float(x) for x in rerr.compute_errors(sim.Q[I], qe)]
+
+
+def sample_index(N, S):
+    return np.array(sorted(set(range(0, N, S)) | {1, N - 2, N - 1}))
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **arrays)
+    print("wrote", name, os.path.getsize(path) // 1024, "KiB", flush=True)
+
+
+# ---------------------------------------------------------------------------
+def make_small():
+    N = 16
+    g = grid(N)
+    # grid inputs (to pin the lean grid builders)
+    garr = {}
+    for pos in ("pc", "pu", "pv"):
+        garr["sqrtg_" + pos] = getattr(g, "metric_tensor_" + pos)[:, :, 0]
+        for nm in ("prod_ex_elon_", "prod_ex_elat_", "prod_ey_elon_", "prod_ey_elat_",
+                   "determinant_ll2contra_"):
+            garr[nm + pos] = getattr(g, nm + pos)
+        garr["lon_" + pos] = getattr(g, pos).lon
+        garr["lat_" + pos] = getattr(g, pos).lat
+    for c in "XYZ":
+        garr[c + "_pc"] = getattr(g.pc, c)
+    save("grid_N16.npz", **garr)
+
+    # halo index maps: push index-valued fields through the reference gather
+    P = N + g.ng
+    ii, jj = np.meshgrid(np.arange(P), np.arange(P), indexing="ij")
+    code = (np.arange(6)[None, None, :] * P + ii[:, :, None]) * P + jj[:, :, None]
+    h = rhalo.get_halo_data_interpolation(code.astype(float), g)
+    save("halo_index_N16.npz", east=h[0].astype(np.int64), west=h[1].astype(np.int64),
+         north=h[2].astype(np.int64), south=h[3].astype(np.int64))
+    # copy fill with distinct Qx / Qy (x/y swap on rotated edges)
+    rng = np.random.default_rng(7)
+    Qx, Qy = rng.standard_normal((P, P, 6)), rng.standard_normal((P, P, 6))
+    Qx0, Qy0 = Qx.copy(), Qy.copy()
+    rint.ghost_cells_adjacent_panels(Qx, Qy, g, None)
+    save("copyfill_N16.npz", Qx_in=Qx0, Qy_in=Qy0, Qx_out=Qx, Qy_out=Qy)
+
+    # Lagrange fill of the two analytic test fields, degrees 0..4
+    out = {}
+    for ic in (1, 2):
+        for degree in (0, 1, 2, 3, 4):
+            sim = types.SimpleNamespace(ic=ic, degree=degree)
+            Qe = rtest.q_scalar_field(g.pc.lon, g.pc.lat, sim)
+            Qn = np.zeros_like(Qe)
+            Qn[g.i0:g.iend, g.j0:g.jend, :] = Qe[g.i0:g.iend, g.j0:g.jend, :]
+            rlag.lagrange_poly_ghostcell_pc(g, sim)
+            rint.ghost_cell_pc_lagrange_interpolation(Qn, g, sim)
+            out["ic%d_deg%d" % (ic, degree)] = Qn
+            out["linf_ic%d_deg%d" % (ic, degree)] = np.array(rerr.compute_errors(Qn, Qe)[0])
+            if ic == 1:
+                out["kmin_E_deg%d" % degree] = np.asarray(sim.stencil_ghost_pc[0][0])
+                out["poly_E_deg%d" % degree] = np.asarray(sim.lagrange_poly_ghost_pc[0])
+    save("halofill_N16.npz", **out)
+
+    # steps: every tuple x every wind field; Q after 1 and 20 steps
+    steps = {}
+    inter = {}
+    for vf in (1, 2, 3, 4):
+        for name, tup in TUPLES.items():
+            sim = new_sim(g, vf, tup)
+            key = "vf%d_%s" % (vf, name)
+            if vf == 1 and name == "default":
+                steps["Q0"] = sim.Q.copy()
+            advance(g, sim, 0, 1)
+            steps[key + "_k1"] = sim.Q.copy()
+            if name in ("default", "PL07-RK1", "AVLT-RK2-DG-AF", "L04-L04-PL07-PR") and vf in (1, 2):
+                for nm in ("q_L", "q_R", "dq", "q6", "f_upw", "dF"):
+                    inter[key + "_px_" + nm] = getattr(sim.px, nm).copy()
+                    inter[key + "_py_" + nm] = getattr(sim.py, nm).copy()
+                inter[key + "_div"] = sim.div.copy()
+                inter[key + "_cx"] = sim.cx.copy()
+                inter[key + "_cy"] = sim.cy.copy()
+                inter[key + "_uavg"] = sim.U_pu.ucontra_averaged.copy()
+                inter[key + "_vavg"] = sim.U_pv.vcontra_averaged.copy()
+                inter[key + "_ucontra"] = sim.U_pu.ucontra.copy()
+                inter[key + "_vcontra"] = sim.U_pv.vcontra.copy()
+                inter[key + "_upos"] = sim.U_pu.upos.copy()
+                inter[key + "_vpos"] = sim.U_pv.vpos.copy()
+            advance(g, sim, 1, 20)
+            steps[key + "_k20"] = sim.Q.copy()
+            if name in ("default", "AVLT-RK2-DG-PR") and vf >= 2:
+                # wind state after update_adv of step 20
+                inter[key + "_k20_ucontra"] = sim.U_pu.ucontra.copy()
+                inter[key + "_k20_vcontra"] = sim.U_pv.vcontra.copy()
+                inter[key + "_k20_ucontra_old"] = sim.U_pu.ucontra_old.copy()
+                inter[key + "_k20_pc_ulon"] = sim.U_pc.ulon.copy()
+                inter[key + "_k20_pc_vlat"] = sim.U_pc.vlat.copy()
+    save("steps_N16.npz", **steps)
+    save("intermediates_N16.npz", **inter)
+
+
+def make_kmin():
+    out = {}
+    for N in (16, 32, 48, 96, 192, 384, 768, 1536, 3072):
+        # duck-typed grid: only what lagrange_poly_ghostcell_pc reads (src/lagrange.py:29-69)
+        a = np.pi / 4
+        dx = 2 * a / N
+        P = N + 8
+        xc = np.linspace(-a + dx / 2.0 - 4 * dx, a - dx / 2.0 + 4 * dx, P)
+        X, Y, Z, lon, lat = rtr.equiangular_gnomonic_map(xc, xc, P, P, 1.0)
+        g = types.SimpleNamespace(N=N, ng=8, ngl=4, ngr=4, i0=4, iend=N + 4, j0=4, jend=N + 4,
+                                  dx=dx, dy=dx, projection="gnomonic_equiangular",
+                                  pc=types.SimpleNamespace(X=X, Y=Y, Z=Z))
+        sim = types.SimpleNamespace(degree=3)
+        rlag.lagrange_poly_ghostcell_pc(g, sim)
+        for s, side in enumerate("EWNS"):
+            out["kmin_%s_N%d" % (side, N)] = np.asarray(sim.stencil_ghost_pc[0][s]).astype(np.int32)
+            out["kmax_%s_N%d" % (side, N)] = np.asarray(sim.stencil_ghost_pc[1][s]).astype(np.int32)
+        out["poly_E_N%d" % N] = np.asarray(sim.lagrange_poly_ghost_pc[0])
+        print("kmin", N, flush=True)
+    save("lagrange_tables.npz", **out)
+
+
+def make_norms():
+    table = []
+    for N in (16, 32, 48):
+        g = grid(N)
+        for vf in (1, 2, 3):
+            for name in ("default", "PL07-RK1", "PL07-RK1-DG-PR", "AVLT-RK2-DG-AF", "AVLT-RK2-DG-PR"):
+                if N == 48 and not (vf == 1 and name == "default"):
+                    continue
+                sim = new_sim(g, vf, TUPLES[name])
+                nsteps = int(sim.Tf / sim.dt)
+                m0, _ = rdiag.mass_computation(sim.Q, g, 1.0)
+                t = time.time()
+                advance(g, sim, 0, nsteps)
+                e = errors(g, sim, nsteps)
+                _, dm = rdiag.mass_computation(sim.Q, g, m0)
+                row = dict(N=N, vf=vf, scheme=name, tuple=TUPLES[name], steps=nsteps, dt=sim.dt,
+                           cfl=float(sim.CFL), linf=e[0], l1=e[1], l2=e[2], mass_change=float(dm),
+                           sumQ=float(np.sum(sim.Q[g.i0:g.iend, g.j0:g.jend, :])),
+                           cpu_s=time.time() - t)
+                table.append(row)
+                print(row, flush=True)
+                if N == 48:
+                    save("config1_N48_final.npz", Q=sim.Q[g.i0:g.iend, g.j0:g.jend, :])
+    with open(os.path.join(HERE, "norms.json"), "w") as f:
+        json.dump(table, f, indent=1)
+
+
+def make_big(N, vf, tup_name, checkpoints, S):
+    t = time.time()
+    g = grid(N)
+    print("grid", N, time.time() - t, flush=True)
+    sim = new_sim(g, vf, TUPLES[tup_name])
+    idx = sample_index(N, S) + g.i0
+    out = {"sample_index": idx, "dt": np.array(sim.dt), "tuple": np.array(TUPLES[tup_name]),
+           "vf": np.array(vf), "N": np.array(N), "cfl": np.array(sim.CFL)}
+    k = 0
+    for kk in checkpoints:
+        t = time.time()
+        advance(g, sim, k, kk)
+        k = kk
+        out["Q_k%d" % k] = sim.Q[np.ix_(idx, idx, np.arange(6))]
+        out["sumQ_k%d" % k] = np.array(np.sum(sim.Q[g.i0:g.iend, g.j0:g.jend, :]))
+        out["err_k%d" % k] = np.array(errors(g, sim, k))
+        out["mass_k%d" % k] = np.array(rdiag.mass_computation(sim.Q, g, 1.0)[0])
+        print("N", N, "step", k, "errs", out["err_k%d" % k], "cpu", time.time() - t, flush=True)
+        save("config_N%d_vf%d.npz" % (N, vf), **out)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "small"
+    if what in ("small", "all"):
+        make_small()
+    if what in ("kmin", "all"):
+        make_kmin()
+    if what in ("norms", "all"):
+        make_norms()
+    if what in ("big384", "all"):
+        make_big(384, 1, "default", [1, 10, 100, 1000, 4800], 8)
+    if what in ("big768", "all"):
+        make_big(768, 2, "AVLT-RK2-DG-PR", [1, 10, 50], 16)
+    if what in ("big1536", "all"):
+        make_big(1536, 3, "default", [1, 5, 20], 32)

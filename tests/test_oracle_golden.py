@@ -1,0 +1,109 @@
+"""CPU: pin the numpy oracle against fixtures produced by the unmodified reference."""
+import numpy as np
+import pytest
+
+from golden_common import TUPLES, DT16, INTER_KEYS, load, have, relerr
+from oracle.grid import LeanGrid
+from oracle import halo, step as ost
+
+
+@pytest.fixture(scope="module")
+def g16():
+    return LeanGrid(16)
+
+
+def test_grid_bit_exact(g16):
+    ref = load("grid_N16.npz")
+    for pos in ("pc", "pu", "pv"):
+        assert np.array_equal(ref["sqrtg_" + pos], getattr(g16, "metric_tensor_" + pos)[:, :, 0])
+        for nm in ("prod_ex_elon_", "prod_ex_elat_", "prod_ey_elon_", "prod_ey_elat_",
+                   "determinant_ll2contra_"):
+            assert np.array_equal(ref[nm + pos], getattr(g16, nm + pos)), nm + pos
+        assert np.array_equal(ref["lon_" + pos], getattr(g16, pos).lon)
+        assert np.array_equal(ref["lat_" + pos], getattr(g16, pos).lat)
+
+
+def test_halo_index_maps_bit_exact(g16):
+    ref = load("halo_index_N16.npz")
+    P = 24
+    maps = halo.index_maps(g16)
+    for s, side in enumerate(("east", "west", "north", "south")):
+        nb, I, J = maps[s]
+        assert np.array_equal((nb * P + I) * P + J, ref[side]), side
+
+
+def test_copy_fill(g16):
+    ref = load("copyfill_N16.npz")
+    Qx, Qy = ref["Qx_in"].copy(), ref["Qy_in"].copy()
+    halo.copy_fill(Qx, Qy, g16)
+    assert np.array_equal(Qx, ref["Qx_out"]) and np.array_equal(Qy, ref["Qy_out"])
+
+
+@pytest.mark.parametrize("degree", [0, 1, 2, 3, 4])
+def test_lagrange_fill(g16, degree):
+    ref = load("halofill_N16.npz")
+    tables = halo.lagrange_tables(g16, degree)
+    assert np.array_equal(tables[0][0][0], ref["kmin_E_deg%d" % degree])
+    assert np.array_equal(tables[1][0], ref["poly_E_deg%d" % degree])
+    for ic in (1, 2):
+        Qe = ost.q_scalar_field(g16.pc.lon, g16.pc.lat, ic)
+        Qn = np.zeros_like(Qe)
+        I = np.s_[4:20, 4:20, :]
+        Qn[I] = Qe[I]
+        halo.dg_fill(Qn, g16, tables)
+        assert np.array_equal(Qn, ref["ic%d_deg%d" % (ic, degree)])
+        assert ost.compute_errors(Qn, Qe)[0] == float(ref["linf_ic%d_deg%d" % (ic, degree)])
+
+
+@pytest.mark.skipif(not have("lagrange_tables.npz"), reason="fixture not generated")
+@pytest.mark.parametrize("N", [16, 32, 48, 96, 192, 384, 768, 1536, 3072])
+def test_stencil_tables_bit_exact(N):
+    ref = load("lagrange_tables.npz")
+    g = LeanGrid.centres_only(N)
+    (kmin, kmax), poly = halo.lagrange_tables(g, 3)
+    for s, side in enumerate("EWNS"):
+        assert np.array_equal(kmin[s], ref["kmin_%s_N%d" % (side, N)]), (side, N)
+        assert np.array_equal(kmax[s], ref["kmax_%s_N%d" % (side, N)]), (side, N)
+    assert np.array_equal(poly[0], ref["poly_E_N%d" % N])
+    assert np.max(np.abs(poly[0].sum(axis=2) - 1.0)) < 1e-14
+
+
+@pytest.mark.parametrize("vf", [1, 2, 3, 4])
+def test_steps_all_tuples(g16, vf):
+    ref = load("steps_N16.npz")
+    inter = load("intermediates_N16.npz")
+    for name, tup in TUPLES.items():
+        recon, dp, split, et, mt, mf = tup
+        sim = ost.Simulation(g16, DT16[vf], 5, 2, vf, 1, recon, dp, split, et, mt, mf)
+        ost.init_vars_adv(g16, sim)
+        if vf == 1 and name == "default":
+            assert np.array_equal(sim.Q, ref["Q0"])
+        key = "vf%d_%s" % (vf, name)
+        ost.run(g16, sim, 1)
+        assert np.array_equal(sim.Q, ref[key + "_k1"]), key
+        if name in INTER_KEYS and vf in (1, 2):
+            for nm in ("q_L", "q_R", "dq", "q6", "f_upw", "dF"):
+                assert np.array_equal(getattr(sim.px, nm), inter[key + "_px_" + nm]), (key, nm)
+                assert np.array_equal(getattr(sim.py, nm), inter[key + "_py_" + nm]), (key, nm)
+            assert np.array_equal(sim.div, inter[key + "_div"])
+            assert np.array_equal(sim.U_pu.ucontra_averaged, inter[key + "_uavg"])
+            assert np.array_equal(sim.U_pu.upos, inter[key + "_upos"])
+        ost.run(g16, sim, 19, 1)
+        assert np.array_equal(sim.Q, ref[key + "_k20"]), key
+
+
+@pytest.mark.skipif(not have("norms.json"), reason="fixture not generated")
+def test_full_period_norms_n16():
+    import json, os
+    from golden_common import GOLDEN
+    rows = [r for r in json.load(open(os.path.join(GOLDEN, "norms.json")))
+            if r["N"] == 16 and r["vf"] == 1]
+    g = LeanGrid(16)
+    for r in rows:
+        recon, dp, split, et, mt, mf = r["tuple"]
+        sim = ost.Simulation(g, r["dt"], 5, 2, 1, 1, recon, dp, split, et, mt, mf)
+        ost.init_vars_adv(g, sim)
+        ost.run(g, sim, r["steps"])
+        e = ost.final_errors(g, sim, r["steps"])
+        for a, b in zip(e, (r["linf"], r["l1"], r["l2"])):
+            assert abs(a - b) <= 1e-13 * abs(b), r["scheme"]
