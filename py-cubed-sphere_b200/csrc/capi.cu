@@ -1,0 +1,478 @@
+// C ABI of libpycs_b200.so (declared in include/pycs_b200.h): handle lifetime,
+// reference-layout <-> device-layout transfers and the operator / step drivers.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "pycs_common.cuh"
+
+static thread_local std::string g_err;
+void pycs_set_error(const std::string& msg) { g_err = msg; }
+int pycs_cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+  g_err = buf;
+  return PYCS_ERR_CUDA;
+}
+static int arg_fail(const char* msg) {
+  g_err = msg;
+  return PYCS_ERR_ARG;
+}
+
+int pycs_field_shape(const Geo& g, int f, int* ni, int* nj, int* np) {
+  if (f < 0 || f >= PYCS_F_COUNT) return arg_fail("unknown field id");
+  *ni = pycs_field_is_u(f) ? g.P + 1 : g.P;
+  *nj = pycs_field_is_v(f) ? g.P + 1 : g.P;
+  *np = pycs_field_single_panel(f) ? 1 : 6;
+  return 0;
+}
+
+int pycs_field_ptr(pycs_handle h, int f, double** out) {
+  if (f < 0 || f >= PYCS_F_COUNT) return arg_fail("unknown field id");
+  if (!h->f[f]) {
+    size_t n = (size_t)(pycs_field_single_panel(f) ? 1 : 6) * h->g.ps;
+    CK(cudaMalloc(&h->f[f], n * sizeof(double)));
+    CK(cudaMemsetAsync(h->f[f], 0, n * sizeof(double), h->stream));
+  }
+  *out = h->f[f];
+  return 0;
+}
+
+// --------------------------------------------------------------------------- layout kernels
+namespace {
+// host reference layout [i][j][6] (staged on the device) -> panel-major padded
+__global__ void to_device_layout(Geo g, int ni, int nj, int np, const double* __restrict__ src,
+                                 double* __restrict__ dst) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= nj) return;
+  const double* s = src + ((long long)i * nj + j) * 6;
+  for (int p = 0; p < np; ++p) dst[gidx(g, p, i, j)] = s[p];
+}
+__global__ void from_device_layout(Geo g, int ni, int nj, int np, const double* __restrict__ src,
+                                   double* __restrict__ dst) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= nj) return;
+  double* d = dst + ((long long)i * nj + j) * 6;
+  for (int p = 0; p < 6; ++p) d[p] = src[gidx(g, np == 1 ? 0 : p, i, j)];
+}
+__global__ void fill_kernel(double* p, long long n, double v) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) p[k] = v;
+}
+}  // namespace
+
+static int ensure_stage(pycs_handle h, size_t bytes) {
+  if (h->stage_bytes < bytes) {
+    if (h->stage_dev) cudaFree(h->stage_dev);
+    h->stage_dev = nullptr;
+    h->stage_bytes = 0;
+    CK(cudaMalloc(&h->stage_dev, bytes));
+    h->stage_bytes = bytes;
+  }
+  return 0;
+}
+static int ensure_pinned(pycs_handle h, size_t bytes) {
+  if (h->pin_bytes < bytes) {
+    if (h->stage_pin) cudaFreeHost(h->stage_pin);
+    h->stage_pin = nullptr;
+    h->pin_bytes = 0;
+    CK(cudaMallocHost(&h->stage_pin, bytes));
+    h->pin_bytes = bytes;
+  }
+  return 0;
+}
+
+// --------------------------------------------------------------------------- lifetime
+extern "C" const char* pycs_last_error(void) { return g_err.c_str(); }
+
+extern "C" int pycs_create(const pycs_params* prm, pycs_handle* out) {
+  if (!prm || !out) return arg_fail("null argument");
+  if (prm->N < 8) return arg_fail("N must be >= 8");
+  if (prm->recon < 1 || prm->recon > 4 || prm->dp < 1 || prm->dp > 2 || prm->opsplit < 1 || prm->opsplit > 3 ||
+      prm->et < 1 || prm->et > 3 || prm->mt < 1 || prm->mt > 2 || prm->mf < 1 || prm->mf > 3 || prm->vf < 1 ||
+      prm->vf > 4)
+    return arg_fail("scheme selector out of range (src/advection_ic.py:85-149)");
+  // the only combinations the reference can run (src/discrete_operators.py:72-81)
+  bool ok = (prm->opsplit <= 2 && prm->mt == 1) || (prm->opsplit == 3 && prm->mt == 2);
+  if (!ok) return arg_fail("invalid opsplit/mt combination: SP-AVLT|SP-L04 need MT-0, SP-PL07 needs MT-PL07");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_err = "no CUDA device: libpycs_b200 has no CPU fallback";
+    return PYCS_ERR_CUDA;
+  }
+  if (prm->device < 0 || prm->device >= ndev) return arg_fail("bad device ordinal");
+  CK(cudaSetDevice(prm->device));
+  pycs_handle h = new (std::nothrow) pycs_handle_s();
+  if (!h) return PYCS_ERR_NOMEM;
+  memset(h, 0, sizeof *h);
+  h->prm = *prm;
+  h->device = prm->device;
+  Geo& g = h->g;
+  g.N = prm->N;
+  g.P = prm->N + 2 * PYCS_NG;
+  g.lo = PYCS_NG;
+  g.hi = PYCS_NG + prm->N;
+  g.ld = ((PYCS_JOFF + g.P + 1 + 15) / 16) * 16;
+  g.ps = (long long)(g.P + 1) * g.ld;
+  g.dx = prm->dx;
+  g.dy = prm->dy;
+  g.dt = prm->dt;
+  cudaDeviceProp dp;
+  CK(cudaGetDeviceProperties(&dp, prm->device));
+  h->sm_count = dp.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&h->ev0));
+  CK(cudaEventCreate(&h->ev1));
+  CK(cudaMalloc(&h->red_out, 16 * sizeof(double)));
+  CK(cudaMemset(h->red_out, 0, 16 * sizeof(double)));
+  CK(cudaMalloc(&h->halo_buf, sizeof(double) * 4 * 6 * 4 * g.P));
+  pycs_build_halo_maps(g, &h->maps);
+  *out = h;
+  return 0;
+}
+
+extern "C" int pycs_destroy(pycs_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (int k = 0; k < PYCS_F_COUNT; ++k)
+    if (h->f[k]) cudaFree(h->f[k]);
+  if (h->kminE) cudaFree(h->kminE);
+  if (h->wE) cudaFree(h->wE);
+  if (h->halo_buf) cudaFree(h->halo_buf);
+  if (h->red_part) cudaFree(h->red_part);
+  if (h->red_out) cudaFree(h->red_out);
+  if (h->stage_dev) cudaFree(h->stage_dev);
+  if (h->stage_pin) cudaFreeHost(h->stage_pin);
+  cudaEventDestroy(h->ev0);
+  cudaEventDestroy(h->ev1);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+extern "C" int pycs_device_info(pycs_handle h, int32_t* sm_count, char* name, int32_t name_len) {
+  cudaDeviceProp dp;
+  CK(cudaGetDeviceProperties(&dp, h->device));
+  if (sm_count) *sm_count = dp.multiProcessorCount;
+  if (name && name_len > 0) {
+    strncpy(name, dp.name, name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  return 0;
+}
+
+extern "C" int pycs_synchronize(pycs_handle h) {
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int pycs_set_dt(pycs_handle h, double dt) {
+  h->g.dt = dt;
+  h->prm.dt = dt;
+  return 0;
+}
+
+extern "C" int pycs_launch_count(pycs_handle h, int64_t* count) {
+  *count = h->launches;
+  return 0;
+}
+
+// --------------------------------------------------------------------------- transfers
+static int upload_from(pycs_handle h, int field, const double* host, bool pinned_src) {
+  int ni, nj, np;
+  TRY(pycs_field_shape(h->g, field, &ni, &nj, &np));
+  double* dst;
+  TRY(pycs_field_ptr(h, field, &dst));
+  size_t bytes = (size_t)ni * nj * 6 * sizeof(double);
+  TRY(ensure_stage(h, bytes));
+  (void)pinned_src;
+  CK(cudaMemcpyAsync(h->stage_dev, host, bytes, cudaMemcpyHostToDevice, h->stream));
+  dim3 grid((nj + 127) / 128, ni);
+  to_device_layout<<<grid, 128, 0, h->stream>>>(h->g, ni, nj, np, h->stage_dev, dst);
+  CKL(h);
+  return 0;
+}
+
+extern "C" int pycs_upload_field(pycs_handle h, int32_t field, const double* host) {
+  if (!host) return arg_fail("null host pointer");
+  CK(cudaSetDevice(h->device));
+  TRY(upload_from(h, field, host, false));
+  CK(cudaStreamSynchronize(h->stream));
+  if (field == PYCS_F_Q) h->qcur = 0;
+  if (field == PYCS_F_SQRTG_PC) h->a2_valid = 0;
+  return 0;
+}
+
+static int download_to(pycs_handle h, int field, double* host) {
+  int ni, nj, np;
+  TRY(pycs_field_shape(h->g, field, &ni, &nj, &np));
+  double* src;
+  TRY(pycs_field_ptr(h, field, &src));
+  size_t bytes = (size_t)ni * nj * 6 * sizeof(double);
+  TRY(ensure_stage(h, bytes));
+  dim3 grid((nj + 127) / 128, ni);
+  from_device_layout<<<grid, 128, 0, h->stream>>>(h->g, ni, nj, np, src, h->stage_dev);
+  CKL(h);
+  CK(cudaMemcpyAsync(host, h->stage_dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+  return 0;
+}
+
+extern "C" int pycs_download_field(pycs_handle h, int32_t field, double* host) {
+  if (!host) return arg_fail("null host pointer");
+  CK(cudaSetDevice(h->device));
+  TRY(download_to(h, field, host));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int pycs_copy_field(pycs_handle h, int32_t dst, int32_t src) {
+  double *d, *s;
+  TRY(pycs_field_ptr(h, dst, &d));
+  TRY(pycs_field_ptr(h, src, &s));
+  if (pycs_field_single_panel(dst) != pycs_field_single_panel(src)) return arg_fail("shape mismatch");
+  size_t n = (size_t)(pycs_field_single_panel(dst) ? 1 : 6) * h->g.ps;
+  CK(cudaMemcpyAsync(d, s, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return 0;
+}
+
+extern "C" int pycs_fill_field(pycs_handle h, int32_t field, double value) {
+  double* d;
+  TRY(pycs_field_ptr(h, field, &d));
+  long long n = (long long)(pycs_field_single_panel(field) ? 1 : 6) * h->g.ps;
+  fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d, n, value);
+  CKL(h);
+  return 0;
+}
+
+extern "C" int pycs_upload_lagrange(pycs_handle h, int32_t degree, const int32_t* kmin_east,
+                                    const double* weights_east) {
+  if (degree < 0 || degree > 7 || !kmin_east || !weights_east) return arg_fail("bad Lagrange table");
+  CK(cudaSetDevice(h->device));
+  int order = degree + 1, P = h->g.P;
+  // validate the stencil range here: the kernels index neighbour strips with it
+  for (int k = 0; k < 4 * P; ++k)
+    if (kmin_east[k] < 0 || kmin_east[k] + order > P) return arg_fail("Kmin outside [0, P-order]");
+  if (h->kminE) cudaFree(h->kminE);
+  if (h->wE) cudaFree(h->wE);
+  h->kminE = nullptr;
+  h->wE = nullptr;
+  CK(cudaMalloc(&h->kminE, sizeof(int) * 4 * P));
+  CK(cudaMalloc(&h->wE, sizeof(double) * 4 * P * order));
+  CK(cudaMemcpy(h->kminE, kmin_east, sizeof(int) * 4 * P, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->wE, weights_east, sizeof(double) * 4 * P * order, cudaMemcpyHostToDevice));
+  h->degree = degree;
+  h->order = order;
+  return 0;
+}
+
+// --------------------------------------------------------------------------- halo API
+extern "C" int pycs_halo_gather(pycs_handle h, int32_t fx, int32_t fy, double* east, double* west,
+                                double* north, double* south) {
+  double *x, *y;
+  TRY(pycs_field_ptr(h, fx, &x));
+  TRY(pycs_field_ptr(h, fy, &y));
+  TRY(k_halo_gather(h, x, y, h->halo_buf));
+  int P = h->g.P, n = 4 * P;
+  std::vector<double> tmp((size_t)4 * 6 * n);
+  CK(cudaMemcpyAsync(tmp.data(), h->halo_buf, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  double* outs[4] = {east, west, north, south};
+  for (int s = 0; s < 4; ++s)
+    for (int p = 0; p < 6; ++p)
+      for (int t = 0; t < n; ++t) outs[s][(size_t)t * 6 + p] = tmp[((size_t)s * 6 + p) * n + t];
+  return 0;
+}
+
+extern "C" int pycs_halo_fill_dg(pycs_handle h, int32_t field) {
+  double* q;
+  TRY(pycs_field_ptr(h, field, &q));
+  return k_dg_fill(h, q);
+}
+
+extern "C" int pycs_halo_fill_copy(pycs_handle h, int32_t fx, int32_t fy) {
+  double *x, *y;
+  TRY(pycs_field_ptr(h, fx, &x));
+  TRY(pycs_field_ptr(h, fy, &y));
+  TRY(k_halo_gather(h, x, y, h->halo_buf));
+  return k_halo_scatter_copy(h, x, y, h->halo_buf);
+}
+
+extern "C" int pycs_halo_fill_scalar(pycs_handle h, int32_t fx, int32_t fy) {
+  if (h->prm.et == 3) return pycs_halo_fill_dg(h, fx);      // src/edges_treatment.py:289-290
+  return pycs_halo_fill_copy(h, fx, fy);
+}
+
+extern "C" int pycs_halo_fill_vector(pycs_handle h) { return k_wind_ghost_fill(h); }
+
+// --------------------------------------------------------------------------- operators
+extern "C" int pycs_time_averaged_velocity(pycs_handle h) { return k_time_averaged_velocity(h); }
+
+extern "C" int pycs_cfl(pycs_handle h, int32_t dst, int32_t src, int32_t dir) {
+  double *d, *s;
+  TRY(pycs_field_ptr(h, dst, &d));
+  TRY(pycs_field_ptr(h, src, &s));
+  return k_cfl(h, d, s, dir);
+}
+
+extern "C" int pycs_ppm_reconstruction(pycs_handle h, int32_t fx, int32_t fy) {
+  double *x, *y;
+  TRY(pycs_field_ptr(h, fx, &x));
+  TRY(pycs_field_ptr(h, fy, &y));
+  TRY(k_recon(h, x, y));
+  if (h->prm.et == 2) TRY(k_edges_extrapolation(h, x, y));   // src/reconstruction_1d.py:392-394
+  return 0;
+}
+
+extern "C" int pycs_numerical_flux(pycs_handle h, int32_t fx, int32_t fy) {
+  double *x, *y;
+  TRY(pycs_field_ptr(h, fx, &x));
+  TRY(pycs_field_ptr(h, fy, &y));
+  return k_flux(h, x, y);
+}
+
+extern "C" int pycs_compute_fluxes(pycs_handle h, int32_t fx, int32_t fy) {
+  TRY(pycs_ppm_reconstruction(h, fx, fy));
+  return pycs_numerical_flux(h, fx, fy);
+}
+
+extern "C" int pycs_F_operator(pycs_handle h) { return k_flux_diff(h, 0); }
+extern "C" int pycs_G_operator(pycs_handle h) { return k_flux_diff(h, 1); }
+extern "C" int pycs_average_flux_cube_edges(pycs_handle h) { return k_average_flux_edges(h); }
+
+// divergence, operator by operator (src/discrete_operators.py:18-101)
+extern "C" int pycs_divergence(pycs_handle h) {
+  double *Q, *gQ, *cx, *cy, *ua, *va;
+  TRY(pycs_field_ptr(h, PYCS_F_Q, &Q));
+  TRY(pycs_field_ptr(h, PYCS_F_GQ, &gQ));
+  TRY(pycs_field_ptr(h, PYCS_F_CX, &cx));
+  TRY(pycs_field_ptr(h, PYCS_F_CY, &cy));
+  TRY(pycs_field_ptr(h, PYCS_F_PU_UAVG, &ua));
+  TRY(pycs_field_ptr(h, PYCS_F_PV_VAVG, &va));
+  TRY(k_mul_metric(h, gQ, Q));                                  // :31
+  TRY(k_cfl(h, cx, ua, 0));                                     // :34-35
+  TRY(k_cfl(h, cy, va, 1));
+  TRY(pycs_compute_fluxes(h, PYCS_F_Q, PYCS_F_Q));              // :38
+  TRY(k_flux_diff(h, 0));                                       // :42-43
+  TRY(k_flux_diff(h, 1));
+  TRY(k_inner_update(h));                                       // :45-73
+  if (h->prm.et != 3) TRY(pycs_halo_fill_copy(h, PYCS_F_QX, PYCS_F_QY));   // :76-78
+  TRY(pycs_compute_fluxes(h, PYCS_F_QY, PYCS_F_QX));            // :81 (swapped)
+  if (h->prm.mf == 2) TRY(k_average_flux_edges(h));             // :85-86
+  TRY(k_flux_diff(h, 0));                                       // :89-90
+  TRY(k_flux_diff(h, 1));
+  return k_div_and_fix(h);                                      // :95-101
+}
+
+// make PYCS_F_Q the current state if the fused path left it in Q_NEXT
+static int normalize_q(pycs_handle h) {
+  if (h->qcur == 1) {
+    double* t = h->f[PYCS_F_Q];
+    h->f[PYCS_F_Q] = h->f[PYCS_F_Q_NEXT];
+    h->f[PYCS_F_Q_NEXT] = t;
+    h->qcur = 0;
+  }
+  return 0;
+}
+
+extern "C" int pycs_adv_time_step(pycs_handle h, int64_t k, double t) {
+  (void)k; (void)t;
+  CK(cudaSetDevice(h->device));
+  TRY(normalize_q(h));
+  TRY(pycs_halo_fill_scalar(h, PYCS_F_Q, PYCS_F_Q));            // src/advection_timestep.py:28
+  if (h->prm.vf >= 2) {                                         // :31-37
+    TRY(k_wind_ghost_fill(h));
+    TRY(k_time_averaged_velocity(h));
+  }
+  TRY(pycs_divergence(h));                                      // :40
+  return k_q_update(h);                                         // :43
+}
+
+extern "C" int pycs_update_adv(pycs_handle h, double t) { return k_update_adv(h, t); }
+extern "C" int pycs_init_wind(pycs_handle h) { return k_wind_interior(h, 0.0, 1, 1); }
+extern "C" int pycs_convert_wind_interior(pycs_handle h) { return k_wind_interior(h, 0.0, 1, 0); }
+
+static int run_steps(pycs_handle h, int64_t k0, int64_t nsteps, int fused) {
+  CK(cudaSetDevice(h->device));
+  if (fused && !k_fused_supported(h)) return arg_fail("no fused step kernel for this scheme tuple");
+  for (int64_t k = k0 + 1; k <= k0 + nsteps; ++k) {
+    double t = (double)k * h->g.dt;                             // t = k*dt, src/advection_sphere.py:47
+    if (fused) {
+      TRY(k_fused_step(h, k, t));
+    } else {
+      TRY(pycs_adv_time_step(h, k, t));
+      TRY(k_update_adv(h, t));
+    }
+  }
+  if (fused) TRY(normalize_q(h));
+  return 0;
+}
+
+extern "C" int pycs_fused_supported(pycs_handle h, int32_t* yes) {
+  *yes = k_fused_supported(h);
+  return 0;
+}
+
+extern "C" int pycs_run(pycs_handle h, int64_t k0, int64_t nsteps, int32_t fused) {
+  return run_steps(h, k0, nsteps, fused);
+}
+
+extern "C" int pycs_run_timed(pycs_handle h, int64_t k0, int64_t nsteps, int32_t fused, float* ms) {
+  CK(cudaSetDevice(h->device));
+  h->last_step_kernel_ms = 0.f;
+  h->last_step_kernel_launches = 0;
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaEventRecord(h->ev0, h->stream));
+  int r = run_steps(h, k0, nsteps, fused);
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaEventSynchronize(h->ev1));
+  if (r) return r;
+  CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return 0;
+}
+
+extern "C" int pycs_last_step_kernel_ms(pycs_handle h, float* ms, int64_t* launches) {
+  *ms = h->last_step_kernel_ms;
+  *launches = h->last_step_kernel_launches;
+  return 0;
+}
+
+extern "C" int pycs_adv_time_step_host(pycs_handle h, double* Q, int64_t k, double t, int32_t fused) {
+  if (!Q) return arg_fail("null Q");
+  CK(cudaSetDevice(h->device));
+  TRY(normalize_q(h));
+  TRY(upload_from(h, PYCS_F_Q, Q, true));
+  if (fused) {
+    if (!k_fused_supported(h)) return arg_fail("no fused step kernel for this scheme tuple");
+    TRY(k_fused_step(h, k, t));
+    TRY(normalize_q(h));
+  } else {
+    TRY(pycs_adv_time_step(h, k, t));
+    TRY(k_update_adv(h, t));
+  }
+  TRY(download_to(h, PYCS_F_Q, Q));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// --------------------------------------------------------------------------- diagnostics
+extern "C" int pycs_errors(pycs_handle h, const double* qexact_interior, double* out3) {
+  // stage the (N,N,6) exact field into the interior of USER_B
+  const Geo& g = h->g;
+  TRY(normalize_q(h));
+  std::vector<double> full((size_t)g.P * g.P * 6, 0.0);
+  for (int i = 0; i < g.N; ++i)
+    memcpy(&full[(((size_t)(i + g.lo)) * g.P + g.lo) * 6], qexact_interior + (size_t)i * g.N * 6,
+           sizeof(double) * g.N * 6);
+  TRY(pycs_upload_field(h, PYCS_F_USER_B, full.data()));
+  double* qe;
+  TRY(pycs_field_ptr(h, PYCS_F_USER_B, &qe));
+  return k_errors(h, qe, out3);
+}
+
+extern "C" int pycs_mass(pycs_handle h, double* mass) {
+  TRY(normalize_q(h));
+  return k_mass(h, mass);
+}

@@ -1,0 +1,132 @@
+// Internal definitions shared by the translation units of libpycs_b200.so.
+//
+// Device layout (DESIGN.md "Data layout in HBM"): every field is panel-major,
+// [panel][i][j] with j contiguous.  A row has `ld` doubles, column j lives at
+// offset j + JOFF so that the first interior column (j0 = 4) starts a 128-byte
+// line; a panel has P+1 rows (enough for x-edge fields) and `ld` >= JOFF+P+1
+// (enough for y-edge fields), so all fields share one geometry.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/pycs_b200.h"
+
+#define PYCS_JOFF 12
+#define PYCS_NG 4          // ngl = ngr = 4  (src/cs_datastruct.py:225-231)
+
+struct Geo {
+  int N, P, ld, lo, hi;    // lo = i0 = j0 = 4, hi = iend = jend = N + 4
+  long long ps;            // panel stride in doubles = (P + 1) * ld
+  double dx, dy, dt;
+};
+
+__host__ __device__ __forceinline__ long long gidx(const Geo& g, int p, int i, int j) {
+  return (long long)p * g.ps + (long long)i * g.ld + (j + PYCS_JOFF);
+}
+
+// Affine source map of one (panel, side) halo strip: entry [a][b] of the halo
+// array comes from panel nb at (ci + ai*a + bi*b, cj + aj*a + bj*b); rot = the
+// neighbour's axes are transposed w.r.t. ours (x/y field swap of
+// src/halo_data.py:224,258,371,388).
+struct SideMap { int nb, ci, ai, bi, cj, aj, bj, rot; };
+struct HaloMaps { SideMap m[6][4]; };   // side: 0 E, 1 W, 2 N, 3 S
+
+enum { SIDE_E = 0, SIDE_W = 1, SIDE_N = 2, SIDE_S = 3 };
+
+struct pycs_handle_s {
+  pycs_params prm;
+  Geo g;
+  int device;
+  int sm_count;
+  cudaStream_t stream;
+  double* f[PYCS_F_COUNT];
+  // Lagrange tables (east), device
+  int degree, order;
+  int* kminE;
+  double* wE;
+  HaloMaps maps;
+  // halo gather buffers for the copy fill: E, W (4,P,6 each) then N, S (P,4,6)
+  double* halo_buf;
+  // reductions
+  double* red_part;     // per-block partials
+  double* red_out;      // small device result vector
+  int red_blocks;
+  // staging for reference-layout transfers
+  double* stage_dev;
+  size_t stage_bytes;
+  double* stage_pin;
+  size_t pin_bytes;
+  long long launches;
+  // fused step bookkeeping
+  int qcur;             // which of Q / Q_NEXT currently holds the state
+  cudaEvent_t ev0, ev1;
+  float last_step_kernel_ms;
+  long long last_step_kernel_launches;
+  // deferred MF-PR correction scalar (device): m0 / a2 of the previous fused step
+  double a2;            // sum sqrtg^2 over the interior (static)
+  int a2_valid;
+};
+
+// error plumbing ------------------------------------------------------------
+void pycs_set_error(const std::string& msg);
+int pycs_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+#define CK(call)                                                                 \
+  do {                                                                           \
+    cudaError_t e__ = (call);                                                    \
+    if (e__ != cudaSuccess) return pycs_cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+#define CKL(h)                                                        \
+  do {                                                                \
+    (h)->launches++;                                                  \
+    cudaError_t e__ = cudaGetLastError();                             \
+    if (e__ != cudaSuccess) return pycs_cuda_fail(e__, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+#define TRY(call)            \
+  do {                       \
+    int r__ = (call);        \
+    if (r__ != 0) return r__; \
+  } while (0)
+
+int pycs_field_shape(const Geo& g, int field, int* ni, int* nj, int* npanels);
+int pycs_field_ptr(pycs_handle h, int field, double** out);   // lazy allocation
+inline bool pycs_field_is_u(int f) {
+  return f == PYCS_F_CX || (f >= PYCS_F_PX_FL && f <= PYCS_F_PX_FUPW) ||
+         (f >= PYCS_F_PU_ULON && f <= PYCS_F_PU_UOLD) || f == PYCS_F_SQRTG_PU ||
+         (f >= PYCS_F_PU_EXLON && f <= PYCS_F_PU_DET) || f == PYCS_F_PU_LON || f == PYCS_F_PU_LAT;
+}
+inline bool pycs_field_is_v(int f) {
+  return f == PYCS_F_CY || (f >= PYCS_F_PY_FL && f <= PYCS_F_PY_FUPW) ||
+         (f >= PYCS_F_PV_ULON && f <= PYCS_F_PV_VOLD) || f == PYCS_F_SQRTG_PV ||
+         (f >= PYCS_F_PV_EXLON && f <= PYCS_F_PV_DET) || f == PYCS_F_PV_LON || f == PYCS_F_PV_LAT;
+}
+inline bool pycs_field_single_panel(int f) { return f >= PYCS_F_SQRTG_PC && f <= PYCS_F_SQRTG_PV; }
+
+// launchers implemented in the kernel translation units -----------------------
+// halo.cu
+void pycs_build_halo_maps(const Geo& g, HaloMaps* maps);
+int k_halo_gather(pycs_handle h, const double* fx, const double* fy, double* buf);
+int k_halo_scatter_copy(pycs_handle h, double* fx, double* fy, const double* buf);
+int k_dg_fill(pycs_handle h, double* q);
+// ppm.cu
+int k_cfl(pycs_handle h, double* dst, const double* src, int dir);
+int k_mul_metric(pycs_handle h, double* gq, const double* q);
+int k_recon(pycs_handle h, const double* qx, const double* qy);
+int k_edges_extrapolation(pycs_handle h, const double* qx, const double* qy);
+int k_flux(pycs_handle h, const double* qx, const double* qy);
+int k_flux_diff(pycs_handle h, int dir);
+int k_inner_update(pycs_handle h);
+int k_average_flux_edges(pycs_handle h);
+int k_div_and_fix(pycs_handle h);
+int k_q_update(pycs_handle h);
+int k_errors(pycs_handle h, const double* qexact_dev, double* out3_host);
+int k_mass(pycs_handle h, double* out_host);
+int k_sum_sq_metric(pycs_handle h, double* out_host);
+// wind.cu
+int k_time_averaged_velocity(pycs_handle h);
+int k_wind_ghost_fill(pycs_handle h);
+int k_update_adv(pycs_handle h, double t);
+int k_wind_interior(pycs_handle h, double t, int convert_interior_only, int do_velocity);
+// fused.cu
+int k_fused_supported(pycs_handle h);
+int k_fused_step(pycs_handle h, long long k, double t);
+// layout.cu (in capi.cu)

@@ -1,0 +1,281 @@
+// Wind path kernels.  Reference (file:line under /root/reference):
+//   src/advection_ic.py:287-313      velocity_adv                     -> velocity_kernel
+//   src/sphgeo.py:120-133            latlon <-> contravariant         -> ll2contra / contra2ll
+//   src/advection_timestep.py:48-75  update_adv                       -> k_update_adv
+//   src/averaged_velocity.py:14-62   time_averaged_velocity           -> averaged_kernel
+//   src/interpolation.py:347-430     wind_edges2center_cubic_...      -> ring_kernel (+ dg fill)
+//   src/interpolation.py:436-532     wind_center2ghostedge_cubic_...  -> ghost_edge_kernel
+//   src/edges_treatment.py:306-347   RK2 line copies for ET-S72/PL07  -> rk2_copy_kernel
+// Compiled with -fmad=false (same rounding as the numpy expressions; only the
+// device sin/cos may differ from libm by an ulp).
+#include "pycs_common.cuh"
+#include "cube_edges.cuh"
+
+namespace {
+
+constexpr int BX = 128;
+#define PI_ 3.141592653589793
+
+struct Conv { const double *exlon, *exlat, *eylon, *eylat, *det; };
+
+__device__ __forceinline__ void ll2contra(double ulon, double vlat, const Conv& c, long long id,
+                                          double* u, double* v) {
+  double a = c.eylat[id] * ulon - c.eylon[id] * vlat;      // src/sphgeo.py:121-124
+  double b = -c.exlat[id] * ulon + c.exlon[id] * vlat;
+  *u = a / c.det[id];
+  *v = b / c.det[id];
+}
+
+// velocity_adv on the interior edge points of one position (pu: i in [lo,hi], j in [lo,hi);
+// pv: i in [lo,hi), j in [lo,hi])
+__global__ void velocity_kernel(Geo g, int vf, double t, int is_pu, const double* __restrict__ lon,
+                                const double* __restrict__ lat, double* __restrict__ ulon,
+                                double* __restrict__ vlat) {
+  int j = g.lo + blockIdx.x * BX + threadIdx.x, i = g.lo + blockIdx.y, p = blockIdx.z;
+  int ih = is_pu ? g.hi : g.hi - 1, jh = is_pu ? g.hi - 1 : g.hi;
+  if (i > ih || j > jh) return;
+  long long id = gidx(g, p, i, j);
+  double lo_ = lon[id], la = lat[id], u, v;
+  const double pi = PI_;
+  if (vf == 1) {
+    double alpha = -45.0 * (1.0 / (180.0 / pi));
+    double u0 = 2.0 * pi / 5.0;
+    u = u0 * (cos(la) * cos(alpha) + sin(la) * cos(lo_) * sin(alpha));
+    v = -u0 * sin(lo_) * sin(alpha);
+  } else if (vf == 2) {
+    double T = 5.0, k = 2.0;
+    double lonp = lo_ - 2 * pi * t / T;
+    double s1 = sin((lonp + pi));
+    u = k * (s1 * s1) * (sin(2. * la)) * (cos(pi * t / T)) + 2. * pi * cos(la) / T;
+    v = k * (sin(2 * (lonp + pi))) * (cos(la)) * (cos(pi * t / T));
+  } else if (vf == 3) {
+    double T = 5.0, k = 1.0;
+    double s1 = sin((lo_ + pi) / 2.0), c1 = cos(la);
+    u = -k * (s1 * s1) * (sin(2.0 * la)) * (c1 * c1) * (cos(pi * t / T));
+    v = (k / 2.0) * (sin((lo_ + pi))) * (pow(c1, 3.0)) * (cos(pi * t / T));
+  } else {
+    double c3 = pow(cos(la), 3.0);
+    u = -1 * (sin(lo_) * sin(lo_) * c3);
+    v = -4 * c3 * sin(la) * cos(lo_) * sin(lo_);
+  }
+  ulon[id] = u;
+  vlat[id] = v;
+}
+
+// ll -> contravariant on a rectangle [i0,i1) x [j0,j1)
+__global__ void convert_kernel(Geo g, int i0, int i1, int j0, int j1, Conv c,
+                               const double* __restrict__ ulon, const double* __restrict__ vlat,
+                               double* __restrict__ uc, double* __restrict__ vc) {
+  int j = j0 + blockIdx.x * BX + threadIdx.x, i = i0 + blockIdx.y, p = blockIdx.z;
+  if (j >= j1 || i >= i1) return;
+  long long id = gidx(g, p, i, j);
+  ll2contra(ulon[id], vlat[id], c, id, &uc[id], &vc[id]);
+}
+
+__global__ void copy2_kernel(Geo g, int ni, int nj, double* __restrict__ d, const double* __restrict__ s) {
+  int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y, p = blockIdx.z;
+  if (j >= nj || i >= ni) return;
+  long long id = gidx(g, p, i, j);
+  d[id] = s[id];
+}
+
+// RK2 departure velocity at edges lo..hi along DIR (src/averaged_velocity.py:36-62)
+template <int DIR>
+__global__ void averaged_rk2_kernel(Geo g, const double* __restrict__ u, const double* __restrict__ uold,
+                                    double* __restrict__ uavg, double dto2) {
+  int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y, p = blockIdx.z;
+  int ni = DIR == 0 ? g.P + 1 : g.P, nj = DIR == 0 ? g.P : g.P + 1;
+  if (j >= nj || i >= ni) return;
+  int s = DIR == 0 ? i : j;
+  if (s < g.lo || s > g.hi) return;
+  const long long st = DIR == 0 ? g.ld : 1;
+  long long id = gidx(g, p, i, j);
+  double uu = u[id];
+  double a = uu * dto2 / (DIR == 0 ? g.dx : g.dy);
+  double u0 = 1.5 * uu - 0.5 * uold[id];
+  double r;
+  if (uu >= 0) {
+    double um = 1.5 * u[id - st] - 0.5 * uold[id - st];
+    r = (1.0 - a) * u0 + a * um;
+  } else {
+    double up = 1.5 * u[id + st] - 0.5 * uold[id + st];
+    r = -a * up + (1.0 + a) * u0;
+  }
+  uavg[id] = r;
+}
+
+// Centre winds on the boundary ring + lat-lon conversion (src/interpolation.py:359-425)
+__global__ void ring_kernel(Geo g, const double* __restrict__ u, const double* __restrict__ v,
+                            double* __restrict__ uc, double* __restrict__ vc,
+                            double* __restrict__ ulon, double* __restrict__ vlat,
+                            const double* __restrict__ exlon, const double* __restrict__ exlat,
+                            const double* __restrict__ eylon, const double* __restrict__ eylat) {
+  int j = g.lo + blockIdx.x * BX + threadIdx.x, i = g.lo + blockIdx.y, p = blockIdx.z;
+  if (j >= g.hi || i >= g.hi) return;
+  int lo = g.lo, hi = g.hi;
+  bool ring = i < lo + PYCS_NG || i >= hi - PYCS_NG || j < lo + PYCS_NG || j >= hi - PYCS_NG;
+  if (!ring) return;
+  const double a1 = 5.0 / 16.0, a2 = 15.0 / 16.0, a3 = -5.0 / 16.0, a4 = 1.0 / 16.0;
+  const double b1 = -1.0 / 16.0, b2 = 9.0 / 16.0, b3 = 9.0 / 16.0, b4 = -1.0 / 16.0;
+  long long id = gidx(g, p, i, j);
+  const long long L = g.ld;
+  double x, y;
+  if (i == lo) x = a1 * u[id] + a2 * u[id + L] + a3 * u[id + 2 * L] + a4 * u[id + 3 * L];
+  else if (i == hi - 1) x = a4 * u[id - 2 * L] + a3 * u[id - L] + a2 * u[id] + a1 * u[id + L];
+  else x = b1 * u[id - L] + b2 * u[id] + b3 * u[id + L] + b4 * u[id + 2 * L];
+  if (j == lo) y = a1 * v[id] + a2 * v[id + 1] + a3 * v[id + 2] + a4 * v[id + 3];
+  else if (j == hi - 1) y = a4 * v[id - 2] + a3 * v[id - 1] + a2 * v[id] + a1 * v[id + 1];
+  else y = b1 * v[id - 1] + b2 * v[id] + b3 * v[id + 1] + b4 * v[id + 2];
+  uc[id] = x;
+  vc[id] = y;
+  ulon[id] = exlon[id] * x + eylon[id] * y;               // src/sphgeo.py:131-132
+  vlat[id] = exlat[id] * x + eylat[id] * y;
+}
+
+// Ghost edges from ghost centres + conversion (src/interpolation.py:443-532).
+// DIR = 0: U_pu, edges along i (S/N ghost rows for i in [lo,hi], lines lo-1 and hi+1 for all j);
+// DIR = 1: U_pv, edges along j.
+template <int DIR>
+__global__ void ghost_edge_kernel(Geo g, const double* __restrict__ culon, const double* __restrict__ cvlat,
+                                  double* __restrict__ ulon, double* __restrict__ vlat,
+                                  double* __restrict__ uc, double* __restrict__ vc, Conv c) {
+  int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y, p = blockIdx.z;
+  int s = DIR == 0 ? i : j, o = DIR == 0 ? j : i;
+  if (o >= g.P || s < g.lo - 1 || s > g.hi + 1) return;
+  bool line = (s == g.lo - 1 || s == g.hi + 1);
+  bool ghost_o = (o < g.lo || o >= g.hi);
+  if (!(line || ghost_o)) return;
+  const long long st = DIR == 0 ? g.ld : 1;
+  const double a1 = 9.0 / 16.0, a2 = -1.0 / 16.0;
+  long long id = gidx(g, p, i, j);
+  double ul = a1 * (culon[id] + culon[id - st]) + a2 * (culon[id + st] + culon[id - 2 * st]);
+  double vl = a1 * (cvlat[id] + cvlat[id - st]) + a2 * (cvlat[id + st] + cvlat[id - 2 * st]);
+  ulon[id] = ul;
+  vlat[id] = vl;
+  ll2contra(ul, vl, c, id, &uc[id], &vc[id]);
+}
+
+// src/edges_treatment.py:311-347: ghost line of the normal wind beyond each cube edge
+__global__ void rk2_copy_kernel(Geo g, double* __restrict__ u, double* __restrict__ v) {
+  int t = blockIdx.x * BX + threadIdx.x;
+  if (t >= g.N) return;
+  CubeEdge ce = cube_edge(blockIdx.y);
+  double sg = ce.a.side == ce.b.side ? -1.0 : 1.0;
+  for (int d = 0; d < 2; ++d) {
+    EdgeEnd dst = d == 0 ? ce.a : ce.b, src = d == 0 ? ce.b : ce.a;
+    int ts = ce.flip ? g.N - 1 - t : t;
+    int di = dst.side == 0 ? g.lo - 1 : g.hi + 1;
+    int si = src.side == 0 ? g.lo + 1 : g.hi - 1;
+    double* dp = dst.dir == 0 ? u + gidx(g, dst.panel, di, g.lo + t) : v + gidx(g, dst.panel, g.lo + t, di);
+    const double* sp = src.dir == 0 ? u + gidx(g, src.panel, si, g.lo + ts) : v + gidx(g, src.panel, g.lo + ts, si);
+    *dp = sg * (*sp);
+  }
+}
+
+inline dim3 grid_all(int ni, int nj) { return dim3((nj + BX - 1) / BX, ni, 6); }
+
+}  // namespace
+
+#define F(h, id, var)    \
+  double* var = nullptr; \
+  TRY(pycs_field_ptr(h, id, &var))
+
+static int get_conv(pycs_handle h, int base, Conv* c) {
+  double* p[5];
+  for (int k = 0; k < 5; ++k) TRY(pycs_field_ptr(h, base + k, &p[k]));
+  c->exlon = p[0]; c->exlat = p[1]; c->eylon = p[2]; c->eylat = p[3]; c->det = p[4];
+  return 0;
+}
+
+int k_time_averaged_velocity(pycs_handle h) {
+  const Geo& g = h->g;
+  F(h, PYCS_F_PU_UCONTRA, u); F(h, PYCS_F_PU_UOLD, uo); F(h, PYCS_F_PU_UAVG, ua);
+  F(h, PYCS_F_PV_VCONTRA, v); F(h, PYCS_F_PV_VOLD, vo); F(h, PYCS_F_PV_VAVG, va);
+  if (h->prm.dp == 1) {                        // RK1: plain copies (:30-32)
+    copy2_kernel<<<grid_all(g.P + 1, g.P), BX, 0, h->stream>>>(g, g.P + 1, g.P, ua, u);
+    CKL(h);
+    copy2_kernel<<<grid_all(g.P, g.P + 1), BX, 0, h->stream>>>(g, g.P, g.P + 1, va, v);
+    CKL(h);
+  } else {
+    double dto2 = g.dt * 0.5;
+    averaged_rk2_kernel<0><<<grid_all(g.P + 1, g.P), BX, 0, h->stream>>>(g, u, uo, ua, dto2);
+    CKL(h);
+    averaged_rk2_kernel<1><<<grid_all(g.P, g.P + 1), BX, 0, h->stream>>>(g, v, vo, va, dto2);
+    CKL(h);
+  }
+  return 0;
+}
+
+int k_wind_ghost_fill(pycs_handle h) {
+  const Geo& g = h->g;
+  F(h, PYCS_F_PU_UCONTRA, u); F(h, PYCS_F_PV_VCONTRA, v);
+  if (h->prm.et == 3) {
+    F(h, PYCS_F_PC_UCONTRA, cu); F(h, PYCS_F_PC_VCONTRA, cv);
+    F(h, PYCS_F_PC_ULON, cul); F(h, PYCS_F_PC_VLAT, cvl);
+    F(h, PYCS_F_PC_EXLON, exlon); F(h, PYCS_F_PC_EXLAT, exlat);
+    F(h, PYCS_F_PC_EYLON, eylon); F(h, PYCS_F_PC_EYLAT, eylat);
+    ring_kernel<<<dim3((g.N + BX - 1) / BX, g.N, 6), BX, 0, h->stream>>>(g, u, v, cu, cv, cul, cvl, exlon,
+                                                                         exlat, eylon, eylat);
+    CKL(h);
+    TRY(k_dg_fill(h, cul));
+    TRY(k_dg_fill(h, cvl));
+    F(h, PYCS_F_PU_ULON, uul); F(h, PYCS_F_PU_VLAT, uvl); F(h, PYCS_F_PU_VCONTRA, uvc);
+    F(h, PYCS_F_PV_ULON, vul); F(h, PYCS_F_PV_VLAT, vvl); F(h, PYCS_F_PV_UCONTRA, vuc);
+    Conv cpu, cpv;
+    TRY(get_conv(h, PYCS_F_PU_EXLON, &cpu));
+    TRY(get_conv(h, PYCS_F_PV_EXLON, &cpv));
+    ghost_edge_kernel<0><<<grid_all(g.P + 1, g.P), BX, 0, h->stream>>>(g, cul, cvl, uul, uvl, u, uvc, cpu);
+    CKL(h);
+    ghost_edge_kernel<1><<<grid_all(g.P, g.P + 1), BX, 0, h->stream>>>(g, cul, cvl, vul, vvl, vuc, v, cpv);
+    CKL(h);
+  } else if (h->prm.dp == 2) {
+    rk2_copy_kernel<<<dim3((g.N + BX - 1) / BX, 12), BX, 0, h->stream>>>(g, u, v);
+    CKL(h);
+  }
+  return 0;
+}
+
+// velocity at time t on the interior edge points; convert_interior_only = 1 for the
+// init block (src/advection_vars.py:37-53), 0 for update_adv (whole arrays, :65-75)
+int k_wind_interior(pycs_handle h, double t, int convert_interior_only, int do_velocity) {
+  const Geo& g = h->g;
+  double *ulon_ = nullptr, *ulat_ = nullptr, *vlon_ = nullptr, *vlat_ = nullptr;
+  if (do_velocity) {
+    TRY(pycs_field_ptr(h, PYCS_F_PU_LON, &ulon_)); TRY(pycs_field_ptr(h, PYCS_F_PU_LAT, &ulat_));
+    TRY(pycs_field_ptr(h, PYCS_F_PV_LON, &vlon_)); TRY(pycs_field_ptr(h, PYCS_F_PV_LAT, &vlat_));
+  }
+  F(h, PYCS_F_PU_ULON, uul); F(h, PYCS_F_PU_VLAT, uvl); F(h, PYCS_F_PU_UCONTRA, uuc); F(h, PYCS_F_PU_VCONTRA, uvc);
+  F(h, PYCS_F_PV_ULON, vul); F(h, PYCS_F_PV_VLAT, vvl); F(h, PYCS_F_PV_UCONTRA, vuc); F(h, PYCS_F_PV_VCONTRA, vvc);
+  dim3 gr((g.N + 1 + BX - 1) / BX, g.N + 1, 6);
+  if (do_velocity) {
+    velocity_kernel<<<gr, BX, 0, h->stream>>>(g, h->prm.vf, t, 1, ulon_, ulat_, uul, uvl);
+    CKL(h);
+    velocity_kernel<<<gr, BX, 0, h->stream>>>(g, h->prm.vf, t, 0, vlon_, vlat_, vul, vvl);
+    CKL(h);
+  }
+  Conv cpu, cpv;
+  TRY(get_conv(h, PYCS_F_PU_EXLON, &cpu));
+  TRY(get_conv(h, PYCS_F_PV_EXLON, &cpv));
+  if (convert_interior_only) {
+    convert_kernel<<<gr, BX, 0, h->stream>>>(g, g.lo, g.hi + 1, g.lo, g.hi, cpu, uul, uvl, uuc, uvc);
+    CKL(h);
+    convert_kernel<<<gr, BX, 0, h->stream>>>(g, g.lo, g.hi, g.lo, g.hi + 1, cpv, vul, vvl, vuc, vvc);
+    CKL(h);
+  } else {
+    F(h, PYCS_F_PU_UOLD, uo); F(h, PYCS_F_PV_VOLD, vo);
+    copy2_kernel<<<grid_all(g.P + 1, g.P), BX, 0, h->stream>>>(g, g.P + 1, g.P, uo, uuc);   // :61-62
+    CKL(h);
+    copy2_kernel<<<grid_all(g.P, g.P + 1), BX, 0, h->stream>>>(g, g.P, g.P + 1, vo, vvc);
+    CKL(h);
+    convert_kernel<<<grid_all(g.P + 1, g.P), BX, 0, h->stream>>>(g, 0, g.P + 1, 0, g.P, cpu, uul, uvl, uuc, uvc);
+    CKL(h);
+    convert_kernel<<<grid_all(g.P, g.P + 1), BX, 0, h->stream>>>(g, 0, g.P, 0, g.P + 1, cpv, vul, vvl, vuc, vvc);
+    CKL(h);
+  }
+  return 0;
+}
+
+int k_update_adv(pycs_handle h, double t) {
+  if (h->prm.vf < 2) return 0;               // src/advection_timestep.py:50
+  return k_wind_interior(h, t, 0, 1);
+}

@@ -1,0 +1,347 @@
+"""GPU parity tests: the CUDA path (through the C ABI and the reference-named
+Python surface) against the numpy oracle and the golden fixtures written by
+the unmodified reference.
+
+Tolerances (BASELINE.json north_star): fields and error norms within 1e-12
+relative (max|a-b| / max|b|); index maps and copy fills bit-exact.  The
+operator kernels are compiled without FMA contraction, so most comparisons are
+in fact exact; the tolerance is what is asserted.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from golden_common import TUPLES, DT16, INTER_KEYS, GOLDEN, load, have, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pycs_b200  # noqa: F401
+    from pycs_b200 import (cs_datastruct, advection_ic, advection_vars, advection_timestep, device, halo_data,
+                           interpolation, reconstruction_1d, flux, discrete_operators, edges_treatment,
+                           lagrange, advection_sphere, diagnostics, cfl, averaged_velocity)
+    import types
+    return types.SimpleNamespace(**locals())
+
+
+@pytest.fixture(scope="module")
+def g16(mods):
+    return mods.cs_datastruct.cubed_sphere(16)
+
+
+def make_sim(mods, g, vf, tup, ic=2, dt=None):
+    recon, dp, split, et, mt, mf = tup
+    dt = DT16[vf] * 16 / g.N if dt is None else dt
+    sim = mods.advection_ic.adv_simulation_par(g, dt, 5, ic, vf, 1, recon, dp, split, et, mt, mf)
+    mods.advection_vars.init_vars_adv(g, sim)
+    return sim
+
+
+def oracle_sim(N, vf, tup, ic=2, dt=None):
+    from oracle.grid import LeanGrid
+    from oracle import step as ost
+    og = LeanGrid(N)
+    recon, dp, split, et, mt, mf = tup
+    dt = DT16[vf] * 16 / N if dt is None else dt
+    osim = ost.Simulation(og, dt, 5, ic, vf, 1, recon, dp, split, et, mt, mf)
+    ost.init_vars_adv(og, osim)
+    return og, osim, ost
+
+
+# ------------------------------------------------------------------ halo / index maps
+def test_halo_index_maps_bit_exact(mods, g16):
+    ref = load("halo_index_N16.npz")
+    P = 24
+    dev = mods.device.Device(16, g16.dx, g16.dy, 0.01)
+    g16.dev = dev
+    ii, jj = np.meshgrid(np.arange(P), np.arange(P), indexing="ij")
+    code = ((np.arange(6)[None, None, :] * P + ii[:, :, None]) * P + jj[:, :, None]).astype(float)
+    E, W, N_, S = mods.halo_data.get_halo_data_interpolation(code, g16)
+    for got, side in ((E, "east"), (W, "west"), (N_, "north"), (S, "south")):
+        assert np.array_equal(got.astype(np.int64), ref[side]), side
+    # the _NS / _WE variants pick Qx or Qy per rotated edge
+    cf = load("copyfill_N16.npz")
+    from oracle import halo as ohalo
+    from oracle.grid import LeanGrid
+    og = LeanGrid(16)
+    exp = ohalo.gather(cf["Qx_in"], cf["Qy_in"], og)
+    n, s = mods.halo_data.get_halo_data_interpolation_NS(cf["Qx_in"].copy(), cf["Qy_in"].copy(), g16)
+    e, w = mods.halo_data.get_halo_data_interpolation_WE(cf["Qx_in"].copy(), cf["Qy_in"].copy(), g16)
+    for got, want in zip((e, w, n, s), exp):
+        assert np.array_equal(got, want)
+
+
+def test_copy_fill_bit_exact(mods, g16):
+    ref = load("copyfill_N16.npz")
+    dev = mods.device.Device(16, g16.dx, g16.dy, 0.01, et=1)
+    g16.dev = dev
+    Qx, Qy = ref["Qx_in"].copy(), ref["Qy_in"].copy()
+    mods.interpolation.ghost_cells_adjacent_panels(Qx, Qy, g16, None)
+    assert np.array_equal(Qx, ref["Qx_out"]) and np.array_equal(Qy, ref["Qy_out"])
+    # same array for both (the adv_time_step call): corners take the S/N values
+    from oracle import halo as ohalo
+    from oracle.grid import LeanGrid
+    Q = ref["Qx_in"].copy()
+    Qo = Q.copy()
+    mods.interpolation.ghost_cells_adjacent_panels(Q, Q, g16, None)
+    ohalo.copy_fill(Qo, Qo, LeanGrid(16))
+    assert np.array_equal(Q, Qo)
+
+
+@pytest.mark.parametrize("degree", [0, 1, 2, 3, 4])
+def test_lagrange_fill_all_degrees(mods, g16, degree):
+    """interpolation.par path (src/interpolation_test.py:104-176) at N=16."""
+    import types
+    from oracle import step as ost
+    ref = load("halofill_N16.npz")
+    dev = mods.device.Device(16, g16.dx, g16.dy, 0.01)
+    sim = types.SimpleNamespace(degree=degree, dev=dev)
+    mods.lagrange.lagrange_poly_ghostcell_pc(g16, sim)
+    assert np.array_equal(sim.stencil_ghost_pc[0][0], ref["kmin_E_deg%d" % degree])
+    for ic in (1, 2):
+        Qe = ost.q_scalar_field(g16.pc.lon, g16.pc.lat, ic)
+        Qn = np.zeros_like(Qe)
+        I = np.s_[4:20, 4:20, :]
+        Qn[I] = Qe[I]
+        mods.interpolation.ghost_cell_pc_lagrange_interpolation(Qn, g16, sim)
+        want = ref["ic%d_deg%d" % (ic, degree)]
+        assert np.max(np.abs(Qn - want)) <= 1e-14
+        assert abs(np.max(np.abs(Qn - Qe)) - float(ref["linf_ic%d_deg%d" % (ic, degree)])) <= 1e-14
+
+
+@pytest.mark.parametrize("N", [96, 384, 1536])
+def test_lagrange_fill_sizes_vs_oracle(mods, N):
+    """Config 5 sizes: all ghost cells incl. corners against the oracle (<= 1e-14 abs)."""
+    import types
+    from oracle import halo as ohalo, step as ost
+    from oracle.grid import LeanGrid
+    og = LeanGrid.centres_only(N)
+    dev = mods.device.Device(N, og.dx, og.dy, 0.01)
+    sim = types.SimpleNamespace(degree=3, dev=dev)
+    mods.lagrange.lagrange_poly_ghostcell_pc(og, sim)
+    Qe = ost.q_scalar_field(og.pc.lon, og.pc.lat, 1)
+    Qn = np.zeros_like(Qe)
+    I = np.s_[4:N + 4, 4:N + 4, :]
+    Qn[I] = Qe[I]
+    Qo = Qn.copy()
+    mods.interpolation.ghost_cell_pc_lagrange_interpolation(Qn, og, sim)
+    ohalo.dg_fill(Qo, og, ohalo.lagrange_tables(og, 3))
+    assert np.max(np.abs(Qn - Qo)) <= 1e-14
+    dev.close()
+
+
+# ------------------------------------------------------------------ steps, every tuple
+@pytest.mark.parametrize("vf", [1, 2, 3, 4])
+def test_steps_all_tuples_vs_golden(mods, g16, vf):
+    ref = load("steps_N16.npz")
+    inter = load("intermediates_N16.npz")
+    for name, tup in TUPLES.items():
+        sim = make_sim(mods, g16, vf, tup)
+        key = "vf%d_%s" % (vf, name)
+        if vf == 1 and name == "default":
+            assert np.array_equal(np.asarray(sim.Q), ref["Q0"])
+        mods.advection_timestep.adv_time_step(g16, sim, 1, sim.dt)
+        mods.advection_timestep.update_adv(g16, sim, sim.dt)
+        assert relerr(np.asarray(sim.Q), ref[key + "_k1"]) <= TOL, key
+        if name in INTER_KEYS and vf in (1, 2):
+            for nm in ("q_L", "q_R", "dq", "q6", "f_upw", "dF"):
+                assert relerr(np.asarray(getattr(sim.px, nm)), inter[key + "_px_" + nm]) <= TOL, (key, nm)
+                assert relerr(np.asarray(getattr(sim.py, nm)), inter[key + "_py_" + nm]) <= TOL, (key, nm)
+            assert relerr(np.asarray(sim.div), inter[key + "_div"]) <= 1e-10, key   # div ~ cancellation
+            assert relerr(np.asarray(sim.U_pu.ucontra_averaged), inter[key + "_uavg"]) <= TOL
+            assert relerr(np.asarray(sim.U_pv.vcontra_averaged), inter[key + "_vavg"]) <= TOL
+            assert relerr(np.asarray(sim.cx), inter[key + "_cx"]) <= TOL
+            assert np.array_equal(sim.U_pu.upos, inter[key + "_upos"])
+            assert np.array_equal(sim.U_pv.vpos, inter[key + "_vpos"])
+        mods.advection_timestep.run_steps(g16, sim, 1, 19, fused=False)
+        assert relerr(np.asarray(sim.Q), ref[key + "_k20"]) <= TOL, key
+        if name in ("default", "AVLT-RK2-DG-PR") and vf >= 2:
+            assert relerr(np.asarray(sim.U_pu.ucontra), inter[key + "_k20_ucontra"]) <= TOL
+            assert relerr(np.asarray(sim.U_pv.vcontra), inter[key + "_k20_vcontra"]) <= TOL
+            assert relerr(np.asarray(sim.U_pu.ucontra_old), inter[key + "_k20_ucontra_old"]) <= TOL
+            assert relerr(np.asarray(sim.U_pc.ulon), inter[key + "_k20_pc_ulon"]) <= TOL
+        sim.dev.close()
+
+
+def test_steady_wind_step_is_bit_exact(mods, g16):
+    """vf = 1: no device trig on the path, operator kernels without FMA -> identical bits."""
+    ref = load("steps_N16.npz")
+    for name in ("default", "PL07-RK1", "CW84-L04-S72-AF", "L04-L04-PL07-PR"):
+        sim = make_sim(mods, g16, 1, TUPLES[name])
+        mods.advection_timestep.run_steps(g16, sim, 0, 1, fused=False)
+        d = np.asarray(sim.Q) - ref["vf1_%s_k1" % name]
+        # MF-PR uses a tree reduction instead of numpy's pairwise sum: last-bit noise only
+        assert np.max(np.abs(d)) <= (4e-16 if TUPLES[name][5] == 3 else 0.0), name
+        sim.dev.close()
+
+
+def test_operator_surface_with_numpy_arrays(mods, g16):
+    """ppm_reconstruction / compute_fluxes / F,G operators called like the reference
+    calls them, on caller-owned numpy arrays, against the oracle."""
+    og, osim, ost = oracle_sim(16, 1, TUPLES["default"])
+    from oracle import ppm as oppm
+    rng = np.random.default_rng(3)
+    for recon in (1, 2, 3, 4):
+        tup = (recon, 1, 1, 3, 1, 3)
+        sim = make_sim(mods, g16, 1, tup)
+        og, osim, ost = oracle_sim(16, 1, tup)
+        Qx = rng.standard_normal((24, 24, 6))
+        Qy = rng.standard_normal((24, 24, 6))
+        mods.reconstruction_1d.ppm_reconstruction(Qx, Qy, sim.px, sim.py, g16, sim)
+        oppm.reconstruct(Qx, osim.px, osim.recon_name, 4, 20)
+        oppm.reconstruct(np.swapaxes(Qy, 0, 1), osim.py, osim.recon_name, 4, 20)
+        I = np.s_[3:21, :, :]
+        assert relerr(np.asarray(sim.px.q_L)[I], osim.px.q_L[I]) <= TOL
+        assert relerr(np.asarray(sim.px.q_R)[I], osim.px.q_R[I]) <= TOL
+        J = np.s_[:, 3:21, :]
+        assert relerr(np.asarray(sim.py.q_L)[J], osim.py.q_L[J]) <= TOL
+        assert relerr(np.asarray(sim.py.q_R)[J], osim.py.q_R[J]) <= TOL
+        mods.flux.compute_fluxes(Qx, Qy, sim.px, sim.py, sim.U_pu, sim.U_pv, sim.cx, sim.cy, g16, sim)
+        ost.compute_fluxes(Qx, Qy, og, osim)
+        assert relerr(np.asarray(sim.px.f_upw), osim.px.f_upw) <= TOL
+        assert relerr(np.asarray(sim.py.f_upw), osim.py.f_upw) <= TOL
+        mods.discrete_operators.F_operator(g16, sim)
+        mods.discrete_operators.G_operator(g16, sim)
+        oppm.flux_difference(osim.px, osim.dt, og.dx, 4, 20)
+        oppm.flux_difference(osim.py, osim.dt, og.dy, 4, 20)
+        assert relerr(np.asarray(sim.px.dF), osim.px.dF) <= TOL
+        assert relerr(np.asarray(sim.py.dF), osim.py.dF) <= TOL
+        sim.dev.close()
+
+
+def test_divergence_known_answer(mods, g16):
+    """Q = 1 with a non-divergent wind: one-step divergence ~ 0 (src/operator_accuracy.py:78,
+    src/advection_ic.py:318-320) and equal to the oracle's."""
+    sim = make_sim(mods, g16, 1, TUPLES["default"], ic=1)
+    og, osim, ost = oracle_sim(16, 1, TUPLES["default"], ic=1)
+    mods.advection_timestep.adv_time_step(g16, sim, 1, sim.dt)
+    ost.adv_time_step(og, osim, 1, osim.dt)
+    d = np.asarray(sim.div)[4:20, 4:20, :]
+    assert np.max(np.abs(d)) < 5e-2
+    assert np.max(np.abs(d - osim.div[4:20, 4:20, :])) <= 1e-12
+    sim.dev.close()
+
+
+# ------------------------------------------------------------------ configs of BASELINE.json
+@pytest.mark.skipif(not have("config1_N48_final.npz"), reason="fixture not generated")
+@pytest.mark.parametrize("fused", [False, True])
+def test_config1_n48_full_revolution(mods, fused):
+    """Config 1: N=48, Gaussian hill, solid-body rotation, one revolution (600 steps)."""
+    rows = json.load(open(os.path.join(GOLDEN, "norms.json")))
+    row = [r for r in rows if r["N"] == 48][0]
+    g = mods.cs_datastruct.cubed_sphere(48)
+    sim = mods.advection_ic.adv_simulation_par(g, row["dt"], 5, 2, 1, 2, *row["tuple"])
+    sim.fused = fused
+    if fused:
+        mods.advection_vars.init_vars_adv(g, sim)
+        if not sim.dev.fused_supported():
+            pytest.skip("no fused kernel for this tuple")
+    linf, l1, l2 = mods.advection_sphere.adv_sphere(g, None, sim, "sphere", False, False)
+    Qref = load("config1_N48_final.npz")["Q"]
+    assert relerr(np.asarray(sim.Q)[4:52, 4:52, :], Qref) <= TOL
+    for a, b in zip((linf, l1, l2), (row["linf"], row["l1"], row["l2"])):
+        assert abs(a - b) <= TOL * abs(b)
+    assert sim.mass_change <= 1e-13
+    sim.dev.close()
+
+
+def _check_big(mods, fname, fused, max_k=None):
+    ref = load(fname)
+    N, vf = int(ref["N"]), int(ref["vf"])
+    tup = tuple(int(x) for x in ref["tuple"])
+    g = mods.cs_datastruct.cubed_sphere(N)
+    sim = mods.advection_ic.adv_simulation_par(g, float(ref["dt"]), 5, 2, vf, 1, *tup)
+    mods.advection_vars.init_vars_adv(g, sim)
+    if fused and not sim.dev.fused_supported():
+        pytest.skip("no fused kernel for this tuple")
+    assert abs(sim.CFL - float(ref["cfl"])) <= 1e-12 * float(ref["cfl"])
+    idx = ref["sample_index"]
+    ks = sorted(int(k[3:]) for k in ref.files if k.startswith("Q_k"))
+    k = 0
+    I = np.s_[4:N + 4, 4:N + 4, :]
+    from oracle import step as ost
+    for kk in ks:
+        if max_k and kk > max_k:
+            break
+        mods.advection_timestep.run_steps(g, sim, k, kk - k, fused=fused)
+        k = kk
+        Q = np.asarray(sim.Q)
+        assert relerr(Q[np.ix_(idx, idx, np.arange(6))], ref["Q_k%d" % k]) <= TOL, (fname, k)
+        assert abs(np.sum(Q[I]) - float(ref["sumQ_k%d" % k])) <= 1e-11 * abs(float(ref["sumQ_k%d" % k]))
+        qe = mods.advection_ic.qexact_adv(g.pc.lon[I], g.pc.lat[I], k * sim.dt, sim)
+        for a, b in zip(ost.compute_errors(Q[I], qe), ref["err_k%d" % k]):
+            assert abs(a - b) <= 1e-11 * abs(b) + 1e-15, (fname, k)
+    sim.dev.close()
+
+
+@pytest.mark.skipif(not have("config_N384_vf1.npz"), reason="fixture not generated")
+@pytest.mark.parametrize("fused", [False, True])
+def test_config2_n384(mods, fused):
+    """Config 2: N=384 default scheme; checkpoints up to the full period (4800 steps)."""
+    _check_big(mods, "config_N384_vf1.npz", fused)
+
+
+@pytest.mark.skipif(not have("config_N768_vf2.npz"), reason="fixture not generated")
+@pytest.mark.parametrize("fused", [False, True])
+def test_config3_n768_deformational(mods, fused):
+    """Config 3: N=768, Nair-Lauritzen non-divergent flow, RK2, first 50 steps."""
+    _check_big(mods, "config_N768_vf2.npz", fused)
+
+
+@pytest.mark.skipif(not have("config_N1536_vf3.npz"), reason="fixture not generated")
+@pytest.mark.parametrize("fused", [False, True])
+def test_config4_n1536_divergent(mods, fused):
+    """Config 4: N=1536, divergent flow, first 20 steps."""
+    _check_big(mods, "config_N1536_vf3.npz", fused)
+
+
+# ------------------------------------------------------------------ fused vs operator path
+@pytest.mark.parametrize("N", [16, 20, 50, 130])
+@pytest.mark.parametrize("vf,name", [(1, "default"), (3, "default"), (2, "AVLT-RK2-DG-PR"),
+                                     (1, "PL07-RK1-DG-PR"), (3, "L04-AVLT-DG-PR")])
+def test_fused_matches_operator_path(mods, N, vf, name):
+    g = mods.cs_datastruct.cubed_sphere(N)
+    a = make_sim(mods, g, vf, TUPLES[name])
+    if not a.dev.fused_supported():
+        a.dev.close()
+        pytest.skip("no fused kernel for this tuple")
+    b = make_sim(mods, g, vf, TUPLES[name])
+    mods.advection_timestep.run_steps(g, a, 0, 12, fused=True)
+    mods.advection_timestep.run_steps(g, b, 0, 12, fused=False)
+    assert relerr(np.asarray(a.Q), np.asarray(b.Q)) <= TOL
+    a.dev.close()
+    b.dev.close()
+
+
+def test_full_size_properties_n1536(mods):
+    """Size-independent checks at BASELINE.json's full size: mass conservation and
+    linearity of the (unlimited PPM-PL07) step, fused path."""
+    N = 1536
+    g = mods.cs_datastruct.cubed_sphere(N)
+    sim = make_sim(mods, g, 1, TUPLES["default"])
+    fused = sim.dev.fused_supported()
+    I = np.s_[4:N + 4, 4:N + 4, :]
+    m0, _ = mods.diagnostics.mass_computation(sim.Q, g, 1.0)
+    Q1 = np.asarray(sim.Q).copy()
+    rng = np.random.default_rng(0)
+    Q2 = np.zeros_like(Q1)
+    Q2[I] = 1.0 + 0.1 * rng.standard_normal((N, N, 6))
+    outs = []
+    for Qin in (Q1, Q2, 2.0 * Q1 - 3.0 * Q2):
+        sim.Q[...] = Qin
+        mods.advection_timestep.run_steps(g, sim, 0, 3, fused=fused)
+        outs.append(np.asarray(sim.Q)[I].copy())
+        if Qin is Q1:
+            _, dm = mods.diagnostics.mass_computation(sim.Q, g, m0)
+            assert dm <= 1e-13
+    assert relerr(outs[2], 2.0 * outs[0] - 3.0 * outs[1]) <= 1e-12
+    sim.dev.close()

@@ -1,0 +1,87 @@
+"""CPU: host-side logic of the product and the C-ABI library surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from golden_common import load, have, GOLDEN
+
+import pycs_b200  # noqa: F401  (import shim)
+from pycs_b200 import cs_datastruct, lagrange, device
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "pycs_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(pycs_[a-zA-Z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 35
+    assert os.path.exists(device.LIB_PATH), "library not built: run __graft_entry__.build()"
+    lib = ctypes.CDLL(device.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    # the python binding lists the same entry points
+    bound = device.load_library()
+    for n in names:
+        assert hasattr(bound, n)
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(device.PycsError) as e:
+        device.Device(16, 0.1, 0.1, 0.01)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_grid_matches_reference_bits():
+    ref = load("grid_N16.npz")
+    g = cs_datastruct.cubed_sphere(16, "gnomonic_equiangular", False, False)
+    for pos in ("pc", "pu", "pv"):
+        assert np.array_equal(ref["sqrtg_" + pos], getattr(g, "metric_tensor_" + pos)[:, :, 0]), pos
+        for nm in ("prod_ex_elon_", "prod_ex_elat_", "prod_ey_elon_", "prod_ey_elat_", "determinant_ll2contra_"):
+            assert np.array_equal(ref[nm + pos], getattr(g, nm + pos)), nm + pos
+        assert np.array_equal(ref["lon_" + pos], getattr(g, pos).lon)
+        assert np.array_equal(ref["lat_" + pos], getattr(g, pos).lat)
+    for c in "XYZ":
+        assert np.array_equal(ref[c + "_pc"], getattr(g.pc, c))
+
+
+@pytest.mark.skipif(not have("lagrange_tables.npz"), reason="fixture not generated")
+@pytest.mark.parametrize("N", [16, 48, 96, 384, 768, 1536, 3072])
+def test_product_stencil_tables_bit_exact(N):
+    """Halo index maps: Kmin / Kmax of the host precompute are bit-exact."""
+    ref = load("lagrange_tables.npz")
+    import types
+    from oracle.grid import LeanGrid          # only as a cheap source of pc.X/Y/Z at large N
+    g = LeanGrid.centres_only(N)
+    kmin, kmax, w = lagrange.ghost_tables(g, 3)
+    assert np.array_equal(kmin, ref["kmin_E_N%d" % N])
+    assert np.array_equal(kmax, ref["kmax_E_N%d" % N])
+    assert np.array_equal(w, ref["poly_E_N%d" % N])
+    sim = types.SimpleNamespace(degree=3)
+    lagrange.lagrange_poly_ghostcell_pc(g, sim)
+    for s, side in enumerate("EWNS"):
+        assert np.array_equal(sim.stencil_ghost_pc[0][s], ref["kmin_%s_N%d" % (side, N)])
+        assert np.array_equal(sim.stencil_ghost_pc[1][s], ref["kmax_%s_N%d" % (side, N)])
+
+
+@pytest.mark.parametrize("degree", [0, 1, 2, 3, 4])
+def test_product_tables_all_degrees(degree):
+    ref = load("halofill_N16.npz")
+    g = cs_datastruct.cubed_sphere(16)
+    kmin, kmax, w = lagrange.ghost_tables(g, degree)
+    assert np.array_equal(kmin, ref["kmin_E_deg%d" % degree])
+    assert np.array_equal(w, ref["poly_E_deg%d" % degree])
+
+
+def test_invalid_scheme_combination_refused_before_touching_gpu():
+    from pycs_b200 import advection_ic
+    g = cs_datastruct.cubed_sphere(16)
+    with pytest.raises(device.PycsError):
+        advection_ic.adv_simulation_par(g, 0.01, 5, 2, 1, 1, 3, 1, 3, 3, 1, 3)   # SP-PL07 with MT-0
+    with pytest.raises(SystemExit):
+        advection_ic.adv_simulation_par(g, 0.01, 5, 9, 1, 1, 3, 1, 1, 3, 1, 3)   # bad ic
