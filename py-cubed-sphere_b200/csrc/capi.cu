@@ -137,6 +137,7 @@ extern "C" int pycs_destroy(pycs_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  k_fused_release(h);
   for (int k = 0; k < PYCS_F_COUNT; ++k)
     if (h->f[k]) cudaFree(h->f[k]);
   if (h->kminE) cudaFree(h->kminE);
@@ -368,6 +369,7 @@ extern "C" int pycs_divergence(pycs_handle h) {
 
 // make PYCS_F_Q the current state if the fused path left it in Q_NEXT
 static int normalize_q(pycs_handle h) {
+  TRY(k_fused_flush(h));
   if (h->qcur == 1) {
     double* t = h->f[PYCS_F_Q];
     h->f[PYCS_F_Q] = h->f[PYCS_F_Q_NEXT];

@@ -129,4 +129,6 @@ int k_wind_interior(pycs_handle h, double t, int convert_interior_only, int do_v
 // fused.cu
 int k_fused_supported(pycs_handle h);
 int k_fused_step(pycs_handle h, long long k, double t);
+int k_fused_flush(pycs_handle h);
+void k_fused_release(pycs_handle h);
 // layout.cu (in capi.cu)
