@@ -357,8 +357,13 @@ __global__ void dg_phase1_corr_kernel(Geo g, HaloMaps maps, double* __restrict__
   q[gidx(g, p, i, j)] = acc;
 }
 
-__global__ void dg_phase2_plain_kernel(Geo g, HaloMaps maps, double* __restrict__ q,
-                                       const int* __restrict__ kminE, const double* __restrict__ wE, int order) {
+// Corner stencils straddle the interior / ghost boundary of the neighbour strip:
+// interior sources still miss the pending term, ghost sources already have it.
+__global__ void dg_phase2_corr_kernel(Geo g, HaloMaps maps, double* __restrict__ q,
+                                      const int* __restrict__ kminE, const double* __restrict__ wE, int order,
+                                      const double* __restrict__ sgc, const double* __restrict__ corr_p,
+                                      int apply_corr) {
+  const double corr = apply_corr ? *corr_p : 0.0;
   int t = threadIdx.x;
   int gl = t >> 3, c = t & 7;
   int k = (c < 4) ? c : g.hi + (c - 4);
@@ -370,7 +375,9 @@ __global__ void dg_phase2_plain_kernel(Geo g, HaloMaps maps, double* __restrict_
   double acc = 0.0;
   for (int l = 0; l < order; ++l) {
     int a_ = gl, b_ = km + l;
-    double v = q[gidx(g, m.nb, m.ci + m.ai * a_ + m.bi * b_, m.cj + m.aj * a_ + m.bj * b_)];
+    int si = m.ci + m.ai * a_ + m.bi * b_, sj = m.cj + m.aj * a_ + m.bj * b_;
+    double v = q[gidx(g, m.nb, si, sj)];
+    if (si >= g.lo && si < g.hi && sj >= g.lo && sj < g.hi) v = fma(sgc[gidx(g, 0, si, sj)], corr, v);
     acc = __dadd_rn(acc, __dmul_rn(v, w[l]));
   }
   int i = (s == SIDE_E) ? g.hi + gl : gl;
@@ -386,6 +393,16 @@ __global__ void flush_corr_kernel(Geo g, double* __restrict__ q, const double* _
   if (j >= g.hi) return;
   long long id = gidx(g, p, i, j);
   q[id] = fma(sgc[gidx(g, 0, i, j)], corr, q[id]);
+}
+
+// ghost ring of the buffer the last step read (filled at the start of that step) ->
+// the buffer it wrote, so that Q looks exactly like the reference's after the step
+__global__ void copy_ring_kernel(Geo g, double* __restrict__ dst, const double* __restrict__ src) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, p = blockIdx.z;
+  if (j >= g.P) return;
+  if (i >= g.lo && i < g.hi && j >= g.lo && j < g.hi) return;
+  long long id = gidx(g, p, i, j);
+  dst[id] = src[id];
 }
 
 __global__ void recip_kernel(Geo g, const double* __restrict__ s, double* __restrict__ d) {
@@ -421,6 +438,7 @@ struct FusedState {
   double* part = nullptr;
   int npart_cap = 0;
   int pending = 0;             // partials of the last step wait to be applied
+  int ring_pending = 0;        // ghost ring of the current buffer is stale
   int npart = 0;
   int tb = 160, rows = 0, nstrips = 0, wcols = 0, nchunks = 0;
 };
@@ -488,15 +506,24 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
 // path (download, operator kernels, diagnostics) sees the reference's Q
 int k_fused_flush(pycs_handle h) {
   auto it = g_fused.find(h);
-  if (it == g_fused.end() || !it->second.pending) return 0;
+  if (it == g_fused.end()) return 0;
   FusedState& fs = it->second;
   const Geo& g = h->g;
-  double *sgc, *q;
+  double *sgc, *q, *qo;
   TRY(pycs_field_ptr(h, PYCS_F_SQRTG_PC, &sgc));
   TRY(pycs_field_ptr(h, h->qcur ? PYCS_F_Q_NEXT : PYCS_F_Q, &q));
-  flush_corr_kernel<<<dim3((g.N + 127) / 128, g.N, 6), 128, 0, h->stream>>>(g, q, sgc, fs.part, fs.npart, 1.0 / h->a2);
-  CKL(h);
-  fs.pending = 0;
+  TRY(pycs_field_ptr(h, h->qcur ? PYCS_F_Q : PYCS_F_Q_NEXT, &qo));
+  if (fs.pending) {
+    flush_corr_kernel<<<dim3((g.N + 127) / 128, g.N, 6), 128, 0, h->stream>>>(g, q, sgc, fs.part, fs.npart,
+                                                                             1.0 / h->a2);
+    CKL(h);
+    fs.pending = 0;
+  }
+  if (fs.ring_pending) {
+    copy_ring_kernel<<<dim3((g.P + 127) / 128, g.P, 6), 128, 0, h->stream>>>(g, q, qo);
+    CKL(h);
+    fs.ring_pending = 0;
+  }
   return 0;
 }
 
@@ -540,7 +567,8 @@ int k_fused_step(pycs_handle h, long long k, double t) {
       g, h->maps, qcur, h->kminE, h->wE, h->order, sgc, fs.part, pend ? fs.npart : 0,
       pend ? 1.0 / h->a2 : 0.0, h->red_out + 8);
   CKL(h);
-  dg_phase2_plain_kernel<<<12, 32, 0, h->stream>>>(g, h->maps, qcur, h->kminE, h->wE, h->order);
+  dg_phase2_corr_kernel<<<12, 32, 0, h->stream>>>(g, h->maps, qcur, h->kminE, h->wE, h->order, sgc,
+                                                  h->red_out + 8, pend);
   CKL(h);
   // 2. winds (src/advection_timestep.py:31-37)
   if (h->prm.vf >= 2) {
@@ -570,6 +598,7 @@ int k_fused_step(pycs_handle h, long long k, double t) {
   h->last_step_kernel_launches++;
   h->qcur ^= 1;
   fs.pending = (h->prm.mf == 3) ? 1 : 0;
+  fs.ring_pending = 1;
   // 4. wind refresh for the next step (src/advection_timestep.py:48-75)
   if (h->prm.vf >= 2) TRY(k_update_adv(h, t));
   return 0;
