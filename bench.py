@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""Benchmark of the fp64 cubed-sphere PPM advection step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config 4 of BASELINE.json): N=1536 cells per panel edge, Nair-Lauritzen
+divergent flow (vf=3), Gaussian hill, par-default scheme PPM-PL07 / RK1 / SP-AVLT /
+ET-DG / MT-0 / MF-PR, dt = 0.00625*16/N.  A step = adv_time_step + update_adv.
+metric = cell-updates/s = 6 N^2 K / time.  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+TUPLE = (3, 1, 1, 3, 1, 3)      # recon, dp, opsplit, et, mt, mf  (par/advection.par defaults)
+VF, IC = 3, 2
+BYTES_PER_CELL = 40.0           # Q r/w, two winds, sqrt(g)
+
+
+def workload(N):
+    return {"workload": "config4: N=%d vf=3 divergent flow, Gaussian hill, PPM-PL07/RK1/SP-AVLT/ET-DG/MT-0/MF-PR" % N,
+            "N": N, "cells": 6 * N * N, "dt": 0.00625 * 16 / N,
+            "l2": "inputs (566 MB/step at N=1536) exceed the 126 MB L2"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:   # region shorter than the sampling period: take whatever we have
+            for ts, line in self.rows[-3:]:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                    mx = float(f[2])
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------- CPU arm
+def oracle_state(g, N):
+    from oracle import step as ost
+    sim = ost.Simulation(g, 0.00625 * 16 / N, 5, IC, VF, 1, *TUPLE)
+    ost.init_vars_adv(g, sim)
+    return sim, ost
+
+
+def cpu_steps(g, sim, ost, k0, n):
+    t = time.perf_counter()
+    ost.run(g, sim, n, k0)
+    return time.perf_counter() - t
+
+
+def run_reference(args):
+    """--impl reference: the reference's own algorithm (numpy oracle port, bit-identical to
+    the reference under the numpy shim) timed on the host cores.  /root/reference is pure
+    Python and does not exist on the GPU box, so there is no oracle/_ref build."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N = args.cpu_n
+    from oracle.grid import LeanGrid
+    g = LeanGrid(N)
+    sim, ost = oracle_state(g, N)
+    k = 0
+    for _ in range(args.warmup):
+        cpu_steps(g, sim, ost, k, 1)
+        k += 1
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_steps(g, sim, ost, k, 1)
+        k += 1
+    value = 6.0 * N * N * args.steps / t
+    cfg = workload(1536)
+    cfg["cpu_sample"] = "N=%d, same scheme and wind" % N
+    line = {"impl": "reference", "metric": "cell-updates/s (fp64 advection step)", "value": value,
+            "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": "port",
+                             "sample": "%d full steps of the numpy oracle at N=%d (whole-array numpy is single "
+                                       "threaded; host has %d cores)" % (args.steps, N, os.cpu_count())},
+            "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import ctypes as C
+    import pycs_b200  # noqa: F401
+    from pycs_b200 import cs_datastruct, advection_ic, advection_vars, advection_timestep
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N = args.n
+    cfg = workload(N)
+    dt = cfg["dt"]
+    t_setup = time.time()
+    g = cs_datastruct.cubed_sphere(N)
+    sim = advection_ic.adv_simulation_par(g, dt, 5, IC, VF, 1, *TUPLE, device=local)
+    advection_vars.init_vars_adv(g, sim)
+    dev = sim.dev
+    if not dev.fused_supported():
+        raise RuntimeError("fused kernel unavailable")
+    setup_s = time.time() - t_setup
+    sm, name = dev.sm_count()
+    Q0 = np.asarray(sim.Q).copy()
+
+    def barrier():
+        dev.call("pycs_synchronize")
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident run: W warm-up steps, then K timed steps (CUDA events on the handle's stream)
+    dev.call("pycs_run", 0, args.warmup, 1)
+    barrier()
+    l0 = dev.launches()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    ms = C.c_float()
+    t0 = time.time()
+    dev.call("pycs_run_timed", args.warmup, args.steps, 1, C.byref(ms))
+    t1 = time.time()
+    barrier()
+    clocks = sampler.stop(t0, t1)
+    launches = dev.launches() - l0
+    ms_total = float(ms.value)
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    cells = 6.0 * N * N
+    value = world * cells * args.steps / (ms_total * 1e-3)
+
+    # ---- roofline: the step kernel alone, CUDA events around back-to-back launches
+    kms = C.c_float()
+    reps = max(20, args.steps)
+    dev.call("pycs_time_step_kernel", 5, 1, C.byref(kms))
+    dev.call("pycs_time_step_kernel", reps, 1, C.byref(kms))
+    k_ms = float(kms.value) / reps
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_CELL * cells / (k_ms * 1e-3) / 1e9
+    tb, rows, nblk = C.c_int32(), C.c_int32(), C.c_int32()
+    dev.call("pycs_step_kernel_info", C.byref(tb), C.byref(rows), C.byref(nblk))
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "fused_step_kernel<%d,PPM-PL07,SP-AVLT>" % tb.value,
+                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": BYTES_PER_CELL * cells,
+                "peak_source": peak_src, "grid": {"ctas": nblk.value, "threads": tb.value, "rows_per_chunk": rows.value},
+                "share_of_step": k_ms / (ms_total / args.steps)}
+
+    # ---- end to end: adv_time_step through host buffers (pinned), H2D + step + D2H every step
+    sim.Q[...] = Q0
+    hostQ = torch.empty(Q0.shape, dtype=torch.float64, pin_memory=True)
+    hq = hostQ.numpy()
+    hq[...] = Q0
+    ptr = hq.ctypes.data_as(C.POINTER(C.c_double))
+    e2e_steps = max(3, min(args.steps, 10))
+    for k in range(1, 3):
+        dev.call("pycs_adv_time_step_host", ptr, k, k * dt, 1)
+    barrier()
+    te = time.perf_counter()
+    for k in range(3, 3 + e2e_steps):
+        dev.call("pycs_adv_time_step_host", ptr, k, k * dt, 1)
+    barrier()
+    te = time.perf_counter() - te
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([te], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        te = float(tt.item())
+    e2e = {"value": world * cells * e2e_steps / te, "unit": "cell-updates/s", "h2d_bytes_per_step": int(Q0.nbytes),
+           "d2h_bytes_per_step": int(Q0.nbytes), "ms_per_step": 1e3 * te / e2e_steps, "steps": e2e_steps,
+           "api": "pycs_adv_time_step_host (adv_time_step + update_adv on a host numpy Q)"}
+
+    # ---- CPU baseline (rank 0, N=1 only): the numpy oracle on the same grid
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        Nc = args.cpu_n
+        from oracle.grid import LeanGrid
+        og = LeanGrid(Nc)
+        osim, ost = oracle_state(og, Nc)
+        cpu_steps(og, osim, ost, 0, 1)
+        nst = args.cpu_steps
+        tc = cpu_steps(og, osim, ost, 1, nst)
+        cpu = {"value": 6.0 * Nc * Nc * nst / tc, "unit": "cell-updates/s", "cores": 1, "kind": "port",
+               "sample": "%d steps of the numpy oracle at N=%d, same scheme and wind (%.1f s; numpy whole-array "
+                         "ops are single threaded, host has %d cores)" % (nst, Nc, tc, os.cpu_count())}
+
+    if rank == 0:
+        line = {"metric": "cell-updates/s (fp64 advection step)", "value": value, "unit": "cell-updates/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": int(launches), "clocks": clocks, "device": name, "sm_count": sm,
+                "setup_s": setup_s,
+                "wind_path": "separable (U(t)=U(0)cos(pi t/T) scaled in-kernel; last step runs the wind kernels)"}
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--n", type=int, default=1536)
+    ap.add_argument("--cpu-n", type=int, default=768, help="N of the CPU sample (bounded: ~4 s/step at 768)")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 5:
+            args.steps = 5          # bounded sample: a CPU step takes seconds
+        args.warmup = min(args.warmup, 1)
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -176,9 +176,12 @@ int pycs_errors(pycs_handle h, const double* qexact_interior, double* out3);
 int pycs_mass(pycs_handle h, double* mass);
 /* Number of kernels launched by this handle since creation (bench bookkeeping). */
 int pycs_launch_count(pycs_handle h, int64_t* count);
-/* Kernel-only duration of the fused step kernel launches in the last
- * pycs_run_timed call (ms summed over its launches) and their number. */
-int pycs_last_step_kernel_ms(pycs_handle h, float* ms, int64_t* launches);
+/* Device time (ms) of `reps` back-to-back launches of the fused step kernel alone
+ * (no ghost fill; ping-pong buffers), for the roofline figure.  separable != 0 times
+ * the scaled-wind variant.  Leaves Q undefined: upload Q again afterwards. */
+int pycs_time_step_kernel(pycs_handle h, int32_t reps, int32_t separable, float* ms);
+/* Launch geometry of the fused step kernel: threads per CTA, rows per chunk, CTAs. */
+int pycs_step_kernel_info(pycs_handle h, int32_t* threads, int32_t* rows_per_chunk, int32_t* nblocks);
 
 #ifdef __cplusplus
 }

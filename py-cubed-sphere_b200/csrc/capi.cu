@@ -399,10 +399,16 @@ extern "C" int pycs_convert_wind_interior(pycs_handle h) { return k_wind_interio
 static int run_steps(pycs_handle h, int64_t k0, int64_t nsteps, int fused) {
   CK(cudaSetDevice(h->device));
   if (fused && !k_fused_supported(h)) return arg_fail("no fused step kernel for this scheme tuple");
+  // wind field 3 + RK1 is U(0)*cos(pi t/T): all but the last step of a fused run scale
+  // the t = 0 winds inside the step kernel; the last step runs the wind kernels after a
+  // resync so that U_pu / U_pv / U_pc end up as the reference leaves them.
+  bool separable = fused && h->prm.vf == 3 && h->prm.dp == 1 && nsteps >= 2 && !getenv("PYCS_NO_SEPARABLE");
   for (int64_t k = k0 + 1; k <= k0 + nsteps; ++k) {
     double t = (double)k * h->g.dt;                             // t = k*dt, src/advection_sphere.py:47
     if (fused) {
-      TRY(k_fused_step(h, k, t));
+      bool last = (k == k0 + nsteps);
+      if (separable && last) TRY(k_wind_resync(h, k - 1));
+      TRY(k_fused_step(h, k, t, (separable && !last) ? 1 : 0));
     } else {
       TRY(pycs_adv_time_step(h, k, t));
       TRY(k_update_adv(h, t));
@@ -423,8 +429,6 @@ extern "C" int pycs_run(pycs_handle h, int64_t k0, int64_t nsteps, int32_t fused
 
 extern "C" int pycs_run_timed(pycs_handle h, int64_t k0, int64_t nsteps, int32_t fused, float* ms) {
   CK(cudaSetDevice(h->device));
-  h->last_step_kernel_ms = 0.f;
-  h->last_step_kernel_launches = 0;
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaEventRecord(h->ev0, h->stream));
   int r = run_steps(h, k0, nsteps, fused);
@@ -435,9 +439,17 @@ extern "C" int pycs_run_timed(pycs_handle h, int64_t k0, int64_t nsteps, int32_t
   return 0;
 }
 
-extern "C" int pycs_last_step_kernel_ms(pycs_handle h, float* ms, int64_t* launches) {
-  *ms = h->last_step_kernel_ms;
-  *launches = h->last_step_kernel_launches;
+extern "C" int pycs_time_step_kernel(pycs_handle h, int32_t reps, int32_t separable, float* ms) {
+  CK(cudaSetDevice(h->device));
+  if (!k_fused_supported(h)) return arg_fail("no fused step kernel for this scheme tuple");
+  TRY(normalize_q(h));
+  return k_fused_time_kernel(h, reps, separable, ms);
+}
+
+extern "C" int pycs_step_kernel_info(pycs_handle h, int32_t* threads, int32_t* rows_per_chunk, int32_t* nblocks) {
+  int a, b, c;
+  TRY(k_fused_grid_info(h, &a, &b, &c));
+  *threads = a; *rows_per_chunk = b; *nblocks = c;
   return 0;
 }
 
@@ -448,7 +460,7 @@ extern "C" int pycs_adv_time_step_host(pycs_handle h, double* Q, int64_t k, doub
   TRY(upload_from(h, PYCS_F_Q, Q, true));
   if (fused) {
     if (!k_fused_supported(h)) return arg_fail("no fused step kernel for this scheme tuple");
-    TRY(k_fused_step(h, k, t));
+    TRY(k_fused_step(h, k, t, 0));
     TRY(normalize_q(h));
   } else {
     TRY(pycs_adv_time_step(h, k, t));

@@ -39,6 +39,7 @@ struct FusedArgs {
   const double* corr;         // device scalar: pending projection coefficient -sum(s)/a2
   int rows_per_chunk, nstrips, wcols, apply_corr;
   double cdx, cdy;            // dt/dx, dt/dy
+  double ws;                  // separable wind: U(t) = U(0) * ws (MASK & 2)
 };
 
 // ---- PPM edge values of one cell from its 5-point neighbourhood -------------
@@ -121,38 +122,102 @@ __device__ __forceinline__ double ppm_flux(double e, double q6, double dq, doubl
   return fma(-(q6 * c), c * (1.0 / 3.0), f);
 }
 
-template <int TB, int RECON, int SPLIT, int MASK>
+// ---- TMA / mbarrier helpers (cp.async.bulk 1-D row copies into a shared-memory ring) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_row(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// Arrays staged per marched row (slot of row r): Q[r], V[r], SGC[r], SGV[r], RGC[r],
+// SGU[r-1], U[r-2] (+ mask sources VM[r], UM[r-2] for RK2).
+enum { A_Q = 0, A_V = 1, A_SGC = 2, A_SGV = 3, A_RGC = 4, A_SGU = 5, A_U = 6, A_VM = 7, A_UM = 8 };
+
+template <int TB, int RECON, int SPLIT, int MASK, int D>
 __global__ void __launch_bounds__(TB) fused_step_kernel(FusedArgs a) {
   constexpr int MT = (SPLIT == 3) ? 2 : 1;
-  __shared__ double sQ[TB], sX[TB], sF[TB], sG[TB], sC[TB];
+  constexpr int NARR = (MASK & 1) ? 9 : 7;
+  constexpr int TBW = TB + 2;               // staged row: columns jbase-4 .. jbase+TB-3
+  constexpr int PF = D - 4;                 // rows in flight ahead of the consumer
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* ring = reinterpret_cast<double*>(smem_raw);            // [D][NARR][TBW]
+  double* sX = ring + D * NARR * TBW;                            // Qx row r-3
+  double* sF = sX + TBW;                                         // inner y-flux, row r
+  double* sG = sF + TBW;                                         // outer y-flux, row r-3
+  double* sC = sG + TBW;                                         // sqrtg_pv*cy (SPLIT != 1)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sC + TBW);        // [D]
+
   const Geo& g = a.g;
   int b = blockIdx.x;
   const int p = b % 6;
   b /= 6;
   const int strip = b % a.nstrips, chunk = b / a.nstrips;
   const int tid = threadIdx.x;
+  const int e = tid + 1;                    // own element in a staged row
   const int jbase = g.lo + strip * a.wcols;
   const int jend = min(jbase + a.wcols, g.hi);
   const int j = jbase - 3 + tid;
-  const int jc = min(j, g.P - 1);
   const int r0 = g.lo + chunk * a.rows_per_chunk;
   const int r1 = min(r0 + a.rows_per_chunk, g.hi);
+  const int rfirst = r0 - 3, rlast = r1 + 2;
   const bool out_lane = (tid >= 3) && (j < jend);
-  const bool jint = (jc >= g.lo) && (jc < g.hi);
+  const bool jint = (j >= g.lo) && (j < g.hi);
   const long long L = g.ld;
-  const long long col = PYCS_JOFF + jc;
-  const double* __restrict__ Q = a.q + (long long)p * g.ps + col;
-  double* __restrict__ QN = a.qn + (long long)p * g.ps + col;
-  const double* __restrict__ UA = a.ua + (long long)p * g.ps + col;
-  const double* __restrict__ VA = a.va + (long long)p * g.ps + col;
-  const double* __restrict__ UM = a.um + (long long)p * g.ps + col;
-  const double* __restrict__ VM = a.vm + (long long)p * g.ps + col;
-  const double* __restrict__ SGC = a.sgc + col;
-  const double* __restrict__ RGC = a.rgc + col;
-  const double* __restrict__ SGU = a.sgu + col;
-  const double* __restrict__ SGV = a.sgv + col;
   const double corr = a.apply_corr ? *a.corr : 0.0;
   const double cdx = a.cdx, cdy = a.cdy;
+  // staged segment: starts at column jbase-4 (16-byte aligned: JOFF and wcols are even)
+  const int c0 = jbase - 4;
+  int len = min(TBW, g.ld - PYCS_JOFF - c0) & ~1;
+  const uint32_t row_bytes = (uint32_t)len * 8u;
+
+  auto issue = [&](int r) {                 // thread 0 only
+    const int s = (r - rfirst) % D;
+    double* dst = ring + (size_t)s * NARR * TBW;
+    const long long colb = (long long)p * g.ps + PYCS_JOFF + c0;
+    const long long colm = PYCS_JOFF + c0;
+    const long long rr = (long long)r * L, ru = (long long)max(r - 1, 0) * L, r2 = (long long)max(r - 2, 0) * L;
+    mbar_expect_tx(&full[s], row_bytes * NARR);
+    tma_row(dst + A_Q * TBW, a.q + colb + rr, row_bytes, &full[s]);
+    tma_row(dst + A_V * TBW, a.va + colb + rr, row_bytes, &full[s]);
+    tma_row(dst + A_SGC * TBW, a.sgc + colm + rr, row_bytes, &full[s]);
+    tma_row(dst + A_SGV * TBW, a.sgv + colm + rr, row_bytes, &full[s]);
+    tma_row(dst + A_RGC * TBW, a.rgc + colm + rr, row_bytes, &full[s]);
+    tma_row(dst + A_SGU * TBW, a.sgu + colm + ru, row_bytes, &full[s]);
+    tma_row(dst + A_U * TBW, a.ua + colb + r2, row_bytes, &full[s]);
+    if (MASK & 1) {
+      tma_row(dst + A_VM * TBW, a.vm + colb + rr, row_bytes, &full[s]);
+      tma_row(dst + A_UM * TBW, a.um + colb + r2, row_bytes, &full[s]);
+    }
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < D; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int r = rfirst; r < rfirst + PF && r <= rlast; ++r) issue(r);
+  }
+
+  double* __restrict__ QN = a.qn + (long long)p * g.ps + PYCS_JOFF + min(j, g.P - 1) + (long long)r0 * L;
 
   // rolling state, all for column j
   double q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0;       // Q rows r-4 .. r
@@ -161,134 +226,150 @@ __global__ void __launch_bounds__(TB) fused_step_kernel(FusedArgs a) {
   double pyR = 0, py6 = 0, pyd = 0;                    // parabola of Qy, cell r-3
   double fin_prev = 0, fout_prev = 0;                  // x-fluxes at edge r-3
   double cm_prev = 0;                                  // sqrtg_pu * cx at edge r-3 (SPLIT != 1)
+  double gu_prev = 0;                                  // sqrtg_pu at row r-2 (carried from the previous slot)
   double psum = 0;
+  int s = 0, s2 = D - 2, s3 = D - 3;                   // slots of rows r, r-2, r-3
+  uint32_t par = 0;
 
-  for (int r = r0 - 3; r <= r1 + 2; ++r) {
-    const long long ro = (long long)r * L;
-    q0 = q1; q1 = q2; q2 = q3; q3 = q4;
-    y0 = y1; y1 = y2; y2 = y3; y3 = y4;
-    {
-      double v = Q[ro];
-      if (a.apply_corr && jint && r >= g.lo && r < g.hi) v = fma(SGC[ro], corr, v);
-      q4 = v;
-    }
-    const bool have_cell = (r >= r0 + 1);   // cell r-2 has its 5 rows (r-4 >= r0-3)
+  for (int r = rfirst; r <= rlast; ++r) {
+    const double* S = ring + (size_t)s * NARR * TBW;
+    const double* S2 = ring + (size_t)s2 * NARR * TBW;
+    const double* S3 = ring + (size_t)s3 * NARR * TBW;
+    while (!mbar_try_wait(&full[s], par)) {}
+
+    const bool have_cell = (r >= r0 + 1);   // cell r-2 has its 5 rows
     const bool have_edge = (r >= r0 + 2);   // edge r-2: cells r-3 and r-2 both have parabolas
     const bool outp = (r >= r0 + 3);        // output row r-3
 
-    // ---------------- phase 1: inner x-flux at edge r-2 (registers), Qx row r-3
-    double nqL = 0, nqR = 0, nq6 = 0, ndq = 0;          // parabola of Q, cell r-2
-    double u = 0, cxe = 0, sup = 1.0, gue = 0;
+    // ---------------- phase 1: own column -- new row, inner x-flux at edge r-2, Qx row r-3
+    q0 = q1; q1 = q2; q2 = q3; q3 = q4;
+    y0 = y1; y1 = y2; y2 = y3; y3 = y4;
+    q4 = S[A_Q * TBW + e];
+    if (a.apply_corr) {
+      if (jint && r >= g.lo && r < g.hi) {
+        q4 = fma(S[A_SGC * TBW + e], corr, q4);
+        const_cast<double*>(S)[A_Q * TBW + e] = q4;      // neighbours read the corrected value
+      }
+    }
+    const double gu_cur = S[A_SGU * TBW + e];            // sqrtg_pu at row r-1
+    double nqL = 0, nqR = 0, nq6 = 0, ndq = 0;           // parabola of Q, cell r-2
+    double u = 0, cxe = 0, sup = 1.0;
     bool up = true;
-    double fin = 0;
+    double fin = 0, gcc2 = 0;
     if (have_cell) {
-      const long long co = ro - 2 * L;
-      double gl = SGU[co], gr = SGU[co + L], gcc = SGC[co];
-      parabola<RECON, MT>(q0, q1, q2, q3, q4, gl, gr, gcc, nqL, nqR, nq6, ndq);
+      gcc2 = S2[A_SGC * TBW + e];
+      parabola<RECON, MT>(q0, q1, q2, q3, q4, gu_prev, gu_cur, gcc2, nqL, nqR, nq6, ndq);
       if (have_edge) {
-        u = UA[co];
-        double um = MASK ? UM[co] : u;
+        u = S[A_U * TBW + e];
+        if (MASK & 2) u *= a.ws;
+        const double um = (MASK & 1) ? S[A_UM * TBW + e] : u;
         up = um >= 0;
         sup = up ? 1.0 : -1.0;
         cxe = u * cdx;
-        gue = gl;                                   // sqrtg_pu at edge r-2
-        double e = up ? pqR : nqL, s6 = up ? pq6 : nq6, sd = up ? pdq : ndq;
-        fin = ppm_flux(e, s6, sd, sup, cxe) * u;
-        if (MT == 2) fin *= gue;
+        const double ee = up ? pqR : nqL, s6 = up ? pq6 : nq6, sd = up ? pdq : ndq;
+        fin = ppm_flux(ee, s6, sd, sup, cxe) * u;
+        if (MT == 2) fin *= gu_prev;
       }
     }
-    double qx = 0;
     if (outp) {
-      double dFx = -(fin - fin_prev) * cdx;
-      double rg = RGC[ro - 3 * L];
+      const double dFx = -(fin - fin_prev) * cdx;
+      const double rg = S3[A_RGC * TBW + e];
+      double qx;
       if (SPLIT == 1) qx = fma(0.5 * dFx, rg, q1);
       else {
-        double cd = gue * cxe - cm_prev;            // c1x - c2x
+        const double cd = gu_prev * cxe - cm_prev;        // c1x - c2x
         if (SPLIT == 2) qx = fma(0.5 * fma(cd, q1, dFx), rg, q1);
         else qx = 0.5 * (q1 + (q1 + dFx) / (1.0 - cd));
       }
+      sX[e] = qx;
     }
-    sQ[tid] = q4;
-    sX[tid] = qx;
-    __syncthreads();
+    __syncthreads();                                     // barrier A
+    if (tid == 0 && r + PF <= rlast) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(r + PF);
+    }
 
     // ---------------- phase 2: y-fluxes at edge j: inner on row r, outer on row r-3
-    double v_r = VA[ro];
-    double gvo = 0;
     {
-      double vm = MASK ? VM[ro] : v_r;
-      bool vp = vm >= 0;
-      int cu = vp ? tid - 1 : tid;
-      cu = max(2, min(cu, TB - 3));
-      long long mo = ro + (cu - tid);
-      double gl = SGV[mo], gr = SGV[mo + 1], gcc = SGC[mo];
+      double v = S[A_V * TBW + e];
+      if (MASK & 2) v *= a.ws;
+      const double vm = (MASK & 1) ? S[A_VM * TBW + e] : v;
+      const bool vp = vm >= 0;
+      int cu = vp ? e - 1 : e;
+      cu = max(2, min(cu, TBW - 3));
+      const double gl = S[A_SGV * TBW + cu], gr = S[A_SGV * TBW + cu + 1], gcc = S[A_SGC * TBW + cu];
       double eL, eR, s6, sd;
-      parabola<RECON, MT>(sQ[cu - 2], sQ[cu - 1], sQ[cu], sQ[cu + 1], sQ[cu + 2], gl, gr, gcc, eL, eR, s6, sd);
-      double cy = v_r * cdy;
-      double f = ppm_flux(vp ? eR : eL, s6, sd, vp ? 1.0 : -1.0, cy) * v_r;
-      if (MT == 2 || SPLIT != 1) gvo = SGV[ro];
-      if (MT == 2) f *= gvo;
-      sF[tid] = f;
-      if (SPLIT != 1) sC[tid] = gvo * cy;
+      const double* qr = S + A_Q * TBW + cu;
+      parabola<RECON, MT>(qr[-2], qr[-1], qr[0], qr[1], qr[2], gl, gr, gcc, eL, eR, s6, sd);
+      const double cy = v * cdy;
+      double f = ppm_flux(vp ? eR : eL, s6, sd, vp ? 1.0 : -1.0, cy) * v;
+      if (MT == 2 || SPLIT != 1) {
+        const double gvo = S[A_SGV * TBW + e];
+        if (MT == 2) f *= gvo;
+        if (SPLIT != 1) sC[e] = gvo * cy;
+      }
+      sF[e] = f;
     }
     if (outp) {
-      const long long r3 = ro - 3 * L;
-      double v3 = VA[r3];
-      double vm = MASK ? VM[r3] : v3;
-      bool vp = vm >= 0;
-      int cu = vp ? tid - 1 : tid;
-      cu = max(2, min(cu, TB - 3));
-      long long mo = r3 + (cu - tid);
-      double gl = SGV[mo], gr = SGV[mo + 1], gcc = SGC[mo];
+      double v3 = S3[A_V * TBW + e];
+      if (MASK & 2) v3 *= a.ws;
+      const double vm = (MASK & 1) ? S3[A_VM * TBW + e] : v3;
+      const bool vp = vm >= 0;
+      int cu = vp ? e - 1 : e;
+      cu = max(2, min(cu, TBW - 3));
+      const double gl = S3[A_SGV * TBW + cu], gr = S3[A_SGV * TBW + cu + 1], gcc = S3[A_SGC * TBW + cu];
       double eL, eR, s6, sd;
-      parabola<RECON, MT>(sX[cu - 2], sX[cu - 1], sX[cu], sX[cu + 1], sX[cu + 2], gl, gr, gcc, eL, eR, s6, sd);
-      double cy = v3 * cdy;
+      const double* xr = sX + cu;
+      parabola<RECON, MT>(xr[-2], xr[-1], xr[0], xr[1], xr[2], gl, gr, gcc, eL, eR, s6, sd);
+      const double cy = v3 * cdy;
       double f = ppm_flux(vp ? eR : eL, s6, sd, vp ? 1.0 : -1.0, cy) * v3;
-      if (MT == 2) f *= SGV[r3];
-      sG[tid] = f;
+      if (MT == 2) f *= S3[A_SGV * TBW + e];
+      sG[e] = f;
     }
-    __syncthreads();
+    __syncthreads();                                     // barrier B
 
     // ---------------- phase 3: Qy row r, outer x-flux at edge r-2 on Qy, output row r-3
     {
-      int tn = min(tid + 1, TB - 1);
-      double dFy = -(sF[tn] - sF[tid]) * cdy;
-      double rg = RGC[ro];
+      const double dFy = -(sF[e + 1] - sF[e]) * cdy;
+      const double rg = S[A_RGC * TBW + e];
       if (SPLIT == 1) y4 = fma(0.5 * dFy, rg, q4);
       else {
-        double cd = sC[tn] - sC[tid];               // c1y - c2y
+        const double cd = sC[e + 1] - sC[e];              // c1y - c2y
         if (SPLIT == 2) y4 = fma(0.5 * fma(cd, q4, dFy), rg, q4);
         else y4 = 0.5 * (q4 + (q4 + dFy) / (1.0 - cd));
       }
     }
     double fout = 0;
     if (have_cell) {
-      const long long co = ro - 2 * L;
-      double gl = SGU[co], gr = SGU[co + L], gcc = SGC[co];
       double nyL, nyR, ny6, nyd;
-      parabola<RECON, MT>(y0, y1, y2, y3, y4, gl, gr, gcc, nyL, nyR, ny6, nyd);
+      parabola<RECON, MT>(y0, y1, y2, y3, y4, gu_prev, gu_cur, gcc2, nyL, nyR, ny6, nyd);
       if (have_edge) {
-        double e = up ? pyR : nyL, s6 = up ? py6 : ny6, sd = up ? pyd : nyd;
-        fout = ppm_flux(e, s6, sd, sup, cxe) * u;
-        if (MT == 2) fout *= gue;
+        const double ee = up ? pyR : nyL, s6 = up ? py6 : ny6, sd = up ? pyd : nyd;
+        fout = ppm_flux(ee, s6, sd, sup, cxe) * u;
+        if (MT == 2) fout *= gu_prev;
       }
       pyR = nyR; py6 = ny6; pyd = nyd;
     }
     if (outp) {
-      int tn = min(tid + 1, TB - 1);
-      double s = -(fout - fout_prev) * cdx - (sG[tn] - sG[tid]) * cdy;   // pxdF + pydF
-      const long long r3 = ro - 3 * L;
+      const double sdiv = -(fout - fout_prev) * cdx - (sG[e + 1] - sG[e]) * cdy;   // pxdF + pydF
       if (out_lane) {
         // Q - dt*div with div = -(pxdF+pydF)/(dt*sqrtg)  (src/discrete_operators.py:95,
         // src/advection_timestep.py:43)
-        QN[r3] = fma(s, RGC[r3], q1);
-        psum += s;
+        *QN = fma(sdiv, S3[A_RGC * TBW + e], q1);
+        psum += sdiv;
       }
+      QN += L;
     }
     pqR = nqR; pq6 = nq6; pdq = ndq;
     fin_prev = fin;
     fout_prev = fout;
-    if (SPLIT != 1) cm_prev = gue * cxe;
+    if (SPLIT != 1) cm_prev = gu_prev * cxe;
+    gu_prev = gu_cur;
+    // advance the ring: row r+1 -> slot s+1 (rows r-1, r-2 follow in lock step)
+    s = (s + 1 == D) ? 0 : s + 1;
+    s2 = (s2 + 1 == D) ? 0 : s2 + 1;
+    s3 = (s3 + 1 == D) ? 0 : s3 + 1;
+    if (s == 0) par ^= 1;
   }
 
   // per-CTA partial of sum(pxdF + pydF) over its interior outputs (for MF-PR)
@@ -303,6 +384,7 @@ __global__ void __launch_bounds__(TB) fused_step_kernel(FusedArgs a) {
     a.part[blockIdx.x] = t;
   }
 }
+
 
 // ---- Lagrange ghost fill that honours the pending projection term ------------
 // Same arithmetic as dg_phase1_kernel in halo.cu (src/interpolation.py:200-248);
@@ -413,21 +495,54 @@ __global__ void recip_kernel(Geo g, const double* __restrict__ s, double* __rest
   d[id] = (v != 0.0) ? 1.0 / v : 0.0;
 }
 
-template <int TB, int RECON, int SPLIT>
-void launch_variant(const FusedArgs& a, int mask, int nblocks, cudaStream_t st) {
-  if (mask) fused_step_kernel<TB, RECON, SPLIT, 1><<<nblocks, TB, 0, st>>>(a);
-  else fused_step_kernel<TB, RECON, SPLIT, 0><<<nblocks, TB, 0, st>>>(a);
+template <int TB, int MASK, int D>
+size_t fused_smem_bytes() {
+  const int narr = (MASK & 1) ? 9 : 7;
+  return sizeof(double) * (size_t)(TB + 2) * (D * narr + 4) + sizeof(uint64_t) * D + 16;
 }
 
-template <int TB>
-void launch_fused(const FusedArgs& a, int recon, int split, int mask, int nblocks, cudaStream_t st) {
+template <int TB, int RECON, int SPLIT, int MASK, int D>
+cudaError_t launch_kernel(const FusedArgs& a, int nblocks, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = fused_smem_bytes<TB, MASK, D>();
+  auto kern = fused_step_kernel<TB, RECON, SPLIT, MASK, D>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<nblocks, TB, smem, st>>>(a);
+  return cudaSuccess;
+}
+
+template <int TB, int RECON, int SPLIT, int D>
+cudaError_t launch_variant(const FusedArgs& a, int mask, int nblocks, cudaStream_t st) {
+  if (mask == 1) return launch_kernel<TB, RECON, SPLIT, 1, D>(a, nblocks, st);
+  if (mask == 2) return launch_kernel<TB, RECON, SPLIT, 2, D>(a, nblocks, st);
+  return launch_kernel<TB, RECON, SPLIT, 0, D>(a, nblocks, st);
+}
+
+// The par-default scheme (PPM-PL07 / SP-AVLT) is instantiated for every tuning point
+// (threads per CTA x ring depth); the other scheme tuples use 160 threads, depth 6.
+cudaError_t launch_fused(const FusedArgs& a, int recon, int split, int mask, int nblocks, int tb, int depth,
+                         cudaStream_t st) {
+  if (recon == 3 && split == 1) {
+#define TUNE(T, DD) \
+  if (tb == T && depth == DD) return launch_variant<T, 3, 1, DD>(a, mask, nblocks, st)
+    TUNE(128, 5); TUNE(128, 6); TUNE(128, 7);
+    TUNE(160, 5); TUNE(160, 6); TUNE(160, 7);
+    TUNE(256, 5); TUNE(256, 6);
+#undef TUNE
+    return launch_variant<160, 3, 1, 6>(a, mask, nblocks, st);
+  }
 #define CASE(R, S) \
-  if (recon == R && split == S) return launch_variant<TB, R, S>(a, mask, nblocks, st)
-  CASE(3, 1); CASE(3, 2); CASE(3, 3);
+  if (recon == R && split == S) return launch_variant<160, R, S, 6>(a, mask, nblocks, st)
+  CASE(3, 2); CASE(3, 3);
   CASE(1, 1); CASE(1, 2); CASE(1, 3);
   CASE(2, 1); CASE(2, 2); CASE(2, 3);
   CASE(4, 1); CASE(4, 2); CASE(4, 3);
 #undef CASE
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace
@@ -440,7 +555,7 @@ struct FusedState {
   int pending = 0;             // partials of the last step wait to be applied
   int ring_pending = 0;        // ghost ring of the current buffer is stale
   int npart = 0;
-  int tb = 160, rows = 0, nstrips = 0, wcols = 0, nchunks = 0;
+  int tb = 160, depth = 6, rows = 0, nstrips = 0, wcols = 0, nchunks = 0;
 };
 
 #include <map>
@@ -466,11 +581,17 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
     // strips of TB-6 columns; chunks sized so that the grid fills whole waves
     const char* e = getenv("PYCS_FUSED_TB");
     int tb = e ? atoi(e) : 160;
-    if (tb != 128 && tb != 160 && tb != 192 && tb != 256) tb = 160;
+    if (tb != 128 && tb != 160 && tb != 256) tb = 160;
+    const char* ed = getenv("PYCS_FUSED_DEPTH");
+    int depth = ed ? atoi(ed) : 6;
+    if (depth < 5 || depth > 7 || (tb == 256 && depth > 6)) depth = 6;
+    if (!(h->prm.recon == 3 && h->prm.opsplit == 1)) { tb = 160; depth = 6; }
     fs.tb = tb;
+    fs.depth = depth;
     int wmax = tb - 6;
     fs.nstrips = (g.N + wmax - 1) / wmax;
     fs.wcols = (g.N + fs.nstrips - 1) / fs.nstrips;
+    fs.wcols += fs.wcols & 1;                  // even: staged rows start 16-byte aligned
     const char* er = getenv("PYCS_FUSED_ROWS");
     int rows = er ? atoi(er) : 0;
     if (rows <= 0) {
@@ -535,8 +656,76 @@ void k_fused_release(pycs_handle h) {
   g_fused.erase(it);
 }
 
-int k_fused_step(pycs_handle h, long long k, double t) {
-  (void)k;
+// Bring the exposed wind state (U_pu / U_pv / U_pc arrays) to what the reference holds
+// after update_adv(t_kprev), following a stretch of separable-wind steps that did not
+// touch those arrays: wind(t_{kprev-1}) on the interior, the ghost fill of step kprev,
+// then update_adv(t_kprev) (src/advection_timestep.py:31-37, :48-75).
+int k_wind_resync(pycs_handle h, long long kprev) {
+  if (kprev < 1) return 0;
+  TRY(k_wind_interior(h, (double)(kprev - 1) * h->g.dt, 1, 1));
+  TRY(k_wind_ghost_fill(h));
+  return k_update_adv(h, (double)kprev * h->g.dt);
+}
+
+static int launch_step_kernel(pycs_handle h, FusedState& fs, const double* qcur, double* qnext, int pend,
+                              int mask, double ws) {
+  const Geo& g = h->g;
+  double *sgc, *sgu, *sgv, *ua, *va, *um, *vm;
+  TRY(pycs_field_ptr(h, PYCS_F_SQRTG_PC, &sgc));
+  TRY(pycs_field_ptr(h, PYCS_F_SQRTG_PU, &sgu));
+  TRY(pycs_field_ptr(h, PYCS_F_SQRTG_PV, &sgv));
+  TRY(pycs_field_ptr(h, PYCS_F_PU_UAVG, &ua));
+  TRY(pycs_field_ptr(h, PYCS_F_PV_VAVG, &va));
+  TRY(pycs_field_ptr(h, PYCS_F_PU_UCONTRA, &um));
+  TRY(pycs_field_ptr(h, PYCS_F_PV_VCONTRA, &vm));
+  FusedArgs a;
+  a.g = g;
+  a.q = qcur; a.qn = qnext;
+  a.ua = ua; a.va = va; a.um = um; a.vm = vm;
+  a.sgc = sgc; a.rgc = fs.rgc; a.sgu = sgu; a.sgv = sgv;
+  a.part = fs.part;
+  a.corr = h->red_out + 8;
+  a.rows_per_chunk = fs.rows; a.nstrips = fs.nstrips; a.wcols = fs.wcols;
+  a.apply_corr = pend;
+  a.cdx = g.dt / g.dx; a.cdy = g.dt / g.dy;
+  a.ws = ws;
+  CK(launch_fused(a, h->prm.recon, h->prm.opsplit, mask, fs.npart, fs.tb, fs.depth, h->stream));
+  CKL(h);
+  return 0;
+}
+
+// Device time of `reps` back-to-back launches of the step kernel alone (ping-pong
+// buffers, no ghost fill): the roofline measurement of bench.py.  Leaves Q undefined.
+int k_fused_time_kernel(pycs_handle h, int reps, int separable, float* ms) {
+  FusedState& fs = g_fused[h];
+  TRY(fused_setup(h, fs));
+  double *qa, *qb;
+  TRY(pycs_field_ptr(h, PYCS_F_Q, &qa));
+  TRY(pycs_field_ptr(h, PYCS_F_Q_NEXT, &qb));
+  int mask = separable ? 2 : ((h->prm.dp == 2) ? 1 : 0);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaEventRecord(h->ev0, h->stream));
+  for (int r = 0; r < reps; ++r)
+    TRY(launch_step_kernel(h, fs, (r & 1) ? qb : qa, (r & 1) ? qa : qb, h->prm.mf == 3 ? 1 : 0, mask, 0.999));
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaEventSynchronize(h->ev1));
+  CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  fs.pending = 0;
+  fs.ring_pending = 0;
+  return 0;
+}
+
+int k_fused_grid_info(pycs_handle h, int* tb, int* rows, int* nblocks) {
+  FusedState& fs = g_fused[h];
+  TRY(fused_setup(h, fs));
+  *tb = fs.tb; *rows = fs.rows; *nblocks = fs.npart;
+  return 0;
+}
+
+// separable != 0: wind field 3 with RK1 -- U(t) = U(0) cos(pi t / T) exactly
+// (src/advection_ic.py:301-305), so the step reads the t = 0 winds (still in
+// ucontra_averaged) and scales them; no wind kernels run.
+int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   const Geo& g = h->g;
   FusedState& fs = g_fused[h];
   TRY(fused_setup(h, fs));
@@ -548,16 +737,10 @@ int k_fused_step(pycs_handle h, long long k, double t) {
     pycs_set_error("fused step needs pycs_upload_lagrange first");
     return PYCS_ERR_STATE;
   }
-  double *qa, *qb, *sgc, *sgu, *sgv, *ua, *va, *um, *vm;
+  double *qa, *qb, *sgc;
   TRY(pycs_field_ptr(h, PYCS_F_Q, &qa));
   TRY(pycs_field_ptr(h, PYCS_F_Q_NEXT, &qb));
   TRY(pycs_field_ptr(h, PYCS_F_SQRTG_PC, &sgc));
-  TRY(pycs_field_ptr(h, PYCS_F_SQRTG_PU, &sgu));
-  TRY(pycs_field_ptr(h, PYCS_F_SQRTG_PV, &sgv));
-  TRY(pycs_field_ptr(h, PYCS_F_PU_UAVG, &ua));
-  TRY(pycs_field_ptr(h, PYCS_F_PV_VAVG, &va));
-  TRY(pycs_field_ptr(h, PYCS_F_PU_UCONTRA, &um));
-  TRY(pycs_field_ptr(h, PYCS_F_PV_VCONTRA, &vm));
   double* qcur = h->qcur ? qb : qa;
   double* qnext = h->qcur ? qa : qb;
 
@@ -571,35 +754,19 @@ int k_fused_step(pycs_handle h, long long k, double t) {
                                                   h->red_out + 8, pend);
   CKL(h);
   // 2. winds (src/advection_timestep.py:31-37)
-  if (h->prm.vf >= 2) {
+  if (h->prm.vf >= 2 && !separable) {
     TRY(k_wind_ghost_fill(h));
     TRY(k_time_averaged_velocity(h));
   }
   // 3. divergence + Q update
-  FusedArgs a;
-  a.g = g;
-  a.q = qcur; a.qn = qnext;
-  a.ua = ua; a.va = va; a.um = um; a.vm = vm;
-  a.sgc = sgc; a.rgc = fs.rgc; a.sgu = sgu; a.sgv = sgv;
-  a.part = fs.part;
-  a.corr = h->red_out + 8;
-  a.rows_per_chunk = fs.rows; a.nstrips = fs.nstrips; a.wcols = fs.wcols;
-  a.apply_corr = pend;
-  a.cdx = g.dt / g.dx; a.cdy = g.dt / g.dy;
-  int mask = (h->prm.dp == 2) ? 1 : 0;    // RK1: averaged wind == instantaneous wind
-  int nb = fs.npart;
-  switch (fs.tb) {
-    case 128: launch_fused<128>(a, h->prm.recon, h->prm.opsplit, mask, nb, h->stream); break;
-    case 192: launch_fused<192>(a, h->prm.recon, h->prm.opsplit, mask, nb, h->stream); break;
-    case 256: launch_fused<256>(a, h->prm.recon, h->prm.opsplit, mask, nb, h->stream); break;
-    default: launch_fused<160>(a, h->prm.recon, h->prm.opsplit, mask, nb, h->stream); break;
-  }
-  CKL(h);
+  int mask = separable ? 2 : ((h->prm.dp == 2) ? 1 : 0);    // RK1: averaged wind == instantaneous wind
+  double ws = separable ? cos(3.141592653589793 * ((double)(k - 1) * g.dt) / 5.0) : 1.0;
+  TRY(launch_step_kernel(h, fs, qcur, qnext, pend, mask, ws));
   h->last_step_kernel_launches++;
   h->qcur ^= 1;
   fs.pending = (h->prm.mf == 3) ? 1 : 0;
   fs.ring_pending = 1;
   // 4. wind refresh for the next step (src/advection_timestep.py:48-75)
-  if (h->prm.vf >= 2) TRY(k_update_adv(h, t));
+  if (h->prm.vf >= 2 && !separable) TRY(k_update_adv(h, t));
   return 0;
 }

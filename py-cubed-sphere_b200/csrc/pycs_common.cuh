@@ -128,7 +128,10 @@ int k_update_adv(pycs_handle h, double t);
 int k_wind_interior(pycs_handle h, double t, int convert_interior_only, int do_velocity);
 // fused.cu
 int k_fused_supported(pycs_handle h);
-int k_fused_step(pycs_handle h, long long k, double t);
+int k_fused_step(pycs_handle h, long long k, double t, int separable);
+int k_wind_resync(pycs_handle h, long long kprev);
+int k_fused_time_kernel(pycs_handle h, int reps, int separable, float* ms);
+int k_fused_grid_info(pycs_handle h, int* tb, int* rows, int* nblocks);
 int k_fused_flush(pycs_handle h);
 void k_fused_release(pycs_handle h);
 // layout.cu (in capi.cu)

@@ -95,7 +95,8 @@ def load_library():
         "pycs_errors": [h, dp, dp],
         "pycs_mass": [h, dp],
         "pycs_launch_count": [h, C.POINTER(C.c_int64)],
-        "pycs_last_step_kernel_ms": [h, C.POINTER(C.c_float), C.POINTER(C.c_int64)],
+        "pycs_time_step_kernel": [h, C.c_int32, C.c_int32, C.POINTER(C.c_float)],
+        "pycs_step_kernel_info": [h, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
