@@ -204,6 +204,7 @@ extern "C" int pycs_upload_field(pycs_handle h, int32_t field, const double* hos
   CK(cudaStreamSynchronize(h->stream));
   if (field == PYCS_F_Q) h->qcur = 0;
   if (field == PYCS_F_SQRTG_PC) h->a2_valid = 0;
+  if (field >= PYCS_F_SQRTG_PC && field <= PYCS_F_PV_LAT) k_fused_invalidate(h);
   return 0;
 }
 

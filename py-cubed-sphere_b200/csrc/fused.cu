@@ -552,6 +552,9 @@ struct FusedState {
   double* rgc = nullptr;       // 1/sqrtg_pc
   double* part = nullptr;
   int npart_cap = 0;
+  double* bu = nullptr;        // separable wind: ucontra(t = 0) incl. ghost edges
+  double* bv = nullptr;        //                 vcontra(t = 0)
+  int base_valid = 0;
   int pending = 0;             // partials of the last step wait to be applied
   int ring_pending = 0;        // ghost ring of the current buffer is stale
   int npart = 0;
@@ -583,7 +586,7 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
     int tb = e ? atoi(e) : 160;
     if (tb != 128 && tb != 160 && tb != 256) tb = 160;
     const char* ed = getenv("PYCS_FUSED_DEPTH");
-    int depth = ed ? atoi(ed) : 6;
+    int depth = ed ? atoi(ed) : 5;
     if (depth < 5 || depth > 7 || (tb == 256 && depth > 6)) depth = 6;
     if (!(h->prm.recon == 3 && h->prm.opsplit == 1)) { tb = 160; depth = 6; }
     fs.tb = tb;
@@ -653,7 +656,39 @@ void k_fused_release(pycs_handle h) {
   if (it == g_fused.end()) return;
   if (it->second.rgc) cudaFree(it->second.rgc);
   if (it->second.part) cudaFree(it->second.part);
+  if (it->second.bu) cudaFree(it->second.bu);
+  if (it->second.bv) cudaFree(it->second.bv);
   g_fused.erase(it);
+}
+
+// geometry was re-uploaded: 1/sqrtg and the t = 0 winds must be rebuilt
+void k_fused_invalidate(pycs_handle h) {
+  auto it = g_fused.find(h);
+  if (it == g_fused.end()) return;
+  if (it->second.rgc) cudaFree(it->second.rgc);
+  it->second.rgc = nullptr;
+  it->second.base_valid = 0;
+}
+
+// Separable wind (vf = 3, RK1): the step kernel scales the contravariant wind of t = 0
+// (interior + ghost edges, exactly what init_vars_adv leaves in ucontra_averaged,
+// src/advection_vars.py:37-87) by cos(pi t / T).  The copy is private to the fused path:
+// ucontra_averaged itself is overwritten by every non-separable step.  Building it
+// overwrites U_pu / U_pv / U_pc; the resync before the last step of a run restores them.
+static int ensure_base_winds(pycs_handle h, FusedState& fs) {
+  if (fs.base_valid) return 0;
+  const size_t bytes = sizeof(double) * 6 * (size_t)h->g.ps;
+  if (!fs.bu) CK(cudaMalloc(&fs.bu, bytes));
+  if (!fs.bv) CK(cudaMalloc(&fs.bv, bytes));
+  TRY(k_wind_interior(h, 0.0, 1, 1));
+  TRY(k_wind_ghost_fill(h));
+  double *u, *v;
+  TRY(pycs_field_ptr(h, PYCS_F_PU_UCONTRA, &u));
+  TRY(pycs_field_ptr(h, PYCS_F_PV_VCONTRA, &v));
+  CK(cudaMemcpyAsync(fs.bu, u, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(fs.bv, v, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  fs.base_valid = 1;
+  return 0;
 }
 
 // Bring the exposed wind state (U_pu / U_pv / U_pc arrays) to what the reference holds
@@ -681,6 +716,7 @@ static int launch_step_kernel(pycs_handle h, FusedState& fs, const double* qcur,
   FusedArgs a;
   a.g = g;
   a.q = qcur; a.qn = qnext;
+  if (mask == 2) { ua = fs.bu; va = fs.bv; }
   a.ua = ua; a.va = va; a.um = um; a.vm = vm;
   a.sgc = sgc; a.rgc = fs.rgc; a.sgu = sgu; a.sgv = sgv;
   a.part = fs.part;
@@ -703,6 +739,7 @@ int k_fused_time_kernel(pycs_handle h, int reps, int separable, float* ms) {
   TRY(pycs_field_ptr(h, PYCS_F_Q, &qa));
   TRY(pycs_field_ptr(h, PYCS_F_Q_NEXT, &qb));
   int mask = separable ? 2 : ((h->prm.dp == 2) ? 1 : 0);
+  if (separable) TRY(ensure_base_winds(h, fs));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaEventRecord(h->ev0, h->stream));
   for (int r = 0; r < reps; ++r)
@@ -743,6 +780,7 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   TRY(pycs_field_ptr(h, PYCS_F_SQRTG_PC, &sgc));
   double* qcur = h->qcur ? qb : qa;
   double* qnext = h->qcur ? qa : qb;
+  if (separable) TRY(ensure_base_winds(h, fs));
 
   // 1. ghost cells of Q (src/advection_timestep.py:28), folding in the pending MF-PR term
   int pend = fs.pending;

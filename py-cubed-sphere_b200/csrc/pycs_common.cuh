@@ -134,4 +134,5 @@ int k_fused_time_kernel(pycs_handle h, int reps, int separable, float* ms);
 int k_fused_grid_info(pycs_handle h, int* tb, int* rows, int* nblocks);
 int k_fused_flush(pycs_handle h);
 void k_fused_release(pycs_handle h);
+void k_fused_invalidate(pycs_handle h);
 // layout.cu (in capi.cu)

@@ -324,6 +324,24 @@ def test_fused_matches_operator_path(mods, N, vf, name):
     b.dev.close()
 
 
+def test_fused_separable_wind_across_run_calls(mods):
+    """vf = 3 / RK1 scales the t = 0 winds in-kernel: successive pycs_run calls (each ending
+    with a non-separable step that rewrites ucontra_averaged) must keep using wind(0)."""
+    g = mods.cs_datastruct.cubed_sphere(50)
+    a = make_sim(mods, g, 3, TUPLES["default"])
+    b = make_sim(mods, g, 3, TUPLES["default"])
+    k = 0
+    for n in (1, 4, 15, 2, 9):
+        mods.advection_timestep.run_steps(g, a, k, n, fused=True)
+        k += n
+    mods.advection_timestep.run_steps(g, b, 0, k, fused=False)
+    assert relerr(np.asarray(a.Q), np.asarray(b.Q)) <= TOL
+    for nm in ("ucontra", "ucontra_old", "ucontra_averaged"):
+        assert relerr(np.asarray(getattr(a.U_pu, nm)), np.asarray(getattr(b.U_pu, nm))) <= TOL, nm
+    a.dev.close()
+    b.dev.close()
+
+
 def test_full_size_properties_n1536(mods):
     """Size-independent checks at BASELINE.json's full size: mass conservation and
     linearity of the (unlimited PPM-PL07) step, fused path."""
