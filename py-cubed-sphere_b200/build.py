@@ -24,6 +24,7 @@ UNITS = {
     "ppm.cu": ["-fmad=false"],
     "wind.cu": ["-fmad=false"],
     "fused.cu": [],
+    "fused3.cu": [],
 }
 
 

@@ -25,22 +25,12 @@
 // flush kernel before anything else reads Q).  Algebraically identical, one
 // rounding apart from the reference order.
 #include "pycs_common.cuh"
+#include "fused_args.cuh"
+#include "fused3_core.cuh"
+static int f3_strip_capacity(int nw) { return f3::strip_capacity(nw); }
 
 namespace {
 
-struct FusedArgs {
-  Geo g;
-  const double* q;
-  double* qn;
-  const double *ua, *va;      // U_pu.ucontra_averaged, U_pv.vcontra_averaged
-  const double *um, *vm;      // mask sources (U_pu.ucontra, U_pv.vcontra)
-  const double *sgc, *rgc, *sgu, *sgv;
-  double* part;
-  const double* corr;         // device scalar: pending projection coefficient -sum(s)/a2
-  int rows_per_chunk, nstrips, wcols, apply_corr;
-  double cdx, cdy;            // dt/dx, dt/dy
-  double ws;                  // separable wind: U(t) = U(0) * ws (MASK & 2)
-};
 
 // ---- PPM edge values of one cell from its 5-point neighbourhood -------------
 // src/reconstruction_1d.py:36-192 (q3 is the cell itself)
@@ -559,6 +549,8 @@ struct FusedState {
   int ring_pending = 0;        // ghost ring of the current buffer is stale
   int npart = 0;
   int tb = 160, depth = 6, rows = 0, nstrips = 0, wcols = 0, nchunks = 0;
+  int impl = 0;                // 2: block-synchronous kernel (this file), 3: warp-autonomous kernel (fused3.cu)
+  int nw = 3;                  // v3: consumer warps per CTA
 };
 
 #include <map>
@@ -581,26 +573,52 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
     CKL(h);
   }
   if (fs.rows == 0) {
-    // strips of TB-6 columns; chunks sized so that the grid fills whole waves
-    const char* e = getenv("PYCS_FUSED_TB");
-    int tb = e ? atoi(e) : 160;
-    if (tb != 128 && tb != 160 && tb != 256) tb = 160;
+    const char* ei = getenv("PYCS_FUSED_IMPL");
+    int impl = ei ? atoi(ei) : 3;
+    const char* ew = getenv("PYCS_FUSED_NW");
     const char* ed = getenv("PYCS_FUSED_DEPTH");
-    int depth = ed ? atoi(ed) : 5;
-    if (depth < 5 || depth > 7 || (tb == 256 && depth > 6)) depth = 6;
-    if (!(h->prm.recon == 3 && h->prm.opsplit == 1)) { tb = 160; depth = 6; }
-    fs.tb = tb;
-    fs.depth = depth;
-    int wmax = tb - 6;
-    fs.nstrips = (g.N + wmax - 1) / wmax;
-    fs.wcols = (g.N + fs.nstrips - 1) / fs.nstrips;
-    fs.wcols += fs.wcols & 1;                  // even: staged rows start 16-byte aligned
     const char* er = getenv("PYCS_FUSED_ROWS");
     int rows = er ? atoi(er) : 0;
+    int nw = ew ? atoi(ew) : 3, depth = ed ? atoi(ed) : 5;
+    if (impl == 3 && !pycs_fused3_has(h->prm.recon, h->prm.opsplit, nw, depth)) { nw = 3; depth = 5; }
+    if (impl == 3 && !pycs_fused3_has(h->prm.recon, h->prm.opsplit, nw, depth)) impl = 2;   // limited PPM
+    int resident, lag, cols;
+    if (impl == 3) {
+      // strips of up to 57 + 58 (NW-1) columns, one consumer warp per 57/58 of them
+      fs.nw = nw;
+      fs.depth = depth;
+      const int cap = f3_strip_capacity(nw);
+      fs.nstrips = (g.N + cap - 1) / cap;
+      fs.wcols = (g.N + fs.nstrips - 1) / fs.nstrips;
+      fs.wcols += fs.wcols & 1;                  // even: column pairs stay 16-byte aligned
+      const int mask = (h->prm.dp == 2) ? 1 : 0;
+      int per_sm = pycs_fused3_resident(h->prm.recon, h->prm.opsplit, mask, nw, depth);
+      if (per_sm < 1) {
+        pycs_set_error("fused3 kernel: occupancy query failed");
+        return PYCS_ERR_CUDA;
+      }
+      resident = h->sm_count * per_sm;
+      lag = 6;
+    } else {
+      // strips of TB-6 columns; chunks sized so that the grid fills whole waves
+      const char* e = getenv("PYCS_FUSED_TB");
+      int tb = e ? atoi(e) : 160;
+      if (tb != 128 && tb != 160 && tb != 256) tb = 160;
+      if (depth < 5 || depth > 7 || (tb == 256 && depth > 6)) depth = 5;
+      if (!(h->prm.recon == 3 && h->prm.opsplit == 1)) { tb = 160; depth = 6; }
+      fs.tb = tb;
+      fs.depth = depth;
+      int wmax = tb - 6;
+      fs.nstrips = (g.N + wmax - 1) / wmax;
+      fs.wcols = (g.N + fs.nstrips - 1) / fs.nstrips;
+      fs.wcols += fs.wcols & 1;                  // even: staged rows start 16-byte aligned
+      resident = h->sm_count * (depth == 5 ? 4 : 3);
+      lag = 4;
+    }
+    fs.impl = impl;
+    cols = 6 * fs.nstrips;
     if (rows <= 0) {
-      // aim at an integer number of waves of resident CTAs (4 CTAs/SM at <=96 regs)
-      int resident = h->sm_count * 4;
-      int cols = 6 * fs.nstrips;
+      // whole waves of resident CTAs: time ~ waves * (rows + ramp)
       int best = 0;
       double best_cost = 1e30;
       for (int nch = 1; nch <= g.N; ++nch) {
@@ -608,7 +626,7 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
         if (rr < 8 && nch > 1) break;
         int nb = cols * ((g.N + rr - 1) / rr);
         int waves = (nb + resident - 1) / resident;
-        double cost = (double)waves * (rr + 4.0);      // time ~ waves * (rows + ramp)
+        double cost = (double)waves * (rr + lag);
         if (cost < best_cost) { best_cost = cost; best = rr; }
       }
       rows = best;
@@ -616,7 +634,7 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
     fs.rows = rows;
     fs.nchunks = (g.N + rows - 1) / rows;
   }
-  int nb = 6 * fs.nstrips * fs.nchunks;
+  int nb = 6 * fs.nstrips * fs.nchunks * (fs.impl == 3 ? fs.nw : 1);   // MF-PR partial sums
   if (fs.npart_cap < nb) {
     if (fs.part) cudaFree(fs.part);
     CK(cudaMalloc(&fs.part, sizeof(double) * nb));
@@ -725,7 +743,10 @@ static int launch_step_kernel(pycs_handle h, FusedState& fs, const double* qcur,
   a.apply_corr = pend;
   a.cdx = g.dt / g.dx; a.cdy = g.dt / g.dy;
   a.ws = ws;
-  CK(launch_fused(a, h->prm.recon, h->prm.opsplit, mask, fs.npart, fs.tb, fs.depth, h->stream));
+  if (fs.impl == 3)
+    CK(pycs_launch_fused3(a, h->prm.recon, h->prm.opsplit, mask, fs.nw, fs.depth, fs.npart / fs.nw, h->stream));
+  else
+    CK(launch_fused(a, h->prm.recon, h->prm.opsplit, mask, fs.npart, fs.tb, fs.depth, h->stream));
   CKL(h);
   return 0;
 }
@@ -755,7 +776,9 @@ int k_fused_time_kernel(pycs_handle h, int reps, int separable, float* ms) {
 int k_fused_grid_info(pycs_handle h, int* tb, int* rows, int* nblocks) {
   FusedState& fs = g_fused[h];
   TRY(fused_setup(h, fs));
-  *tb = fs.tb; *rows = fs.rows; *nblocks = fs.npart;
+  *tb = fs.impl == 3 ? (fs.nw + 1) * 32 : fs.tb;
+  *rows = fs.rows;
+  *nblocks = fs.impl == 3 ? fs.npart / fs.nw : fs.npart;
   return 0;
 }
 

@@ -1,0 +1,25 @@
+// Arguments of the fused step kernels (fused.cu: v2 block-synchronous kernel;
+// fused3.cu: v3 warp-autonomous kernel).
+#pragma once
+#include "pycs_common.cuh"
+
+struct FusedArgs {
+  Geo g;
+  const double* q;
+  double* qn;
+  const double *ua, *va;      // U_pu.ucontra_averaged, U_pv.vcontra_averaged
+  const double *um, *vm;      // mask sources (U_pu.ucontra, U_pv.vcontra)
+  const double *sgc, *rgc, *sgu, *sgv;
+  double* part;
+  const double* corr;         // device scalar: pending projection coefficient -sum(s)/a2
+  int rows_per_chunk, nstrips, wcols, apply_corr;
+  double cdx, cdy;            // dt/dx, dt/dy
+  double ws;                  // separable wind: U(t) = U(0) * ws (MASK & 2)
+};
+
+// fused3.cu
+cudaError_t pycs_launch_fused3(const FusedArgs& a, int recon, int split, int mask, int nw, int depth, int nblocks,
+                               cudaStream_t st);
+// resident CTAs per SM of the v3 kernel for this template point (occupancy API); < 0 on error
+int pycs_fused3_resident(int recon, int split, int mask, int nw, int depth);
+bool pycs_fused3_has(int recon, int split, int nw, int depth);

@@ -1,0 +1,150 @@
+"""CPU test of the v3 fused step kernel's arithmetic and indexing.
+
+tests/emul/fused3_emul.cpp compiles the kernel's per-lane code
+(py-cubed-sphere_b200/csrc/fused3_core.cuh, shared verbatim with the CUDA kernel) with g++
+and replays the CTA / warp / lane decomposition and the staged-row ring on the host.  Here
+its output for one step is compared with the numpy oracle's divergence + Q update on the
+same ghost-filled state (tolerance 1e-13 of max|Q|; the reference bar is 1e-12).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from golden_common import TUPLES, DT16
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "emul", "fused3_emul.cpp")
+LIB = os.path.join(HERE, "emul", "libf3emul.so")
+CORE = os.path.join(HERE, "..", "py-cubed-sphere_b200", "csrc", "fused3_core.cuh")
+JOFF = 12
+
+
+@pytest.fixture(scope="module")
+def emul():
+    if (not os.path.exists(LIB)) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(CORE)):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-x", "c++",
+                        "-o", LIB, SRC], check=True)
+    lib = C.CDLL(LIB)
+    dp = C.POINTER(C.c_double)
+    lib.f3_emul_step.argtypes = [C.c_int] * 7 + [dp] * 11 + [C.c_double, C.c_int, C.c_double, C.c_double, C.c_double]
+    lib.f3_emul_step.restype = C.c_int
+    lib.f3_emul_grid.argtypes = [C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 3
+    lib.f3_emul_grid.restype = C.c_int
+    lib.f3_emul_ld.argtypes = [C.c_int]
+    lib.f3_emul_ld.restype = C.c_int
+    return lib
+
+
+def to_dev(a, ld, single=False):
+    """reference layout [i][j][p] -> device layout [p][i][ld] (column j at j + JOFF)."""
+    ni, nj, _ = a.shape
+    P1 = max(ni, nj)
+    npan = 1 if single else 6
+    out = np.zeros((npan, P1 if P1 % 2 else P1 + 1, ld))
+    out = np.zeros((npan, (min(ni, nj) + 1), ld))
+    for p in range(npan):
+        out[p, :ni, JOFF:JOFF + nj] = a[:, :, p]
+    return out
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def one_step(emul, N, vf, tup, pre_steps, nw=3, depth=5, rows=None, pending=False, separable=False):
+    from oracle.grid import LeanGrid
+    from oracle import step as ost, wind as owind
+    recon, dp, split, et, mt, mf = tup
+    g = LeanGrid(N)
+    dt = DT16[vf] * 16 / N
+    sim = ost.Simulation(g, dt, 5, 2, vf, 1, recon, dp, split, et, mt, mf)
+    ost.init_vars_adv(g, sim)
+    base_u, base_v = sim.U_pu.ucontra_averaged.copy(), sim.U_pv.vcontra_averaged.copy()
+    ost.run(g, sim, pre_steps)
+    k = pre_steps + 1
+    # the head of adv_time_step (src/advection_timestep.py:28-37)
+    ost.ghost_fill_scalar(sim.Q, sim.Q, g, sim)
+    if vf >= 2:
+        owind.ghost_fill_vector(sim.U_pu, sim.U_pv, sim.U_pc, g, sim)
+        owind.time_averaged_velocity(g, sim)
+    P = N + 8
+    ld = emul.f3_emul_ld(N)
+    I = np.s_[4:N + 4, 4:N + 4, :]
+    mtc = g.metric_tensor_pc
+    Qin = sim.Q.copy()
+    corr = 0.0
+    if pending:
+        # the device holds Q without the previous step's projection term on the interior
+        corr = 3.0e-3
+        Qin[I] = Qin[I] - mtc[I] * corr
+    if separable:
+        ws = np.cos(np.pi * ((k - 1) * dt) / 5.0)
+        ua, va, mask = base_u, base_v, 2
+    else:
+        ws = 1.0
+        ua, va, mask = sim.U_pu.ucontra_averaged, sim.U_pv.vcontra_averaged, (1 if dp == 2 else 0)
+    q = to_dev(Qin, ld)
+    qn = np.zeros_like(q)
+    rgc = np.zeros_like(mtc)
+    rgc[mtc != 0] = 1.0 / mtc[mtc != 0]
+    arrs = [to_dev(ua, ld), to_dev(va, ld), to_dev(sim.U_pu.ucontra, ld), to_dev(sim.U_pv.vcontra, ld),
+            to_dev(mtc, ld, True), to_dev(rgc, ld, True), to_dev(g.metric_tensor_pu, ld, True),
+            to_dev(g.metric_tensor_pv, ld, True)]
+    rows = rows or N
+    ns, wc, nch = C.c_int(), C.c_int(), C.c_int()
+    npart = emul.f3_emul_grid(N, nw, rows, C.byref(ns), C.byref(wc), C.byref(nch))
+    part = np.zeros(npart)
+    rc = emul.f3_emul_step(N, recon, split, mask, nw, depth, rows, ptr(q), ptr(qn), *[ptr(a) for a in arrs],
+                           ptr(part), corr, 1 if pending else 0, dt / g.dx, dt / g.dy, ws)
+    assert rc == 0
+    got = np.transpose(qn[:, 4:N + 4, JOFF + 4:JOFF + 4 + N], (1, 2, 0)).copy()
+    if mf == 3:                                          # deferred projection (src/discrete_operators.py:98-101)
+        a2 = np.sum(mtc[I] * mtc[I])
+        got += mtc[I] * (-np.sum(part) / a2)
+    # the oracle's step on the same state
+    ost.divergence(g, sim)
+    want = sim.Q[I] - sim.dt * sim.div[I]
+    return got, want
+
+
+CASES = [
+    (16, 1, "default", 2), (20, 1, "default", 0), (50, 3, "default", 3), (130, 1, "default", 1),
+    (16, 2, "AVLT-RK2-DG-PR", 3), (50, 2, "AVLT-RK2-DG-PR", 2),
+    (16, 1, "PL07-RK1-DG-PR", 2), (50, 3, "PL07-RK1-DG-PR", 1),
+    (16, 4, "default", 2),
+]
+
+
+@pytest.mark.parametrize("N,vf,name,pre", CASES)
+def test_emulated_kernel_matches_oracle(emul, N, vf, name, pre):
+    got, want = one_step(emul, N, vf, TUPLES[name], pre)
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("tup", [(1, 1, 1, 3, 1, 3), (1, 2, 2, 3, 1, 1), (3, 1, 2, 3, 1, 3), (1, 1, 3, 3, 2, 1)])
+def test_emulated_kernel_other_schemes(emul, tup):
+    """PPM-0 reconstruction, SP-L04 / SP-PL07 splittings, RK2 masks (tuples outside the named set)."""
+    got, want = one_step(emul, 20, 2, tup, 2)
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("rows,nw,depth", [(7, 3, 5), (16, 3, 6), (9, 4, 5), (50, 2, 7)])
+def test_emulated_kernel_chunks_and_shapes(emul, rows, nw, depth):
+    """Row chunks shorter than the panel, other CTA widths and ring depths: same result."""
+    got, want = one_step(emul, 50, 3, TUPLES["default"], 2, nw=nw, depth=depth, rows=rows)
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+
+
+def test_emulated_kernel_pending_projection(emul):
+    """The producer's patch: Q stored without the previous MF-PR term + apply_corr == Q with it."""
+    got, want = one_step(emul, 50, 1, TUPLES["default"], 2, pending=True)
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+
+
+def test_emulated_kernel_separable_wind(emul):
+    """vf = 3 / RK1: wind(0) * cos(pi t / T) scaled inside the kernel."""
+    got, want = one_step(emul, 50, 3, TUPLES["default"], 4, separable=True)
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
