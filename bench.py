@@ -44,7 +44,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -54,6 +54,12 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
+
+    def wait_first(self, timeout=5.0):
+        """nvidia-smi needs a moment to start: do not open the timed region before it samples."""
+        t = time.time()
+        while self.proc and not self.rows and time.time() - t < timeout:
+            time.sleep(0.02)
 
     def stop(self, t0, t1):
         if not self.proc:
@@ -73,8 +79,8 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        if not sm:   # region shorter than the sampling period: take whatever we have
-            for ts, line in self.rows[-3:]:
+        if not sm:   # region shorter than the sampling period: take the nearest samples
+            for ts, line in sorted(self.rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))[:3]:
                 f = [x.strip() for x in line.split(",")]
                 try:
                     sm.append(float(f[1]))
@@ -133,7 +139,7 @@ def run_reference(args):
     cfg["cpu_sample"] = "N=%d, same scheme and wind" % N
     line = {"impl": "reference", "metric": "cell-updates/s (fp64 advection step)", "value": value,
             "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": "port",
                              "sample": "%d full steps of the numpy oracle at N=%d (whole-array numpy is single "
@@ -148,7 +154,7 @@ def run_gpu(args):
     import torch
     import ctypes as C
     import pycs_b200  # noqa: F401
-    from pycs_b200 import cs_datastruct, advection_ic, advection_vars, advection_timestep
+    from pycs_b200 import cs_datastruct, advection_ic, advection_vars, advection_timestep, parallel
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -166,6 +172,10 @@ def run_gpu(args):
     dev = sim.dev
     if not dev.fused_supported():
         raise RuntimeError("fused kernel unavailable")
+    rows = (4, N + 4)
+    if world > 1:
+        # strong scaling: the rows of every panel are split over the ranks (csrc/mgpu.cu)
+        rows = parallel.shard(sim)
     setup_s = time.time() - t_setup
     sm, name = dev.sm_count()
     Q0 = np.asarray(sim.Q).copy()
@@ -183,7 +193,7 @@ def run_gpu(args):
     l0 = dev.launches()
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.25)
+    sampler.wait_first()
     ms = C.c_float()
     t0 = time.time()
     dev.call("pycs_run_timed", args.warmup, args.steps, 1, C.byref(ms))
@@ -197,8 +207,9 @@ def run_gpu(args):
         tt = torch.tensor([ms_total], device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total = float(tt.item())
-    cells = 6.0 * N * N
-    value = world * cells * args.steps / (ms_total * 1e-3)
+    cells = 6.0 * N * N                      # whole sphere: the ranks share one problem
+    own_cells = 6.0 * N * (rows[1] - rows[0])
+    value = cells * args.steps / (ms_total * 1e-3)
 
     # ---- roofline: the step kernel alone, CUDA events around back-to-back launches
     kms = C.c_float()
@@ -206,8 +217,13 @@ def run_gpu(args):
     dev.call("pycs_time_step_kernel", 5, 1, C.byref(kms))
     dev.call("pycs_time_step_kernel", reps, 1, C.byref(kms))
     k_ms = float(kms.value) / reps
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([k_ms], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        k_ms = float(tt.item())
     peak, peak_src = measured_peak()
-    achieved = BYTES_PER_CELL * cells / (k_ms * 1e-3) / 1e9
+    achieved = BYTES_PER_CELL * own_cells / (k_ms * 1e-3) / 1e9
     tb, rows, nblk = C.c_int32(), C.c_int32(), C.c_int32()
     dev.call("pycs_step_kernel_info", C.byref(tb), C.byref(rows), C.byref(nblk))
     traffic = None
@@ -219,7 +235,8 @@ def run_gpu(args):
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "fused_step_kernel<%d,PPM-PL07,SP-AVLT>" % tb.value,
-                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": BYTES_PER_CELL * cells,
+                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": BYTES_PER_CELL * own_cells,
+                "per": "GPU (each rank updates %d of %d rows of every panel)" % (rows[1] - rows[0], N),
                 "peak_source": peak_src, "grid": {"ctas": nblk.value, "threads": tb.value, "rows_per_chunk": rows.value},
                 "share_of_step": k_ms / (ms_total / args.steps)}
 
@@ -243,8 +260,8 @@ def run_gpu(args):
         tt = torch.tensor([te], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         te = float(tt.item())
-    e2e = {"value": world * cells * e2e_steps / te, "unit": "cell-updates/s", "h2d_bytes_per_step": int(Q0.nbytes),
-           "d2h_bytes_per_step": int(Q0.nbytes), "ms_per_step": 1e3 * te / e2e_steps, "steps": e2e_steps,
+    e2e = {"value": cells * e2e_steps / te, "unit": "cell-updates/s", "h2d_bytes_per_step": int(Q0.nbytes) * world,
+           "d2h_bytes_per_step": int(Q0.nbytes) * world, "ms_per_step": 1e3 * te / e2e_steps, "steps": e2e_steps,
            "api": "pycs_adv_time_step_host (adv_time_step + update_adv on a host numpy Q)"}
 
     # ---- CPU baseline (rank 0, N=1 only): the numpy oracle on the same grid
@@ -264,10 +281,12 @@ def run_gpu(args):
     if rank == 0:
         line = {"metric": "cell-updates/s (fp64 advection step)", "value": value, "unit": "cell-updates/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks, "device": name, "sm_count": sm,
                 "setup_s": setup_s,
+                "parallelism": "single GPU" if world == 1 else
+                "%d row slabs per panel, peer-mapped halo stores over NVLink (csrc/mgpu.cu)" % world,
                 "wind_path": "separable (U(t)=U(0)cos(pi t/T) scaled in-kernel; last step runs the wind kernels)"}
         print(json.dumps(line))
     if world > 1:
@@ -278,8 +297,8 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--n", type=int, default=1536)
     ap.add_argument("--cpu-n", type=int, default=768, help="N of the CPU sample (bounded: ~4 s/step at 768)")

@@ -168,6 +168,21 @@ int pycs_run_timed(pycs_handle h, int64_t k0, int64_t nsteps, int32_t fused, flo
 int pycs_adv_time_step_host(pycs_handle h, double* Q_inout, int64_t k, double t, int32_t fused);
 int pycs_synchronize(pycs_handle h);
 
+/* ---- multi-GPU (the reference is single process) ------------------------ */
+/* One process per GPU.  Rank `rank` of `world` (2..8) owns a slab of rows of every panel;
+ * after each fused step it stores its boundary rows / strips straight into the peers' Q
+ * arrays (CUDA IPC over NVLink) and raises a flag the peers' next step waits on.
+ * pycs_mgpu_init: after the state upload; returns 3 cudaIpcMemHandle_t (192 bytes).  The
+ * caller all-gathers them (torch.distributed) and passes the world*192 bytes to
+ * pycs_mgpu_connect.  Afterwards pycs_run(fused=1) advances the own slab; pycs_download_field
+ * returns an array whose rows [row_lo,row_hi) (pycs_mgpu_row_range, padded-panel index) are valid. */
+int pycs_mgpu_init(pycs_handle h, int32_t rank, int32_t world, unsigned char* handles_out);
+int pycs_mgpu_connect(pycs_handle h, const unsigned char* all_handles);
+int pycs_mgpu_row_range(pycs_handle h, int32_t* row_lo, int32_t* row_hi);
+/* Host-only: the slab and the scatter jobs (peer, i0, i1, j0, j1) of one rank. */
+int pycs_mgpu_plan(int32_t N, int32_t world, int32_t rank, int32_t* row_lo, int32_t* row_hi,
+                   int32_t* jobs5, int32_t max_jobs, int32_t* njobs);
+
 /* ---- diagnostics (next row f2) -------------------------------------------------- */
 /* compute_errors (src/errors.py:99-113) of Q against a host reference field
  * qexact given on the interior (N,N,6): out = {Linf, L1, L2}. */

@@ -10,5 +10,5 @@ __all__ = [
     "constants", "configuration", "cs_datastruct", "sphgeo", "lagrange", "halo_data", "interpolation",
     "edges_treatment", "reconstruction_1d", "flux", "cfl", "averaged_velocity", "discrete_operators",
     "advection_ic", "advection_vars", "advection_timestep", "advection_sphere", "errors", "diagnostics",
-    "output", "device",
+    "output", "device", "parallel",
 ]

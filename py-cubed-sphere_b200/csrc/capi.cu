@@ -6,6 +6,7 @@
 #include <new>
 #include <vector>
 #include "pycs_common.cuh"
+#include "mgpu.cuh"
 
 static thread_local std::string g_err;
 void pycs_set_error(const std::string& msg) { g_err = msg; }
@@ -119,6 +120,8 @@ extern "C" int pycs_create(const pycs_params* prm, pycs_handle* out) {
   g.dx = prm->dx;
   g.dy = prm->dy;
   g.dt = prm->dt;
+  h->row_lo = g.lo;
+  h->row_hi = g.hi;
   cudaDeviceProp dp;
   CK(cudaGetDeviceProperties(&dp, prm->device));
   h->sm_count = dp.multiProcessorCount;
@@ -138,6 +141,7 @@ extern "C" int pycs_destroy(pycs_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   k_fused_release(h);
+  k_mg_release(h);
   for (int k = 0; k < PYCS_F_COUNT; ++k)
     if (h->f[k]) cudaFree(h->f[k]);
   if (h->kminE) cudaFree(h->kminE);
@@ -400,6 +404,7 @@ extern "C" int pycs_convert_wind_interior(pycs_handle h) { return k_wind_interio
 static int run_steps(pycs_handle h, int64_t k0, int64_t nsteps, int fused) {
   CK(cudaSetDevice(h->device));
   if (fused && !k_fused_supported(h)) return arg_fail("no fused step kernel for this scheme tuple");
+  if (h->mg && !fused) return arg_fail("multi-GPU handles run the fused step only");
   // wind field 3 + RK1 is U(0)*cos(pi t/T): all but the last step of a fused run scale
   // the t = 0 winds inside the step kernel; the last step runs the wind kernels after a
   // resync so that U_pu / U_pv / U_pc end up as the reference leaves them.
@@ -469,6 +474,40 @@ extern "C" int pycs_adv_time_step_host(pycs_handle h, double* Q, int64_t k, doub
   }
   TRY(download_to(h, PYCS_F_Q, Q));
   CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// --------------------------------------------------------------------------- multi-GPU
+extern "C" int pycs_mgpu_init(pycs_handle h, int32_t rank, int32_t world, unsigned char* handles_out) {
+  if (!handles_out) return arg_fail("null handle buffer");
+  CK(cudaSetDevice(h->device));
+  TRY(normalize_q(h));
+  return k_mg_init(h, rank, world, handles_out);
+}
+extern "C" int pycs_mgpu_connect(pycs_handle h, const unsigned char* all_handles) {
+  if (!all_handles) return arg_fail("null handle buffer");
+  CK(cudaSetDevice(h->device));
+  return k_mg_connect(h, all_handles);
+}
+extern "C" int pycs_mgpu_row_range(pycs_handle h, int32_t* row_lo, int32_t* row_hi) {
+  *row_lo = h->row_lo;
+  *row_hi = h->row_hi;
+  return 0;
+}
+extern "C" int pycs_mgpu_plan(int32_t N, int32_t world, int32_t rank, int32_t* row_lo, int32_t* row_hi,
+                              int32_t* jobs5, int32_t max_jobs, int32_t* njobs) {
+  if (N < 8 || world < 1 || world > MG_MAX_WORLD || rank < 0 || rank >= world) return arg_fail("bad plan arguments");
+  int a, b;
+  pycs_mgpu_rows(N, world, rank, &a, &b);
+  *row_lo = a;
+  *row_hi = b;
+  MgJob jobs[MG_MAX_JOBS];
+  int n = world > 1 ? pycs_mgpu_plan_jobs(N, world, rank, jobs, MG_MAX_JOBS) : 0;
+  *njobs = n;
+  for (int k = 0; k < n && k < max_jobs && k < MG_MAX_JOBS; ++k) {
+    jobs5[5 * k] = jobs[k].peer; jobs5[5 * k + 1] = jobs[k].i0; jobs5[5 * k + 2] = jobs[k].i1;
+    jobs5[5 * k + 3] = jobs[k].j0; jobs5[5 * k + 4] = jobs[k].j1;
+  }
   return 0;
 }
 

@@ -27,6 +27,7 @@
 #include "pycs_common.cuh"
 #include "fused_args.cuh"
 #include "fused3_core.cuh"
+#include "mgpu.cuh"
 static int f3_strip_capacity(int nw) { return f3::strip_capacity(nw); }
 
 namespace {
@@ -164,8 +165,8 @@ __global__ void __launch_bounds__(TB) fused_step_kernel(FusedArgs a) {
   const int jbase = g.lo + strip * a.wcols;
   const int jend = min(jbase + a.wcols, g.hi);
   const int j = jbase - 3 + tid;
-  const int r0 = g.lo + chunk * a.rows_per_chunk;
-  const int r1 = min(r0 + a.rows_per_chunk, g.hi);
+  const int r0 = a.row_lo + chunk * a.rows_per_chunk;
+  const int r1 = min(r0 + a.rows_per_chunk, a.row_hi);
   const int rfirst = r0 - 3, rlast = r1 + 2;
   const bool out_lane = (tid >= 3) && (j < jend);
   const bool jint = (j >= g.lo) && (j < g.hi);
@@ -550,7 +551,7 @@ struct FusedState {
   int npart = 0;
   int tb = 160, depth = 6, rows = 0, nstrips = 0, wcols = 0, nchunks = 0;
   int impl = 0;                // 2: block-synchronous kernel (this file), 3: warp-autonomous kernel (fused3.cu)
-  int nw = 3;                  // v3: consumer warps per CTA
+  int nw = 3, pf = 3, minb = 3; // v3: consumer warps per CTA, rows in flight, register cap (CTAs/SM)
 };
 
 #include <map>
@@ -573,26 +574,31 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
     CKL(h);
   }
   if (fs.rows == 0) {
+    const int nrows = h->row_hi - h->row_lo;       // rows this handle updates (multi-GPU: its slab)
     const char* ei = getenv("PYCS_FUSED_IMPL");
-    int impl = ei ? atoi(ei) : 3;
+    int impl = ei ? atoi(ei) : 2;     // v2 is the faster one so far (profiles/r1_sweep_v3.log)
     const char* ew = getenv("PYCS_FUSED_NW");
     const char* ed = getenv("PYCS_FUSED_DEPTH");
     const char* er = getenv("PYCS_FUSED_ROWS");
     int rows = er ? atoi(er) : 0;
+    const char* ep = getenv("PYCS_FUSED_PF");
+    const char* em = getenv("PYCS_FUSED_MINB");
     int nw = ew ? atoi(ew) : 3, depth = ed ? atoi(ed) : 5;
-    if (impl == 3 && !pycs_fused3_has(h->prm.recon, h->prm.opsplit, nw, depth)) { nw = 3; depth = 5; }
-    if (impl == 3 && !pycs_fused3_has(h->prm.recon, h->prm.opsplit, nw, depth)) impl = 2;   // limited PPM
+    int pf = ep ? atoi(ep) : 3, minb = em ? atoi(em) : 3;
+    if (impl == 3 && !pycs_fused3_has(h->prm.recon, h->prm.opsplit, nw, pf, minb)) { nw = 3; pf = 3; minb = 3; }
+    if (impl == 3 && !pycs_fused3_has(h->prm.recon, h->prm.opsplit, nw, pf, minb)) impl = 2;   // limited PPM
     int resident, lag, cols;
     if (impl == 3) {
       // strips of up to 57 + 58 (NW-1) columns, one consumer warp per 57/58 of them
       fs.nw = nw;
-      fs.depth = depth;
+      fs.pf = pf;
+      fs.minb = minb;
       const int cap = f3_strip_capacity(nw);
       fs.nstrips = (g.N + cap - 1) / cap;
       fs.wcols = (g.N + fs.nstrips - 1) / fs.nstrips;
       fs.wcols += fs.wcols & 1;                  // even: column pairs stay 16-byte aligned
       const int mask = (h->prm.dp == 2) ? 1 : 0;
-      int per_sm = pycs_fused3_resident(h->prm.recon, h->prm.opsplit, mask, nw, depth);
+      int per_sm = pycs_fused3_resident(h->prm.recon, h->prm.opsplit, mask, nw, pf, minb);
       if (per_sm < 1) {
         pycs_set_error("fused3 kernel: occupancy query failed");
         return PYCS_ERR_CUDA;
@@ -621,10 +627,10 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
       // whole waves of resident CTAs: time ~ waves * (rows + ramp)
       int best = 0;
       double best_cost = 1e30;
-      for (int nch = 1; nch <= g.N; ++nch) {
-        int rr = (g.N + nch - 1) / nch;
+      for (int nch = 1; nch <= nrows; ++nch) {
+        int rr = (nrows + nch - 1) / nch;
         if (rr < 8 && nch > 1) break;
-        int nb = cols * ((g.N + rr - 1) / rr);
+        int nb = cols * ((nrows + rr - 1) / rr);
         int waves = (nb + resident - 1) / resident;
         double cost = (double)waves * (rr + lag);
         if (cost < best_cost) { best_cost = cost; best = rr; }
@@ -632,7 +638,7 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
       rows = best;
     }
     fs.rows = rows;
-    fs.nchunks = (g.N + rows - 1) / rows;
+    fs.nchunks = (nrows + rows - 1) / rows;
   }
   int nb = 6 * fs.nstrips * fs.nchunks * (fs.impl == 3 ? fs.nw : 1);   // MF-PR partial sums
   if (fs.npart_cap < nb) {
@@ -656,7 +662,14 @@ int k_fused_flush(pycs_handle h) {
   TRY(pycs_field_ptr(h, h->qcur ? PYCS_F_Q_NEXT : PYCS_F_Q, &q));
   TRY(pycs_field_ptr(h, h->qcur ? PYCS_F_Q : PYCS_F_Q_NEXT, &qo));
   if (fs.pending) {
-    flush_corr_kernel<<<dim3((g.N + 127) / 128, g.N, 6), 128, 0, h->stream>>>(g, q, sgc, fs.part, fs.npart,
+    const double* sums = fs.part;
+    int nsums = fs.npart;
+    if (h->mg) {                     // per-rank sums of the last exchange, once they have all arrived
+      TRY(k_mg_wait(h));
+      sums = k_mg_sums(h);
+      nsums = h->mg->world;
+    }
+    flush_corr_kernel<<<dim3((g.N + 127) / 128, g.N, 6), 128, 0, h->stream>>>(g, q, sgc, sums, nsums,
                                                                              1.0 / h->a2);
     CKL(h);
     fs.pending = 0;
@@ -678,6 +691,9 @@ void k_fused_release(pycs_handle h) {
   if (it->second.bv) cudaFree(it->second.bv);
   g_fused.erase(it);
 }
+
+// the rows this handle updates changed (pycs_mgpu_init): recompute the launch geometry
+void k_fused_reset_grid(pycs_handle h) { g_fused[h].rows = 0; }
 
 // geometry was re-uploaded: 1/sqrtg and the t = 0 winds must be rebuilt
 void k_fused_invalidate(pycs_handle h) {
@@ -740,11 +756,12 @@ static int launch_step_kernel(pycs_handle h, FusedState& fs, const double* qcur,
   a.part = fs.part;
   a.corr = h->red_out + 8;
   a.rows_per_chunk = fs.rows; a.nstrips = fs.nstrips; a.wcols = fs.wcols;
+  a.row_lo = h->row_lo; a.row_hi = h->row_hi;
   a.apply_corr = pend;
   a.cdx = g.dt / g.dx; a.cdy = g.dt / g.dy;
   a.ws = ws;
   if (fs.impl == 3)
-    CK(pycs_launch_fused3(a, h->prm.recon, h->prm.opsplit, mask, fs.nw, fs.depth, fs.npart / fs.nw, h->stream));
+    CK(pycs_launch_fused3(a, h->prm.recon, h->prm.opsplit, mask, fs.nw, fs.pf, fs.minb, fs.npart / fs.nw, h->stream));
   else
     CK(launch_fused(a, h->prm.recon, h->prm.opsplit, mask, fs.npart, fs.tb, fs.depth, h->stream));
   CKL(h);
@@ -805,10 +822,18 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   double* qnext = h->qcur ? qa : qb;
   if (separable) TRY(ensure_base_winds(h, fs));
 
+  // 0. multi-GPU: the peers' halo rows, boundary strips and MF-PR sums of the last step are in
+  const double* sums = fs.part;
+  int nsums = fs.npart;
+  if (h->mg) {
+    TRY(k_mg_wait(h));
+    sums = k_mg_sums(h);
+    nsums = h->mg->world;
+  }
   // 1. ghost cells of Q (src/advection_timestep.py:28), folding in the pending MF-PR term
   int pend = fs.pending;
   dg_phase1_corr_kernel<<<dim3((g.N + 127) / 128, 4, 24), 128, 0, h->stream>>>(
-      g, h->maps, qcur, h->kminE, h->wE, h->order, sgc, fs.part, pend ? fs.npart : 0,
+      g, h->maps, qcur, h->kminE, h->wE, h->order, sgc, sums, pend ? nsums : 0,
       pend ? 1.0 / h->a2 : 0.0, h->red_out + 8);
   CKL(h);
   dg_phase2_corr_kernel<<<12, 32, 0, h->stream>>>(g, h->maps, qcur, h->kminE, h->wE, h->order, sgc,
@@ -823,6 +848,7 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   int mask = separable ? 2 : ((h->prm.dp == 2) ? 1 : 0);    // RK1: averaged wind == instantaneous wind
   double ws = separable ? cos(3.141592653589793 * ((double)(k - 1) * g.dt) / 5.0) : 1.0;
   TRY(launch_step_kernel(h, fs, qcur, qnext, pend, mask, ws));
+  if (h->mg) TRY(k_mg_exchange(h, qnext, fs.part, fs.npart));
   h->last_step_kernel_launches++;
   h->qcur ^= 1;
   fs.pending = (h->prm.mf == 3) ? 1 : 0;

@@ -31,20 +31,32 @@ struct alignas(16) dbl2 { double x, y; };
 
 namespace f3 {
 
-constexpr int NC = 2;              // columns per lane
-constexpr int WARP_COLS = 32 * NC; // columns marched by one consumer warp
-constexpr int SXW = WARP_COLS + 8; // private Qx row: 4 pad columns on each side
-// arrays staged per row in a ring slot
-enum { A_Q = 0, A_V = 1, A_SGC = 2, A_SGV = 3, A_RGC = 4, A_SGU = 5, A_U = 6, A_VM = 7, A_UM = 8 };
+constexpr int NC = 2;               // columns per lane
+constexpr int CSTEP = 32;           // lane l owns columns cw0 + l and cw0 + 32 + l (conflict-free LDS.64)
+constexpr int WARP_COLS = 32 * NC;  // columns marched by one consumer warp
+constexpr int WARP_USE = WARP_COLS - 6;   // of which outputs (3 halo columns on each side)
+constexpr int SXW = WARP_COLS + 8;  // private Qx row: 4 pad columns on each side
+// Arrays staged per row.  Short ring (each row is needed by one march step only):
+//   Q[r], U[r-2], sqrtg_pu[r-1] (+ mask source UM[r-2]);
+// long ring (row r is needed by march steps r .. r+3):
+//   V[r], sqrtg_pv[r], sqrtg_pc[r], 1/sqrtg_pc[r] (+ mask source VM[r]).
+enum { S_Q = 0, S_U = 1, S_SGU = 2, S_UM = 3 };
+enum { L_V = 0, L_SGV = 1, L_SGC = 2, L_RGC = 3, L_VM = 4 };
 
-template <int NW> struct RowWidth { static constexpr int value = 58 * NW + 12; };   // doubles per staged row
+template <int NW> struct RowWidth { static constexpr int value = WARP_USE * NW + 14; };   // doubles per staged row
 
-PYCS_HD dbl2 ld2(const double* p) { return *reinterpret_cast<const dbl2*>(p); }
+// Pointers to the staged rows one march step reads, already offset to the lane's first column.
+struct RowPtrs {
+  const double *q, *u, *um, *su1;        // short slot of row r
+  const double *v0, *vm0, *sgv0, *sgc0, *rg0;   // long slot of row r
+  const double *sgc2;                    // long slot of row r-2
+  const double *v3, *vm3, *sgv3, *sgc3, *rg3;   // long slot of row r-3
+};
+
 PYCS_HD void st2(double* p, double a, double b) {
   dbl2 v; v.x = a; v.y = b;
   *reinterpret_cast<dbl2*>(p) = v;
 }
-PYCS_HD double pick(const dbl2& v, int c) { return c == 0 ? v.x : v.y; }
 
 // src/reconstruction_1d.py:36-62 (q3 is the cell itself)
 template <int RECON>
@@ -118,34 +130,25 @@ PYCS_HD void lane_init(Lane& L) {
 }
 
 // ---- phase 1: row r enters; inner x-flux at edge r-2; Qx row r-3 -> qx[NC] -------------
-// R0..R3: ring slots of rows r, r-1, r-2, r-3; ca: index of the lane's first column in a
-// staged row (even).
-template <int RECON, int SPLIT, int MASK, int RW>
-PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const double* R0, const double* R1, const double* R2,
-                           const double* R3, int ca, double cdx, double ws, double qx[NC]) {
+template <int RECON, int SPLIT, int MASK>
+PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, double cdx, double ws, double qx[NC]) {
   constexpr int MT = (SPLIT == 3) ? 2 : 1;
-  const dbl2 qn = ld2(R0 + A_Q * RW + ca);
-  const dbl2 u2 = ld2(R2 + A_U * RW + ca);
-  const dbl2 su1 = ld2(R1 + A_SGU * RW + ca);
-  const dbl2 sc3 = ld2(R3 + A_SGC * RW + ca);
-  const dbl2 sc2 = ld2(R2 + A_SGC * RW + ca);
-  const dbl2 rg = ld2(R3 + A_RGC * RW + ca);
-  dbl2 um2 = u2;
-  if (MASK & 1) um2 = ld2(R2 + A_UM * RW + ca);
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
+    const int o = c * CSTEP;
     double* q = L.qw[c];
     q[0] = q[1]; q[1] = q[2]; q[2] = q[3]; q[3] = q[4];
-    q[4] = pick(qn, c);
+    q[4] = R.q[o];
     double l2, r2;                                   // cell r-2
     edge_values<RECON>(q[0], q[1], q[2], q[3], q[4], l2, r2);
-    double ub = pick(u2, c);
+    double ub = R.u[o];
     if (MASK & 2) ub *= ws;
-    const bool up = ((MASK & 1) ? pick(um2, c) : ub) >= 0.0;
-    const double su1c = pick(su1, c);
+    const bool up = ((MASK & 1) ? R.um[o] : ub) >= 0.0;
+    const double su1c = R.su1[o];
     const double gE = L.su2[c];
     const double gO = up ? L.su3[c] : su1c;
-    const double gC = up ? pick(sc3, c) : pick(sc2, c);
+    const double gC = up ? R.sgc3[o] : R.sgc2[o];
+    const double rg = R.rg3[o];
     double WE, WO, WG, cc;
     edge_weights<MT, !(MASK & 1)>(ub, up, cdx, gE, gO, gC, WE, WO, WG, cc);
     const double E = up ? L.pr[c] : l2, O = up ? L.pl[c] : r2, qc = up ? q[1] : q[2];
@@ -156,38 +159,35 @@ PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const double* R0, const double* R1
       cdv = cmx - L.cmx_prev[c];
       L.cmx_prev[c] = cmx;
     }
-    qx[c] = inner_update<SPLIT>(q[1], L.fin_prev[c] - fin, pick(rg, c), cdv);
+    qx[c] = inner_update<SPLIT>(q[1], L.fin_prev[c] - fin, rg, cdv);
     L.pl[c] = l2; L.pr[c] = r2;
     L.fin_prev[c] = fin;
     L.su3[c] = gE; L.su2[c] = su1c;
-    X.WE[c] = WE; X.WO[c] = WO; X.WG[c] = WG; X.rg3[c] = pick(rg, c);
+    X.WE[c] = WE; X.WO[c] = WO; X.WG[c] = WG; X.rg3[c] = rg;
     X.up[c] = up;
   }
 }
 
 // ---- phase 2: y-fluxes at the lane's NC edges of one row ------------------------------------
-// Rk: ring slot holding V / sqrtg of that row; src: the advected row (Q or Qx) positioned
-// so that src[k] is the value k columns right of the lane's first column.
-template <int RECON, int SPLIT, int MASK, int RW>
-PYCS_HD void yflux_pair(const double* Rk, int ca, const double* src, double cdy, double ws, double f[NC],
-                        double cmy[NC]) {
+// v, vm, sgv, sgc: staged rows of that row (lane-offset); src: the advected row (Q or Qx),
+// lane-offset as well, so that src[k] is the value k columns right of the lane's first column.
+template <int RECON, int SPLIT, int MASK>
+PYCS_HD void yflux_pair(const double* v, const double* vm, const double* sgv, const double* sgc,
+                        const double* src, double cdy, double ws, double f[NC], double cmy[NC]) {
   constexpr int MT = (SPLIT == 3) ? 2 : 1;
-  const dbl2 v2 = ld2(Rk + A_V * RW + ca);
-  const dbl2 sgv = ld2(Rk + A_SGV * RW + ca);
-  dbl2 vm2 = v2;
-  if (MASK & 1) vm2 = ld2(Rk + A_VM * RW + ca);
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    double vb = pick(v2, c);
+    const int o = c * CSTEP;
+    double vb = v[o];
     if (MASK & 2) vb *= ws;
-    const bool vp = ((MASK & 1) ? pick(vm2, c) : vb) >= 0.0;
-    const int e = ca + c;
-    const double gE = pick(sgv, c);
-    const double gO = Rk[A_SGV * RW + (vp ? e - 1 : e + 1)];
-    const double gC = Rk[A_SGC * RW + (vp ? e - 1 : e)];
+    const bool vp = ((MASK & 1) ? vm[o] : vb) >= 0.0;
+    const int up1 = vp ? -1 : 0;                     // upwind cell relative to the edge
+    const double gE = sgv[o];
+    const double gO = sgv[o + 1 + 2 * up1];          // other edge of the upwind cell
+    const double gC = sgc[o + up1];
     double WE, WO, WG, cc;
     edge_weights<MT, !(MASK & 1)>(vb, vp, cdy, gE, gO, gC, WE, WO, WG, cc);
-    const double* s = src + c + (vp ? -1 : 0);      // upwind cell
+    const double* s = src + o + up1;
     double l, r;
     edge_values<RECON>(s[-2], s[-1], s[0], s[1], s[2], l, r);
     const double E = vp ? r : l, O = vp ? l : r;
@@ -197,18 +197,18 @@ PYCS_HD void yflux_pair(const double* Rk, int ca, const double* src, double cdy,
 }
 
 // ---- phase 3: Qy row r; outer x-flux at edge r-2 on Qy; output row r-3 ----------------------
-// F, G: inner (row r) and outer (row r-3) y-fluxes at the lane's columns and at the next
-// column (index NC); CM likewise sqrtg_pv*cy of row r.  out[c] = new Q of row r-3,
-// sdiv[c] = pxdF + pydF of that cell.
-template <int RECON, int SPLIT, int RW>
-PYCS_HD void phase_x_outer(Lane& L, const XEdge& X, const double* R0, int ca, const double F[NC + 1],
-                           const double G[NC + 1], const double CM[NC + 1], double out[NC], double sdiv[NC]) {
-  const dbl2 rg0 = ld2(R0 + A_RGC * RW + ca);
+// F, Fn: inner y-fluxes (row r) at the lane's columns and at the columns right of them;
+// G, Gn likewise the outer y-fluxes of row r-3; CM, CMn sqrtg_pv*cy of row r (SPLIT != 1).
+// out[c] = new Q of row r-3, sdiv[c] = pxdF + pydF of that cell.
+template <int RECON, int SPLIT>
+PYCS_HD void phase_x_outer(Lane& L, const XEdge& X, const RowPtrs& R, const double F[NC], const double Fn[NC],
+                           const double G[NC], const double Gn[NC], const double CM[NC], const double CMn[NC],
+                           double out[NC], double sdiv[NC]) {
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     double* y = L.yw[c];
-    const double cdv = (SPLIT != 1) ? CM[c + 1] - CM[c] : 0.0;
-    const double qy = inner_update<SPLIT>(L.qw[c][4], F[c] - F[c + 1], pick(rg0, c), cdv);
+    const double cdv = (SPLIT != 1) ? CMn[c] - CM[c] : 0.0;
+    const double qy = inner_update<SPLIT>(L.qw[c][4], F[c] - Fn[c], R.rg0[c * CSTEP], cdv);
     y[0] = y[1]; y[1] = y[2]; y[2] = y[3]; y[3] = y[4];
     y[4] = qy;
     double l2, r2;                                   // Qy cell r-2
@@ -216,7 +216,7 @@ PYCS_HD void phase_x_outer(Lane& L, const XEdge& X, const double* R0, int ca, co
     const bool up = X.up[c];
     const double E = up ? L.yr[c] : l2, O = up ? L.yl[c] : r2, qc = up ? y[1] : y[2];
     const double fo = fma(X.WE[c], E, fma(X.WO[c], O, X.WG[c] * qc));
-    const double s = (L.fout_prev[c] - fo) + (G[c] - G[c + 1]);
+    const double s = (L.fout_prev[c] - fo) + (G[c] - Gn[c]);
     out[c] = fma(s, X.rg3[c], L.qw[c][1]);
     sdiv[c] = s;
     L.yl[c] = l2; L.yr[c] = r2;
@@ -224,21 +224,19 @@ PYCS_HD void phase_x_outer(Lane& L, const XEdge& X, const double* R0, int ca, co
   }
 }
 
-// Column range of consumer warp w of a strip whose useful columns are [js0, js1): the warp
-// marches the 64 columns starting at cw0 (even, so that column pairs are 16-byte aligned)
-// and owns the outputs [us, ue).
+// Consumer warp w of a strip whose useful columns start at js0 marches the 64 columns from
+// cw0 = js0 - 3 + 58 w and owns the outputs [us, ue), clipped to the strip end js1.
 PYCS_HD void warp_columns(int js0, int js1, int w, int& cw0, int& us, int& ue) {
-  us = js0;
-  for (int k = 0;; ++k) {
-    cw0 = (us - 3) & ~1;
-    ue = cw0 + WARP_COLS - 3;
-    if (ue > js1) ue = js1;
-    if (ue < us) ue = us;
-    if (k == w) return;
-    us = ue;
-  }
+  us = js0 + WARP_USE * w;
+  cw0 = us - 3;
+  ue = us + WARP_USE;
+  if (ue > js1) ue = js1;
+  if (us > js1) us = js1;
 }
-// useful columns NW consumer warps can cover (first warp 57, the others 58)
-PYCS_HD int strip_capacity(int nw) { return 57 + 58 * (nw - 1); }
+// useful columns NW consumer warps can cover
+PYCS_HD int strip_capacity(int nw) { return WARP_USE * nw; }
+// first staged column of a strip (even, so that the TMA source is 16-byte aligned) and the
+// index of column cw0 of warp w inside a staged row
+PYCS_HD int strip_c0(int js0) { return ((js0 - 3) & ~1) - 4; }
 
 }  // namespace f3

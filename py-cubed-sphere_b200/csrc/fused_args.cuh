@@ -13,13 +13,14 @@ struct FusedArgs {
   double* part;
   const double* corr;         // device scalar: pending projection coefficient -sum(s)/a2
   int rows_per_chunk, nstrips, wcols, apply_corr;
+  int row_lo, row_hi;         // rows this launch updates (the whole interior, or this rank's slab)
   double cdx, cdy;            // dt/dx, dt/dy
   double ws;                  // separable wind: U(t) = U(0) * ws (MASK & 2)
 };
 
-// fused3.cu
-cudaError_t pycs_launch_fused3(const FusedArgs& a, int recon, int split, int mask, int nw, int depth, int nblocks,
-                               cudaStream_t st);
+// v3 launcher: nw consumer warps, pf rows in flight, minb = register cap as CTAs per SM
+cudaError_t pycs_launch_fused3(const FusedArgs& a, int recon, int split, int mask, int nw, int pf, int minb,
+                               int nblocks, cudaStream_t st);
 // resident CTAs per SM of the v3 kernel for this template point (occupancy API); < 0 on error
-int pycs_fused3_resident(int recon, int split, int mask, int nw, int depth);
-bool pycs_fused3_has(int recon, int split, int nw, int depth);
+int pycs_fused3_resident(int recon, int split, int mask, int nw, int pf, int minb);
+bool pycs_fused3_has(int recon, int split, int nw, int pf, int minb);

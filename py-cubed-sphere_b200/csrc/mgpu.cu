@@ -1,0 +1,227 @@
+// Multi-GPU layer of the fused step: row-slab decomposition with peer-mapped halo stores.
+//
+// The reference is single process ("new design").  Rank k of W owns the rows
+// [row_lo, row_hi) of all six panels.  One step needs, besides the own rows,
+//   * the 3 rows above and below the slab (the 7x7 dependence box of the split scheme), and
+//   * the four 4-wide boundary strips of every panel, which feed the Lagrange ghost fill
+//     (src/halo_data.py:15-185 gathers exactly these) -- every rank then fills all ghost
+//     cells it needs locally with the unchanged ghost-fill kernels;
+//   * one scalar per rank for the MF-PR projection (src/discrete_operators.py:98-101).
+// After its step kernel each rank stores those pieces of its new rows directly into the
+// peers' Q arrays at their natural positions (CUDA IPC mappings over NVLink, no staging, no
+// NCCL call on the data path), publishes its partial sum and raises a per-rank flag with
+// system-scope release; the next step starts with a kernel that spins on the W flags.
+// Everything is stream ordered on the handle's stream: there is no host synchronisation in
+// the step loop.  Flags are epoch counters, so buffers (the two ping-pong Q arrays) are
+// reused without resets; a peer can be at most one step ahead.
+#include <cstring>
+#include "pycs_common.cuh"
+#include "mgpu.cuh"
+
+namespace {
+
+__global__ void mg_wait_kernel(const MgSync* sync, int world, long long epoch) {
+  const int d = threadIdx.x;
+  if (d >= world) return;
+  const volatile long long* f = &sync->flag[d];
+  for (unsigned n = 0;; ++n) {
+    long long v = *f;
+    if (v >= epoch) break;
+    if (n > (1u << 26)) __trap();      // a lost peer must not hang the GPU
+    __nanosleep(40);
+  }
+  __threadfence_system();
+}
+
+struct ScatterJob { double* dst; int i0, i1, j0, j1; };
+struct ScatterJobs { int n; ScatterJob job[MG_MAX_JOBS]; };
+
+// copy the rectangles [i0,i1) x [j0,j1) of all six panels of src into the same positions of dst
+__global__ void mg_scatter_kernel(Geo g, ScatterJobs jobs, const double* __restrict__ src) {
+  const ScatterJob jb = jobs.job[blockIdx.z];
+  const int w = jb.j1 - jb.j0, n = (jb.i1 - jb.i0) * w;
+  const int p = blockIdx.y;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int i = jb.i0 + t / w, j = jb.j0 + t % w;
+    const long long id = gidx(g, p, i, j);
+    jb.dst[id] = src[id];
+  }
+  __threadfence_system();
+}
+
+struct PeerSync { MgSync* s[MG_MAX_WORLD]; };
+
+// reduce this rank's MF-PR partials in a fixed order, publish the sum and raise the flag
+__global__ void mg_publish_kernel(PeerSync peers, int world, int rank, const double* __restrict__ part, int npart,
+                                  int parity, long long epoch) {
+  __shared__ double sh[32];
+  double v = 0.0;
+  for (int k = threadIdx.x; k < npart; k += blockDim.x) v += part[k];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    sh[0] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < world) {
+    MgSync* s = peers.s[threadIdx.x];
+    s->psum[parity][rank] = sh[0];
+    __threadfence_system();            // data stores of the scatter kernel and the sum before the flag
+    *((volatile long long*)&s->flag[rank]) = epoch;
+  }
+}
+
+}  // namespace
+
+// ---- host-side plan (no GPU needed: exercised by the CPU tests) ----------------------------
+void pycs_mgpu_rows(int N, int world, int rank, int* row_lo, int* row_hi) {
+  const int base = N / world, rem = N % world;
+  const int off = rank * base + (rank < rem ? rank : rem);
+  *row_lo = PYCS_NG + off;
+  *row_hi = *row_lo + base + (rank < rem ? 1 : 0);
+}
+
+int pycs_mgpu_plan_jobs(int N, int world, int rank, MgJob* jobs, int max_jobs) {
+  const int lo = PYCS_NG, hi = PYCS_NG + N;
+  int a, b, n = 0;
+  pycs_mgpu_rows(N, world, rank, &a, &b);
+  auto add = [&](int peer, int i0, int i1, int j0, int j1) {
+    if (n < max_jobs) jobs[n] = MgJob{peer, i0, i1, j0, j1};
+    ++n;
+  };
+  for (int d = 0; d < world; ++d) {
+    if (d == rank) continue;
+    add(d, a, b, lo, lo + PYCS_NG);                           // S strips of my rows
+    add(d, a, b, hi - PYCS_NG, hi);                           // N strips
+    if (rank == 0) add(d, lo, lo + PYCS_NG, lo, hi);          // W strips (first slab)
+    if (rank == world - 1) add(d, hi - PYCS_NG, hi, lo, hi);  // E strips (last slab)
+    if (d == rank - 1) add(d, a, a + 3, lo, hi);              // lower neighbour's halo rows
+    if (d == rank + 1) add(d, b - 3, b, lo, hi);              // upper neighbour's halo rows
+  }
+  return n;
+}
+
+// ---- device-side state ---------------------------------------------------------------------
+int k_mg_init(pycs_handle h, int rank, int world, unsigned char* handles_out) {
+  if (world < 2 || world > MG_MAX_WORLD || rank < 0 || rank >= world) {
+    pycs_set_error("pycs_mgpu_init: world must be 2..8 and 0 <= rank < world");
+    return PYCS_ERR_ARG;
+  }
+  if (h->g.N / world < PYCS_NG) {
+    pycs_set_error("pycs_mgpu_init: fewer than 4 rows per rank");
+    return PYCS_ERR_ARG;
+  }
+  if (h->mg) {
+    pycs_set_error("pycs_mgpu_init: already initialised");
+    return PYCS_ERR_STATE;
+  }
+  MgpuState* mg = new MgpuState();
+  memset(mg, 0, sizeof *mg);
+  mg->rank = rank;
+  mg->world = world;
+  TRY(pycs_field_ptr(h, PYCS_F_Q, &mg->alloc[0]));
+  TRY(pycs_field_ptr(h, PYCS_F_Q_NEXT, &mg->alloc[1]));
+  CK(cudaMalloc(&mg->sync, sizeof(MgSync)));
+  CK(cudaMemset(mg->sync, 0, sizeof(MgSync)));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaIpcMemHandle_t hd[3];
+  CK(cudaIpcGetMemHandle(&hd[0], mg->alloc[0]));
+  CK(cudaIpcGetMemHandle(&hd[1], mg->alloc[1]));
+  CK(cudaIpcGetMemHandle(&hd[2], mg->sync));
+  memcpy(handles_out, hd, sizeof hd);
+  pycs_mgpu_rows(h->g.N, world, rank, &h->row_lo, &h->row_hi);
+  MgJob jobs[MG_MAX_JOBS];
+  mg->njobs = pycs_mgpu_plan_jobs(h->g.N, world, rank, jobs, MG_MAX_JOBS);
+  if (mg->njobs > MG_MAX_JOBS) {
+    delete mg;
+    pycs_set_error("pycs_mgpu_init: too many scatter jobs");
+    return PYCS_ERR_ARG;
+  }
+  memcpy(mg->jobs, jobs, sizeof(MgJob) * mg->njobs);
+  h->mg = mg;
+  k_fused_reset_grid(h);
+  return 0;
+}
+
+int k_mg_connect(pycs_handle h, const unsigned char* all_handles) {
+  MgpuState* mg = h->mg;
+  if (!mg) {
+    pycs_set_error("pycs_mgpu_connect before pycs_mgpu_init");
+    return PYCS_ERR_STATE;
+  }
+  for (int d = 0; d < mg->world; ++d) {
+    if (d == mg->rank) {
+      mg->peer_q[0][d] = mg->alloc[0];
+      mg->peer_q[1][d] = mg->alloc[1];
+      mg->peer_sync[d] = mg->sync;
+      continue;
+    }
+    cudaIpcMemHandle_t hd[3];
+    memcpy(hd, all_handles + (size_t)d * sizeof hd, sizeof hd);
+    void* p[3];
+    for (int k = 0; k < 3; ++k) CK(cudaIpcOpenMemHandle(&p[k], hd[k], cudaIpcMemLazyEnablePeerAccess));
+    mg->peer_q[0][d] = (double*)p[0];
+    mg->peer_q[1][d] = (double*)p[1];
+    mg->peer_sync[d] = (MgSync*)p[2];
+  }
+  mg->connected = 1;
+  return 0;
+}
+
+void k_mg_release(pycs_handle h) {
+  MgpuState* mg = h->mg;
+  if (!mg) return;
+  for (int d = 0; d < mg->world; ++d) {
+    if (d == mg->rank || !mg->connected) continue;
+    cudaIpcCloseMemHandle(mg->peer_q[0][d]);
+    cudaIpcCloseMemHandle(mg->peer_q[1][d]);
+    cudaIpcCloseMemHandle(mg->peer_sync[d]);
+  }
+  if (mg->sync) cudaFree(mg->sync);
+  delete mg;
+  h->mg = nullptr;
+}
+
+// wait until every rank has delivered the data of exchange `epoch` (stream ordered)
+int k_mg_wait(pycs_handle h) {
+  MgpuState* mg = h->mg;
+  mg_wait_kernel<<<1, 32, 0, h->stream>>>(mg->sync, mg->world, mg->epoch);
+  CKL(h);
+  return 0;
+}
+
+// where the W per-rank MF-PR sums of the last exchange live (this rank's copy)
+const double* k_mg_sums(pycs_handle h) { return h->mg->sync->psum[h->mg->epoch & 1]; }
+
+// after the step kernel wrote the own rows of `qnext`: deliver halos, sum and flag to the peers
+int k_mg_exchange(pycs_handle h, const double* qnext, const double* part, int npart) {
+  MgpuState* mg = h->mg;
+  if (!mg->connected) {
+    pycs_set_error("multi-GPU step before pycs_mgpu_connect");
+    return PYCS_ERR_STATE;
+  }
+  const int idx = (qnext == mg->alloc[0]) ? 0 : 1;
+  ScatterJobs js;
+  js.n = mg->njobs;
+  int nmax = 1;
+  for (int k = 0; k < mg->njobs; ++k) {
+    const MgJob& j = mg->jobs[k];
+    js.job[k] = ScatterJob{mg->peer_q[idx][j.peer], j.i0, j.i1, j.j0, j.j1};
+    const int n = (j.i1 - j.i0) * (j.j1 - j.j0);
+    if (n > nmax) nmax = n;
+  }
+  int gx = (nmax + 255) / 256;
+  if (gx > 16) gx = 16;
+  mg_scatter_kernel<<<dim3(gx, 6, mg->njobs), 256, 0, h->stream>>>(h->g, js, qnext);
+  CKL(h);
+  PeerSync ps;
+  for (int d = 0; d < mg->world; ++d) ps.s[d] = mg->peer_sync[d];
+  mg->epoch += 1;
+  mg_publish_kernel<<<1, 256, 0, h->stream>>>(ps, mg->world, mg->rank, part, npart, (int)(mg->epoch & 1),
+                                             mg->epoch);
+  CKL(h);
+  return 0;
+}

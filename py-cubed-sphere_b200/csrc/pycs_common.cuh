@@ -33,6 +33,7 @@ struct HaloMaps { SideMap m[6][4]; };   // side: 0 E, 1 W, 2 N, 3 S
 
 enum { SIDE_E = 0, SIDE_W = 1, SIDE_N = 2, SIDE_S = 3 };
 
+struct MgpuState;
 struct pycs_handle_s {
   pycs_params prm;
   Geo g;
@@ -65,6 +66,9 @@ struct pycs_handle_s {
   // deferred MF-PR correction scalar (device): m0 / a2 of the previous fused step
   double a2;            // sum sqrtg^2 over the interior (static)
   int a2_valid;
+  // rows this handle updates: [lo, hi) or, with pycs_mgpu_init, this rank's slab of every panel
+  int row_lo, row_hi;
+  struct MgpuState* mg;   // multi-GPU state (mgpu.cu), null on a single GPU
 };
 
 // error plumbing ------------------------------------------------------------

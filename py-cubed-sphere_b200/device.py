@@ -97,11 +97,16 @@ def load_library():
         "pycs_launch_count": [h, C.POINTER(C.c_int64)],
         "pycs_time_step_kernel": [h, C.c_int32, C.c_int32, C.POINTER(C.c_float)],
         "pycs_step_kernel_info": [h, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
+        "pycs_mgpu_init": [h, C.c_int32, C.c_int32, C.c_char_p],
+        "pycs_mgpu_connect": [h, C.c_char_p],
+        "pycs_mgpu_row_range": [h, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int
+    lib.pycs_mgpu_plan.argtypes = [C.c_int32] * 3 + [C.POINTER(C.c_int32)] * 3 + [C.c_int32, C.POINTER(C.c_int32)]
+    lib.pycs_mgpu_plan.restype = C.c_int
     lib.pycs_last_error.restype = C.c_char_p
     lib.pycs_last_error.argtypes = []
     _lib = lib
@@ -179,10 +184,38 @@ class Device:
         self.call("pycs_fused_supported", C.byref(y))
         return bool(y.value)
 
+    # -- multi-GPU (one process per GPU; see include/pycs_b200.h) ------------
+    def mgpu_setup(self, rank, world, all_gather_bytes):
+        """Shard the fused step over `world` ranks.  `all_gather_bytes(b)` must return the list of
+        every rank's byte string in rank order (e.g. torch.distributed.all_gather_object)."""
+        buf = C.create_string_buffer(192)
+        self.call("pycs_mgpu_init", rank, world, buf)
+        parts = all_gather_bytes(buf.raw)
+        if len(parts) != world or any(len(p) != 192 for p in parts):
+            raise PycsError("mgpu_setup: expected %d handle blocks of 192 bytes" % world)
+        self.call("pycs_mgpu_connect", b"".join(parts))
+        return self.row_range()
+
+    def row_range(self):
+        a, b = C.c_int32(), C.c_int32()
+        self.call("pycs_mgpu_row_range", C.byref(a), C.byref(b))
+        return a.value, b.value
+
     def launches(self):
         n = C.c_int64()
         self.call("pycs_launch_count", C.byref(n))
         return n.value
+
+
+def mgpu_plan(N, world, rank):
+    """Host-only view of the decomposition: (row_lo, row_hi, [(peer, i0, i1, j0, j1), ...])."""
+    lib = load_library()
+    a, b, n = C.c_int32(), C.c_int32(), C.c_int32()
+    jobs = (C.c_int32 * (5 * 40))()
+    rc = lib.pycs_mgpu_plan(N, world, rank, C.byref(a), C.byref(b), jobs, 40, C.byref(n))
+    if rc != 0:
+        raise PycsError(lib.pycs_last_error().decode())
+    return a.value, b.value, [tuple(jobs[5 * k:5 * k + 5]) for k in range(n.value)]
 
 
 class DeviceArray:

@@ -14,8 +14,9 @@ tup = (3, 1, 1, 3, 1, 3)
 if which == "v2":
     configs = [dict(IMPL=2, TB=tb, DEPTH=d, ROWS=rows) for tb in (128, 160) for d in (5, 6) for rows in (0, 48, 96)]
 else:
-    configs = [dict(IMPL=3, NW=nw, DEPTH=d, ROWS=rows) for nw, d in ((3, 5), (3, 6), (3, 7), (4, 5), (4, 6), (7, 5), (7, 6))
-               for rows in (0, 48, 96, 192, 384)]
+    pts = ((3, 3, 3), (3, 2, 3), (3, 4, 3), (3, 2, 4), (3, 3, 4), (3, 3, 13), (3, 4, 13), (2, 3, 4), (2, 4, 4), (2, 4, 5),
+           (4, 2, 2), (4, 3, 2), (4, 2, 3))
+    configs = [dict(IMPL=3, NW=nw, PF=pf, MINB=mb, ROWS=rows) for nw, pf, mb in pts for rows in (0, 64, 128)]
 for cfg in configs:
     for k, v in cfg.items():
         os.environ["PYCS_FUSED_" + k] = str(v)

@@ -2,7 +2,7 @@
 //
 // Compiles py-cubed-sphere_b200/csrc/fused3_core.cuh (the per-lane arithmetic the CUDA
 // kernel runs, shared verbatim) with g++ and replays the kernel's decomposition on the
-// CPU: CTAs = (panel, strip, chunk), consumer warps, 32 lanes x 2 columns, a D-slot ring
+// CPU: CTAs = (panel, strip, chunk), consumer warps, 32 lanes x 2 columns, the two rings
 // of staged rows filled the way the TMA producer fills it (row segment copy + MF-PR
 // patch), the warp-private Qx row and the lane-to-lane flux exchange.  tests/ compares its
 // output with the numpy oracle, which validates the numerics and every index of the kernel
@@ -31,12 +31,14 @@ struct Args {
 template <int RECON, int SPLIT, int MASK, int NW>
 void run(const Args& a) {
   constexpr int RW = RowWidth<NW>::value;
-  constexpr int NARR = (MASK & 1) ? 9 : 7;
-  constexpr int SLOT = NARR * RW;
-  const int D = a.depth;
+  constexpr int NS = (MASK & 1) ? 4 : 3, NL = (MASK & 1) ? 5 : 4;
+  constexpr int SSLOT = NS * RW, LSLOT = NL * RW;
+  const int PF = a.depth, DS = PF + 1, DL = PF + 4;        // "depth" = rows in flight
   const int nchunks = (a.N + a.rows_per_chunk - 1) / a.rows_per_chunk;
-  std::vector<dbl2> ringbuf((size_t)(D * SLOT + NW * SXW) / 2 + 8);
-  double* ring = reinterpret_cast<double*>(ringbuf.data());
+  std::vector<double> ringbuf((size_t)DS * SSLOT + (size_t)DL * LSLOT + NW * SXW);
+  double* ringS = ringbuf.data();
+  double* ringL = ringS + DS * SSLOT;
+  double* sxall = ringL + DL * LSLOT;
   for (int blk = 0; blk < 6 * a.nstrips * nchunks; ++blk) {
     int b = blk;
     const int p = b % 6;
@@ -44,68 +46,86 @@ void run(const Args& a) {
     const int strip = b % a.nstrips, chunk = b / a.nstrips;
     const int js0 = a.lo + strip * a.wcols;
     const int js1 = std::min(js0 + a.wcols, a.hi);
-    const int r0 = a.lo + chunk * a.rows_per_chunk;
+    const int r0 = a.lo + chunk * a.rows_per_chunk;   // single GPU: row_lo = lo, row_hi = hi
     const int r1 = std::min(r0 + a.rows_per_chunk, a.hi);
     const int rfirst = r0 - 3, rlast = r1 + 2;
-    const int c0 = ((js0 - 3) & ~1) - 4;
+    const int c0 = strip_c0(js0);
     const int len = std::min(RW, a.ld - JOFF - c0) & ~1;
     const long long colb = (long long)p * a.ps + JOFF + c0, colm = JOFF + c0;
     for (int warp = 0; warp < NW; ++warp) {
-      std::fill(ring, ring + D * SLOT + NW * SXW, 0.0);
-      double* sxrow = ring + D * SLOT + warp * SXW;
+      std::fill(ringbuf.begin(), ringbuf.end(), 0.0);
+      double* sxrow = sxall + warp * SXW;
       int cw0, us, ue;
       warp_columns(js0, js1, warp, cw0, us, ue);
       Lane L[32];
       for (int l = 0; l < 32; ++l) lane_init(L[l]);
-      int o0 = 0, o1 = (D - 1) * SLOT, o2 = (D - 2) * SLOT, o3 = (D - 3) * SLOT;
+      int oS = 0, oL0 = 0, oL1 = (DL - 1) * LSLOT, oL2 = (DL - 2) * LSLOT, oL3 = (DL - 3) * LSLOT;
       for (int r = rfirst; r <= rlast; ++r) {
-        // producer: stage row r into its slot, patch the pending MF-PR term
+        // producer: stage row r into its slots, patch the pending MF-PR term
         {
-          const int s = (r - rfirst) % D;
-          double* dst = ring + s * SLOT;
-          const long long rr = (long long)r * a.ld;
-          auto cp = [&](int arr, const double* src) { std::memcpy(dst + arr * RW, src, sizeof(double) * len); };
-          cp(A_Q, a.q + colb + rr); cp(A_V, a.va + colb + rr);
-          cp(A_SGC, a.sgc + colm + rr); cp(A_SGV, a.sgv + colm + rr); cp(A_RGC, a.rgc + colm + rr);
-          cp(A_SGU, a.sgu + colm + rr); cp(A_U, a.ua + colb + rr);
-          if (MASK & 1) { cp(A_VM, a.vm + colb + rr); cp(A_UM, a.um + colb + rr); }
+          const int k = r - rfirst;
+          double* dS = ringS + (k % DS) * SSLOT;
+          double* dL = ringL + (k % DL) * LSLOT;
+          const long long rr = (long long)r * a.ld, rm1 = (long long)std::max(r - 1, 0) * a.ld,
+                          rm2 = (long long)std::max(r - 2, 0) * a.ld;
+          auto cp = [&](double* dst, const double* src) { std::memcpy(dst, src, sizeof(double) * len); };
+          cp(dS + S_Q * RW, a.q + colb + rr); cp(dL + L_V * RW, a.va + colb + rr);
+          cp(dL + L_SGC * RW, a.sgc + colm + rr); cp(dL + L_SGV * RW, a.sgv + colm + rr);
+          cp(dL + L_RGC * RW, a.rgc + colm + rr); cp(dS + S_SGU * RW, a.sgu + colm + rm1);
+          cp(dS + S_U * RW, a.ua + colb + rm2);
+          if (MASK & 1) { cp(dL + L_VM * RW, a.vm + colb + rr); cp(dS + S_UM * RW, a.um + colb + rm2); }
           if (a.apply_corr && r >= a.lo && r < a.hi)
-            for (int k = 0; k < len; ++k) {
-              const int j = c0 + k;
-              if (j >= a.lo && j < a.hi) dst[A_Q * RW + k] = fma(dst[A_SGC * RW + k], a.corr, dst[A_Q * RW + k]);
+            for (int i = 0; i < len; ++i) {
+              const int j = c0 + i;
+              if (j >= a.lo && j < a.hi) dS[S_Q * RW + i] = fma(dL[L_SGC * RW + i], a.corr, dS[S_Q * RW + i]);
             }
-          if (s * SLOT != o0) std::abort();
+          if ((k % DS) * SSLOT != oS || (k % DL) * LSLOT != oL0) std::abort();
         }
-        const double *R0 = ring + o0, *R1 = ring + o1, *R2 = ring + o2, *R3 = ring + o3;
+        RowPtrs R[32];
         XEdge X[32];
-        double F[32][NC + 1], G[32][NC + 1], CF[32][NC + 1], CG[NC];
+        double F[32][NC], G[32][NC], CF[32][NC], CG[NC], Fn[32][NC], Gn[32][NC], CFn[32][NC];
         for (int l = 0; l < 32; ++l) {                 // phase 1
+          const int ca = cw0 - c0 + l;
+          RowPtrs& P = R[l];
+          P.q = ringS + oS + S_Q * RW + ca; P.u = ringS + oS + S_U * RW + ca;
+          P.um = ringS + oS + S_UM * RW + ca; P.su1 = ringS + oS + S_SGU * RW + ca;
+          P.v0 = ringL + oL0 + L_V * RW + ca; P.vm0 = ringL + oL0 + L_VM * RW + ca;
+          P.sgv0 = ringL + oL0 + L_SGV * RW + ca; P.sgc0 = ringL + oL0 + L_SGC * RW + ca;
+          P.rg0 = ringL + oL0 + L_RGC * RW + ca; P.sgc2 = ringL + oL2 + L_SGC * RW + ca;
+          P.v3 = ringL + oL3 + L_V * RW + ca; P.vm3 = ringL + oL3 + L_VM * RW + ca;
+          P.sgv3 = ringL + oL3 + L_SGV * RW + ca; P.sgc3 = ringL + oL3 + L_SGC * RW + ca;
+          P.rg3 = ringL + oL3 + L_RGC * RW + ca;
           double qx[NC];
-          phase_x_inner<RECON, SPLIT, MASK, RW>(L[l], X[l], R0, R1, R2, R3, cw0 - c0 + NC * l, a.cdx, a.ws, qx);
-          st2(sxrow + 4 + NC * l, qx[0], qx[1]);
+          phase_x_inner<RECON, SPLIT, MASK>(L[l], X[l], P, a.cdx, a.ws, qx);
+          sxrow[4 + l] = qx[0];
+          sxrow[4 + l + CSTEP] = qx[1];
         }
         for (int l = 0; l < 32; ++l) {                 // phase 2 (after __syncwarp)
-          const int ca = cw0 - c0 + NC * l;
           CF[l][0] = CF[l][1] = 0.0;
-          yflux_pair<RECON, SPLIT, MASK, RW>(R0, ca, R0 + A_Q * RW + ca, a.cdy, a.ws, F[l], CF[l]);
-          yflux_pair<RECON, SPLIT, MASK, RW>(R3, ca, sxrow + 4 + NC * l, a.cdy, a.ws, G[l], CG);
+          yflux_pair<RECON, SPLIT, MASK>(R[l].v0, R[l].vm0, R[l].sgv0, R[l].sgc0, R[l].q, a.cdy, a.ws, F[l], CF[l]);
+          yflux_pair<RECON, SPLIT, MASK>(R[l].v3, R[l].vm3, R[l].sgv3, R[l].sgc3, sxrow + 4 + l, a.cdy, a.ws, G[l], CG);
         }
-        for (int l = 0; l < 32; ++l) {                 // __shfl_down(.., 1): lane 31 keeps its own value
-          const int n = l < 31 ? l + 1 : l;
-          F[l][NC] = F[n][0]; G[l][NC] = G[n][0]; CF[l][NC] = CF[n][0];
+        for (int l = 0; l < 32; ++l) {                 // shuffles: right neighbour of each own column
+          const int n = l < 31 ? l + 1 : l;            // __shfl_down keeps the own value in lane 31
+          Fn[l][0] = l == 31 ? F[0][1] : F[n][0]; Fn[l][1] = F[n][1];
+          Gn[l][0] = l == 31 ? G[0][1] : G[n][0]; Gn[l][1] = G[n][1];
+          CFn[l][0] = l == 31 ? CF[0][1] : CF[n][0]; CFn[l][1] = CF[n][1];
         }
         for (int l = 0; l < 32; ++l) {                 // phase 3
-          const int ca = cw0 - c0 + NC * l, col = cw0 + NC * l;
+          const int col = cw0 + l;
           double out[NC], sdiv[NC];
-          phase_x_outer<RECON, SPLIT, RW>(L[l], X[l], R0, ca, F[l], G[l], CF[l], out, sdiv);
+          phase_x_outer<RECON, SPLIT>(L[l], X[l], R[l], F[l], Fn[l], G[l], Gn[l], CF[l], CFn[l], out, sdiv);
           if (r >= r0 + 3) {
             double* QN = a.qn + (long long)p * a.ps + JOFF + (long long)(r - 3) * a.ld;
-            for (int c = 0; c < NC; ++c)
-              if (col + c >= us && col + c < ue) { QN[col + c] = out[c]; L[l].psum += sdiv[c]; }
+            for (int c = 0; c < NC; ++c) {
+              const int cc = col + c * CSTEP;
+              if (cc >= us && cc < ue) { QN[cc] = out[c]; L[l].psum += sdiv[c]; }
+            }
           }
         }
-        o3 = o2; o2 = o1; o1 = o0;
-        o0 = (o0 + SLOT == D * SLOT) ? 0 : o0 + SLOT;
+        oS = (oS + SSLOT == DS * SSLOT) ? 0 : oS + SSLOT;
+        oL3 = oL2; oL2 = oL1; oL1 = oL0;
+        oL0 = (oL0 + LSLOT == DL * LSLOT) ? 0 : oL0 + LSLOT;
       }
       // warp reduction in the kernel's order (shfl_down tree)
       double v[32];
@@ -160,7 +180,7 @@ int f3_emul_step(int N, int recon, int split, int mask, int nw, int depth, int r
   a.rows_per_chunk = rows_per_chunk; a.depth = depth;
   int nchunks;
   f3_emul_grid(N, nw, rows_per_chunk, &a.nstrips, &a.wcols, &nchunks);
-  if (depth < 5) return -2;
+  if (depth < 1) return -2;
   if (nw == 3) return run_scheme<3>(a, recon, split, mask);
   if (nw == 4) return run_scheme<4>(a, recon, split, mask);
   if (nw == 2) return run_scheme<2>(a, recon, split, mask);

@@ -324,6 +324,25 @@ def test_fused_matches_operator_path(mods, N, vf, name):
     b.dev.close()
 
 
+@pytest.mark.parametrize("N,vf,name", [(16, 1, "default"), (50, 3, "default"), (130, 2, "AVLT-RK2-DG-PR"),
+                                       (130, 1, "PL07-RK1-DG-PR"), (1536, 3, "default")])
+def test_fused_v3_kernel_matches_operator_path(mods, N, vf, name, monkeypatch):
+    """The warp-autonomous v3 step kernel (csrc/fused3.cu; PYCS_FUSED_IMPL=3) against the
+    operator path, several run calls (separable wind + pending projection across calls)."""
+    monkeypatch.setenv("PYCS_FUSED_IMPL", "3")
+    g = mods.cs_datastruct.cubed_sphere(N)
+    a = make_sim(mods, g, vf, TUPLES[name])
+    b = make_sim(mods, g, vf, TUPLES[name])
+    k = 0
+    for n in ((1, 4, 7) if N < 1000 else (3,)):
+        mods.advection_timestep.run_steps(g, a, k, n, fused=True)
+        k += n
+    mods.advection_timestep.run_steps(g, b, 0, k, fused=False)
+    assert relerr(np.asarray(a.Q), np.asarray(b.Q)) <= TOL
+    a.dev.close()
+    b.dev.close()
+
+
 def test_fused_separable_wind_across_run_calls(mods):
     """vf = 3 / RK1 scales the t = 0 winds in-kernel: successive pycs_run calls (each ending
     with a non-separable step that rewrites ucontra_averaged) must keep using wind(0)."""
