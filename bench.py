@@ -172,10 +172,10 @@ def run_gpu(args):
     dev = sim.dev
     if not dev.fused_supported():
         raise RuntimeError("fused kernel unavailable")
-    rows = (4, N + 4)
+    slab = (4, N + 4)
     if world > 1:
         # strong scaling: the rows of every panel are split over the ranks (csrc/mgpu.cu)
-        rows = parallel.shard(sim)
+        slab = parallel.shard(sim)
     setup_s = time.time() - t_setup
     sm, name = dev.sm_count()
     Q0 = np.asarray(sim.Q).copy()
@@ -208,7 +208,7 @@ def run_gpu(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total = float(tt.item())
     cells = 6.0 * N * N                      # whole sphere: the ranks share one problem
-    own_cells = 6.0 * N * (rows[1] - rows[0])
+    own_cells = 6.0 * N * (slab[1] - slab[0])
     value = cells * args.steps / (ms_total * 1e-3)
 
     # ---- roofline: the step kernel alone, CUDA events around back-to-back launches
@@ -236,7 +236,7 @@ def run_gpu(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "fused_step_kernel<%d,PPM-PL07,SP-AVLT>" % tb.value,
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": BYTES_PER_CELL * own_cells,
-                "per": "GPU (each rank updates %d of %d rows of every panel)" % (rows[1] - rows[0], N),
+                "per": "GPU (each rank updates %d of %d rows of every panel)" % (slab[1] - slab[0], N),
                 "peak_source": peak_src, "grid": {"ctas": nblk.value, "threads": tb.value, "rows_per_chunk": rows.value},
                 "share_of_step": k_ms / (ms_total / args.steps)}
 
