@@ -25,6 +25,7 @@ UNITS = {
     "wind.cu": ["-fmad=false"],
     "fused.cu": [],
     "fused3.cu": [],
+    "fused2b.cu": [],
     "mgpu.cu": [],
 }
 

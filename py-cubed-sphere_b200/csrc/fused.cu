@@ -399,61 +399,95 @@ __device__ double reduce_partials(const double* __restrict__ part, int n, double
   return t;
 }
 
-__global__ void dg_phase1_corr_kernel(Geo g, HaloMaps maps, double* __restrict__ q,
-                                      const int* __restrict__ kminE, const double* __restrict__ wE, int order,
-                                      const double* __restrict__ sgc, const double* __restrict__ part,
-                                      int npart, double inv_a2, double* __restrict__ corr_out) {
-  __shared__ double sh[32];
-  double corr = 0.0;
-  if (npart > 0) {
-    corr = -reduce_partials(part, npart, sh) * inv_a2;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *corr_out = corr;
-  }
-  int k = g.lo + blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= g.hi) return;
-  int gl = blockIdx.y;
-  int p = blockIdx.z >> 2, s = blockIdx.z & 3;
+// One ghost cell of phase 1 (src/interpolation.py:200-248): side s of panel p, ghost layer gl,
+// position k along the edge.  Same operations in the same order as dg_phase1_kernel in halo.cu.
+__device__ __forceinline__ double dg_phase1_value(const Geo& g, const HaloMaps& maps, const double* __restrict__ q,
+                                                  const int* __restrict__ kminE, const double* __restrict__ wE,
+                                                  int order, const double* __restrict__ sgc, double corr, int p,
+                                                  int s, int gl, int k) {
   const SideMap& m = maps.m[p][s];
-  int ge = (s == SIDE_E || s == SIDE_N) ? gl : PYCS_NG - 1 - gl;
-  int km = kminE[ge * g.P + k];
+  const int ge = (s == SIDE_E || s == SIDE_N) ? gl : PYCS_NG - 1 - gl;
+  const int km = kminE[ge * g.P + k];
   const double* w = wE + ((long long)ge * g.P + k) * order;
   double acc = 0.0;
   for (int l = 0; l < order; ++l) {
     double v = (s < 2) ? halo_src(q, sgc, g, m, gl, km + l, corr) : halo_src(q, sgc, g, m, km + l, gl, corr);
     acc = __dadd_rn(acc, __dmul_rn(v, w[l]));
   }
-  int i, j;
-  if (s == SIDE_E) { i = g.hi + gl; j = k; }
-  else if (s == SIDE_W) { i = gl; j = k; }
-  else if (s == SIDE_N) { i = k; j = g.hi + gl; }
-  else { i = k; j = gl; }
-  q[gidx(g, p, i, j)] = acc;
+  return acc;
 }
 
-// Corner stencils straddle the interior / ghost boundary of the neighbour strip:
-// interior sources still miss the pending term, ghost sources already have it.
-__global__ void dg_phase2_corr_kernel(Geo g, HaloMaps maps, double* __restrict__ q,
-                                      const int* __restrict__ kminE, const double* __restrict__ wE, int order,
-                                      const double* __restrict__ sgc, const double* __restrict__ corr_p,
-                                      int apply_corr) {
-  const double corr = apply_corr ? *corr_p : 0.0;
-  int t = threadIdx.x;
-  int gl = t >> 3, c = t & 7;
-  int k = (c < 4) ? c : g.hi + (c - 4);
-  int p = blockIdx.x >> 1, s = blockIdx.x & 1;
+// The whole Lagrange ghost fill in ONE launch (it sits on the per-step critical path, and on
+// several GPUs between the peers' flags and the step kernel):
+//   * multi-GPU: every CTA first waits for the flags of exchange `epoch` (null on one GPU);
+//   * blocks [0, nb1): phase 1, one thread per edge ghost cell;
+//   * last 3 blocks: the 12 x 32 corner cells of phase 2 (src/interpolation.py:250-314).  A
+//     corner stencil reads the neighbour's strip, whose ends are that neighbour's phase-1
+//     ghosts; instead of waiting for them they are recomputed in registers (same arithmetic,
+//     same bits), so corners depend on interior cells only.
+// The pending MF-PR term (corr * sqrtg on interior cells) is folded into every source value.
+__global__ void dg_fill_fused_kernel(Geo g, HaloMaps maps, double* __restrict__ q, const int* __restrict__ kminE,
+                                     const double* __restrict__ wE, int order, const double* __restrict__ sgc,
+                                     const double* __restrict__ part, int npart, double inv_a2,
+                                     double* __restrict__ corr_out, const long long* __restrict__ flags, int world,
+                                     long long epoch, int nbx) {
+  __shared__ double sh[32];
+  if (flags) {
+    if (threadIdx.x < world) {
+      const volatile long long* f = flags + threadIdx.x;
+      for (unsigned n = 0; *f < epoch; ++n) {
+        if (n > (1u << 26)) __trap();          // a lost peer must not hang the GPU
+        __nanosleep(40);
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+  }
+  double corr = 0.0;
+  if (npart > 0) {
+    corr = -reduce_partials(part, npart, sh) * inv_a2;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *corr_out = corr;
+  }
+  const int nb1 = nbx * 4 * 24;
+  if ((int)blockIdx.x < nb1) {
+    const int bx = blockIdx.x % nbx, gl = (blockIdx.x / nbx) & 3, ps = blockIdx.x / (4 * nbx);
+    const int k = g.lo + bx * blockDim.x + threadIdx.x;
+    if (k >= g.hi) return;
+    const int p = ps >> 2, s = ps & 3;
+    const double acc = dg_phase1_value(g, maps, q, kminE, wE, order, sgc, corr, p, s, gl, k);
+    int i, j;
+    if (s == SIDE_E) { i = g.hi + gl; j = k; }
+    else if (s == SIDE_W) { i = gl; j = k; }
+    else if (s == SIDE_N) { i = k; j = g.hi + gl; }
+    else { i = k; j = gl; }
+    q[gidx(g, p, i, j)] = acc;
+    return;
+  }
+  // corners: 12 (panel, E|W) x 4 layers x 8 positions
+  const int t = ((int)blockIdx.x - nb1) * blockDim.x + threadIdx.x;
+  if (t >= 12 * 32) return;
+  const int c32 = t & 31, pe = t >> 5;
+  const int gl = c32 >> 3, c = c32 & 7;
+  const int k = (c < 4) ? c : g.hi + (c - 4);
+  const int p = pe >> 1, s = pe & 1;
   const SideMap& m = maps.m[p][s];
-  int ge = (s == SIDE_E) ? gl : PYCS_NG - 1 - gl;
-  int km = kminE[ge * g.P + k];
+  const int ge = (s == SIDE_E) ? gl : PYCS_NG - 1 - gl;
+  const int km = kminE[ge * g.P + k];
   const double* w = wE + ((long long)ge * g.P + k) * order;
   double acc = 0.0;
   for (int l = 0; l < order; ++l) {
-    int a_ = gl, b_ = km + l;
-    int si = m.ci + m.ai * a_ + m.bi * b_, sj = m.cj + m.aj * a_ + m.bj * b_;
-    double v = q[gidx(g, m.nb, si, sj)];
-    if (si >= g.lo && si < g.hi && sj >= g.lo && sj < g.hi) v = fma(sgc[gidx(g, 0, si, sj)], corr, v);
+    const int b_ = km + l;
+    const int si = m.ci + m.ai * gl + m.bi * b_, sj = m.cj + m.aj * gl + m.bj * b_;
+    const bool ii = si >= g.lo && si < g.hi, jj = sj >= g.lo && sj < g.hi;
+    double v;
+    if (ii && jj) v = fma(sgc[gidx(g, 0, si, sj)], corr, q[gidx(g, m.nb, si, sj)]);
+    else if (ii) v = dg_phase1_value(g, maps, q, kminE, wE, order, sgc, corr, m.nb, sj >= g.hi ? SIDE_N : SIDE_S,
+                                     sj >= g.hi ? sj - g.hi : sj, si);
+    else v = dg_phase1_value(g, maps, q, kminE, wE, order, sgc, corr, m.nb, si >= g.hi ? SIDE_E : SIDE_W,
+                             si >= g.hi ? si - g.hi : si, sj);
     acc = __dadd_rn(acc, __dmul_rn(v, w[l]));
   }
-  int i = (s == SIDE_E) ? g.hi + gl : gl;
+  const int i = (s == SIDE_E) ? g.hi + gl : gl;
   q[gidx(g, p, i, k)] = acc;
 }
 
@@ -587,6 +621,10 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
     int pf = ep ? atoi(ep) : 3, minb = em ? atoi(em) : 3;
     if (impl == 3 && !pycs_fused3_has(h->prm.recon, h->prm.opsplit, nw, pf, minb)) { nw = 3; pf = 3; minb = 3; }
     if (impl == 3 && !pycs_fused3_has(h->prm.recon, h->prm.opsplit, nw, pf, minb)) impl = 2;   // limited PPM
+    const char* etb = getenv("PYCS_FUSED_TB");
+    int tb4 = etb ? atoi(etb) : 160, pf4 = ep ? atoi(ep) : 2, minb4 = em ? atoi(em) : 4;
+    if (impl == 4 && !pycs_fused2b_has(h->prm.recon, h->prm.opsplit, tb4, pf4, minb4)) { tb4 = 160; pf4 = 2; minb4 = 4; }
+    if (impl == 4 && !pycs_fused2b_has(h->prm.recon, h->prm.opsplit, tb4, pf4, minb4)) impl = 2;   // limited PPM
     int resident, lag, cols;
     if (impl == 3) {
       // strips of up to 57 + 58 (NW-1) columns, one consumer warp per 57/58 of them
@@ -601,6 +639,23 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
       int per_sm = pycs_fused3_resident(h->prm.recon, h->prm.opsplit, mask, nw, pf, minb);
       if (per_sm < 1) {
         pycs_set_error("fused3 kernel: occupancy query failed");
+        return PYCS_ERR_CUDA;
+      }
+      resident = h->sm_count * per_sm;
+      lag = 6;
+    } else if (impl == 4) {
+      // v2b: strips of TB-6 columns, one column per thread
+      fs.tb = tb4;
+      fs.pf = pf4;
+      fs.minb = minb4;
+      const int wmax = tb4 - 6;
+      fs.nstrips = (g.N + wmax - 1) / wmax;
+      fs.wcols = (g.N + fs.nstrips - 1) / fs.nstrips;
+      fs.wcols += fs.wcols & 1;
+      const int mask = (h->prm.dp == 2) ? 1 : 0;
+      int per_sm = pycs_fused2b_resident(h->prm.recon, h->prm.opsplit, mask, tb4, pf4, minb4);
+      if (per_sm < 1) {
+        pycs_set_error("fused2b kernel: occupancy query failed");
         return PYCS_ERR_CUDA;
       }
       resident = h->sm_count * per_sm;
@@ -762,6 +817,8 @@ static int launch_step_kernel(pycs_handle h, FusedState& fs, const double* qcur,
   a.ws = ws;
   if (fs.impl == 3)
     CK(pycs_launch_fused3(a, h->prm.recon, h->prm.opsplit, mask, fs.nw, fs.pf, fs.minb, fs.npart / fs.nw, h->stream));
+  else if (fs.impl == 4)
+    CK(pycs_launch_fused2b(a, h->prm.recon, h->prm.opsplit, mask, fs.tb, fs.pf, fs.minb, fs.npart, h->stream));
   else
     CK(launch_fused(a, h->prm.recon, h->prm.opsplit, mask, fs.npart, fs.tb, fs.depth, h->stream));
   CKL(h);
@@ -825,20 +882,25 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   // 0. multi-GPU: the peers' halo rows, boundary strips and MF-PR sums of the last step are in
   const double* sums = fs.part;
   int nsums = fs.npart;
-  if (h->mg) {
-    TRY(k_mg_wait(h));
+  const long long* mgflags = nullptr;
+  int mgworld = 0;
+  long long mgepoch = 0;
+  if (h->mg) {                       // the wait is folded into the ghost-fill kernel
     sums = k_mg_sums(h);
     nsums = h->mg->world;
+    mgflags = h->mg->sync->flag;
+    mgworld = h->mg->world;
+    mgepoch = h->mg->epoch;
   }
   // 1. ghost cells of Q (src/advection_timestep.py:28), folding in the pending MF-PR term
   int pend = fs.pending;
-  dg_phase1_corr_kernel<<<dim3((g.N + 127) / 128, 4, 24), 128, 0, h->stream>>>(
-      g, h->maps, qcur, h->kminE, h->wE, h->order, sgc, sums, pend ? nsums : 0,
-      pend ? 1.0 / h->a2 : 0.0, h->red_out + 8);
-  CKL(h);
-  dg_phase2_corr_kernel<<<12, 32, 0, h->stream>>>(g, h->maps, qcur, h->kminE, h->wE, h->order, sgc,
-                                                  h->red_out + 8, pend);
-  CKL(h);
+  {
+    const int nbx = (g.N + 127) / 128;
+    dg_fill_fused_kernel<<<nbx * 4 * 24 + 3, 128, 0, h->stream>>>(
+        g, h->maps, qcur, h->kminE, h->wE, h->order, sgc, sums, pend ? nsums : 0, pend ? 1.0 / h->a2 : 0.0,
+        h->red_out + 8, mgflags, mgworld, mgepoch, nbx);
+    CKL(h);
+  }
   // 2. winds (src/advection_timestep.py:31-37)
   if (h->prm.vf >= 2 && !separable) {
     TRY(k_wind_ghost_fill(h));

@@ -1,0 +1,278 @@
+// Fused advection step, v2b: the block-synchronous march of fused.cu (one column per thread,
+// many warps per SM) running the lean arithmetic of fused3_core.cuh.
+//
+// ncu on v2 (profiles/r1_fused_v2_ncu.md) showed an instruction-issue bound kernel (336
+// instructions per thread-row); v3 (fused3.cu) cut the instruction count but its two columns
+// per lane cost so many registers that only 9 consumer warps fit on an SM
+// (profiles/r1_fused_v3_ncu.md).  v2b keeps v2's occupancy (one column per thread, ~90
+// registers, 4-5 CTAs of 160 threads per SM) and takes from v3:
+//   * the weight form of the flux and the per-edge weights shared by inner / outer x-flux;
+//   * no ramp-up predicates: the first rows of a chunk run on zero-initialised windows, only
+//     the stores are predicated;
+//   * the two-level row ring (Q, u, sqrtg_pu: one row + prefetch; v, sqrtg_pv, sqrtg_pc,
+//     1/sqrtg_pc: four rows + prefetch), filled by thread 0 with cp.async.bulk (TMA) row
+//     copies signalled on one mbarrier per row.
+// Per marched row: phase 1 (own column: new row, inner x-flux, Qx) | barrier | phase 2
+// (y-fluxes of Q row r and of Qx row r-3 at the thread's edge) | barrier | phase 3 (Qy, outer
+// x-flux, output row r-3).
+#include "fused_args.cuh"
+#define F3_NAMESPACE f1
+#define F3_NC 1
+#define F3_CSTEP 0
+#include "fused3_core.cuh"
+
+namespace {
+
+using namespace f1;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_row(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+template <int TB, int RECON, int SPLIT, int MASK, int PF, int MINB>
+__global__ void __launch_bounds__(TB, MINB) fused2b_kernel(FusedArgs a) {
+  constexpr int RW = TB + 6;                 // staged row: columns jbase-6 .. jbase+TB-1
+  constexpr int NS = (MASK & 1) ? 4 : 3, NL = (MASK & 1) ? 5 : 4;
+  constexpr int DS = PF + 1, DL = PF + 4;
+  constexpr int SSLOT = NS * RW, LSLOT = NL * RW;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* ringS = reinterpret_cast<double*>(smem_raw);           // [DS][NS][RW]
+  double* ringL = ringS + DS * SSLOT;                            // [DL][NL][RW]
+  double* sX = ringL + DL * LSLOT;                               // Qx row r-3
+  double* sF = sX + RW;                                          // inner y-flux, row r
+  double* sG = sF + RW;                                          // outer y-flux, row r-3
+  double* sC = sG + RW;                                          // sqrtg_pv*cy (SPLIT != 1)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sC + RW);         // [DL]
+
+  const Geo& g = a.g;
+  int b = blockIdx.x;
+  const int p = b % 6;
+  b /= 6;
+  const int strip = b % a.nstrips, chunk = b / a.nstrips;
+  const int tid = threadIdx.x;
+  const int e = tid + 3;                     // own element in a staged row (the y-stencil reaches e-3 .. e+2)
+  const int jbase = g.lo + strip * a.wcols;
+  const int jend = min(jbase + a.wcols, g.hi);
+  const int j = jbase - 3 + tid;
+  const int r0 = a.row_lo + chunk * a.rows_per_chunk;
+  const int r1 = min(r0 + a.rows_per_chunk, a.row_hi);
+  const int rfirst = r0 - 3, rlast = r1 + 2;
+  const bool out_lane = (tid >= 3) && (j < jend);
+  const bool jint = (j >= g.lo) && (j < g.hi);
+  const double corr = a.apply_corr ? *a.corr : 0.0;
+  const double cdx = a.cdx, cdy = a.cdy, ws = a.ws;
+  const int c0 = jbase - 6;                  // 16-byte aligned: JOFF and wcols are even
+  const int len = min(RW, g.ld - PYCS_JOFF - c0) & ~1;
+  const uint32_t row_bytes = (uint32_t)len * 8u;
+
+  for (int k = tid; k < DS * SSLOT + DL * LSLOT + 4 * RW; k += TB) ringS[k] = 0.0;
+  if (tid == 0) {
+    for (int s = 0; s < DL; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int r) {                  // thread 0 only
+    const int k = r - rfirst;
+    double* dS = ringS + (k % DS) * SSLOT;
+    double* dL = ringL + (k % DL) * LSLOT;
+    uint64_t* bar = &full[k % DL];
+    const long long colb = (long long)p * g.ps + PYCS_JOFF + c0;
+    const long long colm = PYCS_JOFF + c0;
+    const long long rr = (long long)r * g.ld, r1_ = (long long)max(r - 1, 0) * g.ld,
+                    r2_ = (long long)max(r - 2, 0) * g.ld;
+    mbar_expect_tx(bar, row_bytes * (NS + NL));
+    tma_row(dS + S_Q * RW, a.q + colb + rr, row_bytes, bar);
+    tma_row(dL + L_V * RW, a.va + colb + rr, row_bytes, bar);
+    tma_row(dL + L_SGC * RW, a.sgc + colm + rr, row_bytes, bar);
+    tma_row(dL + L_SGV * RW, a.sgv + colm + rr, row_bytes, bar);
+    tma_row(dL + L_RGC * RW, a.rgc + colm + rr, row_bytes, bar);
+    tma_row(dS + S_SGU * RW, a.sgu + colm + r1_, row_bytes, bar);
+    tma_row(dS + S_U * RW, a.ua + colb + r2_, row_bytes, bar);
+    if (MASK & 1) {
+      tma_row(dL + L_VM * RW, a.vm + colb + rr, row_bytes, bar);
+      tma_row(dS + S_UM * RW, a.um + colb + r2_, row_bytes, bar);
+    }
+  };
+  if (tid == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int r = rfirst; r < rfirst + PF && r <= rlast; ++r) issue(r);
+  }
+
+  double* __restrict__ QN = a.qn + (long long)p * g.ps + PYCS_JOFF + min(j, g.P - 1) + (long long)r0 * g.ld;
+  Lane L;
+  lane_init(L);
+  int oS = 0;
+  int oL0 = 0, oL1 = (DL - 1) * LSLOT, oL2 = (DL - 2) * LSLOT, oL3 = (DL - 3) * LSLOT;
+  int sb = 0;
+  uint32_t parb = 0;
+#pragma unroll 1
+  for (int r = rfirst; r <= rlast; ++r) {
+    while (!mbar_try_wait(&full[sb], parb)) {}
+    RowPtrs R;
+    R.q = ringS + oS + S_Q * RW + e;
+    R.u = ringS + oS + S_U * RW + e;
+    R.um = ringS + oS + S_UM * RW + e;
+    R.su1 = ringS + oS + S_SGU * RW + e;
+    R.v0 = ringL + oL0 + L_V * RW + e;
+    R.vm0 = ringL + oL0 + L_VM * RW + e;
+    R.sgv0 = ringL + oL0 + L_SGV * RW + e;
+    R.sgc0 = ringL + oL0 + L_SGC * RW + e;
+    R.rg0 = ringL + oL0 + L_RGC * RW + e;
+    R.sgc2 = ringL + oL2 + L_SGC * RW + e;
+    R.v3 = ringL + oL3 + L_V * RW + e;
+    R.vm3 = ringL + oL3 + L_VM * RW + e;
+    R.sgv3 = ringL + oL3 + L_SGV * RW + e;
+    R.sgc3 = ringL + oL3 + L_SGC * RW + e;
+    R.rg3 = ringL + oL3 + L_RGC * RW + e;
+    // pending MF-PR term on the own interior cell of the new row (neighbours read it after barrier A)
+    if (a.apply_corr && jint && r >= g.lo && r < g.hi) {
+      double* qp = ringS + oS + S_Q * RW + e;
+      *qp = fma(R.sgc0[0], corr, *qp);
+    }
+    // ---------------- phase 1: own column
+    XEdge X;
+    double qx[1];
+    phase_x_inner<RECON, SPLIT, MASK>(L, X, R, cdx, ws, qx);
+    sX[e] = qx[0];
+    __syncthreads();                                   // barrier A
+    if (tid == 0 && r + PF <= rlast) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(r + PF);
+    }
+    // ---------------- phase 2: y-fluxes at edge j: inner on Q row r, outer on Qx row r-3
+    double F[1], G[1], CF[1] = {0.0}, CG[1];
+    yflux_pair<RECON, SPLIT, MASK>(R.v0, R.vm0, R.sgv0, R.sgc0, R.q, cdy, ws, F, CF);
+    yflux_pair<RECON, SPLIT, MASK>(R.v3, R.vm3, R.sgv3, R.sgc3, sX + e, cdy, ws, G, CG);
+    sF[e] = F[0];
+    sG[e] = G[0];
+    if (SPLIT != 1) sC[e] = CF[0];
+    __syncthreads();                                   // barrier B
+    // ---------------- phase 3: Qy row r, outer x-flux on Qy, output row r-3
+    double Fn[1], Gn[1], CFn[1] = {0.0}, out[1], sdiv[1];
+    Fn[0] = sF[e + 1];
+    Gn[0] = sG[e + 1];
+    if (SPLIT != 1) CFn[0] = sC[e + 1];
+    phase_x_outer<RECON, SPLIT>(L, X, R, F, Fn, G, Gn, CF, CFn, out, sdiv);
+    if (r >= r0 + 3) {
+      if (out_lane) {
+        *QN = out[0];
+        L.psum += sdiv[0];
+      }
+      QN += g.ld;
+    }
+    oS = (oS + SSLOT == DS * SSLOT) ? 0 : oS + SSLOT;
+    oL3 = oL2; oL2 = oL1; oL1 = oL0;
+    oL0 = (oL0 + LSLOT == DL * LSLOT) ? 0 : oL0 + LSLOT;
+    if (++sb == DL) { sb = 0; parb ^= 1u; }
+  }
+  // per-CTA partial of sum(pxdF + pydF) over its outputs (MF-PR), fixed order
+  __syncthreads();
+  double v = L.psum;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((tid & 31) == 0) sF[tid >> 5] = v;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < TB / 32; ++w) t += sF[w];
+    a.part[blockIdx.x] = t;
+  }
+}
+
+template <int TB, int PF, int MASK>
+constexpr size_t smem_bytes() {
+  return sizeof(double) * (size_t)(TB + 6) * ((PF + 1) * ((MASK & 1) ? 4 : 3) + (PF + 4) * ((MASK & 1) ? 5 : 4) + 4) +
+         sizeof(uint64_t) * (PF + 4) + 16;
+}
+
+template <int TB, int RECON, int SPLIT, int MASK, int PF, int MINB>
+cudaError_t launch_one(const FusedArgs& a, int nblocks, cudaStream_t st, int* resident) {
+  static bool configured = false;
+  const size_t smem = smem_bytes<TB, PF, MASK>();
+  auto kern = fused2b_kernel<TB, RECON, SPLIT, MASK, PF, MINB>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (resident) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(resident, kern, TB, smem);
+  kern<<<nblocks, TB, smem, st>>>(a);
+  return cudaSuccess;
+}
+
+template <int TB, int RECON, int SPLIT, int PF, int MINB>
+cudaError_t launch_mask(const FusedArgs& a, int mask, int nblocks, cudaStream_t st, int* resident) {
+  if (mask == 1) return launch_one<TB, RECON, SPLIT, 1, PF, MINB>(a, nblocks, st, resident);
+  if (mask == 2) return launch_one<TB, RECON, SPLIT, 2, PF, MINB>(a, nblocks, st, resident);
+  return launch_one<TB, RECON, SPLIT, 0, PF, MINB>(a, nblocks, st, resident);
+}
+
+#define F2B_DEFAULT_TB 160
+#define F2B_DEFAULT_PF 2
+#define F2B_DEFAULT_MINB 4
+cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb, int pf, int minb, int nblocks,
+                     cudaStream_t st, int* resident) {
+  if (recon == 3 && split == 1) {
+#define TUNE(T, P, M) \
+  if (tb == T && pf == P && minb == M) return launch_mask<T, 3, 1, P, M>(a, mask, nblocks, st, resident)
+    TUNE(160, 1, 4); TUNE(160, 2, 4); TUNE(160, 1, 5); TUNE(160, 2, 5); TUNE(160, 3, 4);
+    TUNE(128, 1, 5); TUNE(128, 2, 5); TUNE(128, 2, 6); TUNE(128, 3, 5);
+    TUNE(192, 1, 4); TUNE(192, 2, 4); TUNE(192, 2, 3);
+    TUNE(256, 1, 3); TUNE(256, 2, 3); TUNE(256, 2, 2);
+#undef TUNE
+    return cudaErrorInvalidValue;
+  }
+  if (tb != F2B_DEFAULT_TB || pf != F2B_DEFAULT_PF || minb != F2B_DEFAULT_MINB) return cudaErrorInvalidValue;
+#define CASE(R, S) \
+  if (recon == R && split == S) \
+    return launch_mask<F2B_DEFAULT_TB, R, S, F2B_DEFAULT_PF, F2B_DEFAULT_MINB>(a, mask, nblocks, st, resident)
+  CASE(3, 2); CASE(3, 3); CASE(1, 1); CASE(1, 2); CASE(1, 3);
+#undef CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+bool pycs_fused2b_has(int recon, int split, int tb, int pf, int minb) {
+  if (recon != 1 && recon != 3) return false;
+  if (recon == 3 && split == 1) {
+    const int t[][3] = {{160, 1, 4}, {160, 2, 4}, {160, 1, 5}, {160, 2, 5}, {160, 3, 4}, {128, 1, 5}, {128, 2, 5},
+                        {128, 2, 6}, {128, 3, 5}, {192, 1, 4}, {192, 2, 4}, {192, 2, 3}, {256, 1, 3}, {256, 2, 3},
+                        {256, 2, 2}};
+    for (auto& x : t)
+      if (x[0] == tb && x[1] == pf && x[2] == minb) return true;
+    return false;
+  }
+  return tb == F2B_DEFAULT_TB && pf == F2B_DEFAULT_PF && minb == F2B_DEFAULT_MINB;
+}
+
+cudaError_t pycs_launch_fused2b(const FusedArgs& a, int recon, int split, int mask, int tb, int pf, int minb,
+                                int nblocks, cudaStream_t st) {
+  return dispatch(a, recon, split, mask, tb, pf, minb, nblocks, st, nullptr);
+}
+
+int pycs_fused2b_resident(int recon, int split, int mask, int tb, int pf, int minb) {
+  FusedArgs a{};
+  int n = 0;
+  if (dispatch(a, recon, split, mask, tb, pf, minb, 0, nullptr, &n) != cudaSuccess) return -1;
+  return n;
+}

@@ -19,7 +19,8 @@
 // The three weights depend on the wind and the metric only, so they are computed once per
 // edge and serve the inner and the outer operator; dt/dx and the final "* u" are folded
 // in (flux' = f * u * dt/dx), so dF = flux'[i] - flux'[i+1].
-#pragma once
+#ifndef PYCS_FUSED3_CORE_PRELUDE
+#define PYCS_FUSED3_CORE_PRELUDE
 #if defined(__CUDACC__)
 #define PYCS_HD __host__ __device__ __forceinline__
 typedef double2 dbl2;
@@ -28,11 +29,23 @@ typedef double2 dbl2;
 #define PYCS_HD inline
 struct alignas(16) dbl2 { double x, y; };
 #endif
+#endif
 
-namespace f3 {
+// The body below can be included more than once with different
+//   F3_NAMESPACE (default f3), F3_NC (columns per lane, default 2), F3_CSTEP (distance between
+//   a lane's columns, default 32)
+// fused3.cu uses f3 / 2 / 32 (warp-autonomous kernel), fused2b.cu uses f1 / 1 / 0 (one column
+// per thread, block-synchronous kernel).
+#ifndef F3_NAMESPACE
+#define F3_NAMESPACE f3
+#define F3_NC 2
+#define F3_CSTEP 32
+#endif
 
-constexpr int NC = 2;               // columns per lane
-constexpr int CSTEP = 32;           // lane l owns columns cw0 + l and cw0 + 32 + l (conflict-free LDS.64)
+namespace F3_NAMESPACE {
+
+constexpr int NC = F3_NC;           // columns per lane
+constexpr int CSTEP = F3_CSTEP;     // lane l owns columns cw0 + l and cw0 + CSTEP + l (conflict-free LDS.64)
 constexpr int WARP_COLS = 32 * NC;  // columns marched by one consumer warp
 constexpr int WARP_USE = WARP_COLS - 6;   // of which outputs (3 halo columns on each side)
 constexpr int SXW = WARP_COLS + 8;  // private Qx row: 4 pad columns on each side
@@ -239,4 +252,7 @@ PYCS_HD int strip_capacity(int nw) { return WARP_USE * nw; }
 // index of column cw0 of warp w inside a staged row
 PYCS_HD int strip_c0(int js0) { return ((js0 - 3) & ~1) - 4; }
 
-}  // namespace f3
+}  // namespace F3_NAMESPACE
+#undef F3_NAMESPACE
+#undef F3_NC
+#undef F3_CSTEP

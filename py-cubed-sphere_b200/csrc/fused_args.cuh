@@ -24,3 +24,8 @@ cudaError_t pycs_launch_fused3(const FusedArgs& a, int recon, int split, int mas
 // resident CTAs per SM of the v3 kernel for this template point (occupancy API); < 0 on error
 int pycs_fused3_resident(int recon, int split, int mask, int nw, int pf, int minb);
 bool pycs_fused3_has(int recon, int split, int nw, int pf, int minb);
+// v2b launcher (fused2b.cu): tb threads per CTA, pf rows in flight, minb = register cap as CTAs per SM
+cudaError_t pycs_launch_fused2b(const FusedArgs& a, int recon, int split, int mask, int tb, int pf, int minb,
+                                int nblocks, cudaStream_t st);
+int pycs_fused2b_resident(int recon, int split, int mask, int tb, int pf, int minb);
+bool pycs_fused2b_has(int recon, int split, int tb, int pf, int minb);

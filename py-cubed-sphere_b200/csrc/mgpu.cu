@@ -35,26 +35,36 @@ __global__ void mg_wait_kernel(const MgSync* sync, int world, long long epoch) {
 
 struct ScatterJob { double* dst; int i0, i1, j0, j1; };
 struct ScatterJobs { int n; ScatterJob job[MG_MAX_JOBS]; };
-
-// copy the rectangles [i0,i1) x [j0,j1) of all six panels of src into the same positions of dst
-__global__ void mg_scatter_kernel(Geo g, ScatterJobs jobs, const double* __restrict__ src) {
-  const ScatterJob jb = jobs.job[blockIdx.z];
-  const int w = jb.j1 - jb.j0, n = (jb.i1 - jb.i0) * w;
-  const int p = blockIdx.y;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-    const int i = jb.i0 + t / w, j = jb.j0 + t % w;
-    const long long id = gidx(g, p, i, j);
-    jb.dst[id] = src[id];
-  }
-  __threadfence_system();
-}
-
 struct PeerSync { MgSync* s[MG_MAX_WORLD]; };
 
-// reduce this rank's MF-PR partials in a fixed order, publish the sum and raise the flag
-__global__ void mg_publish_kernel(PeerSync peers, int world, int rank, const double* __restrict__ part, int npart,
-                                  int parity, long long epoch) {
+// One launch per step: (1) copy the rectangles [i0,i1) x [j0,j1) of all six panels of src into
+// the same positions of the peers' arrays; (2) the last block to finish reduces this rank's
+// MF-PR partials in a fixed order, publishes the sum and raises the flag on every rank
+// (system-scope fences order the data stores before the flag).
+__global__ void mg_exchange_kernel(Geo g, ScatterJobs jobs, const double* __restrict__ src, PeerSync peers,
+                                   int world, int rank, const double* __restrict__ part, int npart, int parity,
+                                   long long epoch, unsigned* __restrict__ counter) {
   __shared__ double sh[32];
+  __shared__ int last;
+  {
+    const ScatterJob jb = jobs.job[blockIdx.z];
+    const int w = jb.j1 - jb.j0, n = (jb.i1 - jb.i0) * w;
+    const int p = blockIdx.y;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+      const int i = jb.i0 + t / w, j = jb.j0 + t % w;
+      const long long id = gidx(g, p, i, j);
+      jb.dst[id] = src[id];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+    last = (atomicAdd(counter, 1u) == total - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system();
   double v = 0.0;
   for (int k = threadIdx.x; k < npart; k += blockDim.x) v += part[k];
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -64,12 +74,13 @@ __global__ void mg_publish_kernel(PeerSync peers, int world, int rank, const dou
     double t = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
     sh[0] = t;
+    *counter = 0;
   }
   __syncthreads();
   if (threadIdx.x < world) {
     MgSync* s = peers.s[threadIdx.x];
     s->psum[parity][rank] = sh[0];
-    __threadfence_system();            // data stores of the scatter kernel and the sum before the flag
+    __threadfence_system();
     *((volatile long long*)&s->flag[rank]) = epoch;
   }
 }
@@ -126,6 +137,8 @@ int k_mg_init(pycs_handle h, int rank, int world, unsigned char* handles_out) {
   TRY(pycs_field_ptr(h, PYCS_F_Q_NEXT, &mg->alloc[1]));
   CK(cudaMalloc(&mg->sync, sizeof(MgSync)));
   CK(cudaMemset(mg->sync, 0, sizeof(MgSync)));
+  CK(cudaMalloc(&mg->counter, sizeof(unsigned)));
+  CK(cudaMemset(mg->counter, 0, sizeof(unsigned)));
   CK(cudaStreamSynchronize(h->stream));
   cudaIpcMemHandle_t hd[3];
   CK(cudaIpcGetMemHandle(&hd[0], mg->alloc[0]));
@@ -181,6 +194,7 @@ void k_mg_release(pycs_handle h) {
     cudaIpcCloseMemHandle(mg->peer_sync[d]);
   }
   if (mg->sync) cudaFree(mg->sync);
+  if (mg->counter) cudaFree(mg->counter);
   delete mg;
   h->mg = nullptr;
 }
@@ -215,13 +229,12 @@ int k_mg_exchange(pycs_handle h, const double* qnext, const double* part, int np
   }
   int gx = (nmax + 255) / 256;
   if (gx > 16) gx = 16;
-  mg_scatter_kernel<<<dim3(gx, 6, mg->njobs), 256, 0, h->stream>>>(h->g, js, qnext);
-  CKL(h);
   PeerSync ps;
   for (int d = 0; d < mg->world; ++d) ps.s[d] = mg->peer_sync[d];
   mg->epoch += 1;
-  mg_publish_kernel<<<1, 256, 0, h->stream>>>(ps, mg->world, mg->rank, part, npart, (int)(mg->epoch & 1),
-                                             mg->epoch);
+  mg_exchange_kernel<<<dim3(gx, 6, mg->njobs), 256, 0, h->stream>>>(h->g, js, qnext, ps, mg->world, mg->rank, part,
+                                                                    npart, (int)(mg->epoch & 1), mg->epoch,
+                                                                    mg->counter);
   CKL(h);
   return 0;
 }

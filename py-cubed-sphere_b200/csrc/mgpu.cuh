@@ -16,6 +16,7 @@ struct MgpuState {
   double* alloc[2];                  // this rank's two Q allocations, in export order
   double* peer_q[2][MG_MAX_WORLD];   // peer_q[i][d]: allocation i of rank d, mapped here
   MgSync* sync;
+  unsigned* counter;                 // blocks of the exchange kernel that have finished
   MgSync* peer_sync[MG_MAX_WORLD];
   long long epoch;                   // exchanges issued so far
   int njobs;
