@@ -230,11 +230,13 @@ def run_gpu(args):
     tp = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            # one ncu --set full capture of the same kernel at the single-GPU size (profiles/)
+            traffic = tj.get("dram_bytes_per_launch") if world == 1 else None
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "fused_step_kernel<%d,PPM-PL07,SP-AVLT>" % tb.value,
+                "traffic": traffic, "kernel": dev.step_kernel_name(),
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": BYTES_PER_CELL * own_cells,
                 "per": "GPU (each rank updates %d of %d rows of every panel)" % (slab[1] - slab[0], N),
                 "peak_source": peak_src, "grid": {"ctas": nblk.value, "threads": tb.value, "rows_per_chunk": rows.value},

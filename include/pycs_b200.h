@@ -197,6 +197,8 @@ int pycs_launch_count(pycs_handle h, int64_t* count);
 int pycs_time_step_kernel(pycs_handle h, int32_t reps, int32_t separable, float* ms);
 /* Launch geometry of the fused step kernel: threads per CTA, rows per chunk, CTAs. */
 int pycs_step_kernel_info(pycs_handle h, int32_t* threads, int32_t* rows_per_chunk, int32_t* nblocks);
+/* Which fused step kernel (and tuning point) this handle launches. */
+int pycs_step_kernel_name(pycs_handle h, char* name, int32_t name_len);
 
 #ifdef __cplusplus
 }

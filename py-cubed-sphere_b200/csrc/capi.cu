@@ -459,6 +459,12 @@ extern "C" int pycs_step_kernel_info(pycs_handle h, int32_t* threads, int32_t* r
   return 0;
 }
 
+extern "C" int pycs_step_kernel_name(pycs_handle h, char* name, int32_t name_len) {
+  if (!name || name_len < 2) return arg_fail("bad name buffer");
+  if (!k_fused_supported(h)) return arg_fail("no fused step kernel for this scheme tuple");
+  return k_fused_kernel_name(h, name, name_len);
+}
+
 extern "C" int pycs_adv_time_step_host(pycs_handle h, double* Q, int64_t k, double t, int32_t fused) {
   if (!Q) return arg_fail("null Q");
   CK(cudaSetDevice(h->device));

@@ -24,6 +24,7 @@
 // when the next consumer loads Q (the next step's fill + fused kernel, or the
 // flush kernel before anything else reads Q).  Algebraically identical, one
 // rounding apart from the reference order.
+#include <cstdio>
 #include "pycs_common.cuh"
 #include "fused_args.cuh"
 #include "fused3_core.cuh"
@@ -610,7 +611,7 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
   if (fs.rows == 0) {
     const int nrows = h->row_hi - h->row_lo;       // rows this handle updates (multi-GPU: its slab)
     const char* ei = getenv("PYCS_FUSED_IMPL");
-    int impl = ei ? atoi(ei) : 2;     // v2 is the faster one so far (profiles/r1_sweep_v3.log)
+    int impl = ei ? atoi(ei) : 4;     // v2b: fastest so far (profiles/r1_sweep_v2b.log); 2 = v2, 3 = v3
     const char* ew = getenv("PYCS_FUSED_NW");
     const char* ed = getenv("PYCS_FUSED_DEPTH");
     const char* er = getenv("PYCS_FUSED_ROWS");
@@ -844,6 +845,21 @@ int k_fused_time_kernel(pycs_handle h, int reps, int separable, float* ms) {
   CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
   fs.pending = 0;
   fs.ring_pending = 0;
+  return 0;
+}
+
+int k_fused_kernel_name(pycs_handle h, char* out, int len) {
+  FusedState& fs = g_fused[h];
+  TRY(fused_setup(h, fs));
+  if (fs.impl == 3)
+    snprintf(out, len, "fused3_kernel<recon=%d,split=%d,NW=%d,PF=%d,MINB=%d> (csrc/fused3.cu)", h->prm.recon,
+             h->prm.opsplit, fs.nw, fs.pf, fs.minb);
+  else if (fs.impl == 4)
+    snprintf(out, len, "fused2b_kernel<TB=%d,recon=%d,split=%d,PF=%d,MINB=%d> (csrc/fused2b.cu)", fs.tb, h->prm.recon,
+             h->prm.opsplit, fs.pf, fs.minb);
+  else
+    snprintf(out, len, "fused_step_kernel<TB=%d,recon=%d,split=%d,D=%d> (csrc/fused.cu)", fs.tb, h->prm.recon,
+             h->prm.opsplit, fs.depth);
   return 0;
 }
 

@@ -49,7 +49,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 
 template <int TB, int RECON, int SPLIT, int MASK, int PF, int MINB>
-__global__ void __launch_bounds__(TB, MINB) fused2b_kernel(FusedArgs a) {
+__global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
+  // MINB >= 10: register cap of MINB - 10 CTAs/SM and the march loop unrolled by the window length
   constexpr int RW = TB + 6;                 // staged row: columns jbase-6 .. jbase+TB-1
   constexpr int NS = (MASK & 1) ? 4 : 3, NL = (MASK & 1) ? 5 : 4;
   constexpr int DS = PF + 1, DL = PF + 4;
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(TB, MINB) fused2b_kernel(FusedArgs a) {
   int oL0 = 0, oL1 = (DL - 1) * LSLOT, oL2 = (DL - 2) * LSLOT, oL3 = (DL - 3) * LSLOT;
   int sb = 0;
   uint32_t parb = 0;
-#pragma unroll 1
+#pragma unroll(MINB >= 10 ? 5 : 1)
   for (int r = rfirst; r <= rlast; ++r) {
     while (!mbar_try_wait(&full[sb], parb)) {}
     RowPtrs R;
@@ -234,7 +235,7 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb,
   if (recon == 3 && split == 1) {
 #define TUNE(T, P, M) \
   if (tb == T && pf == P && minb == M) return launch_mask<T, 3, 1, P, M>(a, mask, nblocks, st, resident)
-    TUNE(160, 1, 4); TUNE(160, 2, 4); TUNE(160, 1, 5); TUNE(160, 2, 5); TUNE(160, 3, 4);
+    TUNE(160, 1, 4); TUNE(160, 2, 4); TUNE(160, 2, 14); TUNE(160, 1, 14); TUNE(128, 2, 15); TUNE(160, 1, 5); TUNE(160, 2, 5); TUNE(160, 3, 4);
     TUNE(128, 1, 5); TUNE(128, 2, 5); TUNE(128, 2, 6); TUNE(128, 3, 5);
     TUNE(192, 1, 4); TUNE(192, 2, 4); TUNE(192, 2, 3);
     TUNE(256, 1, 3); TUNE(256, 2, 3); TUNE(256, 2, 2);
@@ -255,7 +256,7 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb,
 bool pycs_fused2b_has(int recon, int split, int tb, int pf, int minb) {
   if (recon != 1 && recon != 3) return false;
   if (recon == 3 && split == 1) {
-    const int t[][3] = {{160, 1, 4}, {160, 2, 4}, {160, 1, 5}, {160, 2, 5}, {160, 3, 4}, {128, 1, 5}, {128, 2, 5},
+    const int t[][3] = {{160, 1, 4}, {160, 2, 4}, {160, 2, 14}, {160, 1, 14}, {128, 2, 15}, {160, 1, 5}, {160, 2, 5}, {160, 3, 4}, {128, 1, 5}, {128, 2, 5},
                         {128, 2, 6}, {128, 3, 5}, {192, 1, 4}, {192, 2, 4}, {192, 2, 3}, {256, 1, 3}, {256, 2, 3},
                         {256, 2, 2}};
     for (auto& x : t)

@@ -136,6 +136,7 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable);
 int k_wind_resync(pycs_handle h, long long kprev);
 int k_fused_time_kernel(pycs_handle h, int reps, int separable, float* ms);
 int k_fused_grid_info(pycs_handle h, int* tb, int* rows, int* nblocks);
+int k_fused_kernel_name(pycs_handle h, char* out, int len);
 int k_fused_flush(pycs_handle h);
 void k_fused_release(pycs_handle h);
 void k_fused_invalidate(pycs_handle h);

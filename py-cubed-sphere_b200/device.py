@@ -97,6 +97,7 @@ def load_library():
         "pycs_launch_count": [h, C.POINTER(C.c_int64)],
         "pycs_time_step_kernel": [h, C.c_int32, C.c_int32, C.POINTER(C.c_float)],
         "pycs_step_kernel_info": [h, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
+        "pycs_step_kernel_name": [h, C.c_char_p, C.c_int32],
         "pycs_mgpu_init": [h, C.c_int32, C.c_int32, C.c_char_p],
         "pycs_mgpu_connect": [h, C.c_char_p],
         "pycs_mgpu_row_range": [h, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
@@ -200,6 +201,11 @@ class Device:
         a, b = C.c_int32(), C.c_int32()
         self.call("pycs_mgpu_row_range", C.byref(a), C.byref(b))
         return a.value, b.value
+
+    def step_kernel_name(self):
+        buf = C.create_string_buffer(256)
+        self.call("pycs_step_kernel_name", buf, 256)
+        return buf.value.decode()
 
     def launches(self):
         n = C.c_int64()
