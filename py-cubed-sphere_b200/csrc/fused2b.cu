@@ -48,6 +48,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// one lane of a converged warp (the CUTLASS idiom: the compiler keeps the TMA operands in
+// uniform registers instead of uniformising per-thread values with a loop per instruction)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 template <int TB, int RECON, int SPLIT, int MASK, int PF, int MINB>
 __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   // MINB >= 10: register cap of MINB - 10 CTAs/SM and the march loop unrolled by the window length
@@ -70,6 +78,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   b /= 6;
   const int strip = b % a.nstrips, chunk = b / a.nstrips;
   const int tid = threadIdx.x;
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp index, provably warp-uniform
   const int e = tid + 3;                     // own element in a staged row (the y-stencil reaches e-3 .. e+2)
   const int jbase = g.lo + strip * a.wcols;
   const int jend = min(jbase + a.wcols, g.hi);
@@ -92,31 +101,53 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   }
   __syncthreads();
 
+  // TMA row copies are issued by one elected lane of warp 0 (one row per marched row, PF rows ahead).  Its slot
+  // offsets rotate in registers and the global addresses are base + row * ld: the issue path
+  // sits between barrier A and barrier B of warp 0, so it is kept short.
+  const uint32_t ringS_a = smem_u32(ringS), ringL_a = smem_u32(ringL), full_a = smem_u32(full);
+  const double* const gq = a.q + (long long)p * g.ps + PYCS_JOFF + c0;
+  const double* const gv = a.va + (long long)p * g.ps + PYCS_JOFF + c0;
+  const double* const gu = a.ua + (long long)p * g.ps + PYCS_JOFF + c0;
+  const double* const gvm = a.vm + (long long)p * g.ps + PYCS_JOFF + c0;
+  const double* const gum = a.um + (long long)p * g.ps + PYCS_JOFF + c0;
+  const double* const gsgc = a.sgc + PYCS_JOFF + c0;
+  const double* const gsgv = a.sgv + PYCS_JOFF + c0;
+  const double* const grgc = a.rgc + PYCS_JOFF + c0;
+  const double* const gsgu = a.sgu + PYCS_JOFF + c0;
+  int iS = 0, iL = 0, ib = 0;                // slot byte offsets / barrier index of the next row to issue
+  auto tma = [&](uint32_t dst, const double* src, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(row_bytes), "r"(bar)
+                 : "memory");
+  };
   auto issue = [&](int r) {                  // thread 0 only
-    const int k = r - rfirst;
-    double* dS = ringS + (k % DS) * SSLOT;
-    double* dL = ringL + (k % DL) * LSLOT;
-    uint64_t* bar = &full[k % DL];
-    const long long colb = (long long)p * g.ps + PYCS_JOFF + c0;
-    const long long colm = PYCS_JOFF + c0;
+    const uint32_t dS = ringS_a + (uint32_t)iS, dL = ringL_a + (uint32_t)iL, bar = full_a + 8u * (uint32_t)ib;
     const long long rr = (long long)r * g.ld, r1_ = (long long)max(r - 1, 0) * g.ld,
                     r2_ = (long long)max(r - 2, 0) * g.ld;
-    mbar_expect_tx(bar, row_bytes * (NS + NL));
-    tma_row(dS + S_Q * RW, a.q + colb + rr, row_bytes, bar);
-    tma_row(dL + L_V * RW, a.va + colb + rr, row_bytes, bar);
-    tma_row(dL + L_SGC * RW, a.sgc + colm + rr, row_bytes, bar);
-    tma_row(dL + L_SGV * RW, a.sgv + colm + rr, row_bytes, bar);
-    tma_row(dL + L_RGC * RW, a.rgc + colm + rr, row_bytes, bar);
-    tma_row(dS + S_SGU * RW, a.sgu + colm + r1_, row_bytes, bar);
-    tma_row(dS + S_U * RW, a.ua + colb + r2_, row_bytes, bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * (NS + NL))
+                 : "memory");
+    tma(dS + 8u * S_Q * RW, gq + rr, bar);
+    tma(dL + 8u * L_V * RW, gv + rr, bar);
+    tma(dL + 8u * L_SGC * RW, gsgc + rr, bar);
+    tma(dL + 8u * L_SGV * RW, gsgv + rr, bar);
+    tma(dL + 8u * L_RGC * RW, grgc + rr, bar);
+    tma(dS + 8u * S_SGU * RW, gsgu + r1_, bar);
+    tma(dS + 8u * S_U * RW, gu + r2_, bar);
     if (MASK & 1) {
-      tma_row(dL + L_VM * RW, a.vm + colb + rr, row_bytes, bar);
-      tma_row(dS + S_UM * RW, a.um + colb + r2_, row_bytes, bar);
+      tma(dL + 8u * L_VM * RW, gvm + rr, bar);
+      tma(dS + 8u * S_UM * RW, gum + r2_, bar);
     }
   };
-  if (tid == 0) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (int r = rfirst; r < rfirst + PF && r <= rlast; ++r) issue(r);
+  if (warp_u == 0) {
+    for (int r = rfirst; r < rfirst + PF && r <= rlast; ++r) {
+      if (elect_one()) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(r);
+      }
+      iS = (iS + 8 * SSLOT == 8 * DS * SSLOT) ? 0 : iS + 8 * SSLOT;
+      iL = (iL + 8 * LSLOT == 8 * DL * LSLOT) ? 0 : iL + 8 * LSLOT;
+      ib = (ib + 1 == DL) ? 0 : ib + 1;
+    }
   }
 
   double* __restrict__ QN = a.qn + (long long)p * g.ps + PYCS_JOFF + min(j, g.P - 1) + (long long)r0 * g.ld;
@@ -156,9 +187,14 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
     phase_x_inner<RECON, SPLIT, MASK>(L, X, R, cdx, ws, qx);
     sX[e] = qx[0];
     __syncthreads();                                   // barrier A
-    if (tid == 0 && r + PF <= rlast) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue(r + PF);
+    if (warp_u == 0 && r + PF <= rlast) {              // warp 0 issues the TMA copies of row r+PF
+      if (elect_one()) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(r + PF);
+      }
+      iS = (iS + 8 * SSLOT == 8 * DS * SSLOT) ? 0 : iS + 8 * SSLOT;
+      iL = (iL + 8 * LSLOT == 8 * DL * LSLOT) ? 0 : iL + 8 * LSLOT;
+      ib = (ib + 1 == DL) ? 0 : ib + 1;
     }
     // ---------------- phase 2: y-fluxes at edge j: inner on Q row r, outer on Qx row r-3
     double F[1], G[1], CF[1] = {0.0}, CG[1];
