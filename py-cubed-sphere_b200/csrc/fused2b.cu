@@ -177,14 +177,15 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
     R.sgc3 = ringL + oL3 + L_SGC * RW + e;
     R.rg3 = ringL + oL3 + L_RGC * RW + e;
     // pending MF-PR term on the own interior cell of the new row (neighbours read it after barrier A)
+    double qnew[1] = {R.q[0]};
     if (a.apply_corr && jint && r >= g.lo && r < g.hi) {
-      double* qp = ringS + oS + S_Q * RW + e;
-      *qp = fma(R.sgc0[0], corr, *qp);
+      qnew[0] = fma(R.sgc0[0], corr, qnew[0]);
+      ringS[oS + S_Q * RW + e] = qnew[0];
     }
     // ---------------- phase 1: own column
     XEdge X;
     double qx[1];
-    phase_x_inner<RECON, SPLIT, MASK>(L, X, R, cdx, ws, qx);
+    phase_x_inner<RECON, SPLIT, MASK>(L, X, R, qnew, cdx, ws, qx);
     sX[e] = qx[0];
     __syncthreads();                                   // barrier A
     if (warp_u == 0 && r + PF <= rlast) {              // warp 0 issues the TMA copies of row r+PF

@@ -202,7 +202,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB % 10) fused3_kernel(FusedA
     R.rg3 = ringL + oL3 + L_RGC * RW + ca;
     XEdge X;
     double qx[NC];
-    phase_x_inner<RECON, SPLIT, MASK>(L, X, R, cdx, ws, qx);
+    const double qnew[NC] = {R.q[0], R.q[CSTEP]};
+    phase_x_inner<RECON, SPLIT, MASK>(L, X, R, qnew, cdx, ws, qx);
     sx[0] = qx[0];
     sx[CSTEP] = qx[1];
     __syncwarp();

@@ -143,15 +143,18 @@ PYCS_HD void lane_init(Lane& L) {
 }
 
 // ---- phase 1: row r enters; inner x-flux at edge r-2; Qx row r-3 -> qx[NC] -------------
+// qnew[c]: Q of row r in the lane's columns (the caller loads it, and patches it when a
+// projection term is pending).
 template <int RECON, int SPLIT, int MASK>
-PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, double cdx, double ws, double qx[NC]) {
+PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, const double qnew[NC], double cdx, double ws,
+                           double qx[NC]) {
   constexpr int MT = (SPLIT == 3) ? 2 : 1;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const int o = c * CSTEP;
     double* q = L.qw[c];
     q[0] = q[1]; q[1] = q[2]; q[2] = q[3]; q[3] = q[4];
-    q[4] = R.q[o];
+    q[4] = qnew[c];
     double l2, r2;                                   // cell r-2
     edge_values<RECON>(q[0], q[1], q[2], q[3], q[4], l2, r2);
     double ub = R.u[o];
@@ -160,7 +163,8 @@ PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, double cdx, doub
     const double su1c = R.su1[o];
     const double gE = L.su2[c];
     const double gO = up ? L.su3[c] : su1c;
-    const double gC = up ? R.sgc3[o] : R.sgc2[o];
+    const double* gcp = up ? R.sgc3 : R.sgc2;       // one load from the selected row
+    const double gC = gcp[o];
     const double rg = R.rg3[o];
     double WE, WO, WG, cc;
     edge_weights<MT, !(MASK & 1)>(ub, up, cdx, gE, gO, gC, WE, WO, WG, cc);

@@ -96,7 +96,8 @@ void run(const Args& a) {
           P.sgv3 = ringL + oL3 + L_SGV * RW + ca; P.sgc3 = ringL + oL3 + L_SGC * RW + ca;
           P.rg3 = ringL + oL3 + L_RGC * RW + ca;
           double qx[NC];
-          phase_x_inner<RECON, SPLIT, MASK>(L[l], X[l], P, a.cdx, a.ws, qx);
+          const double qnew[NC] = {P.q[0], P.q[CSTEP]};
+          phase_x_inner<RECON, SPLIT, MASK>(L[l], X[l], P, qnew, a.cdx, a.ws, qx);
           sxrow[4 + l] = qx[0];
           sxrow[4 + l + CSTEP] = qx[1];
         }
