@@ -25,6 +25,8 @@
 // flush kernel before anything else reads Q).  Algebraically identical, one
 // rounding apart from the reference order.
 #include <cstdio>
+#include <map>
+#include <vector>
 #include "pycs_common.cuh"
 #include "fused_args.cuh"
 #include "fused3_core.cuh"
@@ -374,6 +376,15 @@ __global__ void __launch_bounds__(TB) fused_step_kernel(FusedArgs a) {
     double t = 0.0;
     for (int w = 0; w < TB / 32; ++w) t += sF[w];
     a.part[blockIdx.x] = t;
+    sF[40] = fused_last_writer(a.counter, gridDim.x) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  if (sF[40] != 0.0 && tid < 32) {            // last CTA of the launch: total in a fixed order
+    const double tot = fused_warp_sum(a.part, (int)gridDim.x, tid);
+    if (tid == 0) {
+      *a.sum_out = tot;
+      *a.counter = 0u;
+    }
   }
 }
 
@@ -577,6 +588,9 @@ cudaError_t launch_fused(const FusedArgs& a, int recon, int split, int mask, int
 struct FusedState {
   double* rgc = nullptr;       // 1/sqrtg_pc
   double* part = nullptr;
+  unsigned* counter = nullptr; // last-writer ticket of the step kernels
+  int prof = -1;               // PYCS_STEP_PROFILE: CUDA events around the kernels of every step
+  std::vector<cudaEvent_t> ev; // 4 per profiled step: start, after ghost fill, after step kernel, after exchange
   int npart_cap = 0;
   double* bu = nullptr;        // separable wind: ucontra(t = 0) incl. ghost edges
   double* bv = nullptr;        //                 vcontra(t = 0)
@@ -589,7 +603,6 @@ struct FusedState {
   int nw = 3, pf = 3, minb = 3; // v3: consumer warps per CTA, rows in flight, register cap (CTAs/SM)
 };
 
-#include <map>
 static std::map<pycs_handle, FusedState> g_fused;
 
 int k_fused_supported(pycs_handle h) {
@@ -703,6 +716,10 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
     fs.npart_cap = nb;
   }
   fs.npart = nb;
+  if (!fs.counter) {
+    CK(cudaMalloc(&fs.counter, sizeof(unsigned)));
+    CK(cudaMemsetAsync(fs.counter, 0, sizeof(unsigned), h->stream));
+  }
   return 0;
 }
 
@@ -712,14 +729,36 @@ int k_fused_flush(pycs_handle h) {
   auto it = g_fused.find(h);
   if (it == g_fused.end()) return 0;
   FusedState& fs = it->second;
+  if (fs.prof > 0 && fs.ev.size() >= 8) {      // PYCS_STEP_PROFILE: per-kernel device time of this run
+    cudaStreamSynchronize(h->stream);
+    const size_t ns = fs.ev.size() / 4, skip = ns > 8 ? 4 : 0;
+    double t[4] = {0, 0, 0, 0};
+    for (size_t k = skip; k < ns; ++k) {
+      float ms;
+      for (int j = 0; j < 3; ++j) {
+        cudaEventElapsedTime(&ms, fs.ev[4 * k + j], fs.ev[4 * k + j + 1]);
+        t[j] += ms;
+      }
+      if (k + 1 < ns) {
+        cudaEventElapsedTime(&ms, fs.ev[4 * k + 3], fs.ev[4 * k + 4]);
+        t[3] += ms;
+      }
+    }
+    const double n = (double)(ns - skip);
+    fprintf(stderr, "[pycs step profile] rank %d: %zu steps; ghost fill (+flag wait) %.2f us, winds+step kernel %.2f us, "
+                    "exchange %.2f us, gap to next step %.2f us\n",
+            h->mg ? h->mg->rank : 0, ns - skip, 1e3 * t[0] / n, 1e3 * t[1] / n, 1e3 * t[2] / n, 1e3 * t[3] / n);
+    for (auto e : fs.ev) cudaEventDestroy(e);
+    fs.ev.clear();
+  }
   const Geo& g = h->g;
   double *sgc, *q, *qo;
   TRY(pycs_field_ptr(h, PYCS_F_SQRTG_PC, &sgc));
   TRY(pycs_field_ptr(h, h->qcur ? PYCS_F_Q_NEXT : PYCS_F_Q, &q));
   TRY(pycs_field_ptr(h, h->qcur ? PYCS_F_Q : PYCS_F_Q_NEXT, &qo));
   if (fs.pending) {
-    const double* sums = fs.part;
-    int nsums = fs.npart;
+    const double* sums = h->red_out + 9;   // total of the last step kernel's partials
+    int nsums = 1;
     if (h->mg) {                     // per-rank sums of the last exchange, once they have all arrived
       TRY(k_mg_wait(h));
       sums = k_mg_sums(h);
@@ -743,6 +782,7 @@ void k_fused_release(pycs_handle h) {
   if (it == g_fused.end()) return;
   if (it->second.rgc) cudaFree(it->second.rgc);
   if (it->second.part) cudaFree(it->second.part);
+  if (it->second.counter) cudaFree(it->second.counter);
   if (it->second.bu) cudaFree(it->second.bu);
   if (it->second.bv) cudaFree(it->second.bv);
   g_fused.erase(it);
@@ -810,6 +850,8 @@ static int launch_step_kernel(pycs_handle h, FusedState& fs, const double* qcur,
   a.ua = ua; a.va = va; a.um = um; a.vm = vm;
   a.sgc = sgc; a.rgc = fs.rgc; a.sgu = sgu; a.sgv = sgv;
   a.part = fs.part;
+  a.sum_out = h->red_out + 9;
+  a.counter = fs.counter;
   a.corr = h->red_out + 8;
   a.rows_per_chunk = fs.rows; a.nstrips = fs.nstrips; a.wcols = fs.wcols;
   a.row_lo = h->row_lo; a.row_hi = h->row_hi;
@@ -896,8 +938,8 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   if (separable) TRY(ensure_base_winds(h, fs));
 
   // 0. multi-GPU: the peers' halo rows, boundary strips and MF-PR sums of the last step are in
-  const double* sums = fs.part;
-  int nsums = fs.npart;
+  const double* sums = h->red_out + 9;     // total of the last step kernel's partials
+  int nsums = 1;
   const long long* mgflags = nullptr;
   int mgworld = 0;
   long long mgepoch = 0;
@@ -908,6 +950,15 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
     mgworld = h->mg->world;
     mgepoch = h->mg->epoch;
   }
+  if (fs.prof < 0) fs.prof = getenv("PYCS_STEP_PROFILE") ? 1 : 0;
+  auto mark = [&]() {
+    if (!fs.prof || fs.ev.size() >= 4 * 4096) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, h->stream);
+    fs.ev.push_back(e);
+  };
+  mark();
   // 1. ghost cells of Q (src/advection_timestep.py:28), folding in the pending MF-PR term
   int pend = fs.pending;
   {
@@ -917,6 +968,7 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
         h->red_out + 8, mgflags, mgworld, mgepoch, nbx);
     CKL(h);
   }
+  mark();
   // 2. winds (src/advection_timestep.py:31-37)
   if (h->prm.vf >= 2 && !separable) {
     TRY(k_wind_ghost_fill(h));
@@ -926,7 +978,9 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   int mask = separable ? 2 : ((h->prm.dp == 2) ? 1 : 0);    // RK1: averaged wind == instantaneous wind
   double ws = separable ? cos(3.141592653589793 * ((double)(k - 1) * g.dt) / 5.0) : 1.0;
   TRY(launch_step_kernel(h, fs, qcur, qnext, pend, mask, ws));
-  if (h->mg) TRY(k_mg_exchange(h, qnext, fs.part, fs.npart));
+  mark();
+  if (h->mg) TRY(k_mg_exchange(h, qnext, h->red_out + 9, 1));
+  mark();
   h->last_step_kernel_launches++;
   h->qcur ^= 1;
   fs.pending = (h->prm.mf == 3) ? 1 : 0;

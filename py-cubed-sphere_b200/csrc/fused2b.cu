@@ -233,6 +233,15 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
     double t = 0.0;
     for (int w = 0; w < TB / 32; ++w) t += sF[w];
     a.part[blockIdx.x] = t;
+    sF[40] = fused_last_writer(a.counter, gridDim.x) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  if (sF[40] != 0.0 && tid < 32) {            // last CTA of the launch: total in a fixed order
+    const double tot = fused_warp_sum(a.part, (int)gridDim.x, tid);
+    if (tid == 0) {
+      *a.sum_out = tot;
+      *a.counter = 0u;
+    }
   }
 }
 

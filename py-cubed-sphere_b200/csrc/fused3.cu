@@ -247,7 +247,19 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB % 10) fused3_kernel(FusedA
   // per-warp partial of sum(pxdF + pydF) over its outputs (MF-PR), fixed order
   double v = L.psum;
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  if (lane == 0) a.part[(long long)blockIdx.x * NW + warp] = v;
+  int last = 0;
+  if (lane == 0) {
+    a.part[(long long)blockIdx.x * NW + warp] = v;
+    last = fused_last_writer(a.counter, gridDim.x * NW) ? 1 : 0;
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (last) {                                  // last warp of the launch: total in a fixed order
+    const double tot = fused_warp_sum(a.part, (int)(gridDim.x * NW), lane);
+    if (lane == 0) {
+      *a.sum_out = tot;
+      *a.counter = 0u;
+    }
+  }
 }
 
 template <int NW, int PF, int MASK>

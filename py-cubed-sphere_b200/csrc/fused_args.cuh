@@ -10,13 +10,32 @@ struct FusedArgs {
   const double *ua, *va;      // U_pu.ucontra_averaged, U_pv.vcontra_averaged
   const double *um, *vm;      // mask sources (U_pu.ucontra, U_pv.vcontra)
   const double *sgc, *rgc, *sgu, *sgv;
-  double* part;
+  double* part;               // per-CTA (v3: per-warp) partial sums of pxdF + pydF
+  double* sum_out;            // their total, written by the last CTA of the launch (fixed order)
+  unsigned* counter;          // CTAs (warps) that have written their partial; reset by the last one
   const double* corr;         // device scalar: pending projection coefficient -sum(s)/a2
   int rows_per_chunk, nstrips, wcols, apply_corr;
   int row_lo, row_hi;         // rows this launch updates (the whole interior, or this rank's slab)
   double cdx, cdy;            // dt/dx, dt/dy
   double ws;                  // separable wind: U(t) = U(0) * ws (MASK & 2)
 };
+
+#ifdef __CUDACC__
+// The writer of the last partial of a launch adds them all up: consumers of the MF-PR sum
+// (ghost fill, flush, multi-GPU exchange) then read one scalar instead of reducing the list.
+__device__ __forceinline__ bool fused_last_writer(unsigned* counter, unsigned total) {
+  __threadfence();
+  return atomicAdd(counter, 1u) == total - 1u;
+}
+// one full warp; the result is valid in lane 0
+__device__ __forceinline__ double fused_warp_sum(const double* part, int n, int lane) {
+  __threadfence();
+  double v = 0.0;
+  for (int k = lane; k < n; k += 32) v += __ldcg(part + k);
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif
 
 // v3 launcher: nw consumer warps, pf rows in flight, minb = register cap as CTAs per SM
 cudaError_t pycs_launch_fused3(const FusedArgs& a, int recon, int split, int mask, int nw, int pf, int minb,
