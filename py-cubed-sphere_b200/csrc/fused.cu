@@ -421,11 +421,19 @@ __device__ __forceinline__ double dg_phase1_value(const Geo& g, const HaloMaps& 
   const int ge = (s == SIDE_E || s == SIDE_N) ? gl : PYCS_NG - 1 - gl;
   const int km = kminE[ge * g.P + k];
   const double* w = wE + ((long long)ge * g.P + k) * order;
-  double acc = 0.0;
-  for (int l = 0; l < order; ++l) {
-    double v = (s < 2) ? halo_src(q, sgc, g, m, gl, km + l, corr) : halo_src(q, sgc, g, m, km + l, gl, corr);
-    acc = __dadd_rn(acc, __dmul_rn(v, w[l]));
+  // all loads first (the fill is latency bound: one round trip for the sources instead of `order`)
+  double v[8], ww[8];
+#pragma unroll
+  for (int l = 0; l < 8; ++l) {
+    if (l < order) {
+      v[l] = (s < 2) ? halo_src(q, sgc, g, m, gl, km + l, corr) : halo_src(q, sgc, g, m, km + l, gl, corr);
+      ww[l] = w[l];
+    }
   }
+  double acc = 0.0;
+#pragma unroll
+  for (int l = 0; l < 8; ++l)
+    if (l < order) acc = __dadd_rn(acc, __dmul_rn(v[l], ww[l]));
   return acc;
 }
 
@@ -486,19 +494,25 @@ __global__ void dg_fill_fused_kernel(Geo g, HaloMaps maps, double* __restrict__ 
   const int ge = (s == SIDE_E) ? gl : PYCS_NG - 1 - gl;
   const int km = kminE[ge * g.P + k];
   const double* w = wE + ((long long)ge * g.P + k) * order;
-  double acc = 0.0;
-  for (int l = 0; l < order; ++l) {
-    const int b_ = km + l;
-    const int si = m.ci + m.ai * gl + m.bi * b_, sj = m.cj + m.aj * gl + m.bj * b_;
-    const bool ii = si >= g.lo && si < g.hi, jj = sj >= g.lo && sj < g.hi;
-    double v;
-    if (ii && jj) v = fma(sgc[gidx(g, 0, si, sj)], corr, q[gidx(g, m.nb, si, sj)]);
-    else if (ii) v = dg_phase1_value(g, maps, q, kminE, wE, order, sgc, corr, m.nb, sj >= g.hi ? SIDE_N : SIDE_S,
-                                     sj >= g.hi ? sj - g.hi : sj, si);
-    else v = dg_phase1_value(g, maps, q, kminE, wE, order, sgc, corr, m.nb, si >= g.hi ? SIDE_E : SIDE_W,
-                             si >= g.hi ? si - g.hi : si, sj);
-    acc = __dadd_rn(acc, __dmul_rn(v, w[l]));
+  double v[8], ww[8];
+#pragma unroll
+  for (int l = 0; l < 8; ++l) {
+    if (l < order) {
+      const int b_ = km + l;
+      const int si = m.ci + m.ai * gl + m.bi * b_, sj = m.cj + m.aj * gl + m.bj * b_;
+      const bool ii = si >= g.lo && si < g.hi, jj = sj >= g.lo && sj < g.hi;
+      if (ii && jj) v[l] = fma(sgc[gidx(g, 0, si, sj)], corr, q[gidx(g, m.nb, si, sj)]);
+      else if (ii) v[l] = dg_phase1_value(g, maps, q, kminE, wE, order, sgc, corr, m.nb, sj >= g.hi ? SIDE_N : SIDE_S,
+                                          sj >= g.hi ? sj - g.hi : sj, si);
+      else v[l] = dg_phase1_value(g, maps, q, kminE, wE, order, sgc, corr, m.nb, si >= g.hi ? SIDE_E : SIDE_W,
+                                  si >= g.hi ? si - g.hi : si, sj);
+      ww[l] = w[l];
+    }
   }
+  double acc = 0.0;
+#pragma unroll
+  for (int l = 0; l < 8; ++l)
+    if (l < order) acc = __dadd_rn(acc, __dmul_rn(v[l], ww[l]));
   const int i = (s == SIDE_E) ? g.hi + gl : gl;
   q[gidx(g, p, i, k)] = acc;
 }

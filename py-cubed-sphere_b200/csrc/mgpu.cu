@@ -37,51 +37,44 @@ struct ScatterJob { double* dst; int i0, i1, j0, j1; };
 struct ScatterJobs { int n; ScatterJob job[MG_MAX_JOBS]; };
 struct PeerSync { MgSync* s[MG_MAX_WORLD]; };
 
-// One launch per step: (1) copy the rectangles [i0,i1) x [j0,j1) of all six panels of src into
-// the same positions of the peers' arrays; (2) the last block to finish reduces this rank's
-// MF-PR partials in a fixed order, publishes the sum and raises the flag on every rank
-// (system-scope fences order the data stores before the flag).
+// One launch per step, one CTA per (job, panel): (1) copy the rectangle [i0,i1) x [j0,j1) of
+// one panel of src into the same position of a peer's array (block 0 also delivers this
+// rank's MF-PR sum); (2) system-scope fence, ticket; (3) the last CTA raises the flag on every
+// rank.  Latency, not bandwidth, is what matters here (<= 3 MB per rank and step).
 __global__ void mg_exchange_kernel(Geo g, ScatterJobs jobs, const double* __restrict__ src, PeerSync peers,
-                                   int world, int rank, const double* __restrict__ part, int npart, int parity,
+                                   int world, int rank, const double* __restrict__ sum, int parity,
                                    long long epoch, unsigned* __restrict__ counter) {
-  __shared__ double sh[32];
   __shared__ int last;
   {
-    const ScatterJob jb = jobs.job[blockIdx.z];
+    const ScatterJob jb = jobs.job[blockIdx.y];
     const int w = jb.j1 - jb.j0, n = (jb.i1 - jb.i0) * w;
-    const int p = blockIdx.y;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-      const int i = jb.i0 + t / w, j = jb.j0 + t % w;
-      const long long id = gidx(g, p, i, j);
-      jb.dst[id] = src[id];
+    const int p = blockIdx.x;
+    if (((w | jb.j0) & 1) == 0) {             // 16-byte aligned rectangle: two cells per store
+      const int w2 = w >> 1, n2 = n >> 1;
+      for (int t = threadIdx.x; t < n2; t += blockDim.x) {
+        const int i = jb.i0 + t / w2, j = jb.j0 + 2 * (t % w2);
+        const long long id = gidx(g, p, i, j);
+        *reinterpret_cast<double2*>(jb.dst + id) = *reinterpret_cast<const double2*>(src + id);
+      }
+    } else {
+      for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int i = jb.i0 + t / w, j = jb.j0 + t % w;
+        const long long id = gidx(g, p, i, j);
+        jb.dst[id] = src[id];
+      }
     }
   }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < world)
+    peers.s[threadIdx.x]->psum[parity][rank] = *sum;
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
-    last = (atomicAdd(counter, 1u) == total - 1);
-  }
+  if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x * gridDim.y - 1);
   __syncthreads();
   if (!last) return;
-  __threadfence_system();
-  double v = 0.0;
-  for (int k = threadIdx.x; k < npart; k += blockDim.x) v += part[k];
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
-    sh[0] = t;
-    *counter = 0;
-  }
-  __syncthreads();
+  if (threadIdx.x == 0) *counter = 0;
   if (threadIdx.x < world) {
-    MgSync* s = peers.s[threadIdx.x];
-    s->psum[parity][rank] = sh[0];
     __threadfence_system();
-    *((volatile long long*)&s->flag[rank]) = epoch;
+    *((volatile long long*)&peers.s[threadIdx.x]->flag[rank]) = epoch;
   }
 }
 
@@ -210,7 +203,7 @@ int k_mg_wait(pycs_handle h) {
 // where the W per-rank MF-PR sums of the last exchange live (this rank's copy)
 const double* k_mg_sums(pycs_handle h) { return h->mg->sync->psum[h->mg->epoch & 1]; }
 
-// after the step kernel wrote the own rows of `qnext`: deliver halos, sum and flag to the peers
+// after the step kernel wrote the own rows of `qnext`: deliver halos, sum (*part, one scalar) and flag
 int k_mg_exchange(pycs_handle h, const double* qnext, const double* part, int npart) {
   MgpuState* mg = h->mg;
   if (!mg->connected) {
@@ -227,14 +220,13 @@ int k_mg_exchange(pycs_handle h, const double* qnext, const double* part, int np
     const int n = (j.i1 - j.i0) * (j.j1 - j.j0);
     if (n > nmax) nmax = n;
   }
-  int gx = (nmax + 255) / 256;
-  if (gx > 16) gx = 16;
+  (void)nmax;
+  (void)npart;
   PeerSync ps;
   for (int d = 0; d < mg->world; ++d) ps.s[d] = mg->peer_sync[d];
   mg->epoch += 1;
-  mg_exchange_kernel<<<dim3(gx, 6, mg->njobs), 256, 0, h->stream>>>(h->g, js, qnext, ps, mg->world, mg->rank, part,
-                                                                    npart, (int)(mg->epoch & 1), mg->epoch,
-                                                                    mg->counter);
+  mg_exchange_kernel<<<dim3(6, mg->njobs), 512, 0, h->stream>>>(h->g, js, qnext, ps, mg->world, mg->rank, part,
+                                                                (int)(mg->epoch & 1), mg->epoch, mg->counter);
   CKL(h);
   return 0;
 }
