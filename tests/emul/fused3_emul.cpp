@@ -13,8 +13,10 @@
 #include <cstring>
 #include <vector>
 #include "../../py-cubed-sphere_b200/csrc/fused3_core.cuh"
-
-using namespace f3;
+#define F3_NAMESPACE f1
+#define F3_NC 1
+#define F3_CSTEP 0
+#include "../../py-cubed-sphere_b200/csrc/fused3_core.cuh"
 
 namespace {
 constexpr int JOFF = 12;   // PYCS_JOFF
@@ -30,6 +32,7 @@ struct Args {
 
 template <int RECON, int SPLIT, int MASK, int NW>
 void run(const Args& a) {
+  using namespace f3;
   constexpr int RW = RowWidth<NW>::value;
   constexpr int NS = (MASK & 1) ? 4 : 3, NL = (MASK & 1) ? 5 : 4;
   constexpr int SSLOT = NS * RW, LSLOT = NL * RW;
@@ -138,6 +141,115 @@ void run(const Args& a) {
   }
 }
 
+// ---- v2b (csrc/fused2b.cu): one column per thread, CTA = strip of TB-6 columns -------------
+template <int RECON, int SPLIT, int MASK>
+void run_block(const Args& a, int TB) {
+  using namespace f1;
+  const int RW = TB + 6;
+  const int NS = (MASK & 1) ? 4 : 3, NL = (MASK & 1) ? 5 : 4;
+  const int SSLOT = NS * RW, LSLOT = NL * RW;
+  const int PF = a.depth, DS = PF + 1, DL = PF + 4;
+  const int wmax = TB - 6;
+  const int nstrips = (a.N + wmax - 1) / wmax;
+  int wcols = (a.N + nstrips - 1) / nstrips;
+  wcols += wcols & 1;
+  const int nchunks = (a.N + a.rows_per_chunk - 1) / a.rows_per_chunk;
+  std::vector<double> buf((size_t)DS * SSLOT + (size_t)DL * LSLOT + 4 * RW);
+  double* ringS = buf.data();
+  double* ringL = ringS + DS * SSLOT;
+  double* sX = ringL + DL * LSLOT;
+  double *sF = sX + RW, *sG = sF + RW, *sC = sG + RW;
+  std::vector<Lane> L(TB);
+  std::vector<XEdge> X(TB);
+  std::vector<RowPtrs> R(TB);
+  std::vector<double> F(TB), G(TB), CF(TB);
+  for (int blk = 0; blk < 6 * nstrips * nchunks; ++blk) {
+    int b = blk;
+    const int p = b % 6;
+    b /= 6;
+    const int strip = b % nstrips, chunk = b / nstrips;
+    const int jbase = a.lo + strip * wcols;
+    const int jend = std::min(jbase + wcols, a.hi);
+    const int r0 = a.lo + chunk * a.rows_per_chunk;
+    const int r1 = std::min(r0 + a.rows_per_chunk, a.hi);
+    const int rfirst = r0 - 3, rlast = r1 + 2;
+    const int c0 = jbase - 6;
+    const int len = std::min(RW, a.ld - JOFF - c0) & ~1;
+    const long long colb = (long long)p * a.ps + JOFF + c0, colm = JOFF + c0;
+    std::fill(buf.begin(), buf.end(), 0.0);
+    for (int t = 0; t < TB; ++t) lane_init(L[t]);
+    int oS = 0, oL0 = 0, oL1 = (DL - 1) * LSLOT, oL2 = (DL - 2) * LSLOT, oL3 = (DL - 3) * LSLOT;
+    double psum = 0.0;
+    for (int r = rfirst; r <= rlast; ++r) {
+      {   // TMA row copies of row r
+        const int k = r - rfirst;
+        double* dS = ringS + (k % DS) * SSLOT;
+        double* dL = ringL + (k % DL) * LSLOT;
+        const long long rr = (long long)r * a.ld, rm1 = (long long)std::max(r - 1, 0) * a.ld,
+                        rm2 = (long long)std::max(r - 2, 0) * a.ld;
+        auto cp = [&](double* dst, const double* src) { std::memcpy(dst, src, sizeof(double) * len); };
+        cp(dS + S_Q * RW, a.q + colb + rr); cp(dL + L_V * RW, a.va + colb + rr);
+        cp(dL + L_SGC * RW, a.sgc + colm + rr); cp(dL + L_SGV * RW, a.sgv + colm + rr);
+        cp(dL + L_RGC * RW, a.rgc + colm + rr); cp(dS + S_SGU * RW, a.sgu + colm + rm1);
+        cp(dS + S_U * RW, a.ua + colb + rm2);
+        if (MASK & 1) { cp(dL + L_VM * RW, a.vm + colb + rr); cp(dS + S_UM * RW, a.um + colb + rm2); }
+      }
+      for (int t = 0; t < TB; ++t) {               // patch + phase 1
+        const int e = t + 3, j = jbase - 3 + t;
+        RowPtrs& P = R[t];
+        P.q = ringS + oS + S_Q * RW + e; P.u = ringS + oS + S_U * RW + e;
+        P.um = ringS + oS + S_UM * RW + e; P.su1 = ringS + oS + S_SGU * RW + e;
+        P.v0 = ringL + oL0 + L_V * RW + e; P.vm0 = ringL + oL0 + L_VM * RW + e;
+        P.sgv0 = ringL + oL0 + L_SGV * RW + e; P.sgc0 = ringL + oL0 + L_SGC * RW + e;
+        P.rg0 = ringL + oL0 + L_RGC * RW + e; P.sgc2 = ringL + oL2 + L_SGC * RW + e;
+        P.v3 = ringL + oL3 + L_V * RW + e; P.vm3 = ringL + oL3 + L_VM * RW + e;
+        P.sgv3 = ringL + oL3 + L_SGV * RW + e; P.sgc3 = ringL + oL3 + L_SGC * RW + e;
+        P.rg3 = ringL + oL3 + L_RGC * RW + e;
+        double qnew[1] = {P.q[0]};
+        if (a.apply_corr && j >= a.lo && j < a.hi && r >= a.lo && r < a.hi) {
+          qnew[0] = fma(P.sgc0[0], a.corr, qnew[0]);
+          ringS[oS + S_Q * RW + e] = qnew[0];
+        }
+        double qx[1];
+        phase_x_inner<RECON, SPLIT, MASK>(L[t], X[t], P, qnew, a.cdx, a.ws, qx);
+        sX[e] = qx[0];
+      }
+      for (int t = 0; t < TB; ++t) {               // barrier A; phase 2
+        const int e = t + 3;
+        double f[1], g[1], cf[1] = {0.0}, cg[1];
+        yflux_pair<RECON, SPLIT, MASK>(R[t].v0, R[t].vm0, R[t].sgv0, R[t].sgc0, R[t].q, a.cdy, a.ws, f, cf);
+        yflux_pair<RECON, SPLIT, MASK>(R[t].v3, R[t].vm3, R[t].sgv3, R[t].sgc3, sX + e, a.cdy, a.ws, g, cg);
+        F[t] = f[0]; G[t] = g[0]; CF[t] = cf[0];
+      }
+      for (int t = 0; t < TB; ++t) { sF[t + 3] = F[t]; sG[t + 3] = G[t]; sC[t + 3] = CF[t]; }
+      for (int t = 0; t < TB; ++t) {               // barrier B; phase 3
+        const int e = t + 3, j = jbase - 3 + t;
+        double f[1] = {F[t]}, g[1] = {G[t]}, cf[1] = {CF[t]};
+        double fn[1] = {sF[e + 1]}, gn[1] = {sG[e + 1]}, cfn[1] = {sC[e + 1]}, out[1], sdiv[1];
+        phase_x_outer<RECON, SPLIT>(L[t], X[t], R[t], f, fn, g, gn, cf, cfn, out, sdiv);
+        if (r >= r0 + 3 && t >= 3 && j < jend) {
+          a.qn[(long long)p * a.ps + JOFF + j + (long long)(r - 3) * a.ld] = out[0];
+          L[t].psum += sdiv[0];
+        }
+      }
+      oS = (oS + SSLOT == DS * SSLOT) ? 0 : oS + SSLOT;
+      oL3 = oL2; oL2 = oL1; oL1 = oL0;
+      oL0 = (oL0 + LSLOT == DL * LSLOT) ? 0 : oL0 + LSLOT;
+    }
+    for (int t = 0; t < TB; ++t) psum += L[t].psum;
+    a.part[blk] = psum;
+  }
+}
+
+template <int RECON, int SPLIT>
+int run_block_mask(const Args& a, int mask, int TB) {
+  if (mask == 0) run_block<RECON, SPLIT, 0>(a, TB);
+  else if (mask == 1) run_block<RECON, SPLIT, 1>(a, TB);
+  else if (mask == 2) run_block<RECON, SPLIT, 2>(a, TB);
+  else return -1;
+  return 0;
+}
+
 template <int RECON, int SPLIT, int NW>
 int run_mask(const Args& a, int mask) {
   if (mask == 0) run<RECON, SPLIT, 0, NW>(a);
@@ -159,12 +271,36 @@ extern "C" {
 // geometry helpers (mirror fused_setup in fused.cu)
 int f3_emul_ld(int N) { return ((JOFF + N + 8 + 1 + 15) / 16) * 16; }
 int f3_emul_grid(int N, int nw, int rows_per_chunk, int* nstrips, int* wcols, int* nchunks) {
-  const int cap = strip_capacity(nw);
+  const int cap = f3::strip_capacity(nw);
   *nstrips = (N + cap - 1) / cap;
   *wcols = (N + *nstrips - 1) / *nstrips;
   *wcols += *wcols & 1;
   *nchunks = (N + rows_per_chunk - 1) / rows_per_chunk;
   return 6 * *nstrips * *nchunks * nw;
+}
+// v2b decomposition (csrc/fused2b.cu): TB threads per CTA, one column each; depth = rows in flight.
+// Returns the number of partial sums written to part (one per CTA).
+int f3_emul_step_block(int N, int recon, int split, int mask, int TB, int depth, int rows_per_chunk, const double* q,
+                       double* qn, const double* ua, const double* va, const double* um, const double* vm,
+                       const double* sgc, const double* rgc, const double* sgu, const double* sgv, double* part,
+                       double corr, int apply_corr, double cdx, double cdy, double ws) {
+  Args a;
+  a.N = N; a.P = N + 8; a.ld = f3_emul_ld(N); a.lo = 4; a.hi = N + 4;
+  a.ps = (long long)(a.P + 1) * a.ld;
+  a.q = q; a.qn = qn; a.ua = ua; a.va = va; a.um = um; a.vm = vm;
+  a.sgc = sgc; a.rgc = rgc; a.sgu = sgu; a.sgv = sgv; a.part = part;
+  a.corr = corr; a.apply_corr = apply_corr; a.cdx = cdx; a.cdy = cdy; a.ws = ws;
+  a.rows_per_chunk = rows_per_chunk; a.depth = depth;
+  a.nstrips = a.wcols = 0;
+  if (depth < 1 || TB < 16) return -2;
+#define CASE(R, S) if (recon == R && split == S) return run_block_mask<R, S>(a, mask, TB)
+  CASE(3, 1); CASE(3, 2); CASE(3, 3); CASE(1, 1); CASE(1, 2); CASE(1, 3);
+#undef CASE
+  return -1;
+}
+int f3_emul_block_grid(int N, int TB, int rows_per_chunk) {
+  const int wmax = TB - 6;
+  return 6 * ((N + wmax - 1) / wmax) * ((N + rows_per_chunk - 1) / rows_per_chunk);
 }
 // One launch of the step kernel.  Arrays are in DEVICE layout ([panel][i][ld], column j at
 // j + 12); metric arrays hold one panel.  part has f3_emul_grid(...) entries.

@@ -31,6 +31,10 @@ def emul():
     dp = C.POINTER(C.c_double)
     lib.f3_emul_step.argtypes = [C.c_int] * 7 + [dp] * 11 + [C.c_double, C.c_int, C.c_double, C.c_double, C.c_double]
     lib.f3_emul_step.restype = C.c_int
+    lib.f3_emul_step_block.argtypes = lib.f3_emul_step.argtypes
+    lib.f3_emul_step_block.restype = C.c_int
+    lib.f3_emul_block_grid.argtypes = [C.c_int] * 3
+    lib.f3_emul_block_grid.restype = C.c_int
     lib.f3_emul_grid.argtypes = [C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 3
     lib.f3_emul_grid.restype = C.c_int
     lib.f3_emul_ld.argtypes = [C.c_int]
@@ -54,7 +58,7 @@ def ptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def one_step(emul, N, vf, tup, pre_steps, nw=3, depth=3, rows=None, pending=False, separable=False):
+def one_step(emul, N, vf, tup, pre_steps, nw=3, depth=3, rows=None, pending=False, separable=False, block_tb=0):
     from oracle.grid import LeanGrid
     from oracle import step as ost, wind as owind
     recon, dp, split, et, mt, mf = tup
@@ -94,11 +98,17 @@ def one_step(emul, N, vf, tup, pre_steps, nw=3, depth=3, rows=None, pending=Fals
             to_dev(mtc, ld, True), to_dev(rgc, ld, True), to_dev(g.metric_tensor_pu, ld, True),
             to_dev(g.metric_tensor_pv, ld, True)]
     rows = rows or N
-    ns, wc, nch = C.c_int(), C.c_int(), C.c_int()
-    npart = emul.f3_emul_grid(N, nw, rows, C.byref(ns), C.byref(wc), C.byref(nch))
-    part = np.zeros(npart)
-    rc = emul.f3_emul_step(N, recon, split, mask, nw, depth, rows, ptr(q), ptr(qn), *[ptr(a) for a in arrs],
-                           ptr(part), corr, 1 if pending else 0, dt / g.dx, dt / g.dy, ws)
+    if block_tb:        # v2b decomposition (csrc/fused2b.cu)
+        part = np.zeros(emul.f3_emul_block_grid(N, block_tb, rows))
+        rc = emul.f3_emul_step_block(N, recon, split, mask, block_tb, depth, rows, ptr(q), ptr(qn),
+                                     *[ptr(a) for a in arrs], ptr(part), corr, 1 if pending else 0,
+                                     dt / g.dx, dt / g.dy, ws)
+    else:               # v3 decomposition (csrc/fused3.cu)
+        ns, wc, nch = C.c_int(), C.c_int(), C.c_int()
+        npart = emul.f3_emul_grid(N, nw, rows, C.byref(ns), C.byref(wc), C.byref(nch))
+        part = np.zeros(npart)
+        rc = emul.f3_emul_step(N, recon, split, mask, nw, depth, rows, ptr(q), ptr(qn), *[ptr(a) for a in arrs],
+                               ptr(part), corr, 1 if pending else 0, dt / g.dx, dt / g.dy, ws)
     assert rc == 0
     got = np.transpose(qn[:, 4:N + 4, JOFF + 4:JOFF + 4 + N], (1, 2, 0)).copy()
     if mf == 3:                                          # deferred projection (src/discrete_operators.py:98-101)
@@ -147,4 +157,24 @@ def test_emulated_kernel_pending_projection(emul):
 def test_emulated_kernel_separable_wind(emul):
     """vf = 3 / RK1: wind(0) * cos(pi t / T) scaled inside the kernel."""
     got, want = one_step(emul, 50, 3, TUPLES["default"], 4, separable=True)
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+
+
+# ---- the default kernel's decomposition (v2b, csrc/fused2b.cu: one column per thread) ----------
+@pytest.mark.parametrize("N,vf,name,pre", CASES)
+def test_emulated_v2b_matches_oracle(emul, N, vf, name, pre):
+    got, want = one_step(emul, N, vf, TUPLES[name], pre, depth=2, block_tb=32 if N < 100 else 160)
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("tb,rows,depth,kw", [(32, 7, 1, {}), (64, 16, 2, {"pending": True}),
+                                              (160, 50, 3, {"separable": True}), (128, 9, 2, {"pending": True})])
+def test_emulated_v2b_shapes_patch_separable(emul, tb, rows, depth, kw):
+    got, want = one_step(emul, 50, 3, TUPLES["default"], 3, depth=depth, rows=rows, block_tb=tb, **kw)
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("tup", [(1, 1, 1, 3, 1, 3), (1, 2, 2, 3, 1, 1), (3, 1, 2, 3, 1, 3), (1, 1, 3, 3, 2, 1)])
+def test_emulated_v2b_other_schemes(emul, tup):
+    got, want = one_step(emul, 20, 2, tup, 2, depth=2, block_tb=32)
     assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
