@@ -390,12 +390,12 @@ __global__ void __launch_bounds__(TB) fused_step_kernel(FusedArgs a) {
 
 
 // ---- Lagrange ghost fill that honours the pending projection term ------------
-// Same arithmetic as dg_phase1_kernel in halo.cu (src/interpolation.py:200-248);
-// source cells are interior cells of the neighbour, which still miss sqrtg*corr.
-__device__ __forceinline__ double halo_src(const double* __restrict__ q, const double* __restrict__ sgc,
-                                           const Geo& g, const SideMap& m, int a, int b, double corr) {
-  int i = m.ci + m.ai * a + m.bi * b, j = m.cj + m.aj * a + m.bj * b;
-  return fma(sgc[gidx(g, 0, i, j)], corr, q[gidx(g, m.nb, i, j)]);
+// The fill is linear, so ghost(Q + corr*sqrtg) = ghost(Q) + corr * ghost(sqrtg): the second
+// factor is static and precomputed once (gs: the two-phase fill applied to the sqrtg field
+// itself, kept in the ghost cells of a 6-panel array).  The kernel therefore gathers only Q.
+__device__ __forceinline__ double halo_src(const double* __restrict__ q, const Geo& g, const SideMap& m, int a,
+                                           int b) {
+  return q[gidx(g, m.nb, m.ci + m.ai * a + m.bi * b, m.cj + m.aj * a + m.bj * b)];
 }
 
 // sum of n partials in a fixed order (every CTA gets the same bits)
@@ -415,25 +415,16 @@ __device__ double reduce_partials(const double* __restrict__ part, int n, double
 // position k along the edge.  Same operations in the same order as dg_phase1_kernel in halo.cu.
 __device__ __forceinline__ double dg_phase1_value(const Geo& g, const HaloMaps& maps, const double* __restrict__ q,
                                                   const int* __restrict__ kminE, const double* __restrict__ wE,
-                                                  int order, const double* __restrict__ sgc, double corr, int p,
-                                                  int s, int gl, int k) {
+                                                  int order, int p, int s, int gl, int k) {
   const SideMap& m = maps.m[p][s];
   const int ge = (s == SIDE_E || s == SIDE_N) ? gl : PYCS_NG - 1 - gl;
   const int km = kminE[ge * g.P + k];
   const double* w = wE + ((long long)ge * g.P + k) * order;
-  // all loads first (the fill is latency bound: one round trip for the sources instead of `order`)
-  double v[8], ww[8];
-#pragma unroll
-  for (int l = 0; l < 8; ++l) {
-    if (l < order) {
-      v[l] = (s < 2) ? halo_src(q, sgc, g, m, gl, km + l, corr) : halo_src(q, sgc, g, m, km + l, gl, corr);
-      ww[l] = w[l];
-    }
-  }
   double acc = 0.0;
-#pragma unroll
-  for (int l = 0; l < 8; ++l)
-    if (l < order) acc = __dadd_rn(acc, __dmul_rn(v[l], ww[l]));
+  for (int l = 0; l < order; ++l) {
+    double v = (s < 2) ? halo_src(q, g, m, gl, km + l) : halo_src(q, g, m, km + l, gl);
+    acc = __dadd_rn(acc, __dmul_rn(v, w[l]));
+  }
   return acc;
 }
 
@@ -445,9 +436,9 @@ __device__ __forceinline__ double dg_phase1_value(const Geo& g, const HaloMaps& 
 //     corner stencil reads the neighbour's strip, whose ends are that neighbour's phase-1
 //     ghosts; instead of waiting for them they are recomputed in registers (same arithmetic,
 //     same bits), so corners depend on interior cells only.
-// The pending MF-PR term (corr * sqrtg on interior cells) is folded into every source value.
+// Pending MF-PR term: ghost += corr * gs (see above); gs == nullptr computes the raw fill.
 __global__ void dg_fill_fused_kernel(Geo g, HaloMaps maps, double* __restrict__ q, const int* __restrict__ kminE,
-                                     const double* __restrict__ wE, int order, const double* __restrict__ sgc,
+                                     const double* __restrict__ wE, int order, const double* __restrict__ gs,
                                      const double* __restrict__ part, int npart, double inv_a2,
                                      double* __restrict__ corr_out, const long long* __restrict__ flags, int world,
                                      long long epoch, int nbx) {
@@ -474,13 +465,15 @@ __global__ void dg_fill_fused_kernel(Geo g, HaloMaps maps, double* __restrict__ 
     const int k = g.lo + bx * blockDim.x + threadIdx.x;
     if (k >= g.hi) return;
     const int p = ps >> 2, s = ps & 3;
-    const double acc = dg_phase1_value(g, maps, q, kminE, wE, order, sgc, corr, p, s, gl, k);
+    double acc = dg_phase1_value(g, maps, q, kminE, wE, order, p, s, gl, k);
     int i, j;
     if (s == SIDE_E) { i = g.hi + gl; j = k; }
     else if (s == SIDE_W) { i = gl; j = k; }
     else if (s == SIDE_N) { i = k; j = g.hi + gl; }
     else { i = k; j = gl; }
-    q[gidx(g, p, i, j)] = acc;
+    const long long id = gidx(g, p, i, j);
+    if (npart > 0) acc = fma(gs[id], corr, acc);
+    q[id] = acc;
     return;
   }
   // corners: 12 (panel, E|W) x 4 layers x 8 positions
@@ -494,27 +487,30 @@ __global__ void dg_fill_fused_kernel(Geo g, HaloMaps maps, double* __restrict__ 
   const int ge = (s == SIDE_E) ? gl : PYCS_NG - 1 - gl;
   const int km = kminE[ge * g.P + k];
   const double* w = wE + ((long long)ge * g.P + k) * order;
-  double v[8], ww[8];
-#pragma unroll
-  for (int l = 0; l < 8; ++l) {
-    if (l < order) {
-      const int b_ = km + l;
-      const int si = m.ci + m.ai * gl + m.bi * b_, sj = m.cj + m.aj * gl + m.bj * b_;
-      const bool ii = si >= g.lo && si < g.hi, jj = sj >= g.lo && sj < g.hi;
-      if (ii && jj) v[l] = fma(sgc[gidx(g, 0, si, sj)], corr, q[gidx(g, m.nb, si, sj)]);
-      else if (ii) v[l] = dg_phase1_value(g, maps, q, kminE, wE, order, sgc, corr, m.nb, sj >= g.hi ? SIDE_N : SIDE_S,
-                                          sj >= g.hi ? sj - g.hi : sj, si);
-      else v[l] = dg_phase1_value(g, maps, q, kminE, wE, order, sgc, corr, m.nb, si >= g.hi ? SIDE_E : SIDE_W,
-                                  si >= g.hi ? si - g.hi : si, sj);
-      ww[l] = w[l];
-    }
-  }
   double acc = 0.0;
-#pragma unroll
-  for (int l = 0; l < 8; ++l)
-    if (l < order) acc = __dadd_rn(acc, __dmul_rn(v[l], ww[l]));
+  for (int l = 0; l < order; ++l) {
+    const int b_ = km + l;
+    const int si = m.ci + m.ai * gl + m.bi * b_, sj = m.cj + m.aj * gl + m.bj * b_;
+    const bool ii = si >= g.lo && si < g.hi, jj = sj >= g.lo && sj < g.hi;
+    double v;
+    if (ii && jj) v = q[gidx(g, m.nb, si, sj)];
+    else if (ii) v = dg_phase1_value(g, maps, q, kminE, wE, order, m.nb, sj >= g.hi ? SIDE_N : SIDE_S,
+                                     sj >= g.hi ? sj - g.hi : sj, si);
+    else v = dg_phase1_value(g, maps, q, kminE, wE, order, m.nb, si >= g.hi ? SIDE_E : SIDE_W,
+                             si >= g.hi ? si - g.hi : si, sj);
+    acc = __dadd_rn(acc, __dmul_rn(v, w[l]));
+  }
   const int i = (s == SIDE_E) ? g.hi + gl : gl;
-  q[gidx(g, p, i, k)] = acc;
+  const long long id = gidx(g, p, i, k);
+  if (npart > 0) acc = fma(gs[id], corr, acc);
+  q[id] = acc;
+}
+
+// sqrtg of the single metric panel copied into the interior of all six panels of dst
+__global__ void spread_metric_kernel(Geo g, const double* __restrict__ sgc, double* __restrict__ dst) {
+  int j = g.lo + blockIdx.x * blockDim.x + threadIdx.x, i = g.lo + blockIdx.y, p = blockIdx.z;
+  if (j >= g.hi) return;
+  dst[gidx(g, p, i, j)] = sgc[gidx(g, 0, i, j)];
 }
 
 // add the pending projection term to the interior (before anything else reads Q)
@@ -601,6 +597,7 @@ cudaError_t launch_fused(const FusedArgs& a, int recon, int split, int mask, int
 // fused-path state kept next to the handle (one per handle, keyed by pointer)
 struct FusedState {
   double* rgc = nullptr;       // 1/sqrtg_pc
+  double* gs = nullptr;        // ghost cells: Lagrange fill of the sqrtg field (static)
   double* part = nullptr;
   unsigned* counter = nullptr; // last-writer ticket of the step kernels
   int prof = -1;               // PYCS_STEP_PROFILE: CUDA events around the kernels of every step
@@ -795,6 +792,7 @@ void k_fused_release(pycs_handle h) {
   auto it = g_fused.find(h);
   if (it == g_fused.end()) return;
   if (it->second.rgc) cudaFree(it->second.rgc);
+  if (it->second.gs) cudaFree(it->second.gs);
   if (it->second.part) cudaFree(it->second.part);
   if (it->second.counter) cudaFree(it->second.counter);
   if (it->second.bu) cudaFree(it->second.bu);
@@ -811,6 +809,8 @@ void k_fused_invalidate(pycs_handle h) {
   if (it == g_fused.end()) return;
   if (it->second.rgc) cudaFree(it->second.rgc);
   it->second.rgc = nullptr;
+  if (it->second.gs) cudaFree(it->second.gs);
+  it->second.gs = nullptr;
   it->second.base_valid = 0;
 }
 
@@ -950,6 +950,19 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   double* qcur = h->qcur ? qb : qa;
   double* qnext = h->qcur ? qa : qb;
   if (separable) TRY(ensure_base_winds(h, fs));
+  if (h->prm.mf == 3 && !fs.gs) {
+    // ghost(sqrtg): the fill applied to the metric field itself, once (see dg_fill_fused_kernel)
+    const size_t bytes = sizeof(double) * 6 * (size_t)g.ps;
+    CK(cudaMalloc(&fs.gs, bytes));
+    CK(cudaMemsetAsync(fs.gs, 0, bytes, h->stream));
+    spread_metric_kernel<<<dim3((g.N + 127) / 128, g.N, 6), 128, 0, h->stream>>>(g, sgc, fs.gs);
+    CKL(h);
+    const int nbx = (g.N + 127) / 128;
+    dg_fill_fused_kernel<<<nbx * 4 * 24 + 3, 128, 0, h->stream>>>(g, h->maps, fs.gs, h->kminE, h->wE, h->order,
+                                                                  nullptr, nullptr, 0, 0.0, h->red_out + 10, nullptr,
+                                                                  0, 0, nbx);
+    CKL(h);
+  }
 
   // 0. multi-GPU: the peers' halo rows, boundary strips and MF-PR sums of the last step are in
   const double* sums = h->red_out + 9;     // total of the last step kernel's partials
@@ -978,7 +991,7 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   {
     const int nbx = (g.N + 127) / 128;
     dg_fill_fused_kernel<<<nbx * 4 * 24 + 3, 128, 0, h->stream>>>(
-        g, h->maps, qcur, h->kminE, h->wE, h->order, sgc, sums, pend ? nsums : 0, pend ? 1.0 / h->a2 : 0.0,
+        g, h->maps, qcur, h->kminE, h->wE, h->order, fs.gs, sums, pend ? nsums : 0, pend ? 1.0 / h->a2 : 0.0,
         h->red_out + 8, mgflags, mgworld, mgepoch, nbx);
     CKL(h);
   }

@@ -66,9 +66,12 @@ __global__ void mg_exchange_kernel(Geo g, ScatterJobs jobs, const double* __rest
   }
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < world)
     peers.s[threadIdx.x]->psum[parity][rank] = *sum;
-  __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x * gridDim.y - 1);
+  if (threadIdx.x == 0) {
+    // one system-scope fence per CTA: it is cumulative over the stores the barrier ordered before it
+    __threadfence_system();
+    last = (atomicAdd(counter, 1u) == gridDim.x * gridDim.y - 1);
+  }
   __syncthreads();
   if (!last) return;
   if (threadIdx.x == 0) *counter = 0;
