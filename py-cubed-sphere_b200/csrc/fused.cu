@@ -600,6 +600,7 @@ struct FusedState {
   double* gs = nullptr;        // ghost cells: Lagrange fill of the sqrtg field (static)
   double* part = nullptr;
   unsigned* counter = nullptr; // last-writer ticket of the step kernels
+  int mg_fused = 1;            // multi-GPU: v2b stores to the peers itself (PYCS_MG_FUSED=0: separate exchange kernel)
   int prof = -1;               // PYCS_STEP_PROFILE: CUDA events around the kernels of every step
   std::vector<cudaEvent_t> ev; // 4 per profiled step: start, after ghost fill, after step kernel, after exchange
   int npart_cap = 0;
@@ -702,6 +703,7 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
       lag = 4;
     }
     fs.impl = impl;
+    if (const char* emf = getenv("PYCS_MG_FUSED")) fs.mg_fused = atoi(emf);
     cols = 6 * fs.nstrips;
     if (rows <= 0) {
       // whole waves of resident CTAs: time ~ waves * (rows + ramp)
@@ -869,6 +871,8 @@ static int launch_step_kernel(pycs_handle h, FusedState& fs, const double* qcur,
   a.corr = h->red_out + 8;
   a.rows_per_chunk = fs.rows; a.nstrips = fs.nstrips; a.wcols = fs.wcols;
   a.row_lo = h->row_lo; a.row_hi = h->row_hi;
+  a.mg.world = 0;
+  if (h->mg && fs.impl == 4 && fs.mg_fused) TRY(k_mg_fill_args(h, qnext, &a.mg));   // exchange inside the kernel
   a.apply_corr = pend;
   a.cdx = g.dt / g.dx; a.cdy = g.dt / g.dy;
   a.ws = ws;
@@ -1006,7 +1010,7 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   double ws = separable ? cos(3.141592653589793 * ((double)(k - 1) * g.dt) / 5.0) : 1.0;
   TRY(launch_step_kernel(h, fs, qcur, qnext, pend, mask, ws));
   mark();
-  if (h->mg) TRY(k_mg_exchange(h, qnext, h->red_out + 9, 1));
+  if (h->mg && !(fs.impl == 4 && fs.mg_fused)) TRY(k_mg_exchange(h, qnext, h->red_out + 9, 1));
   mark();
   h->last_step_kernel_launches++;
   h->qcur ^= 1;

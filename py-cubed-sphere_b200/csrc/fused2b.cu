@@ -16,6 +16,7 @@
 // (y-fluxes of Q row r and of Qx row r-3 at the thread's edge) | barrier | phase 3 (Qy, outer
 // x-flux, output row r-3).
 #include "fused_args.cuh"
+#include "mgpu.cuh"
 #define F3_NAMESPACE f1
 #define F3_NC 1
 #define F3_CSTEP 0
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   const bool jint = (j >= g.lo) && (j < g.hi);
   const double corr = a.apply_corr ? *a.corr : 0.0;
   const double cdx = a.cdx, cdy = a.cdy, ws = a.ws;
+  const int mgw = a.mg.world;
   const int c0 = jbase - 6;                  // 16-byte aligned: JOFF and wcols are even
   const int len = min(RW, g.ld - PYCS_JOFF - c0) & ~1;
   const uint32_t row_bytes = (uint32_t)len * 8u;
@@ -215,6 +217,20 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
       if (out_lane) {
         *QN = out[0];
         L.psum += sdiv[0];
+        if (mgw > 1) {
+          // fused exchange: the peers need this cell if it lies in a 4-wide boundary strip of the
+          // panel (sources of their ghost fill) or in the 3 rows next to a neighbour's slab
+          const int ro = r - 3;
+          const long long off = QN - a.qn;
+          const bool strip = j < g.lo + PYCS_NG || j >= g.hi - PYCS_NG || ro < g.lo + PYCS_NG || ro >= g.hi - PYCS_NG;
+          if (strip) {
+            for (int d = 0; d < mgw; ++d)
+              if (d != a.mg.rank) a.mg.peer_qn[d][off] = out[0];
+          } else {
+            if (ro < a.row_lo + 3 && a.mg.rank > 0) a.mg.peer_qn[a.mg.rank - 1][off] = out[0];
+            if (ro >= a.row_hi - 3 && a.mg.rank < mgw - 1) a.mg.peer_qn[a.mg.rank + 1][off] = out[0];
+          }
+        }
       }
       QN += g.ld;
     }
@@ -233,14 +249,23 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
     double t = 0.0;
     for (int w = 0; w < TB / 32; ++w) t += sF[w];
     a.part[blockIdx.x] = t;
-    sF[40] = fused_last_writer(a.counter, gridDim.x) ? 1.0 : 0.0;
+    sF[40] = fused_last_writer(a.counter, gridDim.x, mgw > 1) ? 1.0 : 0.0;
   }
   __syncthreads();
   if (sF[40] != 0.0 && tid < 32) {            // last CTA of the launch: total in a fixed order
-    const double tot = fused_warp_sum(a.part, (int)gridDim.x, tid);
+    double tot = fused_warp_sum(a.part, (int)gridDim.x, tid);
     if (tid == 0) {
       *a.sum_out = tot;
       *a.counter = 0u;
+    }
+    if (mgw > 1) {                            // publish this rank's sum, then raise its flag everywhere
+      tot = __shfl_sync(0xffffffffu, tot, 0);
+      if (tid < mgw) {
+        MgSync* sy = a.mg.peer_sync[tid];
+        sy->psum[a.mg.parity][a.mg.rank] = tot;
+        __threadfence_system();
+        *((volatile long long*)&sy->flag[a.mg.rank]) = a.mg.epoch;
+      }
     }
   }
 }

@@ -3,6 +3,17 @@
 #pragma once
 #include "pycs_common.cuh"
 
+// Multi-GPU part of a fused launch (csrc/mgpu.cu): with world > 1 the step kernel itself stores
+// the cells its peers need (boundary strips, halo rows) into their Q arrays over NVLink and its
+// last CTA publishes the MF-PR sum and raises the flags -- compute and exchange in ONE kernel.
+struct MgSync;
+struct FusedMg {
+  int world, rank, parity;
+  long long epoch;
+  double* peer_qn[8];         // the peers' output arrays (same layout, same positions)
+  MgSync* peer_sync[8];
+};
+
 struct FusedArgs {
   Geo g;
   const double* q;
@@ -18,13 +29,15 @@ struct FusedArgs {
   int row_lo, row_hi;         // rows this launch updates (the whole interior, or this rank's slab)
   double cdx, cdy;            // dt/dx, dt/dy
   double ws;                  // separable wind: U(t) = U(0) * ws (MASK & 2)
+  FusedMg mg;                 // world <= 1: single GPU
 };
 
 #ifdef __CUDACC__
 // The writer of the last partial of a launch adds them all up: consumers of the MF-PR sum
 // (ghost fill, flush, multi-GPU exchange) then read one scalar instead of reducing the list.
-__device__ __forceinline__ bool fused_last_writer(unsigned* counter, unsigned total) {
-  __threadfence();
+__device__ __forceinline__ bool fused_last_writer(unsigned* counter, unsigned total, bool sys = false) {
+  if (sys) __threadfence_system();           // peer stores of this CTA before the ticket
+  else __threadfence();
   return atomicAdd(counter, 1u) == total - 1u;
 }
 // one full warp; the result is valid in lane 0

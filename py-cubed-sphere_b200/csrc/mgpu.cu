@@ -17,6 +17,7 @@
 #include <cstring>
 #include "pycs_common.cuh"
 #include "mgpu.cuh"
+#include "fused_args.cuh"
 
 namespace {
 
@@ -231,5 +232,26 @@ int k_mg_exchange(pycs_handle h, const double* qnext, const double* part, int np
   mg_exchange_kernel<<<dim3(6, mg->njobs), 512, 0, h->stream>>>(h->g, js, qnext, ps, mg->world, mg->rank, part,
                                                                 (int)(mg->epoch & 1), mg->epoch, mg->counter);
   CKL(h);
+  return 0;
+}
+
+// The same exchange done by the step kernel itself (fused2b.cu): fill the multi-GPU part of its
+// arguments for a launch that writes `qnext`, and account for the exchange it will perform.
+int k_mg_fill_args(pycs_handle h, const double* qnext, FusedMg* out) {
+  MgpuState* mg = h->mg;
+  if (!mg->connected) {
+    pycs_set_error("multi-GPU step before pycs_mgpu_connect");
+    return PYCS_ERR_STATE;
+  }
+  const int idx = (qnext == mg->alloc[0]) ? 0 : 1;
+  mg->epoch += 1;
+  out->world = mg->world;
+  out->rank = mg->rank;
+  out->parity = (int)(mg->epoch & 1);
+  out->epoch = mg->epoch;
+  for (int d = 0; d < MG_MAX_WORLD; ++d) {
+    out->peer_qn[d] = d < mg->world ? mg->peer_q[idx][d] : nullptr;
+    out->peer_sync[d] = d < mg->world ? mg->peer_sync[d] : nullptr;
+  }
   return 0;
 }

@@ -32,3 +32,5 @@ int k_mg_wait(pycs_handle h);
 const double* k_mg_sums(pycs_handle h);
 int k_mg_exchange(pycs_handle h, const double* qnext, const double* part, int npart);
 void k_fused_reset_grid(pycs_handle h);
+struct FusedMg;
+int k_mg_fill_args(pycs_handle h, const double* qnext, FusedMg* out);

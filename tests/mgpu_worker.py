@@ -33,8 +33,11 @@ def main():
     if len(sys.argv) > 1:
         cases = [(int(sys.argv[1]), 3, "default", (10,))]
     worst = 0.0
-    for impl in ("2", "3"):
-        os.environ["PYCS_FUSED_IMPL"] = impl
+    # 4 = default kernel (exchange fused into the step kernel); 4x = same kernel with the separate
+    # exchange launch; 2, 3 = older kernels (separate exchange launch)
+    for impl in ("4", "4x", "2", "3"):
+        os.environ["PYCS_FUSED_IMPL"] = impl[0]
+        os.environ["PYCS_MG_FUSED"] = "0" if impl.endswith("x") else "1"
         for N, vf, name, calls in cases:
             g = cs_datastruct.cubed_sphere(N)
             a = make(g, vf, TUPLES[name], local)
