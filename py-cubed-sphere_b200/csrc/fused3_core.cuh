@@ -163,8 +163,8 @@ PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, const double qne
     const double su1c = R.su1[o];
     const double gE = L.su2[c];
     const double gO = up ? L.su3[c] : su1c;
-    const double* gcp = up ? R.sgc3 : R.sgc2;       // one load from the selected row
-    const double gC = gcp[o];
+    const double gC = up ? R.sgc3[o] : R.sgc2[o];   // both loads are issued early; a pointer select
+                                                    // would put the LDS behind the wind-sign compare
     const double rg = R.rg3[o];
     double WE, WO, WG, cc;
     edge_weights<MT, !(MASK & 1)>(ub, up, cdx, gE, gO, gC, WE, WO, WG, cc);
