@@ -57,7 +57,9 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-template <int TB, int RECON, int SPLIT, int MASK, int PF, int MINB>
+// MG: multi-GPU build -- the kernel stores boundary cells to the peers and publishes sum + flags
+// (kept out of the single-GPU instantiation: the extra code in the unrolled march loop costs ~7 %)
+template <int TB, int RECON, int SPLIT, int MASK, int PF, int MINB, int MG>
 __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   // MINB >= 10: register cap of MINB - 10 CTAs/SM and the march loop unrolled by the window length
   constexpr int RW = TB + 6;                 // staged row: columns jbase-6 .. jbase+TB-1
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   const bool jint = (j >= g.lo) && (j < g.hi);
   const double corr = a.apply_corr ? *a.corr : 0.0;
   const double cdx = a.cdx, cdy = a.cdy, ws = a.ws;
-  const int mgw = a.mg.world;
+  const int mgw = MG ? a.mg.world : 0;
   const int c0 = jbase - 6;                  // 16-byte aligned: JOFF and wcols are even
   const int len = min(RW, g.ld - PYCS_JOFF - c0) & ~1;
   const uint32_t row_bytes = (uint32_t)len * 8u;
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   int oL0 = 0, oL1 = (DL - 1) * LSLOT, oL2 = (DL - 2) * LSLOT, oL3 = (DL - 3) * LSLOT;
   int sb = 0;
   uint32_t parb = 0;
-#pragma unroll(MINB >= 10 ? 5 : 1)
+#pragma unroll((MINB >= 10 && !MG) ? 5 : 1)
   for (int r = rfirst; r <= rlast; ++r) {
     while (!mbar_try_wait(&full[sb], parb)) {}
     RowPtrs R;
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
       if (out_lane) {
         *QN = out[0];
         L.psum += sdiv[0];
-        if (mgw > 1) {
+        if (MG && mgw > 1) {
           // fused exchange: the peers need this cell if it lies in a 4-wide boundary strip of the
           // panel (sources of their ghost fill) or in the 3 rows next to a neighbour's slab
           const int ro = r - 3;
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
       *a.sum_out = tot;
       *a.counter = 0u;
     }
-    if (mgw > 1) {                            // publish this rank's sum, then raise its flag everywhere
+    if (MG && mgw > 1) {                      // publish this rank's sum, then raise its flag everywhere
       tot = __shfl_sync(0xffffffffu, tot, 0);
       if (tid < mgw) {
         MgSync* sy = a.mg.peer_sync[tid];
@@ -276,11 +278,11 @@ constexpr size_t smem_bytes() {
          sizeof(uint64_t) * (PF + 4) + 16;
 }
 
-template <int TB, int RECON, int SPLIT, int MASK, int PF, int MINB>
-cudaError_t launch_one(const FusedArgs& a, int nblocks, cudaStream_t st, int* resident) {
+template <int TB, int RECON, int SPLIT, int MASK, int PF, int MINB, int MG>
+cudaError_t launch_mg(const FusedArgs& a, int nblocks, cudaStream_t st, int* resident) {
   static bool configured = false;
   const size_t smem = smem_bytes<TB, PF, MASK>();
-  auto kern = fused2b_kernel<TB, RECON, SPLIT, MASK, PF, MINB>;
+  auto kern = fused2b_kernel<TB, RECON, SPLIT, MASK, PF, MINB, MG>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -289,6 +291,12 @@ cudaError_t launch_one(const FusedArgs& a, int nblocks, cudaStream_t st, int* re
   if (resident) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(resident, kern, TB, smem);
   kern<<<nblocks, TB, smem, st>>>(a);
   return cudaSuccess;
+}
+
+template <int TB, int RECON, int SPLIT, int MASK, int PF, int MINB>
+cudaError_t launch_one(const FusedArgs& a, int nblocks, cudaStream_t st, int* resident) {
+  if (a.mg.world > 1) return launch_mg<TB, RECON, SPLIT, MASK, PF, MINB, 1>(a, nblocks, st, resident);
+  return launch_mg<TB, RECON, SPLIT, MASK, PF, MINB, 0>(a, nblocks, st, resident);
 }
 
 template <int TB, int RECON, int SPLIT, int PF, int MINB>
