@@ -600,7 +600,7 @@ struct FusedState {
   double* gs = nullptr;        // ghost cells: Lagrange fill of the sqrtg field (static)
   double* part = nullptr;
   unsigned* counter = nullptr; // last-writer ticket of the step kernels
-  int mg_fused = 1;            // multi-GPU: v2b stores to the peers itself (PYCS_MG_FUSED=0: separate exchange kernel)
+  int mg_fused = 0;            // multi-GPU: 1 = v2b stores to the peers itself (PYCS_MG_FUSED=1; measured slower), 0 = exchange kernel
   int prof = -1;               // PYCS_STEP_PROFILE: CUDA events around the kernels of every step
   std::vector<cudaEvent_t> ev; // 4 per profiled step: start, after ghost fill, after step kernel, after exchange
   int npart_cap = 0;

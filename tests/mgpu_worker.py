@@ -33,11 +33,11 @@ def main():
     if len(sys.argv) > 1:
         cases = [(int(sys.argv[1]), 3, "default", (10,))]
     worst = 0.0
-    # 4 = default kernel (exchange fused into the step kernel); 4x = same kernel with the separate
-    # exchange launch; 2, 3 = older kernels (separate exchange launch)
-    for impl in ("4", "4x", "2", "3"):
+    # 4 = default kernel + exchange kernel; 4f = same kernel with the exchange fused into it
+    # (PYCS_MG_FUSED=1); 2, 3 = older kernels (separate exchange launch)
+    for impl in ("4", "4f", "2", "3"):
         os.environ["PYCS_FUSED_IMPL"] = impl[0]
-        os.environ["PYCS_MG_FUSED"] = "0" if impl.endswith("x") else "1"
+        os.environ["PYCS_MG_FUSED"] = "1" if impl.endswith("f") else "0"
         for N, vf, name, calls in cases:
             g = cs_datastruct.cubed_sphere(N)
             a = make(g, vf, TUPLES[name], local)
