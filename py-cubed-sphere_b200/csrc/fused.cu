@@ -443,6 +443,10 @@ __global__ void dg_fill_fused_kernel(Geo g, HaloMaps maps, double* __restrict__ 
                                      double* __restrict__ corr_out, const long long* __restrict__ flags, int world,
                                      long long epoch, int nbx) {
   __shared__ double sh[32];
+  // programmatic dependent launch (no-ops otherwise): this grid may start while the previous
+  // step kernel drains; nothing of it is read before this point
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (flags) {
     if (threadIdx.x < world) {
       const volatile long long* f = flags + threadIdx.x;
@@ -600,6 +604,7 @@ struct FusedState {
   double* gs = nullptr;        // ghost cells: Lagrange fill of the sqrtg field (static)
   double* part = nullptr;
   unsigned* counter = nullptr; // last-writer ticket of the step kernels
+  int pdl = 0;                 // PYCS_PDL=1: ghost fill and step kernel launched with programmatic stream serialization
   int mg_fused = 0;            // multi-GPU: 1 = v2b stores to the peers itself (PYCS_MG_FUSED=1; measured slower), 0 = exchange kernel
   int prof = -1;               // PYCS_STEP_PROFILE: CUDA events around the kernels of every step
   std::vector<cudaEvent_t> ev; // 4 per profiled step: start, after ghost fill, after step kernel, after exchange
@@ -704,6 +709,7 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
     }
     fs.impl = impl;
     if (const char* emf = getenv("PYCS_MG_FUSED")) fs.mg_fused = atoi(emf);
+    if (const char* epd = getenv("PYCS_PDL")) fs.pdl = atoi(epd);
     cols = 6 * fs.nstrips;
     if (rows <= 0) {
       // whole waves of resident CTAs: time ~ waves * (rows + ramp)
@@ -872,6 +878,7 @@ static int launch_step_kernel(pycs_handle h, FusedState& fs, const double* qcur,
   a.rows_per_chunk = fs.rows; a.nstrips = fs.nstrips; a.wcols = fs.wcols;
   a.row_lo = h->row_lo; a.row_hi = h->row_hi;
   a.mg.world = 0;
+  a.pdl = fs.pdl;
   if (h->mg && fs.impl == 4 && fs.mg_fused) TRY(k_mg_fill_args(h, qnext, &a.mg));   // exchange inside the kernel
   a.apply_corr = pend;
   a.cdx = g.dt / g.dx; a.cdy = g.dt / g.dy;
@@ -994,9 +1001,24 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   int pend = fs.pending;
   {
     const int nbx = (g.N + 127) / 128;
-    dg_fill_fused_kernel<<<nbx * 4 * 24 + 3, 128, 0, h->stream>>>(
-        g, h->maps, qcur, h->kminE, h->wE, h->order, fs.gs, sums, pend ? nsums : 0, pend ? 1.0 / h->a2 : 0.0,
-        h->red_out + 8, mgflags, mgworld, mgepoch, nbx);
+    if (fs.pdl && fs.impl == 4) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(nbx * 4 * 24 + 3);
+      cfg.blockDim = dim3(128);
+      cfg.stream = h->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      CK(cudaLaunchKernelEx(&cfg, dg_fill_fused_kernel, g, h->maps, qcur, (const int*)h->kminE, (const double*)h->wE,
+                            h->order, (const double*)fs.gs, sums, pend ? nsums : 0, pend ? 1.0 / h->a2 : 0.0,
+                            h->red_out + 8, mgflags, mgworld, mgepoch, nbx));
+    } else {
+      dg_fill_fused_kernel<<<nbx * 4 * 24 + 3, 128, 0, h->stream>>>(
+          g, h->maps, qcur, h->kminE, h->wE, h->order, fs.gs, sums, pend ? nsums : 0, pend ? 1.0 / h->a2 : 0.0,
+          h->red_out + 8, mgflags, mgworld, mgepoch, nbx);
+    }
     CKL(h);
   }
   mark();

@@ -91,7 +91,6 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   const int rfirst = r0 - 3, rlast = r1 + 2;
   const bool out_lane = (tid >= 3) && (j < jend);
   const bool jint = (j >= g.lo) && (j < g.hi);
-  const double corr = a.apply_corr ? *a.corr : 0.0;
   const double cdx = a.cdx, cdy = a.cdy, ws = a.ws;
   const int mgw = MG ? a.mg.world : 0;
   const int c0 = jbase - 6;                  // 16-byte aligned: JOFF and wcols are even
@@ -104,6 +103,11 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  // programmatic dependent launch: everything above overlaps the tail of the previous kernel
+  // (the ghost fill); its results (ghost cells, corr) are read only below.  No-ops otherwise.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const double corr = a.apply_corr ? *a.corr : 0.0;
 
   // TMA row copies are issued by one elected lane of warp 0 (one row per marched row, PF rows ahead).  Its slot
   // offsets rotate in registers and the global addresses are base + row * ld: the issue path
@@ -289,6 +293,19 @@ cudaError_t launch_mg(const FusedArgs& a, int nblocks, cudaStream_t st, int* res
     configured = true;
   }
   if (resident) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(resident, kern, TB, smem);
+  if (a.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nblocks);
+    cfg.blockDim = dim3(TB);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a);
+  }
   kern<<<nblocks, TB, smem, st>>>(a);
   return cudaSuccess;
 }

@@ -30,6 +30,7 @@ struct FusedArgs {
   double cdx, cdy;            // dt/dx, dt/dy
   double ws;                  // separable wind: U(t) = U(0) * ws (MASK & 2)
   FusedMg mg;                 // world <= 1: single GPU
+  int pdl;                    // launch with programmatic stream serialization (v2b)
 };
 
 #ifdef __CUDACC__
