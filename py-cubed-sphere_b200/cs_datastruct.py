@@ -33,7 +33,11 @@ def _rotate(vec0, shape):
 
 
 class cubed_sphere:
-    def __init__(self, N, transformation="gnomonic_equiangular", showonscreen=False, gridload=False):
+    def __init__(self, N, transformation="gnomonic_equiangular", showonscreen=False, gridload=False,
+                 centres_only=False):
+        """centres_only (not in the reference): build only the cell-centre coordinates (pc), which is
+        all the Lagrange ghost-cell tables and the standalone halo fill read (src/lagrange.py:60-69);
+        lets the interpolation.par path run at N = 3072 without the 50 GB full grid."""
         if transformation not in ("gnomonic_equiangular", "gnomonic_equidistant"):
             print("ERROR: invalid grid transformation.")
             raise SystemExit(1)
@@ -54,7 +58,10 @@ class cubed_sphere:
         edges = np.linspace(-a - 4 * dx, a + 4 * dx, N + 1 + 8)
         cents = np.linspace(-a + dx / 2.0 - 4 * dx, a - dx / 2.0 + 4 * dx, P)
         half = self.R / np.sqrt(3.0)
-        for pos, (xs, ys) in {"pc": (cents, cents), "pu": (edges, cents), "pv": (cents, edges)}.items():
+        positions = {"pc": (cents, cents), "pu": (edges, cents), "pv": (cents, edges)}
+        if centres_only:
+            positions = {"pc": (cents, cents)}
+        for pos, (xs, ys) in positions.items():
             x, y = np.meshgrid(xs, ys, indexing="ij")
             shape = x.shape
             if equiang:
@@ -71,6 +78,8 @@ class cubed_sphere:
             pts.lat = np.arctan2(pts.Z, np.hypot(pts.X, pts.Y))
             pts.lon = np.arctan2(pts.Y, pts.X)
             setattr(self, pos, pts)
+            if centres_only:
+                continue
             # panel-0 tangent vectors (src/cs_transform.py:245-354), chain rule for the
             # equiangular map (:365-397)
             invr3 = self.R / np.sqrt(half**2 + X**2 + Y**2) ** 3

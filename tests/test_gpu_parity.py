@@ -118,7 +118,7 @@ def test_lagrange_fill_all_degrees(mods, g16, degree):
         assert abs(np.max(np.abs(Qn - Qe)) - float(ref["linf_ic%d_deg%d" % (ic, degree)])) <= 1e-14
 
 
-@pytest.mark.parametrize("N", [96, 384, 1536])
+@pytest.mark.parametrize("N", [96, 384, 768, 1536])
 def test_lagrange_fill_sizes_vs_oracle(mods, N):
     """Config 5 sizes: all ghost cells incl. corners against the oracle (<= 1e-14 abs)."""
     import types
