@@ -128,23 +128,32 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
                  "l"(src), "r"(row_bytes), "r"(bar)
                  : "memory");
   };
-  auto issue = [&](int r) {                  // thread 0 only
+  // The copies of a row are issued in two halves (MINB >= 20: the second half after barrier B),
+  // which halves the extra work warp 0 carries into either barrier.
+  constexpr bool SPLIT_ISSUE = (MINB >= 20);
+  auto issue_a = [&](int r) {                // elected lane of warp 0
     const uint32_t dS = ringS_a + (uint32_t)iS, dL = ringL_a + (uint32_t)iL, bar = full_a + 8u * (uint32_t)ib;
-    const long long rr = (long long)r * g.ld, r1_ = (long long)max(r - 1, 0) * g.ld,
-                    r2_ = (long long)max(r - 2, 0) * g.ld;
+    const long long rr = (long long)r * g.ld;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * (NS + NL))
                  : "memory");
     tma(dS + 8u * S_Q * RW, gq + rr, bar);
     tma(dL + 8u * L_V * RW, gv + rr, bar);
     tma(dL + 8u * L_SGC * RW, gsgc + rr, bar);
     tma(dL + 8u * L_SGV * RW, gsgv + rr, bar);
+    if (MASK & 1) tma(dL + 8u * L_VM * RW, gvm + rr, bar);
+  };
+  auto issue_b = [&](int r, int jS, int jL, int jb) {
+    const uint32_t dS = ringS_a + (uint32_t)jS, dL = ringL_a + (uint32_t)jL, bar = full_a + 8u * (uint32_t)jb;
+    const long long rr = (long long)r * g.ld, r1_ = (long long)max(r - 1, 0) * g.ld,
+                    r2_ = (long long)max(r - 2, 0) * g.ld;
     tma(dL + 8u * L_RGC * RW, grgc + rr, bar);
     tma(dS + 8u * S_SGU * RW, gsgu + r1_, bar);
     tma(dS + 8u * S_U * RW, gu + r2_, bar);
-    if (MASK & 1) {
-      tma(dL + 8u * L_VM * RW, gvm + rr, bar);
-      tma(dS + 8u * S_UM * RW, gum + r2_, bar);
-    }
+    if (MASK & 1) tma(dS + 8u * S_UM * RW, gum + r2_, bar);
+  };
+  auto issue = [&](int r) {
+    issue_a(r);
+    issue_b(r, iS, iL, ib);
   };
   if (warp_u == 0) {
     for (int r = rfirst; r < rfirst + PF && r <= rlast; ++r) {
@@ -165,7 +174,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   int oL0 = 0, oL1 = (DL - 1) * LSLOT, oL2 = (DL - 2) * LSLOT, oL3 = (DL - 3) * LSLOT;
   int sb = 0;
   uint32_t parb = 0;
-#pragma unroll((MINB >= 10 && !MG) ? 5 : 1)
+#pragma unroll((MINB >= 10 && !MG) ? 5 : 1)   // MINB 1x / 2x: unrolled by the window length
   for (int r = rfirst; r <= rlast; ++r) {
     while (!mbar_try_wait(&full[sb], parb)) {}
     RowPtrs R;
@@ -196,10 +205,12 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
     phase_x_inner<RECON, SPLIT, MASK>(L, X, R, qnew, cdx, ws, qx);
     sX[e] = qx[0];
     __syncthreads();                                   // barrier A
+    int jS = iS, jL = iL, jb = ib;                     // slots of row r+PF (for the second half)
     if (warp_u == 0 && r + PF <= rlast) {              // warp 0 issues the TMA copies of row r+PF
       if (elect_one()) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue(r + PF);
+        if (SPLIT_ISSUE) issue_a(r + PF);
+        else issue(r + PF);
       }
       iS = (iS + 8 * SSLOT == 8 * DS * SSLOT) ? 0 : iS + 8 * SSLOT;
       iL = (iL + 8 * LSLOT == 8 * DL * LSLOT) ? 0 : iL + 8 * LSLOT;
@@ -213,6 +224,9 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
     sG[e] = G[0];
     if (SPLIT != 1) sC[e] = CF[0];
     __syncthreads();                                   // barrier B
+    if (SPLIT_ISSUE && warp_u == 0 && r + PF <= rlast) {
+      if (elect_one()) issue_b(r + PF, jS, jL, jb);
+    }
     // ---------------- phase 3: Qy row r, outer x-flux on Qy, output row r-3
     double Fn[1], Gn[1], CFn[1] = {0.0}, out[1], sdiv[1];
     Fn[0] = sF[e + 1];
@@ -331,7 +345,8 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb,
   if (recon == 3 && split == 1) {
 #define TUNE(T, P, M) \
   if (tb == T && pf == P && minb == M) return launch_mask<T, 3, 1, P, M>(a, mask, nblocks, st, resident)
-    TUNE(160, 1, 4); TUNE(160, 2, 4); TUNE(160, 2, 14); TUNE(160, 1, 14); TUNE(128, 2, 15); TUNE(160, 1, 5); TUNE(160, 2, 5); TUNE(160, 3, 4);
+    TUNE(160, 1, 4); TUNE(160, 2, 4); TUNE(160, 2, 14); TUNE(160, 1, 14); TUNE(128, 2, 15); TUNE(160, 2, 24);
+    TUNE(160, 3, 24); TUNE(160, 1, 5); TUNE(160, 2, 5); TUNE(160, 3, 4);
     TUNE(128, 1, 5); TUNE(128, 2, 5); TUNE(128, 2, 6); TUNE(128, 3, 5);
     TUNE(192, 1, 4); TUNE(192, 2, 4); TUNE(192, 2, 3);
     TUNE(256, 1, 3); TUNE(256, 2, 3); TUNE(256, 2, 2);
@@ -352,7 +367,7 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb,
 bool pycs_fused2b_has(int recon, int split, int tb, int pf, int minb) {
   if (recon != 1 && recon != 3) return false;
   if (recon == 3 && split == 1) {
-    const int t[][3] = {{160, 1, 4}, {160, 2, 4}, {160, 2, 14}, {160, 1, 14}, {128, 2, 15}, {160, 1, 5}, {160, 2, 5}, {160, 3, 4}, {128, 1, 5}, {128, 2, 5},
+    const int t[][3] = {{160, 1, 4}, {160, 2, 4}, {160, 2, 14}, {160, 1, 14}, {128, 2, 15}, {160, 2, 24}, {160, 3, 24}, {160, 1, 5}, {160, 2, 5}, {160, 3, 4}, {128, 1, 5}, {128, 2, 5},
                         {128, 2, 6}, {128, 3, 5}, {192, 1, 4}, {192, 2, 4}, {192, 2, 3}, {256, 1, 3}, {256, 2, 3},
                         {256, 2, 2}};
     for (auto& x : t)
