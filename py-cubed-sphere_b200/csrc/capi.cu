@@ -84,6 +84,16 @@ static int ensure_pinned(pycs_handle h, size_t bytes) {
   return 0;
 }
 
+// pycs_adv_time_step_host advances Q with the separable wind and leaves the exposed wind arrays
+// behind (wind_stale_k); every other entry point that reads or writes wind state, or changes
+// what it depends on, calls this first.
+static int wind_sync(pycs_handle h) {
+  if (h->wind_stale_k < 0) return 0;
+  const long long k = h->wind_stale_k;
+  h->wind_stale_k = -1;
+  return k_wind_catch_up(h, k);
+}
+
 // --------------------------------------------------------------------------- lifetime
 extern "C" const char* pycs_last_error(void) { return g_err.c_str(); }
 
@@ -122,6 +132,7 @@ extern "C" int pycs_create(const pycs_params* prm, pycs_handle* out) {
   g.dt = prm->dt;
   h->row_lo = g.lo;
   h->row_hi = g.hi;
+  h->wind_stale_k = -1;
   cudaDeviceProp dp;
   CK(cudaGetDeviceProperties(&dp, prm->device));
   h->sm_count = dp.multiProcessorCount;
@@ -175,6 +186,7 @@ extern "C" int pycs_synchronize(pycs_handle h) {
 }
 
 extern "C" int pycs_set_dt(pycs_handle h, double dt) {
+  TRY(wind_sync(h));
   h->g.dt = dt;
   h->prm.dt = dt;
   return 0;
@@ -202,6 +214,7 @@ static int upload_from(pycs_handle h, int field, const double* host, bool pinned
 }
 
 extern "C" int pycs_upload_field(pycs_handle h, int32_t field, const double* host) {
+  TRY(wind_sync(h));
   if (!host) return arg_fail("null host pointer");
   CK(cudaSetDevice(h->device));
   TRY(upload_from(h, field, host, false));
@@ -227,6 +240,7 @@ static int download_to(pycs_handle h, int field, double* host) {
 }
 
 extern "C" int pycs_download_field(pycs_handle h, int32_t field, double* host) {
+  TRY(wind_sync(h));
   if (!host) return arg_fail("null host pointer");
   CK(cudaSetDevice(h->device));
   TRY(download_to(h, field, host));
@@ -235,6 +249,7 @@ extern "C" int pycs_download_field(pycs_handle h, int32_t field, double* host) {
 }
 
 extern "C" int pycs_copy_field(pycs_handle h, int32_t dst, int32_t src) {
+  TRY(wind_sync(h));
   double *d, *s;
   TRY(pycs_field_ptr(h, dst, &d));
   TRY(pycs_field_ptr(h, src, &s));
@@ -245,6 +260,7 @@ extern "C" int pycs_copy_field(pycs_handle h, int32_t dst, int32_t src) {
 }
 
 extern "C" int pycs_fill_field(pycs_handle h, int32_t field, double value) {
+  TRY(wind_sync(h));
   double* d;
   TRY(pycs_field_ptr(h, field, &d));
   long long n = (long long)(pycs_field_single_panel(field) ? 1 : 6) * h->g.ps;
@@ -311,12 +327,19 @@ extern "C" int pycs_halo_fill_scalar(pycs_handle h, int32_t fx, int32_t fy) {
   return pycs_halo_fill_copy(h, fx, fy);
 }
 
-extern "C" int pycs_halo_fill_vector(pycs_handle h) { return k_wind_ghost_fill(h); }
+extern "C" int pycs_halo_fill_vector(pycs_handle h) {
+  TRY(wind_sync(h));
+  return k_wind_ghost_fill(h);
+}
 
 // --------------------------------------------------------------------------- operators
-extern "C" int pycs_time_averaged_velocity(pycs_handle h) { return k_time_averaged_velocity(h); }
+extern "C" int pycs_time_averaged_velocity(pycs_handle h) {
+  TRY(wind_sync(h));
+  return k_time_averaged_velocity(h);
+}
 
 extern "C" int pycs_cfl(pycs_handle h, int32_t dst, int32_t src, int32_t dir) {
+  TRY(wind_sync(h));
   double *d, *s;
   TRY(pycs_field_ptr(h, dst, &d));
   TRY(pycs_field_ptr(h, src, &s));
@@ -333,6 +356,7 @@ extern "C" int pycs_ppm_reconstruction(pycs_handle h, int32_t fx, int32_t fy) {
 }
 
 extern "C" int pycs_numerical_flux(pycs_handle h, int32_t fx, int32_t fy) {
+  TRY(wind_sync(h));
   double *x, *y;
   TRY(pycs_field_ptr(h, fx, &x));
   TRY(pycs_field_ptr(h, fy, &y));
@@ -340,6 +364,7 @@ extern "C" int pycs_numerical_flux(pycs_handle h, int32_t fx, int32_t fy) {
 }
 
 extern "C" int pycs_compute_fluxes(pycs_handle h, int32_t fx, int32_t fy) {
+  TRY(wind_sync(h));
   TRY(pycs_ppm_reconstruction(h, fx, fy));
   return pycs_numerical_flux(h, fx, fy);
 }
@@ -350,6 +375,7 @@ extern "C" int pycs_average_flux_cube_edges(pycs_handle h) { return k_average_fl
 
 // divergence, operator by operator (src/discrete_operators.py:18-101)
 extern "C" int pycs_divergence(pycs_handle h) {
+  TRY(wind_sync(h));
   double *Q, *gQ, *cx, *cy, *ua, *va;
   TRY(pycs_field_ptr(h, PYCS_F_Q, &Q));
   TRY(pycs_field_ptr(h, PYCS_F_GQ, &gQ));
@@ -385,6 +411,7 @@ static int normalize_q(pycs_handle h) {
 }
 
 extern "C" int pycs_adv_time_step(pycs_handle h, int64_t k, double t) {
+  TRY(wind_sync(h));
   (void)k; (void)t;
   CK(cudaSetDevice(h->device));
   TRY(normalize_q(h));
@@ -397,12 +424,22 @@ extern "C" int pycs_adv_time_step(pycs_handle h, int64_t k, double t) {
   return k_q_update(h);                                         // :43
 }
 
-extern "C" int pycs_update_adv(pycs_handle h, double t) { return k_update_adv(h, t); }
-extern "C" int pycs_init_wind(pycs_handle h) { return k_wind_interior(h, 0.0, 1, 1); }
-extern "C" int pycs_convert_wind_interior(pycs_handle h) { return k_wind_interior(h, 0.0, 1, 0); }
+extern "C" int pycs_update_adv(pycs_handle h, double t) {
+  TRY(wind_sync(h));
+  return k_update_adv(h, t);
+}
+extern "C" int pycs_init_wind(pycs_handle h) {
+  TRY(wind_sync(h));
+  return k_wind_interior(h, 0.0, 1, 1);
+}
+extern "C" int pycs_convert_wind_interior(pycs_handle h) {
+  TRY(wind_sync(h));
+  return k_wind_interior(h, 0.0, 1, 0);
+}
 
 static int run_steps(pycs_handle h, int64_t k0, int64_t nsteps, int fused) {
   CK(cudaSetDevice(h->device));
+  TRY(wind_sync(h));
   if (fused && !k_fused_supported(h)) return arg_fail("no fused step kernel for this scheme tuple");
   if (h->mg && !fused) return arg_fail("multi-GPU handles run the fused step only");
   // wind field 3 + RK1 is U(0)*cos(pi t/T): all but the last step of a fused run scale
@@ -446,6 +483,7 @@ extern "C" int pycs_run_timed(pycs_handle h, int64_t k0, int64_t nsteps, int32_t
 }
 
 extern "C" int pycs_time_step_kernel(pycs_handle h, int32_t reps, int32_t separable, float* ms) {
+  TRY(wind_sync(h));
   CK(cudaSetDevice(h->device));
   if (!k_fused_supported(h)) return arg_fail("no fused step kernel for this scheme tuple");
   TRY(normalize_q(h));
@@ -472,9 +510,20 @@ extern "C" int pycs_adv_time_step_host(pycs_handle h, double* Q, int64_t k, doub
   TRY(upload_from(h, PYCS_F_Q, Q, true));
   if (fused) {
     if (!k_fused_supported(h)) return arg_fail("no fused step kernel for this scheme tuple");
-    TRY(k_fused_step(h, k, t, 0));
+    // wind field 3 + RK1 is U(0)*cos(pi t/T): the step scales the t = 0 winds in-kernel and the
+    // exposed wind arrays are caught up lazily (wind_sync) when something reads them
+    const bool separable = h->prm.vf == 3 && h->prm.dp == 1 && !getenv("PYCS_NO_SEPARABLE") &&
+                           fabs(t - (double)k * h->g.dt) <= 1e-12 * (1.0 + fabs(t));   // t = k*dt as in adv_sphere
+    if (separable) {
+      TRY(k_fused_step(h, k, t, 1));
+      h->wind_stale_k = k;
+    } else {
+      TRY(wind_sync(h));
+      TRY(k_fused_step(h, k, t, 0));
+    }
     TRY(normalize_q(h));
   } else {
+    TRY(wind_sync(h));
     TRY(pycs_adv_time_step(h, k, t));
     TRY(k_update_adv(h, t));
   }
@@ -485,6 +534,7 @@ extern "C" int pycs_adv_time_step_host(pycs_handle h, double* Q, int64_t k, doub
 
 // --------------------------------------------------------------------------- multi-GPU
 extern "C" int pycs_mgpu_init(pycs_handle h, int32_t rank, int32_t world, unsigned char* handles_out) {
+  TRY(wind_sync(h));
   if (!handles_out) return arg_fail("null handle buffer");
   CK(cudaSetDevice(h->device));
   TRY(normalize_q(h));

@@ -854,6 +854,18 @@ int k_wind_resync(pycs_handle h, long long kprev) {
   return k_update_adv(h, (double)kprev * h->g.dt);
 }
 
+// Everything the reference's step k leaves in U_pu / U_pv / U_pc, rebuilt from the analytic wind
+// after one or more separable-wind steps that did not touch those arrays: wind(t_{k-1}) on the
+// interior, the ghost fill and the departure velocity of step k (src/advection_timestep.py:31-37),
+// then update_adv(t_k) (:48-75).
+int k_wind_catch_up(pycs_handle h, long long k) {
+  if (k < 1 || h->prm.vf < 2) return 0;
+  TRY(k_wind_interior(h, (double)(k - 1) * h->g.dt, 1, 1));
+  TRY(k_wind_ghost_fill(h));
+  TRY(k_time_averaged_velocity(h));
+  return k_update_adv(h, (double)k * h->g.dt);
+}
+
 static int launch_step_kernel(pycs_handle h, FusedState& fs, const double* qcur, double* qnext, int pend,
                               int mask, double ws) {
   const Geo& g = h->g;

@@ -68,6 +68,9 @@ struct pycs_handle_s {
   int a2_valid;
   // rows this handle updates: [lo, hi) or, with pycs_mgpu_init, this rank's slab of every panel
   int row_lo, row_hi;
+  // >= 0: U_pu / U_pv / U_pc still hold an older step's winds; they must be brought to the state
+  // after update_adv(t_k), k = wind_stale_k, before anything reads them (capi.cu: wind_sync)
+  long long wind_stale_k;
   struct MgpuState* mg;   // multi-GPU state (mgpu.cu), null on a single GPU
 };
 
@@ -134,6 +137,7 @@ int k_wind_interior(pycs_handle h, double t, int convert_interior_only, int do_v
 int k_fused_supported(pycs_handle h);
 int k_fused_step(pycs_handle h, long long k, double t, int separable);
 int k_wind_resync(pycs_handle h, long long kprev);
+int k_wind_catch_up(pycs_handle h, long long k);
 int k_fused_time_kernel(pycs_handle h, int reps, int separable, float* ms);
 int k_fused_grid_info(pycs_handle h, int* tb, int* rows, int* nblocks);
 int k_fused_kernel_name(pycs_handle h, char* out, int len);

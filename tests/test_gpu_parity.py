@@ -364,6 +364,34 @@ def test_fused_separable_wind_across_run_calls(mods):
     b.dev.close()
 
 
+def test_host_step_keeps_wind_state_lazily(mods):
+    """pycs_adv_time_step_host (numpy Q in, numpy Q out) advances with the separable wind and
+    catches the exposed wind arrays up only when they are read: Q after every step and the
+    wind state at the end must equal the operator path's."""
+    import ctypes as C
+    g = mods.cs_datastruct.cubed_sphere(50)
+    a = make_sim(mods, g, 3, TUPLES["default"])
+    b = make_sim(mods, g, 3, TUPLES["default"])
+    Q = np.ascontiguousarray(np.asarray(a.Q))
+    for k in range(1, 8):
+        a.dev.call("pycs_adv_time_step_host", Q.ctypes.data_as(C.POINTER(C.c_double)), k, k * a.dt, 1)
+        mods.advection_timestep.adv_time_step(g, b, k, k * b.dt)
+        mods.advection_timestep.update_adv(g, b, k * b.dt)
+        I = np.s_[4:54, 4:54, :]
+        assert relerr(Q[I], np.asarray(b.Q)[I]) <= TOL, k
+    for obj, names in (("U_pu", ("ucontra", "ucontra_old", "ucontra_averaged", "ulon")),
+                       ("U_pv", ("vcontra", "vcontra_old", "vcontra_averaged", "vlat")), ("U_pc", ("ulon", "vlat"))):
+        for nm in names:
+            x, y = np.asarray(getattr(getattr(a, obj), nm)), np.asarray(getattr(getattr(b, obj), nm))
+            assert relerr(x, y) <= TOL, (obj, nm)
+    # and the state is a valid starting point for more steps of either kind
+    mods.advection_timestep.run_steps(g, a, 7, 3, fused=True)
+    mods.advection_timestep.run_steps(g, b, 7, 3, fused=False)
+    assert relerr(np.asarray(a.Q), np.asarray(b.Q)) <= TOL
+    a.dev.close()
+    b.dev.close()
+
+
 def test_full_size_properties_n1536(mods):
     """Size-independent checks at BASELINE.json's full size: mass conservation and
     linearity of the (unlimited PPM-PL07) step, fused path."""
