@@ -1,4 +1,9 @@
-// Fused advection step for the duo-grid (ET-DG) schemes: the production path.
+// Fused advection step for the duo-grid (ET-DG) schemes: host-side driver of the production
+// path (step sequencing, ghost fill, deferred MF-PR projection, separable wind, multi-GPU
+// hooks) and the first-generation step kernel (v2).  The default step kernel is v2b in
+// fused2b.cu (same march, leaner arithmetic from fused3_core.cuh); v3 is in fused3.cu;
+// PYCS_FUSED_IMPL = 2 | 3 | 4 selects.  v2 remains the kernel of the limited reconstructions
+// (PPM-CW84 / PPM-L04).
 //
 // One kernel does what src/discrete_operators.py:18-101 + src/advection_timestep.py:43
 // do in ~60 whole-array passes: inner x/y PPM fluxes, the splitting update
