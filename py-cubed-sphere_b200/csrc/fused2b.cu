@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   const int rfirst = r0 - 3, rlast = r1 + 2;
   const bool out_lane = (tid >= 3) && (j < jend);
   const bool jint = (j >= g.lo) && (j < g.hi);
-  const double cdx = a.cdx, cdy = a.cdy, ws = a.ws;
+  const double cdx = a.cdx * ((MASK & 2) ? a.ws : 1.0), cdy = a.cdy * ((MASK & 2) ? a.ws : 1.0);   // time factor folded in
   const int mgw = MG ? a.mg.world : 0;
   const int c0 = jbase - 6;                  // 16-byte aligned: JOFF and wcols are even
   const int len = min(RW, g.ld - PYCS_JOFF - c0) & ~1;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
     // ---------------- phase 1: own column
     XEdge X;
     double qx[1];
-    phase_x_inner<RECON, SPLIT, MASK>(L, X, R, qnew, cdx, ws, qx);
+    phase_x_inner<RECON, SPLIT, MASK>(L, X, R, qnew, cdx, qx);
     sX[e] = qx[0];
     __syncthreads();                                   // barrier A
     int jS = iS, jL = iL, jb = ib;                     // slots of row r+PF (for the second half)
@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
     }
     // ---------------- phase 2: y-fluxes at edge j: inner on Q row r, outer on Qx row r-3
     double F[1], G[1], CF[1] = {0.0}, CG[1];
-    yflux_pair<RECON, SPLIT, MASK>(R.v0, R.vm0, R.sgv0, R.sgc0, R.q, cdy, ws, F, CF);
-    yflux_pair<RECON, SPLIT, MASK>(R.v3, R.vm3, R.sgv3, R.sgc3, sX + e, cdy, ws, G, CG);
+    yflux_pair<RECON, SPLIT, MASK>(R.v0, R.vm0, R.sgv0, R.sgc0, R.q, cdy, F, CF);
+    yflux_pair<RECON, SPLIT, MASK>(R.v3, R.vm3, R.sgv3, R.sgc3, sX + e, cdy, G, CG);
     sF[e] = F[0];
     sG[e] = G[0];
     if (SPLIT != 1) sC[e] = CF[0];

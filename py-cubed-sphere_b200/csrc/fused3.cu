@@ -169,7 +169,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB % 10) fused3_kernel(FusedA
   const int col = cw0 + lane;                        // ... and inside the panel (second: + CSTEP)
   double* sx = sxall + warp * SXW + 4 + lane;        // own columns of the private Qx row
   const bool use0 = col >= us && col < ue, use1 = col + CSTEP >= us && col + CSTEP < ue;
-  const double cdx = a.cdx, cdy = a.cdy, ws = a.ws;
+  const double cdx = a.cdx * ((MASK & 2) ? a.ws : 1.0), cdy = a.cdy * ((MASK & 2) ? a.ws : 1.0);   // time factor folded in
   uint64_t* const rowbar = a.apply_corr ? ready : full;
   // row r0 of the output panel; own columns (clamped for lanes that own no output)
   double* __restrict__ QN = a.qn + (long long)p * g.ps + PYCS_JOFF + (long long)r0 * g.ld;
@@ -203,14 +203,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB % 10) fused3_kernel(FusedA
     XEdge X;
     double qx[NC];
     const double qnew[NC] = {R.q[0], R.q[CSTEP]};
-    phase_x_inner<RECON, SPLIT, MASK>(L, X, R, qnew, cdx, ws, qx);
+    phase_x_inner<RECON, SPLIT, MASK>(L, X, R, qnew, cdx, qx);
     sx[0] = qx[0];
     sx[CSTEP] = qx[1];
     __syncwarp();
     double F[NC], G[NC], CF[NC], CG[NC], Fn[NC], Gn[NC], CFn[NC];
     CF[0] = CF[1] = 0.0;
-    yflux_pair<RECON, SPLIT, MASK>(R.v0, R.vm0, R.sgv0, R.sgc0, R.q, cdy, ws, F, CF);
-    yflux_pair<RECON, SPLIT, MASK>(R.v3, R.vm3, R.sgv3, R.sgc3, sx, cdy, ws, G, CG);
+    yflux_pair<RECON, SPLIT, MASK>(R.v0, R.vm0, R.sgv0, R.sgc0, R.q, cdy, F, CF);
+    yflux_pair<RECON, SPLIT, MASK>(R.v3, R.vm3, R.sgv3, R.sgc3, sx, cdy, G, CG);
     // flux at the column right of each own column: next lane's same column; for lane 31 the
     // right neighbour of column cw0+31 is lane 0's second column (its own second column's
     // neighbour lies outside the warp and is never needed)

@@ -85,15 +85,15 @@ PYCS_HD void edge_values(double q1, double q2, double q3, double q4, double q5, 
   }
 }
 
-// Weights of one edge.  ubar: wind used in the flux (time averaged); up: upwind mask;
-// cd = dt/dx; gE, gO, gC: sqrtg at the edge, at the other edge of the upwind cell and at
-// its centre.  c_out = ubar*dt/dx (the CFL number cx of src/cfl.py:10).
-// SAMEMASK: the mask is the sign of ubar itself (RK1), so b = |c| (for u = -0.0 every
+// Weights of one edge.  c = ubar*dt/dx: the CFL number of the wind used in the flux (time
+// averaged; src/cfl.py:10) -- the callers fold a separable wind's time factor into dt/dx, so the
+// scaled wind itself is never formed; up: upwind mask; gE, gO, gC: sqrtg at the edge, at the
+// other edge of the upwind cell and at its centre.
+// SAMEMASK: the mask is the sign of the wind itself (RK1), so b = |c| (for u = -0.0 every
 // weight is zero and the side does not matter).
 template <int MT, bool SAMEMASK>
-PYCS_HD void edge_weights(double ubar, bool up, double cd, double gE, double gO, double gC, double& WE,
-                          double& WO, double& WG, double& c_out) {
-  const double c = ubar * cd;
+PYCS_HD void edge_weights(double c, bool up, double gE, double gO, double gC, double& WE, double& WO,
+                          double& WG) {
   const double b = SAMEMASK ? fabs(c) : (up ? c : -c);
   const double m = 1.0 - b;
   const double t = fma(2.0, m, 1.0);          // 3 - 2b
@@ -103,7 +103,6 @@ PYCS_HD void edge_weights(double ubar, bool up, double cd, double gE, double gO,
   const double w1 = cm * m, w2 = -(cb * m), w3 = cb * t;
   if (MT == 1) { WE = w1 * gE; WO = w2 * gO; WG = w3 * gC; }
   else { WE = w1; WO = w2; WG = w3; }
-  c_out = c;
 }
 
 // inner update of one cell (src/discrete_operators.py:49-73): q + half a flux difference
@@ -146,8 +145,8 @@ PYCS_HD void lane_init(Lane& L) {
 // qnew[c]: Q of row r in the lane's columns (the caller loads it, and patches it when a
 // projection term is pending).
 template <int RECON, int SPLIT, int MASK>
-PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, const double qnew[NC], double cdx, double ws,
-                           double qx[NC]) {
+// cdxw = dt/dx times the time factor of a separable wind (1 otherwise).
+PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, const double qnew[NC], double cdxw, double qx[NC]) {
   constexpr int MT = (SPLIT == 3) ? 2 : 1;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
@@ -157,17 +156,16 @@ PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, const double qne
     q[4] = qnew[c];
     double l2, r2;                                   // cell r-2
     edge_values<RECON>(q[0], q[1], q[2], q[3], q[4], l2, r2);
-    double ub = R.u[o];
-    if (MASK & 2) ub *= ws;
-    const bool up = ((MASK & 1) ? R.um[o] : ub) >= 0.0;
+    const double cc = R.u[o] * cdxw;                // CFL number at edge r-2
+    const bool up = ((MASK & 1) ? R.um[o] : cc) >= 0.0;
     const double su1c = R.su1[o];
     const double gE = L.su2[c];
     const double gO = up ? L.su3[c] : su1c;
     const double gC = up ? R.sgc3[o] : R.sgc2[o];   // both loads are issued early; a pointer select
                                                     // would put the LDS behind the wind-sign compare
     const double rg = R.rg3[o];
-    double WE, WO, WG, cc;
-    edge_weights<MT, !(MASK & 1)>(ub, up, cdx, gE, gO, gC, WE, WO, WG, cc);
+    double WE, WO, WG;
+    edge_weights<MT, !(MASK & 1)>(cc, up, gE, gO, gC, WE, WO, WG);
     const double E = up ? L.pr[c] : l2, O = up ? L.pl[c] : r2, qc = up ? q[1] : q[2];
     const double fin = fma(WE, E, fma(WO, O, WG * qc));
     double cdv = 0.0;
@@ -190,20 +188,19 @@ PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, const double qne
 // lane-offset as well, so that src[k] is the value k columns right of the lane's first column.
 template <int RECON, int SPLIT, int MASK>
 PYCS_HD void yflux_pair(const double* v, const double* vm, const double* sgv, const double* sgc,
-                        const double* src, double cdy, double ws, double f[NC], double cmy[NC]) {
+                        const double* src, double cdyw, double f[NC], double cmy[NC]) {
   constexpr int MT = (SPLIT == 3) ? 2 : 1;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const int o = c * CSTEP;
-    double vb = v[o];
-    if (MASK & 2) vb *= ws;
-    const bool vp = ((MASK & 1) ? vm[o] : vb) >= 0.0;
+    const double cc = v[o] * cdyw;
+    const bool vp = ((MASK & 1) ? vm[o] : cc) >= 0.0;
     const int up1 = vp ? -1 : 0;                     // upwind cell relative to the edge
     const double gE = sgv[o];
     const double gO = sgv[o + 1 + 2 * up1];          // other edge of the upwind cell
     const double gC = sgc[o + up1];
-    double WE, WO, WG, cc;
-    edge_weights<MT, !(MASK & 1)>(vb, vp, cdy, gE, gO, gC, WE, WO, WG, cc);
+    double WE, WO, WG;
+    edge_weights<MT, !(MASK & 1)>(cc, vp, gE, gO, gC, WE, WO, WG);
     const double* s = src + o + up1;
     double l, r;
     edge_values<RECON>(s[-2], s[-1], s[0], s[1], s[2], l, r);

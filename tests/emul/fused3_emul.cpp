@@ -33,6 +33,7 @@ struct Args {
 template <int RECON, int SPLIT, int MASK, int NW>
 void run(const Args& a) {
   using namespace f3;
+  const double cdxw = a.cdx * ((MASK & 2) ? a.ws : 1.0), cdyw = a.cdy * ((MASK & 2) ? a.ws : 1.0);
   constexpr int RW = RowWidth<NW>::value;
   constexpr int NS = (MASK & 1) ? 4 : 3, NL = (MASK & 1) ? 5 : 4;
   constexpr int SSLOT = NS * RW, LSLOT = NL * RW;
@@ -100,14 +101,14 @@ void run(const Args& a) {
           P.rg3 = ringL + oL3 + L_RGC * RW + ca;
           double qx[NC];
           const double qnew[NC] = {P.q[0], P.q[CSTEP]};
-          phase_x_inner<RECON, SPLIT, MASK>(L[l], X[l], P, qnew, a.cdx, a.ws, qx);
+          phase_x_inner<RECON, SPLIT, MASK>(L[l], X[l], P, qnew, cdxw, qx);
           sxrow[4 + l] = qx[0];
           sxrow[4 + l + CSTEP] = qx[1];
         }
         for (int l = 0; l < 32; ++l) {                 // phase 2 (after __syncwarp)
           CF[l][0] = CF[l][1] = 0.0;
-          yflux_pair<RECON, SPLIT, MASK>(R[l].v0, R[l].vm0, R[l].sgv0, R[l].sgc0, R[l].q, a.cdy, a.ws, F[l], CF[l]);
-          yflux_pair<RECON, SPLIT, MASK>(R[l].v3, R[l].vm3, R[l].sgv3, R[l].sgc3, sxrow + 4 + l, a.cdy, a.ws, G[l], CG);
+          yflux_pair<RECON, SPLIT, MASK>(R[l].v0, R[l].vm0, R[l].sgv0, R[l].sgc0, R[l].q, cdyw, F[l], CF[l]);
+          yflux_pair<RECON, SPLIT, MASK>(R[l].v3, R[l].vm3, R[l].sgv3, R[l].sgc3, sxrow + 4 + l, cdyw, G[l], CG);
         }
         for (int l = 0; l < 32; ++l) {                 // shuffles: right neighbour of each own column
           const int n = l < 31 ? l + 1 : l;            // __shfl_down keeps the own value in lane 31
@@ -145,6 +146,7 @@ void run(const Args& a) {
 template <int RECON, int SPLIT, int MASK>
 void run_block(const Args& a, int TB) {
   using namespace f1;
+  const double cdxw = a.cdx * ((MASK & 2) ? a.ws : 1.0), cdyw = a.cdy * ((MASK & 2) ? a.ws : 1.0);
   const int RW = TB + 6;
   const int NS = (MASK & 1) ? 4 : 3, NL = (MASK & 1) ? 5 : 4;
   const int SSLOT = NS * RW, LSLOT = NL * RW;
@@ -211,14 +213,14 @@ void run_block(const Args& a, int TB) {
           ringS[oS + S_Q * RW + e] = qnew[0];
         }
         double qx[1];
-        phase_x_inner<RECON, SPLIT, MASK>(L[t], X[t], P, qnew, a.cdx, a.ws, qx);
+        phase_x_inner<RECON, SPLIT, MASK>(L[t], X[t], P, qnew, cdxw, qx);
         sX[e] = qx[0];
       }
       for (int t = 0; t < TB; ++t) {               // barrier A; phase 2
         const int e = t + 3;
         double f[1], g[1], cf[1] = {0.0}, cg[1];
-        yflux_pair<RECON, SPLIT, MASK>(R[t].v0, R[t].vm0, R[t].sgv0, R[t].sgc0, R[t].q, a.cdy, a.ws, f, cf);
-        yflux_pair<RECON, SPLIT, MASK>(R[t].v3, R[t].vm3, R[t].sgv3, R[t].sgc3, sX + e, a.cdy, a.ws, g, cg);
+        yflux_pair<RECON, SPLIT, MASK>(R[t].v0, R[t].vm0, R[t].sgv0, R[t].sgc0, R[t].q, cdyw, f, cf);
+        yflux_pair<RECON, SPLIT, MASK>(R[t].v3, R[t].vm3, R[t].sgv3, R[t].sgc3, sX + e, cdyw, g, cg);
         F[t] = f[0]; G[t] = g[0]; CF[t] = cf[0];
       }
       for (int t = 0; t < TB; ++t) { sF[t + 3] = F[t]; sG[t + 3] = G[t]; sC[t + 3] = CF[t]; }
