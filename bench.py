@@ -211,17 +211,24 @@ def run_gpu(args):
     own_cells = 6.0 * N * (slab[1] - slab[0])
     value = cells * args.steps / (ms_total * 1e-3)
 
-    # ---- roofline: the step kernel alone, CUDA events around back-to-back launches
+    # ---- roofline: the step kernel alone, CUDA events around back-to-back launches.
+    # kernel_ms: best of 3 bursts of 50 launches (the HBM peak it is compared with is a burst copy,
+    # best of 10); kernel_ms_sustained: average over a long run (the 1 kW power cap shows there).
     kms = C.c_float()
-    reps = max(20, args.steps)
     dev.call("pycs_time_step_kernel", 5, 1, C.byref(kms))
+    bursts = []
+    for _ in range(3):
+        dev.call("pycs_time_step_kernel", 50, 1, C.byref(kms))
+        bursts.append(float(kms.value) / 50)
+    k_ms = min(bursts)
+    reps = max(20, args.steps)
     dev.call("pycs_time_step_kernel", reps, 1, C.byref(kms))
-    k_ms = float(kms.value) / reps
+    k_ms_sustained = float(kms.value) / reps
     if world > 1:
         import torch.distributed as dist
-        tt = torch.tensor([k_ms], device="cuda")
+        tt = torch.tensor([k_ms, k_ms_sustained], device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        k_ms = float(tt.item())
+        k_ms, k_ms_sustained = float(tt[0].item()), float(tt[1].item())
     peak, peak_src = measured_peak()
     achieved = BYTES_PER_CELL * own_cells / (k_ms * 1e-3) / 1e9
     tb, rows, nblk = C.c_int32(), C.c_int32(), C.c_int32()
@@ -237,10 +244,14 @@ def run_gpu(args):
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": dev.step_kernel_name(),
-                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": BYTES_PER_CELL * own_cells,
+                "kernel_ms": k_ms, "kernel_ms_sustained": k_ms_sustained,
+                "frac_sustained": BYTES_PER_CELL * own_cells / (k_ms_sustained * 1e-3) / 1e9 / peak,
+                "timing": "CUDA events on the launch stream; kernel_ms = best of 3 bursts of 50 back-to-back launches, "
+                          "kernel_ms_sustained = average of %d" % reps,
+                "algorithmic_bytes_per_launch": BYTES_PER_CELL * own_cells,
                 "per": "GPU (each rank updates %d of %d rows of every panel)" % (slab[1] - slab[0], N),
                 "peak_source": peak_src, "grid": {"ctas": nblk.value, "threads": tb.value, "rows_per_chunk": rows.value},
-                "share_of_step": k_ms / (ms_total / args.steps)}
+                "share_of_step": k_ms_sustained / (ms_total / args.steps)}
 
     # ---- end to end: adv_time_step through host buffers (pinned), H2D + step + D2H every step
     sim.Q[...] = Q0
