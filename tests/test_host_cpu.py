@@ -85,3 +85,30 @@ def test_invalid_scheme_combination_refused_before_touching_gpu():
         advection_ic.adv_simulation_par(g, 0.01, 5, 2, 1, 1, 3, 1, 3, 3, 1, 3)   # SP-PL07 with MT-0
     with pytest.raises(SystemExit):
         advection_ic.adv_simulation_par(g, 0.01, 5, 9, 1, 1, 3, 1, 1, 3, 1, 3)   # bad ic
+
+
+def test_par_readers_follow_the_reference_format(tmp_path, capsys):
+    """configuration.get_parameters / get_advection_parameters / get_interpolation_parameters read the
+    reference's positional .par format (value on every second line) and return its tuples."""
+    import pycs_b200  # noqa: F401
+    from pycs_b200 import configuration
+    # the package defaults = BASELINE.json config 1
+    N, transf, show, load, test_case, mp = configuration.get_parameters()
+    assert (N, transf, show, load, test_case, mp) == (48, "gnomonic_equiangular", True, False, 5, "sphere")
+    dt, Tf, tc, ic, vf, recon, dp, opsplit, et, mt, mf = configuration.get_advection_parameters()
+    assert (Tf, tc, ic, vf, recon, dp, opsplit, et, mt, mf) == (5.0, 1, 2, 1, 3, 1, 1, 3, 1, 3)
+    assert abs(dt - 0.025 * 16 / 48) < 1e-15 and int(Tf / dt) == 600
+    assert configuration.get_interpolation_parameters() == (1, 1, 2)
+    # a file written the way the reference ships it (title, then comment/value pairs, then free text)
+    (tmp_path / "advection.par").write_text(
+        "#Advection test case parameters \n#Total period definition (seconds)\n5\n#Time step (seconds)\n0.0025\n"
+        "#Initial condition\n2\n#Vector field \n3\n#Test case\n2\n#Reconstruction (1, 2, 3, 4)\n4\n"
+        "#Departure point scheme (1, 2)\n2\n#Operator splitting (1, 2, 3)\n2\n#Edge treatment (1, 2, 3)\n1\n"
+        "#Metric tensor treatment (1, 2)\n1\n#Mass fixer (1, 2, 3)\n2\n#---- Description ----\n#  case(1) - x\n")
+    assert configuration.get_advection_parameters(str(tmp_path)) == (0.0025, 5.0, 2, 2, 3, 4, 2, 2, 1, 1, 2)
+    (tmp_path / "configuration.par").write_text(
+        "#Parameters\n#N\n128\n#Kind of grid\n3\n#Loadable\n0\n#Show\n1\n#Test case\n5\n#Map\n1\n#---\n")
+    assert configuration.get_parameters(str(tmp_path)) == (128, "overlapped", True, True, 5, "mercator")
+    with pytest.raises(SystemExit):
+        configuration.get_interpolation_parameters(str(tmp_path))      # missing file: print + exit
+    capsys.readouterr()
