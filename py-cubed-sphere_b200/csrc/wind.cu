@@ -8,6 +8,7 @@
 //   src/edges_treatment.py:306-347   RK2 line copies for ET-S72/PL07  -> rk2_copy_kernel
 // Compiled with -fmad=false (same rounding as the numpy expressions; only the
 // device sin/cos may differ from libm by an ulp).
+#include <cstdlib>
 #include "pycs_common.cuh"
 #include "cube_edges.cuh"
 
@@ -26,16 +27,9 @@ __device__ __forceinline__ void ll2contra(double ulon, double vlat, const Conv& 
   *v = b / c.det[id];
 }
 
-// velocity_adv on the interior edge points of one position (pu: i in [lo,hi], j in [lo,hi);
-// pv: i in [lo,hi), j in [lo,hi])
-__global__ void velocity_kernel(Geo g, int vf, double t, int is_pu, const double* __restrict__ lon,
-                                const double* __restrict__ lat, double* __restrict__ ulon,
-                                double* __restrict__ vlat) {
-  int j = g.lo + blockIdx.x * BX + threadIdx.x, i = g.lo + blockIdx.y, p = blockIdx.z;
-  int ih = is_pu ? g.hi : g.hi - 1, jh = is_pu ? g.hi - 1 : g.hi;
-  if (i > ih || j > jh) return;
-  long long id = gidx(g, p, i, j);
-  double lo_ = lon[id], la = lat[id], u, v;
+// velocity_adv (src/advection_ic.py:287-313) at one point
+__device__ __forceinline__ void velocity_point(int vf, double t, double lo_, double la, double* uo, double* vo) {
+  double u, v;
   const double pi = PI_;
   if (vf == 1) {
     double alpha = -45.0 * (1.0 / (180.0 / pi));
@@ -58,8 +52,48 @@ __global__ void velocity_kernel(Geo g, int vf, double t, int is_pu, const double
     u = -1 * (sin(lo_) * sin(lo_) * c3);
     v = -4 * c3 * sin(la) * cos(lo_) * sin(lo_);
   }
+  *uo = u;
+  *vo = v;
+}
+
+// velocity_adv on the interior edge points of one position (pu: i in [lo,hi], j in [lo,hi);
+// pv: i in [lo,hi), j in [lo,hi])
+__global__ void velocity_kernel(Geo g, int vf, double t, int is_pu, const double* __restrict__ lon,
+                                const double* __restrict__ lat, double* __restrict__ ulon,
+                                double* __restrict__ vlat) {
+  int j = g.lo + blockIdx.x * BX + threadIdx.x, i = g.lo + blockIdx.y, p = blockIdx.z;
+  int ih = is_pu ? g.hi : g.hi - 1, jh = is_pu ? g.hi - 1 : g.hi;
+  if (i > ih || j > jh) return;
+  long long id = gidx(g, p, i, j);
+  double u, v;
+  velocity_point(vf, t, lon[id], lat[id], &u, &v);
   ulon[id] = u;
   vlat[id] = v;
+}
+
+// update_adv for one position in ONE pass over the whole array (src/advection_timestep.py:48-75):
+// old <- the normal contravariant component; wind at t on the interior edge points; lat-lon ->
+// contravariant everywhere (ghost points keep their lat-lon values).  Same expressions as
+// velocity_kernel + copy2_kernel + convert_kernel, so the results are bit-identical.
+__global__ void update_adv_kernel(Geo g, int vf, double t, int is_pu, int ni, int nj, const double* __restrict__ lon,
+                                  const double* __restrict__ lat, Conv c, double* __restrict__ ulon,
+                                  double* __restrict__ vlat, double* __restrict__ uc, double* __restrict__ vc,
+                                  double* __restrict__ old) {
+  int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y, p = blockIdx.z;
+  if (j >= nj || i >= ni) return;
+  long long id = gidx(g, p, i, j);
+  old[id] = is_pu ? uc[id] : vc[id];
+  int ih = is_pu ? g.hi : g.hi - 1, jh = is_pu ? g.hi - 1 : g.hi;
+  double ul, vl;
+  if (i >= g.lo && i <= ih && j >= g.lo && j <= jh) {
+    velocity_point(vf, t, lon[id], lat[id], &ul, &vl);
+    ulon[id] = ul;
+    vlat[id] = vl;
+  } else {
+    ul = ulon[id];
+    vl = vlat[id];
+  }
+  ll2contra(ul, vl, c, id, &uc[id], &vc[id]);
 }
 
 // ll -> contravariant on a rectangle [i0,i1) x [j0,j1)
@@ -110,26 +144,29 @@ __global__ void ring_kernel(Geo g, const double* __restrict__ u, const double* _
                             double* __restrict__ ulon, double* __restrict__ vlat,
                             const double* __restrict__ exlon, const double* __restrict__ exlat,
                             const double* __restrict__ eylon, const double* __restrict__ eylat) {
-  int j = g.lo + blockIdx.x * BX + threadIdx.x, i = g.lo + blockIdx.y, p = blockIdx.z;
-  if (j >= g.hi || i >= g.hi) return;
-  int lo = g.lo, hi = g.hi;
-  bool ring = i < lo + PYCS_NG || i >= hi - PYCS_NG || j < lo + PYCS_NG || j >= hi - PYCS_NG;
-  if (!ring) return;
+  // one block per interior row: the 4 first / last rows entirely, otherwise the 4 + 4 frame columns
+  const int i = g.lo + blockIdx.y, p = blockIdx.z;
+  const int lo = g.lo, hi = g.hi;
+  const bool full = i < lo + PYCS_NG || i >= hi - PYCS_NG;
+  const int n = full ? g.N : 2 * PYCS_NG;
   const double a1 = 5.0 / 16.0, a2 = 15.0 / 16.0, a3 = -5.0 / 16.0, a4 = 1.0 / 16.0;
   const double b1 = -1.0 / 16.0, b2 = 9.0 / 16.0, b3 = 9.0 / 16.0, b4 = -1.0 / 16.0;
-  long long id = gidx(g, p, i, j);
   const long long L = g.ld;
-  double x, y;
-  if (i == lo) x = a1 * u[id] + a2 * u[id + L] + a3 * u[id + 2 * L] + a4 * u[id + 3 * L];
-  else if (i == hi - 1) x = a4 * u[id - 2 * L] + a3 * u[id - L] + a2 * u[id] + a1 * u[id + L];
-  else x = b1 * u[id - L] + b2 * u[id] + b3 * u[id + L] + b4 * u[id + 2 * L];
-  if (j == lo) y = a1 * v[id] + a2 * v[id + 1] + a3 * v[id + 2] + a4 * v[id + 3];
-  else if (j == hi - 1) y = a4 * v[id - 2] + a3 * v[id - 1] + a2 * v[id] + a1 * v[id + 1];
-  else y = b1 * v[id - 1] + b2 * v[id] + b3 * v[id + 1] + b4 * v[id + 2];
-  uc[id] = x;
-  vc[id] = y;
-  ulon[id] = exlon[id] * x + eylon[id] * y;               // src/sphgeo.py:131-132
-  vlat[id] = exlat[id] * x + eylat[id] * y;
+  for (int t = threadIdx.x; t < n; t += BX) {
+    const int j = full ? lo + t : (t < PYCS_NG ? lo + t : hi - 2 * PYCS_NG + t);
+    long long id = gidx(g, p, i, j);
+    double x, y;
+    if (i == lo) x = a1 * u[id] + a2 * u[id + L] + a3 * u[id + 2 * L] + a4 * u[id + 3 * L];
+    else if (i == hi - 1) x = a4 * u[id - 2 * L] + a3 * u[id - L] + a2 * u[id] + a1 * u[id + L];
+    else x = b1 * u[id - L] + b2 * u[id] + b3 * u[id + L] + b4 * u[id + 2 * L];
+    if (j == lo) y = a1 * v[id] + a2 * v[id + 1] + a3 * v[id + 2] + a4 * v[id + 3];
+    else if (j == hi - 1) y = a4 * v[id - 2] + a3 * v[id - 1] + a2 * v[id] + a1 * v[id + 1];
+    else y = b1 * v[id - 1] + b2 * v[id] + b3 * v[id + 1] + b4 * v[id + 2];
+    uc[id] = x;
+    vc[id] = y;
+    ulon[id] = exlon[id] * x + eylon[id] * y;               // src/sphgeo.py:131-132
+    vlat[id] = exlat[id] * x + eylat[id] * y;
+  }
 }
 
 // Ghost edges from ghost centres + conversion (src/interpolation.py:443-532).
@@ -139,20 +176,34 @@ template <int DIR>
 __global__ void ghost_edge_kernel(Geo g, const double* __restrict__ culon, const double* __restrict__ cvlat,
                                   double* __restrict__ ulon, double* __restrict__ vlat,
                                   double* __restrict__ uc, double* __restrict__ vc, Conv c) {
-  int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y, p = blockIdx.z;
-  int s = DIR == 0 ? i : j, o = DIR == 0 ? j : i;
-  if (o >= g.P || s < g.lo - 1 || s > g.hi + 1) return;
-  bool line = (s == g.lo - 1 || s == g.hi + 1);
-  bool ghost_o = (o < g.lo || o >= g.hi);
-  if (!(line || ghost_o)) return;
+  // one block per row i; it visits only the points this kernel writes:
+  //   DIR = 0 (s = i in [lo-1, hi+1]): the lines s = lo-1, hi+1 for all j, otherwise the ghost columns;
+  //   DIR = 1 (s = j in [lo-1, hi+1]): ghost rows take all s, interior rows only s = lo-1, hi+1.
+  const int i = blockIdx.y, p = blockIdx.z;
+  int n;
+  bool wide;
+  if (DIR == 0) {
+    if (i < g.lo - 1 || i > g.hi + 1) return;
+    wide = (i == g.lo - 1 || i == g.hi + 1);
+    n = wide ? g.P : 2 * PYCS_NG;
+  } else {
+    if (i >= g.P) return;
+    wide = (i < g.lo || i >= g.hi);
+    n = wide ? g.N + 3 : 2;
+  }
   const long long st = DIR == 0 ? g.ld : 1;
   const double a1 = 9.0 / 16.0, a2 = -1.0 / 16.0;
-  long long id = gidx(g, p, i, j);
-  double ul = a1 * (culon[id] + culon[id - st]) + a2 * (culon[id + st] + culon[id - 2 * st]);
-  double vl = a1 * (cvlat[id] + cvlat[id - st]) + a2 * (cvlat[id + st] + cvlat[id - 2 * st]);
-  ulon[id] = ul;
-  vlat[id] = vl;
-  ll2contra(ul, vl, c, id, &uc[id], &vc[id]);
+  for (int t = threadIdx.x; t < n; t += BX) {
+    int j;
+    if (DIR == 0) j = wide ? t : (t < PYCS_NG ? t : g.hi - PYCS_NG + t);
+    else j = wide ? g.lo - 1 + t : (t == 0 ? g.lo - 1 : g.hi + 1);
+    long long id = gidx(g, p, i, j);
+    double ul = a1 * (culon[id] + culon[id - st]) + a2 * (culon[id + st] + culon[id - 2 * st]);
+    double vl = a1 * (cvlat[id] + cvlat[id - st]) + a2 * (cvlat[id + st] + cvlat[id - 2 * st]);
+    ulon[id] = ul;
+    vlat[id] = vl;
+    ll2contra(ul, vl, c, id, &uc[id], &vc[id]);
+  }
 }
 
 // src/edges_treatment.py:311-347: ghost line of the normal wind beyond each cube edge
@@ -214,7 +265,7 @@ int k_wind_ghost_fill(pycs_handle h) {
     F(h, PYCS_F_PC_ULON, cul); F(h, PYCS_F_PC_VLAT, cvl);
     F(h, PYCS_F_PC_EXLON, exlon); F(h, PYCS_F_PC_EXLAT, exlat);
     F(h, PYCS_F_PC_EYLON, eylon); F(h, PYCS_F_PC_EYLAT, eylat);
-    ring_kernel<<<dim3((g.N + BX - 1) / BX, g.N, 6), BX, 0, h->stream>>>(g, u, v, cu, cv, cul, cvl, exlon,
+    ring_kernel<<<dim3(1, g.N, 6), BX, 0, h->stream>>>(g, u, v, cu, cv, cul, cvl, exlon,
                                                                          exlat, eylon, eylat);
     CKL(h);
     TRY(k_dg_fill(h, cul));
@@ -224,9 +275,9 @@ int k_wind_ghost_fill(pycs_handle h) {
     Conv cpu, cpv;
     TRY(get_conv(h, PYCS_F_PU_EXLON, &cpu));
     TRY(get_conv(h, PYCS_F_PV_EXLON, &cpv));
-    ghost_edge_kernel<0><<<grid_all(g.P + 1, g.P), BX, 0, h->stream>>>(g, cul, cvl, uul, uvl, u, uvc, cpu);
+    ghost_edge_kernel<0><<<dim3(1, g.P + 1, 6), BX, 0, h->stream>>>(g, cul, cvl, uul, uvl, u, uvc, cpu);
     CKL(h);
-    ghost_edge_kernel<1><<<grid_all(g.P, g.P + 1), BX, 0, h->stream>>>(g, cul, cvl, vul, vvl, vuc, v, cpv);
+    ghost_edge_kernel<1><<<dim3(1, g.P, 6), BX, 0, h->stream>>>(g, cul, cvl, vul, vvl, vuc, v, cpv);
     CKL(h);
   } else if (h->prm.dp == 2) {
     rk2_copy_kernel<<<dim3((g.N + BX - 1) / BX, 12), BX, 0, h->stream>>>(g, u, v);
@@ -277,5 +328,21 @@ int k_wind_interior(pycs_handle h, double t, int convert_interior_only, int do_v
 
 int k_update_adv(pycs_handle h, double t) {
   if (h->prm.vf < 2) return 0;               // src/advection_timestep.py:50
-  return k_wind_interior(h, t, 0, 1);
+  if (getenv("PYCS_UNFUSED_WIND")) return k_wind_interior(h, t, 0, 1);
+  // one pass per position: wind at t, old <- normal component, conversion of the whole array
+  const Geo& g = h->g;
+  F(h, PYCS_F_PU_LON, ulon_); F(h, PYCS_F_PU_LAT, ulat_); F(h, PYCS_F_PV_LON, vlon_); F(h, PYCS_F_PV_LAT, vlat_);
+  F(h, PYCS_F_PU_ULON, uul); F(h, PYCS_F_PU_VLAT, uvl); F(h, PYCS_F_PU_UCONTRA, uuc); F(h, PYCS_F_PU_VCONTRA, uvc);
+  F(h, PYCS_F_PV_ULON, vul); F(h, PYCS_F_PV_VLAT, vvl); F(h, PYCS_F_PV_UCONTRA, vuc); F(h, PYCS_F_PV_VCONTRA, vvc);
+  F(h, PYCS_F_PU_UOLD, uo); F(h, PYCS_F_PV_VOLD, vo);
+  Conv cpu, cpv;
+  TRY(get_conv(h, PYCS_F_PU_EXLON, &cpu));
+  TRY(get_conv(h, PYCS_F_PV_EXLON, &cpv));
+  update_adv_kernel<<<grid_all(g.P + 1, g.P), BX, 0, h->stream>>>(g, h->prm.vf, t, 1, g.P + 1, g.P, ulon_, ulat_, cpu,
+                                                                  uul, uvl, uuc, uvc, uo);
+  CKL(h);
+  update_adv_kernel<<<grid_all(g.P, g.P + 1), BX, 0, h->stream>>>(g, h->prm.vf, t, 0, g.P, g.P + 1, vlon_, vlat_, cpv,
+                                                                  vul, vvl, vuc, vvc, vo);
+  CKL(h);
+  return 0;
 }
