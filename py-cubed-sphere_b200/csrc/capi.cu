@@ -311,7 +311,8 @@ extern "C" int pycs_halo_gather(pycs_handle h, int32_t fx, int32_t fy, double* e
 extern "C" int pycs_halo_fill_dg(pycs_handle h, int32_t field) {
   double* q;
   TRY(pycs_field_ptr(h, field, &q));
-  return k_dg_fill(h, q);
+  if (getenv("PYCS_DG_TWO_PHASE")) return k_dg_fill(h, q);     // the reference's two phases as two launches
+  return k_dg_fill_single(h, q);
 }
 
 extern "C" int pycs_halo_fill_copy(pycs_handle h, int32_t fx, int32_t fy) {

@@ -813,6 +813,21 @@ void k_fused_release(pycs_handle h) {
   g_fused.erase(it);
 }
 
+// The plain Lagrange ghost fill (src/interpolation.py:154-314) of any centre field in one launch:
+// same arithmetic as dg_phase1_kernel + dg_phase2_kernel of halo.cu, without the dependency
+// between the two phases (corners recompute the neighbour's edge ghosts they read).
+int k_dg_fill_single(pycs_handle h, double* q) {
+  if (!h->kminE) {
+    pycs_set_error("ET-DG ghost fill needs pycs_upload_lagrange first");
+    return PYCS_ERR_STATE;
+  }
+  const int nbx = (h->g.N + 127) / 128;
+  dg_fill_fused_kernel<<<nbx * 4 * 24 + 3, 128, 0, h->stream>>>(h->g, h->maps, q, h->kminE, h->wE, h->order, nullptr,
+                                                                nullptr, 0, 0.0, h->red_out + 10, nullptr, 0, 0, nbx);
+  CKL(h);
+  return 0;
+}
+
 // the rows this handle updates changed (pycs_mgpu_init): recompute the launch geometry
 void k_fused_reset_grid(pycs_handle h) { g_fused[h].rows = 0; }
 

@@ -113,7 +113,8 @@ inline bool pycs_field_single_panel(int f) { return f >= PYCS_F_SQRTG_PC && f <=
 void pycs_build_halo_maps(const Geo& g, HaloMaps* maps);
 int k_halo_gather(pycs_handle h, const double* fx, const double* fy, double* buf);
 int k_halo_scatter_copy(pycs_handle h, double* fx, double* fy, const double* buf);
-int k_dg_fill(pycs_handle h, double* q);
+int k_dg_fill(pycs_handle h, double* q);          // two launches (halo.cu)
+int k_dg_fill_single(pycs_handle h, double* q);   // one launch (fused.cu)
 // ppm.cu
 int k_cfl(pycs_handle h, double* dst, const double* src, int dir);
 int k_mul_metric(pycs_handle h, double* gq, const double* q);

@@ -268,8 +268,8 @@ int k_wind_ghost_fill(pycs_handle h) {
     ring_kernel<<<dim3(1, g.N, 6), BX, 0, h->stream>>>(g, u, v, cu, cv, cul, cvl, exlon,
                                                                          exlat, eylon, eylat);
     CKL(h);
-    TRY(k_dg_fill(h, cul));
-    TRY(k_dg_fill(h, cvl));
+    TRY(k_dg_fill_single(h, cul));
+    TRY(k_dg_fill_single(h, cvl));
     F(h, PYCS_F_PU_ULON, uul); F(h, PYCS_F_PU_VLAT, uvl); F(h, PYCS_F_PU_VCONTRA, uvc);
     F(h, PYCS_F_PV_ULON, vul); F(h, PYCS_F_PV_VLAT, vvl); F(h, PYCS_F_PV_UCONTRA, vuc);
     Conv cpu, cpv;
