@@ -36,6 +36,7 @@
 #include "fused_args.cuh"
 #include "fused3_core.cuh"
 #include "mgpu.cuh"
+#include "ghost_core.cuh"
 static int f3_strip_capacity(int nw) { return f3::strip_capacity(nw); }
 
 namespace {
@@ -398,10 +399,7 @@ __global__ void __launch_bounds__(TB) fused_step_kernel(FusedArgs a) {
 // The fill is linear, so ghost(Q + corr*sqrtg) = ghost(Q) + corr * ghost(sqrtg): the second
 // factor is static and precomputed once (gs: the two-phase fill applied to the sqrtg field
 // itself, kept in the ghost cells of a 6-panel array).  The kernel therefore gathers only Q.
-__device__ __forceinline__ double halo_src(const double* __restrict__ q, const Geo& g, const SideMap& m, int a,
-                                           int b) {
-  return q[gidx(g, m.nb, m.ci + m.ai * a + m.bi * b, m.cj + m.aj * a + m.bj * b)];
-}
+// (device functions in ghost_core.cuh)
 
 // sum of n partials in a fixed order (every CTA gets the same bits)
 __device__ double reduce_partials(const double* __restrict__ part, int n, double* sh) {
@@ -414,23 +412,6 @@ __device__ double reduce_partials(const double* __restrict__ part, int n, double
   for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
   __syncthreads();
   return t;
-}
-
-// One ghost cell of phase 1 (src/interpolation.py:200-248): side s of panel p, ghost layer gl,
-// position k along the edge.  Same operations in the same order as dg_phase1_kernel in halo.cu.
-__device__ __forceinline__ double dg_phase1_value(const Geo& g, const HaloMaps& maps, const double* __restrict__ q,
-                                                  const int* __restrict__ kminE, const double* __restrict__ wE,
-                                                  int order, int p, int s, int gl, int k) {
-  const SideMap& m = maps.m[p][s];
-  const int ge = (s == SIDE_E || s == SIDE_N) ? gl : PYCS_NG - 1 - gl;
-  const int km = kminE[ge * g.P + k];
-  const double* w = wE + ((long long)ge * g.P + k) * order;
-  double acc = 0.0;
-  for (int l = 0; l < order; ++l) {
-    double v = (s < 2) ? halo_src(q, g, m, gl, km + l) : halo_src(q, g, m, km + l, gl);
-    acc = __dadd_rn(acc, __dmul_rn(v, w[l]));
-  }
-  return acc;
 }
 
 // The whole Lagrange ghost fill in ONE launch (it sits on the per-step critical path, and on
@@ -446,7 +427,7 @@ __global__ void dg_fill_fused_kernel(Geo g, HaloMaps maps, double* __restrict__ 
                                      const double* __restrict__ wE, int order, const double* __restrict__ gs,
                                      const double* __restrict__ part, int npart, double inv_a2,
                                      double* __restrict__ corr_out, const long long* __restrict__ flags, int world,
-                                     long long epoch, int nbx) {
+                                     long long epoch, int nbx, const double* __restrict__ corr_in) {
   __shared__ double sh[32];
   // programmatic dependent launch (no-ops otherwise): this grid may start while the previous
   // step kernel drains; nothing of it is read before this point
@@ -464,7 +445,10 @@ __global__ void dg_fill_fused_kernel(Geo g, HaloMaps maps, double* __restrict__ 
     __syncthreads();
   }
   double corr = 0.0;
-  if (npart > 0) {
+  if (corr_in) {                       // projection coefficient already known (ring restore after a run)
+    corr = *corr_in;
+    npart = 1;
+  } else if (npart > 0) {
     corr = -reduce_partials(part, npart, sh) * inv_a2;
     if (blockIdx.x == 0 && threadIdx.x == 0) *corr_out = corr;
   }
@@ -492,23 +476,7 @@ __global__ void dg_fill_fused_kernel(Geo g, HaloMaps maps, double* __restrict__ 
   const int gl = c32 >> 3, c = c32 & 7;
   const int k = (c < 4) ? c : g.hi + (c - 4);
   const int p = pe >> 1, s = pe & 1;
-  const SideMap& m = maps.m[p][s];
-  const int ge = (s == SIDE_E) ? gl : PYCS_NG - 1 - gl;
-  const int km = kminE[ge * g.P + k];
-  const double* w = wE + ((long long)ge * g.P + k) * order;
-  double acc = 0.0;
-  for (int l = 0; l < order; ++l) {
-    const int b_ = km + l;
-    const int si = m.ci + m.ai * gl + m.bi * b_, sj = m.cj + m.aj * gl + m.bj * b_;
-    const bool ii = si >= g.lo && si < g.hi, jj = sj >= g.lo && sj < g.hi;
-    double v;
-    if (ii && jj) v = q[gidx(g, m.nb, si, sj)];
-    else if (ii) v = dg_phase1_value(g, maps, q, kminE, wE, order, m.nb, sj >= g.hi ? SIDE_N : SIDE_S,
-                                     sj >= g.hi ? sj - g.hi : sj, si);
-    else v = dg_phase1_value(g, maps, q, kminE, wE, order, m.nb, si >= g.hi ? SIDE_E : SIDE_W,
-                             si >= g.hi ? si - g.hi : si, sj);
-    acc = __dadd_rn(acc, __dmul_rn(v, w[l]));
-  }
+  double acc = dg_corner_value(g, maps, q, kminE, wE, order, p, s, gl, k);
   const int i = (s == SIDE_E) ? g.hi + gl : gl;
   const long long id = gidx(g, p, i, k);
   if (npart > 0) acc = fma(gs[id], corr, acc);
@@ -609,6 +577,8 @@ struct FusedState {
   double* gs = nullptr;        // ghost cells: Lagrange fill of the sqrtg field (static)
   double* part = nullptr;
   unsigned* counter = nullptr; // last-writer ticket of the step kernels
+  int ghost_fused = 0;         // PYCS_GHOST_FUSED=1: v2b computes the ghost cells itself (single GPU)
+  int last_pend = 0;           // the last step applied a pending projection term (for the ring restore)
   int pdl = 0;                 // PYCS_PDL=1: ghost fill and step kernel launched with programmatic stream serialization
   int mg_fused = 0;            // multi-GPU: 1 = v2b stores to the peers itself (PYCS_MG_FUSED=1; measured slower), 0 = exchange kernel
   int prof = -1;               // PYCS_STEP_PROFILE: CUDA events around the kernels of every step
@@ -715,6 +685,7 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
     fs.impl = impl;
     if (const char* emf = getenv("PYCS_MG_FUSED")) fs.mg_fused = atoi(emf);
     if (const char* epd = getenv("PYCS_PDL")) fs.pdl = atoi(epd);
+    if (const char* egf = getenv("PYCS_GHOST_FUSED")) fs.ghost_fused = atoi(egf);
     cols = 6 * fs.nstrips;
     if (rows <= 0) {
       // whole waves of resident CTAs: time ~ waves * (rows + ramp)
@@ -793,6 +764,15 @@ int k_fused_flush(pycs_handle h) {
     CKL(h);
     fs.pending = 0;
   }
+  if (fs.ring_pending && fs.impl == 4 && fs.ghost_fused && !h->mg && h->kminE) {
+    // the step kernel filled only the ghost cells it needed: rebuild the whole 4-wide ring of the
+    // buffer the last step read (its interior is intact) before it is copied over
+    const int nbx = (g.N + 127) / 128;
+    dg_fill_fused_kernel<<<nbx * 4 * 24 + 3, 128, 0, h->stream>>>(
+        g, h->maps, qo, h->kminE, h->wE, h->order, fs.last_pend ? fs.gs : nullptr, nullptr, 0, 0.0, h->red_out + 10,
+        nullptr, 0, 0, nbx, fs.last_pend ? h->red_out + 8 : nullptr);
+    CKL(h);
+  }
   if (fs.ring_pending) {
     copy_ring_kernel<<<dim3((g.P + 127) / 128, g.P, 6), 128, 0, h->stream>>>(g, q, qo);
     CKL(h);
@@ -823,7 +803,7 @@ int k_dg_fill_single(pycs_handle h, double* q) {
   }
   const int nbx = (h->g.N + 127) / 128;
   dg_fill_fused_kernel<<<nbx * 4 * 24 + 3, 128, 0, h->stream>>>(h->g, h->maps, q, h->kminE, h->wE, h->order, nullptr,
-                                                                nullptr, 0, 0.0, h->red_out + 10, nullptr, 0, 0, nbx);
+                                                                nullptr, 0, 0.0, h->red_out + 10, nullptr, 0, 0, nbx, nullptr);
   CKL(h);
   return 0;
 }
@@ -886,6 +866,29 @@ int k_wind_catch_up(pycs_handle h, long long k) {
   return k_update_adv(h, (double)k * h->g.dt);
 }
 
+// ghost(sqrtg): the Lagrange fill applied to the metric field itself, once (see dg_fill_fused_kernel)
+static int ensure_gs(pycs_handle h, FusedState& fs) {
+  if (h->prm.mf != 3 || fs.gs) return 0;
+  if (!h->kminE) {
+    pycs_set_error("fused step needs pycs_upload_lagrange first");
+    return PYCS_ERR_STATE;
+  }
+  const Geo& g = h->g;
+  double* sgc;
+  TRY(pycs_field_ptr(h, PYCS_F_SQRTG_PC, &sgc));
+  const size_t bytes = sizeof(double) * 6 * (size_t)g.ps;
+  CK(cudaMalloc(&fs.gs, bytes));
+  CK(cudaMemsetAsync(fs.gs, 0, bytes, h->stream));
+  spread_metric_kernel<<<dim3((g.N + 127) / 128, g.N, 6), 128, 0, h->stream>>>(g, sgc, fs.gs);
+  CKL(h);
+  const int nbx = (g.N + 127) / 128;
+  dg_fill_fused_kernel<<<nbx * 4 * 24 + 3, 128, 0, h->stream>>>(g, h->maps, fs.gs, h->kminE, h->wE, h->order, nullptr,
+                                                                nullptr, 0, 0.0, h->red_out + 10, nullptr, 0, 0, nbx,
+                                                                nullptr);
+  CKL(h);
+  return 0;
+}
+
 static int launch_step_kernel(pycs_handle h, FusedState& fs, const double* qcur, double* qnext, int pend,
                               int mask, double ws) {
   const Geo& g = h->g;
@@ -911,6 +914,19 @@ static int launch_step_kernel(pycs_handle h, FusedState& fs, const double* qcur,
   a.row_lo = h->row_lo; a.row_hi = h->row_hi;
   a.mg.world = 0;
   a.pdl = fs.pdl;
+  a.gf.enable = 0;
+  if (fs.impl == 4 && fs.ghost_fused && !h->mg) {
+    a.gf.enable = 1;
+    a.gf.order = h->order;
+    a.gf.kminE = h->kminE;
+    a.gf.wE = h->wE;
+    a.gf.gs = fs.gs;
+    a.gf.sums = h->red_out + 9;
+    a.gf.nsums = 1;
+    a.gf.inv_a2 = pend ? 1.0 / h->a2 : 0.0;
+    a.gf.corr_out = h->red_out + 8;
+    a.gf.maps = h->maps;
+  }
   if (h->mg && fs.impl == 4 && fs.mg_fused) TRY(k_mg_fill_args(h, qnext, &a.mg));   // exchange inside the kernel
   a.apply_corr = pend;
   a.cdx = g.dt / g.dx; a.cdy = g.dt / g.dy;
@@ -935,6 +951,7 @@ int k_fused_time_kernel(pycs_handle h, int reps, int separable, float* ms) {
   TRY(pycs_field_ptr(h, PYCS_F_Q_NEXT, &qb));
   int mask = separable ? 2 : ((h->prm.dp == 2) ? 1 : 0);
   if (separable) TRY(ensure_base_winds(h, fs));
+  TRY(ensure_gs(h, fs));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaEventRecord(h->ev0, h->stream));
   for (int r = 0; r < reps; ++r)
@@ -993,21 +1010,8 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   double* qcur = h->qcur ? qb : qa;
   double* qnext = h->qcur ? qa : qb;
   if (separable) TRY(ensure_base_winds(h, fs));
-  if (h->prm.mf == 3 && !fs.gs) {
-    // ghost(sqrtg): the fill applied to the metric field itself, once (see dg_fill_fused_kernel)
-    const size_t bytes = sizeof(double) * 6 * (size_t)g.ps;
-    CK(cudaMalloc(&fs.gs, bytes));
-    CK(cudaMemsetAsync(fs.gs, 0, bytes, h->stream));
-    spread_metric_kernel<<<dim3((g.N + 127) / 128, g.N, 6), 128, 0, h->stream>>>(g, sgc, fs.gs);
-    CKL(h);
-    const int nbx = (g.N + 127) / 128;
-    dg_fill_fused_kernel<<<nbx * 4 * 24 + 3, 128, 0, h->stream>>>(g, h->maps, fs.gs, h->kminE, h->wE, h->order,
-                                                                  nullptr, nullptr, 0, 0.0, h->red_out + 10, nullptr,
-                                                                  0, 0, nbx);
-    CKL(h);
-  }
+  TRY(ensure_gs(h, fs));
 
-  // 0. multi-GPU: the peers' halo rows, boundary strips and MF-PR sums of the last step are in
   const double* sums = h->red_out + 9;     // total of the last step kernel's partials
   int nsums = 1;
   const long long* mgflags = nullptr;
@@ -1031,7 +1035,8 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   mark();
   // 1. ghost cells of Q (src/advection_timestep.py:28), folding in the pending MF-PR term
   int pend = fs.pending;
-  {
+  const bool ghost_in_kernel = fs.impl == 4 && fs.ghost_fused && !h->mg;
+  if (!ghost_in_kernel) {
     const int nbx = (g.N + 127) / 128;
     if (fs.pdl && fs.impl == 4) {
       cudaLaunchConfig_t cfg = {};
@@ -1045,11 +1050,11 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
       cfg.numAttrs = 1;
       CK(cudaLaunchKernelEx(&cfg, dg_fill_fused_kernel, g, h->maps, qcur, (const int*)h->kminE, (const double*)h->wE,
                             h->order, (const double*)fs.gs, sums, pend ? nsums : 0, pend ? 1.0 / h->a2 : 0.0,
-                            h->red_out + 8, mgflags, mgworld, mgepoch, nbx));
+                            h->red_out + 8, mgflags, mgworld, mgepoch, nbx, (const double*)nullptr));
     } else {
       dg_fill_fused_kernel<<<nbx * 4 * 24 + 3, 128, 0, h->stream>>>(
           g, h->maps, qcur, h->kminE, h->wE, h->order, fs.gs, sums, pend ? nsums : 0, pend ? 1.0 / h->a2 : 0.0,
-          h->red_out + 8, mgflags, mgworld, mgepoch, nbx);
+          h->red_out + 8, mgflags, mgworld, mgepoch, nbx, nullptr);
     }
     CKL(h);
   }
@@ -1068,6 +1073,7 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   mark();
   h->last_step_kernel_launches++;
   h->qcur ^= 1;
+  fs.last_pend = pend;
   fs.pending = (h->prm.mf == 3) ? 1 : 0;
   fs.ring_pending = 1;
   // 4. wind refresh for the next step (src/advection_timestep.py:48-75)

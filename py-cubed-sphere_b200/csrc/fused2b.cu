@@ -17,6 +17,7 @@
 // x-flux, output row r-3).
 #include "fused_args.cuh"
 #include "mgpu.cuh"
+#include "ghost_core.cuh"
 #define F3_NAMESPACE f1
 #define F3_NC 1
 #define F3_CSTEP 0
@@ -107,7 +108,36 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   // (the ghost fill); its results (ghost cells, corr) are read only below.  No-ops otherwise.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  const double corr = a.apply_corr ? *a.corr : 0.0;
+  double corr = 0.0;
+  if (a.gf.enable) {
+    // ---- ghost prologue: the Lagrange ghost cells of the rectangle this CTA stages (rows
+    // rfirst..rlast, columns jbase-3..jend+2), written in place before the TMA copies read them.
+    // Neighbouring CTAs compute the ghost cells they share; the values are identical.
+    if (a.apply_corr) {
+      double sm = 0.0;
+      for (int k = 0; k < a.gf.nsums; ++k) sm += a.gf.sums[k];
+      corr = -sm * a.gf.inv_a2;
+      if (blockIdx.x == 0 && tid == 0) *a.gf.corr_out = corr;
+    }
+    const int cl = jbase - 3, cr = min(jend + 2, g.P - 1);
+    if (rfirst < g.lo || rlast >= g.hi || cl < g.lo || cr >= g.hi) {
+      const int nC = cr - cl + 1, ncell = (rlast - rfirst + 1) * nC;
+      double* qw = const_cast<double*>(a.q);
+      for (int t = tid; t < ncell; t += TB) {
+        const int i = rfirst + t / nC, jj = cl + t % nC;
+        if (i >= g.lo && i < g.hi && jj >= g.lo && jj < g.hi) continue;
+        double v = dg_ghost_cell(g, a.gf.maps, a.q, a.gf.kminE, a.gf.wE, a.gf.order, p, i, jj);
+        const long long id = gidx(g, p, i, jj);
+        if (a.apply_corr) v = fma(a.gf.gs[id], corr, v);
+        qw[id] = v;
+      }
+      asm volatile("fence.proxy.async.global;" ::: "memory");   // generic stores -> TMA (async proxy) reads
+      __threadfence();
+    }
+    __syncthreads();
+  } else if (a.apply_corr) {
+    corr = *a.corr;
+  }
 
   // TMA row copies are issued by one elected lane of warp 0 (one row per marched row, PF rows ahead).  Its slot
   // offsets rotate in registers and the global addresses are base + row * ld: the issue path

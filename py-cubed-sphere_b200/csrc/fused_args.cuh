@@ -14,6 +14,20 @@ struct FusedMg {
   MgSync* peer_sync[8];
 };
 
+// Ghost fill fused into the step kernel (fused2b.cu, single GPU): every CTA computes the ghost
+// cells its own rows / columns touch before it stages them, so the stand-alone ghost-fill launch
+// disappears from the step.
+struct FusedGhost {
+  int enable, order, nsums;
+  const int* kminE;
+  const double* wE;
+  const double* gs;           // ghost(sqrtg), see dg_fill_fused_kernel
+  const double* sums;         // MF-PR sums of the previous step (nsums of them)
+  double inv_a2;
+  double* corr_out;           // the projection coefficient of this launch, for the ring restore
+  HaloMaps maps;
+};
+
 struct FusedArgs {
   Geo g;
   const double* q;
@@ -31,6 +45,7 @@ struct FusedArgs {
   double ws;                  // separable wind: U(t) = U(0) * ws (MASK & 2)
   FusedMg mg;                 // world <= 1: single GPU
   int pdl;                    // launch with programmatic stream serialization (v2b)
+  FusedGhost gf;
 };
 
 #ifdef __CUDACC__
