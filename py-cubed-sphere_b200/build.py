@@ -50,17 +50,25 @@ def build(force=False, verbose=False):
     nvcc = _nvcc()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     headers.append(os.path.join(HERE, "..", "include", "pycs_b200.h"))
-    objs = []
+    objs, jobs = [], []
     for unit, flags in UNITS.items():
         src = os.path.join(CSRC, unit)
         obj = os.path.join(OBJDIR, unit.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + headers):
-            cmd = [nvcc] + ARCH + COMMON + flags + ["-c", src, "-o", obj]
-            r = subprocess.run(cmd, capture_output=True, text=True)
-            log = os.path.join(OBJDIR, unit + ".ptxas.log")
-            with open(log, "w") as f:
-                f.write(r.stdout + r.stderr)
+            jobs.append((unit, [nvcc] + ARCH + COMMON + flags + ["-c", src, "-o", obj]))
+
+    def compile_one(job):
+        unit, cmd = job
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        with open(os.path.join(OBJDIR, unit + ".ptxas.log"), "w") as f:
+            f.write(r.stdout + r.stderr)
+        return unit, r
+
+    # the translation units are independent: compile them side by side
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1) or 1) as pool:
+        for unit, r in pool.map(compile_one, jobs):
             if r.returncode != 0:
                 raise RuntimeError("nvcc failed for %s:\n%s" % (unit, r.stderr))
             if verbose:

@@ -31,15 +31,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_row(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -356,7 +347,8 @@ cudaError_t launch_mg(const FusedArgs& a, int nblocks, cudaStream_t st, int* res
 
 template <int TB, int RECON, int SPLIT, int MASK, int PF, int MINB>
 cudaError_t launch_one(const FusedArgs& a, int nblocks, cudaStream_t st, int* resident) {
-  if (a.mg.world > 1) return launch_mg<TB, RECON, SPLIT, MASK, PF, MINB, 1>(a, nblocks, st, resident);
+  // the multi-GPU build is never unrolled: one instantiation per register cap
+  if (a.mg.world > 1) return launch_mg<TB, RECON, SPLIT, MASK, PF, MINB % 10, 1>(a, nblocks, st, resident);
   return launch_mg<TB, RECON, SPLIT, MASK, PF, MINB, 0>(a, nblocks, st, resident);
 }
 
@@ -375,11 +367,9 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb,
   if (recon == 3 && split == 1) {
 #define TUNE(T, P, M) \
   if (tb == T && pf == P && minb == M) return launch_mask<T, 3, 1, P, M>(a, mask, nblocks, st, resident)
-    TUNE(160, 1, 4); TUNE(160, 2, 4); TUNE(160, 2, 14); TUNE(160, 1, 14); TUNE(128, 2, 15); TUNE(160, 2, 24);
-    TUNE(160, 3, 24); TUNE(160, 1, 5); TUNE(160, 2, 5); TUNE(160, 3, 4);
-    TUNE(128, 1, 5); TUNE(128, 2, 5); TUNE(128, 2, 6); TUNE(128, 3, 5);
-    TUNE(192, 1, 4); TUNE(192, 2, 4); TUNE(192, 2, 3);
-    TUNE(256, 1, 3); TUNE(256, 2, 3); TUNE(256, 2, 2);
+    // (threads, rows in flight, MINB): measured points worth keeping, see profiles/r1_sweep_v2b.log
+    TUNE(160, 2, 14); TUNE(160, 1, 14); TUNE(160, 2, 4); TUNE(160, 1, 4); TUNE(160, 2, 24); TUNE(128, 2, 15);
+    TUNE(128, 2, 5);
 #undef TUNE
     return cudaErrorInvalidValue;
   }
@@ -397,9 +387,7 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb,
 bool pycs_fused2b_has(int recon, int split, int tb, int pf, int minb) {
   if (recon != 1 && recon != 3) return false;
   if (recon == 3 && split == 1) {
-    const int t[][3] = {{160, 1, 4}, {160, 2, 4}, {160, 2, 14}, {160, 1, 14}, {128, 2, 15}, {160, 2, 24}, {160, 3, 24}, {160, 1, 5}, {160, 2, 5}, {160, 3, 4}, {128, 1, 5}, {128, 2, 5},
-                        {128, 2, 6}, {128, 3, 5}, {192, 1, 4}, {192, 2, 4}, {192, 2, 3}, {256, 1, 3}, {256, 2, 3},
-                        {256, 2, 2}};
+    const int t[][3] = {{160, 2, 14}, {160, 1, 14}, {160, 2, 4}, {160, 1, 4}, {160, 2, 24}, {128, 2, 15}, {128, 2, 5}};
     for (auto& x : t)
       if (x[0] == tb && x[1] == pf && x[2] == minb) return true;
     return false;

@@ -14,9 +14,8 @@ tup = (3, 1, 1, 3, 1, 3)
 if which == "v2":
     configs = [dict(IMPL=2, TB=tb, DEPTH=d, ROWS=rows) for tb in (128, 160) for d in (5, 6) for rows in (0, 48, 96)]
 elif which == "v2b":
-    pts = ((160, 2, 14), (160, 2, 24), (160, 3, 24), (160, 1, 14), (128, 2, 15), (160, 1, 4), (160, 2, 4), (160, 1, 5), (160, 2, 5), (160, 3, 4), (128, 1, 5), (128, 2, 5), (128, 2, 6),
-           (128, 3, 5), (192, 1, 4), (192, 2, 4), (192, 2, 3), (256, 1, 3), (256, 2, 3), (256, 2, 2))
-    configs = [dict(IMPL=4, TB=tb, PF=pf, MINB=mb, ROWS=rows) for tb, pf, mb in pts[:3] for rows in (0, 86)]
+    pts = ((160, 2, 14), (160, 1, 14), (160, 2, 4), (160, 1, 4), (160, 2, 24), (128, 2, 15), (128, 2, 5))
+    configs = [dict(IMPL=4, TB=tb, PF=pf, MINB=mb, ROWS=rows) for tb, pf, mb in pts for rows in (0, 96)]
 else:
     pts = ((3, 3, 3), (3, 2, 3), (3, 4, 3), (3, 2, 4), (3, 3, 4), (3, 3, 13), (3, 4, 13), (2, 3, 4), (2, 4, 4), (2, 4, 5),
            (4, 2, 2), (4, 3, 2), (4, 2, 3))
