@@ -18,14 +18,20 @@
 #include "fused_args.cuh"
 #include "mgpu.cuh"
 #include "ghost_core.cuh"
+// PPM-PL07 edge-value coefficients as constant-bank operands (const-slot march only)
+__constant__ double f2b_ppm_coef[5] = {2.0 / 60.0, -13.0 / 60.0, 47.0 / 60.0, 27.0 / 60.0, -3.0 / 60.0};
+#define F3_COEF_BANK f2b_ppm_coef
 #define F3_NAMESPACE f1
 #define F3_NC 1
 #define F3_CSTEP 0
 #include "fused3_core.cuh"
+#undef F3_COEF_BANK
 
 namespace {
 
 using namespace f1;
+
+template <int K> struct IC { static constexpr int value = K; };   // compile-time row phase
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -53,7 +59,11 @@ __device__ __forceinline__ bool elect_one() {
 // (kept out of the single-GPU instantiation: the extra code in the unrolled march loop costs ~7 %)
 template <int TB, int RECON, int SPLIT, int MASK, int PF, int MINB, int MG>
 __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
-  // MINB >= 10: register cap of MINB - 10 CTAs/SM and the march loop unrolled by the window length
+  // MINB >= 10: register cap of MINB % 10 CTAs/SM and the march loop unrolled by the window length;
+  // MINB >= 30: the march runs in groups of DL rows with every ring slot a compile-time constant
+  // (all staged-row loads become [one base register + immediate]) and the TMA issue path keeps
+  // running byte offsets instead of recomputing row * ld (see profiles/r1_sass_static.md)
+  constexpr bool CS = (MINB >= 30) && !MG;
   constexpr int RW = TB + 6;                 // staged row: columns jbase-6 .. jbase+TB-1
   constexpr int NS = (MASK & 1) ? 4 : 3, NL = (MASK & 1) ? 5 : 4;
   constexpr int DS = PF + 1, DL = PF + 4;
@@ -176,113 +186,228 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
     issue_a(r);
     issue_b(r, iS, iL, ib);
   };
-  if (warp_u == 0) {
-    for (int r = rfirst; r < rfirst + PF && r <= rlast; ++r) {
-      if (elect_one()) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue(r);
+  double psum_cta = 0.0;
+  if constexpr (CS) {
+    static_assert(PF == 2, "const-slot march: rings of 3 and 6 rows, windows of 6 registers");
+    static_assert(DL == WLEN && DL % DS == 0, "const-slot march: one period for rings and windows");
+    const long long ld8 = (long long)g.ld * 8;
+    long long o0 = (long long)rfirst * ld8;    // byte offset of the next row to issue
+    auto at = [](const double* base, long long off) {
+      return reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + off);
+    };
+    // k = (row - rfirst) % DL is a compile-time constant everywhere below; o1, o2: offsets of the
+    // rows staged one and two rows late (sqrtg_pu, u)
+    auto issue_k = [&](auto kc, long long o1, long long o2) {   // elected lane of warp 0
+      constexpr int k = decltype(kc)::value;
+      const uint32_t dS = ringS_a + 8u * (uint32_t)((k % DS) * SSLOT), dL = ringL_a + 8u * (uint32_t)(k * LSLOT),
+                     bar = full_a + 8u * (uint32_t)k;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * (NS + NL))
+                   : "memory");
+      tma(dS + 8u * S_Q * RW, at(gq, o0), bar);
+      tma(dL + 8u * L_V * RW, at(gv, o0), bar);
+      tma(dL + 8u * L_SGC * RW, at(gsgc, o0), bar);
+      tma(dL + 8u * L_SGV * RW, at(gsgv, o0), bar);
+      if (MASK & 1) tma(dL + 8u * L_VM * RW, at(gvm, o0), bar);
+      tma(dL + 8u * L_RGC * RW, at(grgc, o0), bar);
+      tma(dS + 8u * S_SGU * RW, at(gsgu, o1), bar);
+      tma(dS + 8u * S_U * RW, at(gu, o2), bar);
+      if (MASK & 1) tma(dS + 8u * S_UM * RW, at(gum, o2), bar);
+    };
+    if (warp_u == 0) {                         // rows rfirst, rfirst + 1 (rfirst >= 1: only row -1 is clamped)
+      if (elect_one()) issue_k(IC<0>{}, o0 - ld8, (long long)max(rfirst - 2, 0) * ld8);
+      o0 += ld8;
+      if (rfirst + 1 <= rlast) {
+        if (elect_one()) issue_k(IC<1>{}, o0 - ld8, o0 - 2 * ld8);
+        o0 += ld8;
       }
-      iS = (iS + 8 * SSLOT == 8 * DS * SSLOT) ? 0 : iS + 8 * SSLOT;
-      iL = (iL + 8 * LSLOT == 8 * DL * LSLOT) ? 0 : iL + 8 * LSLOT;
-      ib = (ib + 1 == DL) ? 0 : ib + 1;
     }
-  }
+    double* __restrict__ QN = a.qn + (long long)p * g.ps + PYCS_JOFF + min(j, g.P - 1) + (long long)r0 * g.ld;
+    Lane L;
+    lane_init(L);
+    const double* const eS = ringS + e;        // the thread's element in slot 0 of either ring
+    const double* const eL = ringL + e;
+    uint32_t parb = 0;
+    // one marched row; false once the chunk is finished
+    auto row = [&](auto kc, int r) -> bool {
+      constexpr int k = decltype(kc)::value;
+      if (r > rlast) return false;
+      constexpr int kS = (k % DS) * SSLOT, kL0 = k * LSLOT, kL2 = ((k + DL - 2) % DL) * LSLOT,
+                    kL3 = ((k + DL - 3) % DL) * LSLOT;
+      while (!mbar_try_wait(&full[k], parb)) {}
+      RowPtrs R;
+      R.q = eS + kS + S_Q * RW;
+      R.u = eS + kS + S_U * RW;
+      R.um = eS + kS + S_UM * RW;
+      R.su1 = eS + kS + S_SGU * RW;
+      R.v0 = eL + kL0 + L_V * RW;
+      R.vm0 = eL + kL0 + L_VM * RW;
+      R.sgv0 = eL + kL0 + L_SGV * RW;
+      R.sgc0 = eL + kL0 + L_SGC * RW;
+      R.rg0 = eL + kL0 + L_RGC * RW;
+      R.sgc2 = eL + kL2 + L_SGC * RW;
+      R.v3 = eL + kL3 + L_V * RW;
+      R.vm3 = eL + kL3 + L_VM * RW;
+      R.sgv3 = eL + kL3 + L_SGV * RW;
+      R.sgc3 = eL + kL3 + L_SGC * RW;
+      R.rg3 = eL + kL3 + L_RGC * RW;
+      double qnew[1] = {R.q[0]};
+      if (a.apply_corr && jint && r >= g.lo && r < g.hi) {
+        qnew[0] = fma(R.sgc0[0], corr, qnew[0]);
+        ringS[kS + S_Q * RW + e] = qnew[0];
+      }
+      // ---------------- phase 1: own column
+      XEdge X;
+      double qx[1];
+      phase_x_inner<RECON, SPLIT, MASK, k>(L, X, R, qnew, cdx, qx);
+      sX[e] = qx[0];
+      __syncthreads();                                   // barrier A
+      if (warp_u == 0 && r + PF <= rlast) {              // warp 0 issues the TMA copies of row r+PF
+        if (elect_one()) issue_k(IC<(k + PF) % DL>{}, o0 - ld8, o0 - 2 * ld8);
+        o0 += ld8;
+      }
+      // ---------------- phase 2: y-fluxes at edge j: inner on Q row r, outer on Qx row r-3
+      double F[1], G[1], CF[1] = {0.0}, CG[1];
+      yflux_pair<RECON, SPLIT, MASK, k>(R.v0, R.vm0, R.sgv0, R.sgc0, R.q, cdy, F, CF);
+      yflux_pair<RECON, SPLIT, MASK, k>(R.v3, R.vm3, R.sgv3, R.sgc3, sX + e, cdy, G, CG);
+      sF[e] = F[0];
+      sG[e] = G[0];
+      if (SPLIT != 1) sC[e] = CF[0];
+      __syncthreads();                                   // barrier B
+      // ---------------- phase 3: Qy row r, outer x-flux on Qy, output row r-3
+      double Fn[1], Gn[1], CFn[1] = {0.0}, out[1], sdiv[1];
+      Fn[0] = sF[e + 1];
+      Gn[0] = sG[e + 1];
+      if (SPLIT != 1) CFn[0] = sC[e + 1];
+      phase_x_outer<RECON, SPLIT, k>(L, X, R, F, Fn, G, Gn, CF, CFn, out, sdiv);
+      if (r >= r0 + 3) {
+        if (out_lane) {
+          *QN = out[0];
+          L.psum += sdiv[0];
+        }
+        QN += g.ld;
+      }
+      return true;
+    };
+    for (int rb = rfirst;; rb += DL, parb ^= 1u) {
+      if (!row(IC<0>{}, rb)) break;
+      if (!row(IC<1>{}, rb + 1)) break;
+      if (!row(IC<2>{}, rb + 2)) break;
+      if (!row(IC<3>{}, rb + 3)) break;
+      if (!row(IC<4>{}, rb + 4)) break;
+      if (!row(IC<5>{}, rb + 5)) break;
+    }
+    psum_cta = L.psum;
+  } else {
+    if (warp_u == 0) {
+      for (int r = rfirst; r < rfirst + PF && r <= rlast; ++r) {
+        if (elect_one()) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          issue(r);
+        }
+        iS = (iS + 8 * SSLOT == 8 * DS * SSLOT) ? 0 : iS + 8 * SSLOT;
+        iL = (iL + 8 * LSLOT == 8 * DL * LSLOT) ? 0 : iL + 8 * LSLOT;
+        ib = (ib + 1 == DL) ? 0 : ib + 1;
+      }
+    }
 
-  double* __restrict__ QN = a.qn + (long long)p * g.ps + PYCS_JOFF + min(j, g.P - 1) + (long long)r0 * g.ld;
-  Lane L;
-  lane_init(L);
-  int oS = 0;
-  int oL0 = 0, oL1 = (DL - 1) * LSLOT, oL2 = (DL - 2) * LSLOT, oL3 = (DL - 3) * LSLOT;
-  int sb = 0;
-  uint32_t parb = 0;
-#pragma unroll((MINB >= 10 && !MG) ? 5 : 1)   // MINB 1x / 2x: unrolled by the window length
-  for (int r = rfirst; r <= rlast; ++r) {
-    while (!mbar_try_wait(&full[sb], parb)) {}
-    RowPtrs R;
-    R.q = ringS + oS + S_Q * RW + e;
-    R.u = ringS + oS + S_U * RW + e;
-    R.um = ringS + oS + S_UM * RW + e;
-    R.su1 = ringS + oS + S_SGU * RW + e;
-    R.v0 = ringL + oL0 + L_V * RW + e;
-    R.vm0 = ringL + oL0 + L_VM * RW + e;
-    R.sgv0 = ringL + oL0 + L_SGV * RW + e;
-    R.sgc0 = ringL + oL0 + L_SGC * RW + e;
-    R.rg0 = ringL + oL0 + L_RGC * RW + e;
-    R.sgc2 = ringL + oL2 + L_SGC * RW + e;
-    R.v3 = ringL + oL3 + L_V * RW + e;
-    R.vm3 = ringL + oL3 + L_VM * RW + e;
-    R.sgv3 = ringL + oL3 + L_SGV * RW + e;
-    R.sgc3 = ringL + oL3 + L_SGC * RW + e;
-    R.rg3 = ringL + oL3 + L_RGC * RW + e;
-    // pending MF-PR term on the own interior cell of the new row (neighbours read it after barrier A)
-    double qnew[1] = {R.q[0]};
-    if (a.apply_corr && jint && r >= g.lo && r < g.hi) {
-      qnew[0] = fma(R.sgc0[0], corr, qnew[0]);
-      ringS[oS + S_Q * RW + e] = qnew[0];
-    }
-    // ---------------- phase 1: own column
-    XEdge X;
-    double qx[1];
-    phase_x_inner<RECON, SPLIT, MASK>(L, X, R, qnew, cdx, qx);
-    sX[e] = qx[0];
-    __syncthreads();                                   // barrier A
-    int jS = iS, jL = iL, jb = ib;                     // slots of row r+PF (for the second half)
-    if (warp_u == 0 && r + PF <= rlast) {              // warp 0 issues the TMA copies of row r+PF
-      if (elect_one()) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (SPLIT_ISSUE) issue_a(r + PF);
-        else issue(r + PF);
+    double* __restrict__ QN = a.qn + (long long)p * g.ps + PYCS_JOFF + min(j, g.P - 1) + (long long)r0 * g.ld;
+    Lane L;
+    lane_init(L);
+    int oS = 0;
+    int oL0 = 0, oL1 = (DL - 1) * LSLOT, oL2 = (DL - 2) * LSLOT, oL3 = (DL - 3) * LSLOT;
+    int sb = 0;
+    uint32_t parb = 0;
+  #pragma unroll((MINB >= 10 && !MG) ? 5 : 1)   // MINB 1x / 2x: unrolled by the window length
+    for (int r = rfirst; r <= rlast; ++r) {
+      while (!mbar_try_wait(&full[sb], parb)) {}
+      RowPtrs R;
+      R.q = ringS + oS + S_Q * RW + e;
+      R.u = ringS + oS + S_U * RW + e;
+      R.um = ringS + oS + S_UM * RW + e;
+      R.su1 = ringS + oS + S_SGU * RW + e;
+      R.v0 = ringL + oL0 + L_V * RW + e;
+      R.vm0 = ringL + oL0 + L_VM * RW + e;
+      R.sgv0 = ringL + oL0 + L_SGV * RW + e;
+      R.sgc0 = ringL + oL0 + L_SGC * RW + e;
+      R.rg0 = ringL + oL0 + L_RGC * RW + e;
+      R.sgc2 = ringL + oL2 + L_SGC * RW + e;
+      R.v3 = ringL + oL3 + L_V * RW + e;
+      R.vm3 = ringL + oL3 + L_VM * RW + e;
+      R.sgv3 = ringL + oL3 + L_SGV * RW + e;
+      R.sgc3 = ringL + oL3 + L_SGC * RW + e;
+      R.rg3 = ringL + oL3 + L_RGC * RW + e;
+      // pending MF-PR term on the own interior cell of the new row (neighbours read it after barrier A)
+      double qnew[1] = {R.q[0]};
+      if (a.apply_corr && jint && r >= g.lo && r < g.hi) {
+        qnew[0] = fma(R.sgc0[0], corr, qnew[0]);
+        ringS[oS + S_Q * RW + e] = qnew[0];
       }
-      iS = (iS + 8 * SSLOT == 8 * DS * SSLOT) ? 0 : iS + 8 * SSLOT;
-      iL = (iL + 8 * LSLOT == 8 * DL * LSLOT) ? 0 : iL + 8 * LSLOT;
-      ib = (ib + 1 == DL) ? 0 : ib + 1;
-    }
-    // ---------------- phase 2: y-fluxes at edge j: inner on Q row r, outer on Qx row r-3
-    double F[1], G[1], CF[1] = {0.0}, CG[1];
-    yflux_pair<RECON, SPLIT, MASK>(R.v0, R.vm0, R.sgv0, R.sgc0, R.q, cdy, F, CF);
-    yflux_pair<RECON, SPLIT, MASK>(R.v3, R.vm3, R.sgv3, R.sgc3, sX + e, cdy, G, CG);
-    sF[e] = F[0];
-    sG[e] = G[0];
-    if (SPLIT != 1) sC[e] = CF[0];
-    __syncthreads();                                   // barrier B
-    if (SPLIT_ISSUE && warp_u == 0 && r + PF <= rlast) {
-      if (elect_one()) issue_b(r + PF, jS, jL, jb);
-    }
-    // ---------------- phase 3: Qy row r, outer x-flux on Qy, output row r-3
-    double Fn[1], Gn[1], CFn[1] = {0.0}, out[1], sdiv[1];
-    Fn[0] = sF[e + 1];
-    Gn[0] = sG[e + 1];
-    if (SPLIT != 1) CFn[0] = sC[e + 1];
-    phase_x_outer<RECON, SPLIT>(L, X, R, F, Fn, G, Gn, CF, CFn, out, sdiv);
-    if (r >= r0 + 3) {
-      if (out_lane) {
-        *QN = out[0];
-        L.psum += sdiv[0];
-        if (MG && mgw > 1) {
-          // fused exchange: the peers need this cell if it lies in a 4-wide boundary strip of the
-          // panel (sources of their ghost fill) or in the 3 rows next to a neighbour's slab
-          const int ro = r - 3;
-          const long long off = QN - a.qn;
-          const bool strip = j < g.lo + PYCS_NG || j >= g.hi - PYCS_NG || ro < g.lo + PYCS_NG || ro >= g.hi - PYCS_NG;
-          if (strip) {
-            for (int d = 0; d < mgw; ++d)
-              if (d != a.mg.rank) a.mg.peer_qn[d][off] = out[0];
-          } else {
-            if (ro < a.row_lo + 3 && a.mg.rank > 0) a.mg.peer_qn[a.mg.rank - 1][off] = out[0];
-            if (ro >= a.row_hi - 3 && a.mg.rank < mgw - 1) a.mg.peer_qn[a.mg.rank + 1][off] = out[0];
+      // ---------------- phase 1: own column
+      XEdge X;
+      double qx[1];
+      phase_x_inner<RECON, SPLIT, MASK>(L, X, R, qnew, cdx, qx);
+      sX[e] = qx[0];
+      __syncthreads();                                   // barrier A
+      int jS = iS, jL = iL, jb = ib;                     // slots of row r+PF (for the second half)
+      if (warp_u == 0 && r + PF <= rlast) {              // warp 0 issues the TMA copies of row r+PF
+        if (elect_one()) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (SPLIT_ISSUE) issue_a(r + PF);
+          else issue(r + PF);
+        }
+        iS = (iS + 8 * SSLOT == 8 * DS * SSLOT) ? 0 : iS + 8 * SSLOT;
+        iL = (iL + 8 * LSLOT == 8 * DL * LSLOT) ? 0 : iL + 8 * LSLOT;
+        ib = (ib + 1 == DL) ? 0 : ib + 1;
+      }
+      // ---------------- phase 2: y-fluxes at edge j: inner on Q row r, outer on Qx row r-3
+      double F[1], G[1], CF[1] = {0.0}, CG[1];
+      yflux_pair<RECON, SPLIT, MASK>(R.v0, R.vm0, R.sgv0, R.sgc0, R.q, cdy, F, CF);
+      yflux_pair<RECON, SPLIT, MASK>(R.v3, R.vm3, R.sgv3, R.sgc3, sX + e, cdy, G, CG);
+      sF[e] = F[0];
+      sG[e] = G[0];
+      if (SPLIT != 1) sC[e] = CF[0];
+      __syncthreads();                                   // barrier B
+      if (SPLIT_ISSUE && warp_u == 0 && r + PF <= rlast) {
+        if (elect_one()) issue_b(r + PF, jS, jL, jb);
+      }
+      // ---------------- phase 3: Qy row r, outer x-flux on Qy, output row r-3
+      double Fn[1], Gn[1], CFn[1] = {0.0}, out[1], sdiv[1];
+      Fn[0] = sF[e + 1];
+      Gn[0] = sG[e + 1];
+      if (SPLIT != 1) CFn[0] = sC[e + 1];
+      phase_x_outer<RECON, SPLIT>(L, X, R, F, Fn, G, Gn, CF, CFn, out, sdiv);
+      if (r >= r0 + 3) {
+        if (out_lane) {
+          *QN = out[0];
+          L.psum += sdiv[0];
+          if (MG && mgw > 1) {
+            // fused exchange: the peers need this cell if it lies in a 4-wide boundary strip of the
+            // panel (sources of their ghost fill) or in the 3 rows next to a neighbour's slab
+            const int ro = r - 3;
+            const long long off = QN - a.qn;
+            const bool strip = j < g.lo + PYCS_NG || j >= g.hi - PYCS_NG || ro < g.lo + PYCS_NG || ro >= g.hi - PYCS_NG;
+            if (strip) {
+              for (int d = 0; d < mgw; ++d)
+                if (d != a.mg.rank) a.mg.peer_qn[d][off] = out[0];
+            } else {
+              if (ro < a.row_lo + 3 && a.mg.rank > 0) a.mg.peer_qn[a.mg.rank - 1][off] = out[0];
+              if (ro >= a.row_hi - 3 && a.mg.rank < mgw - 1) a.mg.peer_qn[a.mg.rank + 1][off] = out[0];
+            }
           }
         }
+        QN += g.ld;
       }
-      QN += g.ld;
+      oS = (oS + SSLOT == DS * SSLOT) ? 0 : oS + SSLOT;
+      oL3 = oL2; oL2 = oL1; oL1 = oL0;
+      oL0 = (oL0 + LSLOT == DL * LSLOT) ? 0 : oL0 + LSLOT;
+      if (++sb == DL) { sb = 0; parb ^= 1u; }
     }
-    oS = (oS + SSLOT == DS * SSLOT) ? 0 : oS + SSLOT;
-    oL3 = oL2; oL2 = oL1; oL1 = oL0;
-    oL0 = (oL0 + LSLOT == DL * LSLOT) ? 0 : oL0 + LSLOT;
-    if (++sb == DL) { sb = 0; parb ^= 1u; }
+    psum_cta = L.psum;
   }
   // per-CTA partial of sum(pxdF + pydF) over its outputs (MF-PR), fixed order
   __syncthreads();
-  double v = L.psum;
+  double v = psum_cta;
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   if ((tid & 31) == 0) sF[tid >> 5] = v;
   __syncthreads();
@@ -369,7 +494,7 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb,
   if (tb == T && pf == P && minb == M) return launch_mask<T, 3, 1, P, M>(a, mask, nblocks, st, resident)
     // (threads, rows in flight, MINB): measured points worth keeping, see profiles/r1_sweep_v2b.log
     TUNE(160, 2, 14); TUNE(160, 1, 14); TUNE(160, 2, 4); TUNE(160, 1, 4); TUNE(160, 2, 24); TUNE(128, 2, 15);
-    TUNE(128, 2, 5);
+    TUNE(128, 2, 5); TUNE(160, 2, 34); TUNE(128, 2, 35);
 #undef TUNE
     return cudaErrorInvalidValue;
   }
@@ -387,7 +512,7 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb,
 bool pycs_fused2b_has(int recon, int split, int tb, int pf, int minb) {
   if (recon != 1 && recon != 3) return false;
   if (recon == 3 && split == 1) {
-    const int t[][3] = {{160, 2, 14}, {160, 1, 14}, {160, 2, 4}, {160, 1, 4}, {160, 2, 24}, {128, 2, 15}, {128, 2, 5}};
+    const int t[][3] = {{160, 2, 14}, {160, 1, 14}, {160, 2, 4}, {160, 1, 4}, {160, 2, 24}, {128, 2, 15}, {128, 2, 5}, {160, 2, 34}, {128, 2, 35}};
     for (auto& x : t)
       if (x[0] == tb && x[1] == pf && x[2] == minb) return true;
     return false;

@@ -72,10 +72,19 @@ PYCS_HD void st2(double* p, double a, double b) {
 }
 
 // src/reconstruction_1d.py:36-62 (q3 is the cell itself)
-template <int RECON>
+// CBANK (device only, needs F3_COEF_BANK = a __constant__ double[5] holding the same five numbers):
+// the coefficients are read as constant-bank operands of the DFMAs instead of being rebuilt with
+// two UMOVs each wherever the uniform registers run out (9 UMOVs per row in the const-slot march).
+template <int RECON, bool CBANK = false>
 PYCS_HD void edge_values(double q1, double q2, double q3, double q4, double q5, double& l, double& r) {
   if (RECON == 3) {
+#if defined(__CUDA_ARCH__) && defined(F3_COEF_BANK)
+    const double a1 = CBANK ? F3_COEF_BANK[0] : 2.0 / 60.0, a2 = CBANK ? F3_COEF_BANK[1] : -13.0 / 60.0,
+                 a3 = CBANK ? F3_COEF_BANK[2] : 47.0 / 60.0, a4 = CBANK ? F3_COEF_BANK[3] : 27.0 / 60.0,
+                 a5 = CBANK ? F3_COEF_BANK[4] : -3.0 / 60.0;
+#else
     const double a1 = 2.0 / 60.0, a2 = -13.0 / 60.0, a3 = 47.0 / 60.0, a4 = 27.0 / 60.0, a5 = -3.0 / 60.0;
+#endif
     r = fma(a5, q5, fma(a4, q4, fma(a3, q3, fma(a2, q2, a1 * q1))));
     l = fma(a1, q5, fma(a2, q4, fma(a3, q3, fma(a4, q2, a5 * q1))));
   } else {
@@ -113,10 +122,17 @@ PYCS_HD double inner_update(double q, double d, double rg, double cdv) {
   return 0.5 * (q + (q + d) / (1.0 - cdv));
 }
 
+// The five-row windows come in two forms.  K < 0 (default): elements 0..4 hold rows r-4..r and
+// shift every row (free when the march is unrolled by 5).  K >= 0: circular buffer of WLEN = 6
+// registers, row r lives in element K = (r - first row) % 6, so a march unrolled by 6 -- the
+// period of the staged-row rings -- touches statically named registers and never moves one.
+constexpr int WLEN = 6;
+template <int K, int I> PYCS_HD constexpr int widx() { return K < 0 ? I : (K + 2 + I) % WLEN; }
+
 // Rolling state of one lane: everything is per column c of the lane's NC columns.
 struct Lane {
-  double qw[NC][5];       // Q   rows r-4 .. r
-  double yw[NC][5];       // Qy  rows r-4 .. r
+  double qw[NC][WLEN];    // Q   rows r-4 .. r (see widx)
+  double yw[NC][WLEN];    // Qy  rows r-4 .. r
   double pl[NC], pr[NC];  // edge values of Q,  cell r-3
   double yl[NC], yr[NC];  // edge values of Qy, cell r-3
   double fin_prev[NC], fout_prev[NC];   // x-fluxes (inner on Q, outer on Qy) at edge r-3
@@ -132,7 +148,7 @@ struct XEdge {            // x-edge r-2 quantities computed in phase 1, reused i
 
 PYCS_HD void lane_init(Lane& L) {
   for (int c = 0; c < NC; ++c) {
-    for (int k = 0; k < 5; ++k) { L.qw[c][k] = 0.0; L.yw[c][k] = 0.0; }
+    for (int k = 0; k < WLEN; ++k) { L.qw[c][k] = 0.0; L.yw[c][k] = 0.0; }
     L.pl[c] = L.pr[c] = L.yl[c] = L.yr[c] = 0.0;
     L.fin_prev[c] = L.fout_prev[c] = 0.0;
     L.su2[c] = L.su3[c] = 0.0;
@@ -144,18 +160,18 @@ PYCS_HD void lane_init(Lane& L) {
 // ---- phase 1: row r enters; inner x-flux at edge r-2; Qx row r-3 -> qx[NC] -------------
 // qnew[c]: Q of row r in the lane's columns (the caller loads it, and patches it when a
 // projection term is pending).
-template <int RECON, int SPLIT, int MASK>
 // cdxw = dt/dx times the time factor of a separable wind (1 otherwise).
+template <int RECON, int SPLIT, int MASK, int K = -1>
 PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, const double qnew[NC], double cdxw, double qx[NC]) {
   constexpr int MT = (SPLIT == 3) ? 2 : 1;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const int o = c * CSTEP;
     double* q = L.qw[c];
-    q[0] = q[1]; q[1] = q[2]; q[2] = q[3]; q[3] = q[4];
-    q[4] = qnew[c];
+    if (K < 0) { q[0] = q[1]; q[1] = q[2]; q[2] = q[3]; q[3] = q[4]; }
+    q[widx<K, 4>()] = qnew[c];
     double l2, r2;                                   // cell r-2
-    edge_values<RECON>(q[0], q[1], q[2], q[3], q[4], l2, r2);
+    edge_values<RECON, (K >= 0)>(q[widx<K, 0>()], q[widx<K, 1>()], q[widx<K, 2>()], q[widx<K, 3>()], q[widx<K, 4>()], l2, r2);
     const double cc = R.u[o] * cdxw;                // CFL number at edge r-2
     const bool up = ((MASK & 1) ? R.um[o] : cc) >= 0.0;
     const double su1c = R.su1[o];
@@ -166,7 +182,7 @@ PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, const double qne
     const double rg = R.rg3[o];
     double WE, WO, WG;
     edge_weights<MT, !(MASK & 1)>(cc, up, gE, gO, gC, WE, WO, WG);
-    const double E = up ? L.pr[c] : l2, O = up ? L.pl[c] : r2, qc = up ? q[1] : q[2];
+    const double E = up ? L.pr[c] : l2, O = up ? L.pl[c] : r2, qc = up ? q[widx<K, 1>()] : q[widx<K, 2>()];
     const double fin = fma(WE, E, fma(WO, O, WG * qc));
     double cdv = 0.0;
     if (SPLIT != 1) {
@@ -174,7 +190,7 @@ PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, const double qne
       cdv = cmx - L.cmx_prev[c];
       L.cmx_prev[c] = cmx;
     }
-    qx[c] = inner_update<SPLIT>(q[1], L.fin_prev[c] - fin, rg, cdv);
+    qx[c] = inner_update<SPLIT>(q[widx<K, 1>()], L.fin_prev[c] - fin, rg, cdv);
     L.pl[c] = l2; L.pr[c] = r2;
     L.fin_prev[c] = fin;
     L.su3[c] = gE; L.su2[c] = su1c;
@@ -186,7 +202,7 @@ PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, const double qne
 // ---- phase 2: y-fluxes at the lane's NC edges of one row ------------------------------------
 // v, vm, sgv, sgc: staged rows of that row (lane-offset); src: the advected row (Q or Qx),
 // lane-offset as well, so that src[k] is the value k columns right of the lane's first column.
-template <int RECON, int SPLIT, int MASK>
+template <int RECON, int SPLIT, int MASK, int K = -1>
 PYCS_HD void yflux_pair(const double* v, const double* vm, const double* sgv, const double* sgc,
                         const double* src, double cdyw, double f[NC], double cmy[NC]) {
   constexpr int MT = (SPLIT == 3) ? 2 : 1;
@@ -199,13 +215,29 @@ PYCS_HD void yflux_pair(const double* v, const double* vm, const double* sgv, co
     const double gE = sgv[o];
     const double gO = sgv[o + 1 + 2 * up1];          // other edge of the upwind cell
     const double gC = sgc[o + up1];
-    double WE, WO, WG;
-    edge_weights<MT, !(MASK & 1)>(cc, vp, gE, gO, gC, WE, WO, WG);
-    const double* s = src + o + up1;
-    double l, r;
-    edge_values<RECON>(s[-2], s[-1], s[0], s[1], s[2], l, r);
-    const double E = vp ? r : l, O = vp ? l : r;
-    f[c] = fma(WE, E, fma(WO, O, WG * s[0]));
+    if (K >= 0) {
+      // a y-edge's weights serve one flux only, so the factored form
+      //   f = c [ m (m E' - b O') + b (3 - 2b) G' ],  E' = E gE, O' = O gO, G' = q gC  (MT-0)
+      // is two FP64 operations shorter than forming the three weights (const-slot march only:
+      // the shifting-window kernels keep the arithmetic they were measured with)
+      const double* s = src + o + up1;
+      double l, r;
+      edge_values<RECON, true>(s[-2], s[-1], s[0], s[1], s[2], l, r);
+      const double E = vp ? r : l, O = vp ? l : r;
+      const double b = !(MASK & 1) ? fabs(cc) : (vp ? cc : -cc);
+      const double m = 1.0 - b, bt = b * fma(2.0, m, 1.0);
+      const double Eg = (MT == 1) ? E * gE : E, Og = (MT == 1) ? O * gO : O, Gg = (MT == 1) ? s[0] * gC : s[0];
+      const double cs = (MT == 2) ? cc * gE : cc;
+      f[c] = cs * fma(m, fma(m, Eg, -(b * Og)), bt * Gg);
+    } else {
+      double WE, WO, WG;
+      edge_weights<MT, !(MASK & 1)>(cc, vp, gE, gO, gC, WE, WO, WG);
+      const double* s = src + o + up1;
+      double l, r;
+      edge_values<RECON>(s[-2], s[-1], s[0], s[1], s[2], l, r);
+      const double E = vp ? r : l, O = vp ? l : r;
+      f[c] = fma(WE, E, fma(WO, O, WG * s[0]));
+    }
     if (SPLIT != 1) cmy[c] = gE * cc;
   }
 }
@@ -214,7 +246,7 @@ PYCS_HD void yflux_pair(const double* v, const double* vm, const double* sgv, co
 // F, Fn: inner y-fluxes (row r) at the lane's columns and at the columns right of them;
 // G, Gn likewise the outer y-fluxes of row r-3; CM, CMn sqrtg_pv*cy of row r (SPLIT != 1).
 // out[c] = new Q of row r-3, sdiv[c] = pxdF + pydF of that cell.
-template <int RECON, int SPLIT>
+template <int RECON, int SPLIT, int K = -1>
 PYCS_HD void phase_x_outer(Lane& L, const XEdge& X, const RowPtrs& R, const double F[NC], const double Fn[NC],
                            const double G[NC], const double Gn[NC], const double CM[NC], const double CMn[NC],
                            double out[NC], double sdiv[NC]) {
@@ -222,16 +254,16 @@ PYCS_HD void phase_x_outer(Lane& L, const XEdge& X, const RowPtrs& R, const doub
   for (int c = 0; c < NC; ++c) {
     double* y = L.yw[c];
     const double cdv = (SPLIT != 1) ? CMn[c] - CM[c] : 0.0;
-    const double qy = inner_update<SPLIT>(L.qw[c][4], F[c] - Fn[c], R.rg0[c * CSTEP], cdv);
-    y[0] = y[1]; y[1] = y[2]; y[2] = y[3]; y[3] = y[4];
-    y[4] = qy;
+    const double qy = inner_update<SPLIT>(L.qw[c][widx<K, 4>()], F[c] - Fn[c], R.rg0[c * CSTEP], cdv);
+    if (K < 0) { y[0] = y[1]; y[1] = y[2]; y[2] = y[3]; y[3] = y[4]; }
+    y[widx<K, 4>()] = qy;
     double l2, r2;                                   // Qy cell r-2
-    edge_values<RECON>(y[0], y[1], y[2], y[3], y[4], l2, r2);
+    edge_values<RECON, (K >= 0)>(y[widx<K, 0>()], y[widx<K, 1>()], y[widx<K, 2>()], y[widx<K, 3>()], y[widx<K, 4>()], l2, r2);
     const bool up = X.up[c];
-    const double E = up ? L.yr[c] : l2, O = up ? L.yl[c] : r2, qc = up ? y[1] : y[2];
+    const double E = up ? L.yr[c] : l2, O = up ? L.yl[c] : r2, qc = up ? y[widx<K, 1>()] : y[widx<K, 2>()];
     const double fo = fma(X.WE[c], E, fma(X.WO[c], O, X.WG[c] * qc));
     const double s = (L.fout_prev[c] - fo) + (G[c] - Gn[c]);
-    out[c] = fma(s, X.rg3[c], L.qw[c][1]);
+    out[c] = fma(s, X.rg3[c], L.qw[c][widx<K, 1>()]);
     sdiv[c] = s;
     L.yl[c] = l2; L.yr[c] = r2;
     L.fout_prev[c] = fo;

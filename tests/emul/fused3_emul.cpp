@@ -28,6 +28,7 @@ struct Args {
   double *qn, *part;
   double corr, cdx, cdy, ws;
   int apply_corr, rows_per_chunk, nstrips, wcols, depth;
+  int circ = 0;      // v2b: circular six-register windows (the const-slot march of fused2b.cu, MINB >= 30)
 };
 
 template <int RECON, int SPLIT, int MASK, int NW>
@@ -143,6 +144,35 @@ void run(const Args& a) {
 }
 
 // ---- v2b (csrc/fused2b.cu): one column per thread, CTA = strip of TB-6 columns -------------
+// compile-time row phase k = (r - first row) % 6 of the circular-window march
+template <int RECON, int SPLIT, int MASK>
+void x_inner_k(int k, f1::Lane& L, f1::XEdge& X, const f1::RowPtrs& R, const double* qnew, double cdxw, double* qx) {
+  using namespace f1;
+  switch (k) {
+    case 0: phase_x_inner<RECON, SPLIT, MASK, 0>(L, X, R, qnew, cdxw, qx); break;
+    case 1: phase_x_inner<RECON, SPLIT, MASK, 1>(L, X, R, qnew, cdxw, qx); break;
+    case 2: phase_x_inner<RECON, SPLIT, MASK, 2>(L, X, R, qnew, cdxw, qx); break;
+    case 3: phase_x_inner<RECON, SPLIT, MASK, 3>(L, X, R, qnew, cdxw, qx); break;
+    case 4: phase_x_inner<RECON, SPLIT, MASK, 4>(L, X, R, qnew, cdxw, qx); break;
+    case 5: phase_x_inner<RECON, SPLIT, MASK, 5>(L, X, R, qnew, cdxw, qx); break;
+    default: phase_x_inner<RECON, SPLIT, MASK>(L, X, R, qnew, cdxw, qx);
+  }
+}
+template <int RECON, int SPLIT>
+void x_outer_k(int k, f1::Lane& L, const f1::XEdge& X, const f1::RowPtrs& R, const double* f, const double* fn,
+               const double* g, const double* gn, const double* cf, const double* cfn, double* out, double* sdiv) {
+  using namespace f1;
+  switch (k) {
+    case 0: phase_x_outer<RECON, SPLIT, 0>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
+    case 1: phase_x_outer<RECON, SPLIT, 1>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
+    case 2: phase_x_outer<RECON, SPLIT, 2>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
+    case 3: phase_x_outer<RECON, SPLIT, 3>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
+    case 4: phase_x_outer<RECON, SPLIT, 4>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
+    case 5: phase_x_outer<RECON, SPLIT, 5>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
+    default: phase_x_outer<RECON, SPLIT>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv);
+  }
+}
+
 template <int RECON, int SPLIT, int MASK>
 void run_block(const Args& a, int TB) {
   using namespace f1;
@@ -183,6 +213,7 @@ void run_block(const Args& a, int TB) {
     int oS = 0, oL0 = 0, oL1 = (DL - 1) * LSLOT, oL2 = (DL - 2) * LSLOT, oL3 = (DL - 3) * LSLOT;
     double psum = 0.0;
     for (int r = rfirst; r <= rlast; ++r) {
+      const int kc = a.circ ? (r - rfirst) % WLEN : -1;
       {   // TMA row copies of row r
         const int k = r - rfirst;
         double* dS = ringS + (k % DS) * SSLOT;
@@ -213,14 +244,19 @@ void run_block(const Args& a, int TB) {
           ringS[oS + S_Q * RW + e] = qnew[0];
         }
         double qx[1];
-        phase_x_inner<RECON, SPLIT, MASK>(L[t], X[t], P, qnew, cdxw, qx);
+        x_inner_k<RECON, SPLIT, MASK>(kc, L[t], X[t], P, qnew, cdxw, qx);
         sX[e] = qx[0];
       }
       for (int t = 0; t < TB; ++t) {               // barrier A; phase 2
         const int e = t + 3;
         double f[1], g[1], cf[1] = {0.0}, cg[1];
-        yflux_pair<RECON, SPLIT, MASK>(R[t].v0, R[t].vm0, R[t].sgv0, R[t].sgc0, R[t].q, cdyw, f, cf);
-        yflux_pair<RECON, SPLIT, MASK>(R[t].v3, R[t].vm3, R[t].sgv3, R[t].sgc3, sX + e, cdyw, g, cg);
+        if (a.circ) {   // K >= 0 selects the factored y-flux of the const-slot march (any phase: K is only a flag here)
+          yflux_pair<RECON, SPLIT, MASK, 0>(R[t].v0, R[t].vm0, R[t].sgv0, R[t].sgc0, R[t].q, cdyw, f, cf);
+          yflux_pair<RECON, SPLIT, MASK, 0>(R[t].v3, R[t].vm3, R[t].sgv3, R[t].sgc3, sX + e, cdyw, g, cg);
+        } else {
+          yflux_pair<RECON, SPLIT, MASK>(R[t].v0, R[t].vm0, R[t].sgv0, R[t].sgc0, R[t].q, cdyw, f, cf);
+          yflux_pair<RECON, SPLIT, MASK>(R[t].v3, R[t].vm3, R[t].sgv3, R[t].sgc3, sX + e, cdyw, g, cg);
+        }
         F[t] = f[0]; G[t] = g[0]; CF[t] = cf[0];
       }
       for (int t = 0; t < TB; ++t) { sF[t + 3] = F[t]; sG[t + 3] = G[t]; sC[t + 3] = CF[t]; }
@@ -228,7 +264,7 @@ void run_block(const Args& a, int TB) {
         const int e = t + 3, j = jbase - 3 + t;
         double f[1] = {F[t]}, g[1] = {G[t]}, cf[1] = {CF[t]};
         double fn[1] = {sF[e + 1]}, gn[1] = {sG[e + 1]}, cfn[1] = {sC[e + 1]}, out[1], sdiv[1];
-        phase_x_outer<RECON, SPLIT>(L[t], X[t], R[t], f, fn, g, gn, cf, cfn, out, sdiv);
+        x_outer_k<RECON, SPLIT>(kc, L[t], X[t], R[t], f, fn, g, gn, cf, cfn, out, sdiv);
         if (r >= r0 + 3 && t >= 3 && j < jend) {
           a.qn[(long long)p * a.ps + JOFF + j + (long long)(r - 3) * a.ld] = out[0];
           L[t].psum += sdiv[0];
@@ -282,11 +318,12 @@ int f3_emul_grid(int N, int nw, int rows_per_chunk, int* nstrips, int* wcols, in
 }
 // v2b decomposition (csrc/fused2b.cu): TB threads per CTA, one column each; depth = rows in flight.
 // Returns the number of partial sums written to part (one per CTA).
-int f3_emul_step_block(int N, int recon, int split, int mask, int TB, int depth, int rows_per_chunk, const double* q,
+int f3_emul_step_block_impl(int circ, int N, int recon, int split, int mask, int TB, int depth, int rows_per_chunk, const double* q,
                        double* qn, const double* ua, const double* va, const double* um, const double* vm,
                        const double* sgc, const double* rgc, const double* sgu, const double* sgv, double* part,
                        double corr, int apply_corr, double cdx, double cdy, double ws) {
   Args a;
+  a.circ = circ;
   a.N = N; a.P = N + 8; a.ld = f3_emul_ld(N); a.lo = 4; a.hi = N + 4;
   a.ps = (long long)(a.P + 1) * a.ld;
   a.q = q; a.qn = qn; a.ua = ua; a.va = va; a.um = um; a.vm = vm;
@@ -299,6 +336,19 @@ int f3_emul_step_block(int N, int recon, int split, int mask, int TB, int depth,
   CASE(3, 1); CASE(3, 2); CASE(3, 3); CASE(1, 1); CASE(1, 2); CASE(1, 3);
 #undef CASE
   return -1;
+}
+#define STEP_BLOCK_ARGS \
+  int N, int recon, int split, int mask, int TB, int depth, int rows_per_chunk, const double *q, double *qn, \
+      const double *ua, const double *va, const double *um, const double *vm, const double *sgc, const double *rgc, \
+      const double *sgu, const double *sgv, double *part, double corr, int apply_corr, double cdx, double cdy, double ws
+#define STEP_BLOCK_PASS \
+  N, recon, split, mask, TB, depth, rows_per_chunk, q, qn, ua, va, um, vm, sgc, rgc, sgu, sgv, part, corr, apply_corr, \
+      cdx, cdy, ws
+int f3_emul_step_block(STEP_BLOCK_ARGS) { return f3_emul_step_block_impl(0, STEP_BLOCK_PASS); }
+// the const-slot march (MINB >= 30): rings of 3 and 6 rows, circular six-register windows
+int f3_emul_step_block_circ(STEP_BLOCK_ARGS) {
+  if (depth != 2) return -2;
+  return f3_emul_step_block_impl(1, STEP_BLOCK_PASS);
 }
 int f3_emul_block_grid(int N, int TB, int rows_per_chunk) {
   const int wmax = TB - 6;

@@ -33,6 +33,8 @@ def emul():
     lib.f3_emul_step.restype = C.c_int
     lib.f3_emul_step_block.argtypes = lib.f3_emul_step.argtypes
     lib.f3_emul_step_block.restype = C.c_int
+    lib.f3_emul_step_block_circ.argtypes = lib.f3_emul_step.argtypes
+    lib.f3_emul_step_block_circ.restype = C.c_int
     lib.f3_emul_block_grid.argtypes = [C.c_int] * 3
     lib.f3_emul_block_grid.restype = C.c_int
     lib.f3_emul_grid.argtypes = [C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 3
@@ -58,7 +60,8 @@ def ptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def one_step(emul, N, vf, tup, pre_steps, nw=3, depth=3, rows=None, pending=False, separable=False, block_tb=0):
+def one_step(emul, N, vf, tup, pre_steps, nw=3, depth=3, rows=None, pending=False, separable=False, block_tb=0,
+             circ=False):
     from oracle.grid import LeanGrid
     from oracle import step as ost, wind as owind
     recon, dp, split, et, mt, mf = tup
@@ -100,9 +103,9 @@ def one_step(emul, N, vf, tup, pre_steps, nw=3, depth=3, rows=None, pending=Fals
     rows = rows or N
     if block_tb:        # v2b decomposition (csrc/fused2b.cu)
         part = np.zeros(emul.f3_emul_block_grid(N, block_tb, rows))
-        rc = emul.f3_emul_step_block(N, recon, split, mask, block_tb, depth, rows, ptr(q), ptr(qn),
-                                     *[ptr(a) for a in arrs], ptr(part), corr, 1 if pending else 0,
-                                     dt / g.dx, dt / g.dy, ws)
+        fn = emul.f3_emul_step_block_circ if circ else emul.f3_emul_step_block
+        rc = fn(N, recon, split, mask, block_tb, depth, rows, ptr(q), ptr(qn),
+                *[ptr(a) for a in arrs], ptr(part), corr, 1 if pending else 0, dt / g.dx, dt / g.dy, ws)
     else:               # v3 decomposition (csrc/fused3.cu)
         ns, wc, nch = C.c_int(), C.c_int(), C.c_int()
         npart = emul.f3_emul_grid(N, nw, rows, C.byref(ns), C.byref(wc), C.byref(nch))
@@ -178,3 +181,25 @@ def test_emulated_v2b_shapes_patch_separable(emul, tb, rows, depth, kw):
 def test_emulated_v2b_other_schemes(emul, tup):
     got, want = one_step(emul, 20, 2, tup, 2, depth=2, block_tb=32)
     assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+
+
+# ---- v2b, const-slot march (MINB >= 30): circular six-register windows, phase = row % 6 ------
+@pytest.mark.parametrize("N,vf,name,pre", CASES)
+def test_emulated_v2b_circular_windows_match_oracle(emul, N, vf, name, pre):
+    got, want = one_step(emul, N, vf, TUPLES[name], pre, depth=2, block_tb=32 if N < 100 else 160, circ=True)
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("tb,rows,kw", [(32, 7, {}), (64, 16, {"pending": True}), (160, 50, {"separable": True}),
+                                        (128, 9, {"pending": True}), (160, 6, {}), (64, 12, {})])
+def test_emulated_v2b_circular_windows_chunk_lengths(emul, tb, rows, kw):
+    """chunks of 13, 22, 56, 15, 12 and 18 marched rows: every exit phase of the six-row group."""
+    got, want = one_step(emul, 50, 3, TUPLES["default"], 3, depth=2, rows=rows, block_tb=tb, circ=True, **kw)
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+
+
+def test_emulated_v2b_circular_windows_against_shifting(emul):
+    """same decomposition, two forms of the y-flux arithmetic (weights / factored): a few ulp apart."""
+    a, _ = one_step(emul, 50, 3, TUPLES["default"], 3, depth=2, rows=11, block_tb=64, circ=True)
+    b, _ = one_step(emul, 50, 3, TUPLES["default"], 3, depth=2, rows=11, block_tb=64, circ=False)
+    assert 0 < np.max(np.abs(a - b)) <= 1e-14 * np.max(np.abs(b))
