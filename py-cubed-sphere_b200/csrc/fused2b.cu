@@ -64,6 +64,10 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   // (all staged-row loads become [one base register + immediate]) and the TMA issue path keeps
   // running byte offsets instead of recomputing row * ld (see profiles/r1_sass_static.md)
   constexpr bool CS = (MINB >= 30) && !MG;
+  // MINB >= 40: every warp issues its share of a row's TMA copies (one mbarrier arrival per warp)
+  // instead of warp 0 carrying all of them into barrier B
+  constexpr bool DI = CS && (MINB >= 40);
+  constexpr int NWARP = TB / 32;
   constexpr int RW = TB + 6;                 // staged row: columns jbase-6 .. jbase+TB-1
   constexpr int NS = (MASK & 1) ? 4 : 3, NL = (MASK & 1) ? 5 : 4;
   constexpr int DS = PF + 1, DL = PF + 4;
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
 
   for (int k = tid; k < DS * SSLOT + DL * LSLOT + 4 * RW; k += TB) ringS[k] = 0.0;
   if (tid == 0) {
-    for (int s = 0; s < DL; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < DL; ++s) mbar_init(&full[s], DI ? NWARP : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -197,24 +201,29 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
     };
     // k = (row - rfirst) % DL is a compile-time constant everywhere below; o1, o2: offsets of the
     // rows staged one and two rows late (sqrtg_pu, u)
-    auto issue_k = [&](auto kc, long long o1, long long o2) {   // elected lane of warp 0
+    // copy c of a row is issued by warp c % NWARP when the issue is distributed, else by warp 0
+    constexpr int NCOPY = NS + NL;
+    auto mine = [&](int c) { return !DI || warp_u == c % NWARP; };
+    const uint32_t my_bytes = DI ? row_bytes * (uint32_t)((NCOPY - warp_u + NWARP - 1) / NWARP) : row_bytes * NCOPY;
+    auto issue_k = [&](auto kc, long long o1, long long o2) {   // elected lane of an issuing warp
       constexpr int k = decltype(kc)::value;
       const uint32_t dS = ringS_a + 8u * (uint32_t)((k % DS) * SSLOT), dL = ringL_a + 8u * (uint32_t)(k * LSLOT),
                      bar = full_a + 8u * (uint32_t)k;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * (NS + NL))
-                   : "memory");
-      tma(dS + 8u * S_Q * RW, at(gq, o0), bar);
-      tma(dL + 8u * L_V * RW, at(gv, o0), bar);
-      tma(dL + 8u * L_SGC * RW, at(gsgc, o0), bar);
-      tma(dL + 8u * L_SGV * RW, at(gsgv, o0), bar);
-      if (MASK & 1) tma(dL + 8u * L_VM * RW, at(gvm, o0), bar);
-      tma(dL + 8u * L_RGC * RW, at(grgc, o0), bar);
-      tma(dS + 8u * S_SGU * RW, at(gsgu, o1), bar);
-      tma(dS + 8u * S_U * RW, at(gu, o2), bar);
-      if (MASK & 1) tma(dS + 8u * S_UM * RW, at(gum, o2), bar);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(my_bytes) : "memory");
+      if (mine(0)) tma(dS + 8u * S_Q * RW, at(gq, o0), bar);
+      if (mine(1)) tma(dL + 8u * L_V * RW, at(gv, o0), bar);
+      if (mine(2)) tma(dL + 8u * L_SGC * RW, at(gsgc, o0), bar);
+      if (mine(3)) tma(dL + 8u * L_SGV * RW, at(gsgv, o0), bar);
+      if (mine(4)) tma(dL + 8u * L_RGC * RW, at(grgc, o0), bar);
+      if (mine(5)) tma(dS + 8u * S_SGU * RW, at(gsgu, o1), bar);
+      if (mine(6)) tma(dS + 8u * S_U * RW, at(gu, o2), bar);
+      if (MASK & 1) {
+        if (mine(7)) tma(dL + 8u * L_VM * RW, at(gvm, o0), bar);
+        if (mine(8)) tma(dS + 8u * S_UM * RW, at(gum, o2), bar);
+      }
     };
-    if (warp_u == 0) {                         // rows rfirst, rfirst + 1 (rfirst >= 1: only row -1 is clamped)
+    if (DI || warp_u == 0) {                   // rows rfirst, rfirst + 1 (rfirst >= 1: only row -1 is clamped)
       if (elect_one()) issue_k(IC<0>{}, o0 - ld8, (long long)max(rfirst - 2, 0) * ld8);
       o0 += ld8;
       if (rfirst + 1 <= rlast) {
@@ -262,7 +271,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
       phase_x_inner<RECON, SPLIT, MASK, k>(L, X, R, qnew, cdx, qx);
       sX[e] = qx[0];
       __syncthreads();                                   // barrier A
-      if (warp_u == 0 && r + PF <= rlast) {              // warp 0 issues the TMA copies of row r+PF
+      if ((DI || warp_u == 0) && r + PF <= rlast) {      // the TMA copies of row r+PF
         if (elect_one()) issue_k(IC<(k + PF) % DL>{}, o0 - ld8, o0 - 2 * ld8);
         o0 += ld8;
       }
@@ -487,6 +496,7 @@ cudaError_t launch_mask(const FusedArgs& a, int mask, int nblocks, cudaStream_t 
 #define F2B_DEFAULT_TB 160
 #define F2B_DEFAULT_PF 2
 #define F2B_DEFAULT_MINB 4
+#define F2B_CS_MINB 34
 cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb, int pf, int minb, int nblocks,
                      cudaStream_t st, int* resident) {
   if (recon == 3 && split == 1) {
@@ -494,14 +504,18 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb,
   if (tb == T && pf == P && minb == M) return launch_mask<T, 3, 1, P, M>(a, mask, nblocks, st, resident)
     // (threads, rows in flight, MINB): measured points worth keeping, see profiles/r1_sweep_v2b.log
     TUNE(160, 2, 14); TUNE(160, 1, 14); TUNE(160, 2, 4); TUNE(160, 1, 4); TUNE(160, 2, 24); TUNE(128, 2, 15);
-    TUNE(128, 2, 5); TUNE(160, 2, 34); TUNE(128, 2, 35);
+    TUNE(128, 2, 5); TUNE(160, 2, 34); TUNE(128, 2, 35); TUNE(160, 2, 44); TUNE(128, 2, 45);
 #undef TUNE
     return cudaErrorInvalidValue;
   }
-  if (tb != F2B_DEFAULT_TB || pf != F2B_DEFAULT_PF || minb != F2B_DEFAULT_MINB) return cudaErrorInvalidValue;
+  // the other schemes: the plain march (MINB 4) and the const-slot march (MINB 34)
+  if (tb != F2B_DEFAULT_TB || pf != F2B_DEFAULT_PF || (minb != F2B_DEFAULT_MINB && minb != F2B_CS_MINB))
+    return cudaErrorInvalidValue;
 #define CASE(R, S) \
   if (recon == R && split == S) \
-    return launch_mask<F2B_DEFAULT_TB, R, S, F2B_DEFAULT_PF, F2B_DEFAULT_MINB>(a, mask, nblocks, st, resident)
+    return minb == F2B_CS_MINB \
+               ? launch_mask<F2B_DEFAULT_TB, R, S, F2B_DEFAULT_PF, F2B_CS_MINB>(a, mask, nblocks, st, resident) \
+               : launch_mask<F2B_DEFAULT_TB, R, S, F2B_DEFAULT_PF, F2B_DEFAULT_MINB>(a, mask, nblocks, st, resident)
   CASE(3, 2); CASE(3, 3); CASE(1, 1); CASE(1, 2); CASE(1, 3);
 #undef CASE
   return cudaErrorInvalidValue;
@@ -512,12 +526,12 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb,
 bool pycs_fused2b_has(int recon, int split, int tb, int pf, int minb) {
   if (recon != 1 && recon != 3) return false;
   if (recon == 3 && split == 1) {
-    const int t[][3] = {{160, 2, 14}, {160, 1, 14}, {160, 2, 4}, {160, 1, 4}, {160, 2, 24}, {128, 2, 15}, {128, 2, 5}, {160, 2, 34}, {128, 2, 35}};
+    const int t[][3] = {{160, 2, 14}, {160, 1, 14}, {160, 2, 4}, {160, 1, 4}, {160, 2, 24}, {128, 2, 15}, {128, 2, 5}, {160, 2, 34}, {128, 2, 35}, {160, 2, 44}, {128, 2, 45}};
     for (auto& x : t)
       if (x[0] == tb && x[1] == pf && x[2] == minb) return true;
     return false;
   }
-  return tb == F2B_DEFAULT_TB && pf == F2B_DEFAULT_PF && minb == F2B_DEFAULT_MINB;
+  return tb == F2B_DEFAULT_TB && pf == F2B_DEFAULT_PF && (minb == F2B_DEFAULT_MINB || minb == F2B_CS_MINB);
 }
 
 cudaError_t pycs_launch_fused2b(const FusedArgs& a, int recon, int split, int mask, int tb, int pf, int minb,
