@@ -628,8 +628,10 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
     if (impl == 3 && !pycs_fused3_has(h->prm.recon, h->prm.opsplit, nw, pf, minb)) { nw = 3; pf = 3; minb = 3; }
     if (impl == 3 && !pycs_fused3_has(h->prm.recon, h->prm.opsplit, nw, pf, minb)) impl = 2;   // limited PPM
     const char* etb = getenv("PYCS_FUSED_TB");
-    int tb4 = etb ? atoi(etb) : 160, pf4 = ep ? atoi(ep) : 2, minb4 = em ? atoi(em) : 14;
-    if (impl == 4 && !pycs_fused2b_has(h->prm.recon, h->prm.opsplit, tb4, pf4, minb4)) { tb4 = 160; pf4 = 2; minb4 = (h->prm.recon == 3 && h->prm.opsplit == 1) ? 14 : 4; }
+    // default: 160 threads, two rows in flight, const-slot march at 4 CTAs/SM (MINB 34:
+    // profiles/r1_sweep_v2b_cs.log, 0.164 ms against 0.183 ms for the shifting-window march MINB 14)
+    int tb4 = etb ? atoi(etb) : 160, pf4 = ep ? atoi(ep) : 2, minb4 = em ? atoi(em) : 34;
+    if (impl == 4 && !pycs_fused2b_has(h->prm.recon, h->prm.opsplit, tb4, pf4, minb4)) { tb4 = 160; pf4 = 2; minb4 = 34; }
     if (impl == 4 && !pycs_fused2b_has(h->prm.recon, h->prm.opsplit, tb4, pf4, minb4)) impl = 2;   // limited PPM
     int resident, lag, cols;
     if (impl == 3) {
