@@ -63,14 +63,17 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   // MINB >= 30: the march runs in groups of DL rows with every ring slot a compile-time constant
   // (all staged-row loads become [one base register + immediate]) and the TMA issue path keeps
   // running byte offsets instead of recomputing row * ld (see profiles/r1_sass_static.md)
-  constexpr bool CS = (MINB >= 30) && !MG;
+  constexpr bool CS = (MINB >= 30) && (MINB < 50) && !MG;
+  // MINB >= 50: two rows per pair of block barriers (rings of 4 and 8 slots, windows of 8 registers)
+  constexpr bool PAIR = (MINB >= 50) && !MG;
   // MINB >= 40: every warp issues its share of a row's TMA copies (one mbarrier arrival per warp)
   // instead of warp 0 carrying all of them into barrier B
   constexpr bool DI = CS && (MINB >= 40);
   constexpr int NWARP = TB / 32;
   constexpr int RW = TB + 6;                 // staged row: columns jbase-6 .. jbase+TB-1
   constexpr int NS = (MASK & 1) ? 4 : 3, NL = (MASK & 1) ? 5 : 4;
-  constexpr int DS = PF + 1, DL = PF + 4;
+  constexpr int DS = PAIR ? 4 : PF + 1, DL = PAIR ? 8 : PF + 4;
+  constexpr int NWORK = PAIR ? 8 : 4;        // work rows: Qx, inner / outer y-flux, sqrtg_pv*cy (per row of a pair)
   constexpr int SSLOT = NS * RW, LSLOT = NL * RW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* ringS = reinterpret_cast<double*>(smem_raw);           // [DS][NS][RW]
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   double* sF = sX + RW;                                          // inner y-flux, row r
   double* sG = sF + RW;                                          // outer y-flux, row r-3
   double* sC = sG + RW;                                          // sqrtg_pv*cy (SPLIT != 1)
-  uint64_t* full = reinterpret_cast<uint64_t*>(sC + RW);         // [DL]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sX + NWORK * RW);   // [DL]
 
   const Geo& g = a.g;
   int b = blockIdx.x;
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   const int len = min(RW, g.ld - PYCS_JOFF - c0) & ~1;
   const uint32_t row_bytes = (uint32_t)len * 8u;
 
-  for (int k = tid; k < DS * SSLOT + DL * LSLOT + 4 * RW; k += TB) ringS[k] = 0.0;
+  for (int k = tid; k < DS * SSLOT + DL * LSLOT + NWORK * RW; k += TB) ringS[k] = 0.0;
   if (tid == 0) {
     for (int s = 0; s < DL; ++s) mbar_init(&full[s], DI ? NWARP : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -191,7 +194,170 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
     issue_b(r, iS, iL, ib);
   };
   double psum_cta = 0.0;
-  if constexpr (CS) {
+  if constexpr (PAIR) {
+    // ---- two rows per pair of barriers.  Step s marches rows (ra, rb) = rfirst + 2s, + 1:
+    //   phase 1 of ra then rb | barrier A | the four y-fluxes | barrier B | TMA issue of step s+2 |
+    //   phase 3 of ra then rb.
+    // Half the barriers per row and two independent rows of FP64 work between them; costs ~16
+    // more registers (two XEdge sets, two flux pairs across barrier B) -> 3 CTAs/SM.
+    // After barrier B of step s nobody reads the ring slots of step s (short ring) and of rows
+    // ra-4, ra-3 (long ring) any more: exactly the slots of step s+2, so its copies start there
+    // (2.7 rows ahead of their first use).  Row phase k = (row - rfirst) % 8 is compile time.
+    static_assert(DS == 4 && DL == WMAX, "two-row march: rings of 4 and 8 slots, windows of 8 registers");
+    constexpr int W = WMAX;
+    double* sXb = sX + 4 * RW;                 // second row of a pair: Qx, F, G, C
+    double *sFb = sXb + RW, *sGb = sFb + RW, *sCb = sGb + RW;
+    const int rlastp = rlast + ((rlast - rfirst + 1) & 1);   // even number of rows (row r1+3 <= P-1 exists; its output is dropped)
+    const long long ld8 = (long long)g.ld * 8;
+    long long o0 = (long long)rfirst * ld8;    // byte offset of the next row to issue
+    auto at = [](const double* base, long long off) {
+      return reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + off);
+    };
+    constexpr int NCOPY = NS + NL;
+    auto issue_k = [&](auto kc, long long o1, long long o2) {   // elected lane of warp 0
+      constexpr int k = decltype(kc)::value;
+      const uint32_t dS = ringS_a + 8u * (uint32_t)((k % DS) * SSLOT), dL = ringL_a + 8u * (uint32_t)(k * LSLOT),
+                     bar = full_a + 8u * (uint32_t)k;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * NCOPY)
+                   : "memory");
+      tma(dS + 8u * S_Q * RW, at(gq, o0), bar);
+      tma(dL + 8u * L_V * RW, at(gv, o0), bar);
+      tma(dL + 8u * L_SGC * RW, at(gsgc, o0), bar);
+      tma(dL + 8u * L_SGV * RW, at(gsgv, o0), bar);
+      tma(dL + 8u * L_RGC * RW, at(grgc, o0), bar);
+      tma(dS + 8u * S_SGU * RW, at(gsgu, o1), bar);
+      tma(dS + 8u * S_U * RW, at(gu, o2), bar);
+      if (MASK & 1) {
+        tma(dL + 8u * L_VM * RW, at(gvm, o0), bar);
+        tma(dS + 8u * S_UM * RW, at(gum, o2), bar);
+      }
+    };
+    if (warp_u == 0) {                         // steps 0 and 1: rows rfirst .. rfirst+3 (rfirst >= 1: only row -1 is clamped)
+      const bool el = elect_one();
+      if (el) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue_k(IC<0>{}, o0 - ld8, (long long)max(rfirst - 2, 0) * ld8);
+      }
+      o0 += ld8;
+      if (el) issue_k(IC<1>{}, o0 - ld8, o0 - 2 * ld8);
+      o0 += ld8;
+      if (rfirst + 2 <= rlastp) {
+        if (el) issue_k(IC<2>{}, o0 - ld8, o0 - 2 * ld8);
+        o0 += ld8;
+        if (el) issue_k(IC<3>{}, o0 - ld8, o0 - 2 * ld8);
+        o0 += ld8;
+      }
+    }
+    double* __restrict__ QN = a.qn + (long long)p * g.ps + PYCS_JOFF + min(j, g.P - 1) + (long long)r0 * g.ld;
+    Lane L;
+    lane_init(L);
+    const double* const eS = ringS + e;
+    const double* const eL = ringL + e;
+    uint32_t parb = 0;
+    auto rowptrs = [&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      constexpr int kS = (k % DS) * SSLOT, kL0 = k * LSLOT, kL2 = ((k + DL - 2) % DL) * LSLOT,
+                    kL3 = ((k + DL - 3) % DL) * LSLOT;
+      RowPtrs R;
+      R.q = eS + kS + S_Q * RW;
+      R.u = eS + kS + S_U * RW;
+      R.um = eS + kS + S_UM * RW;
+      R.su1 = eS + kS + S_SGU * RW;
+      R.v0 = eL + kL0 + L_V * RW;
+      R.vm0 = eL + kL0 + L_VM * RW;
+      R.sgv0 = eL + kL0 + L_SGV * RW;
+      R.sgc0 = eL + kL0 + L_SGC * RW;
+      R.rg0 = eL + kL0 + L_RGC * RW;
+      R.sgc2 = eL + kL2 + L_SGC * RW;
+      R.v3 = eL + kL3 + L_V * RW;
+      R.vm3 = eL + kL3 + L_VM * RW;
+      R.sgv3 = eL + kL3 + L_SGV * RW;
+      R.sgc3 = eL + kL3 + L_SGC * RW;
+      R.rg3 = eL + kL3 + L_RGC * RW;
+      return R;
+    };
+    // one step = two marched rows; false once the chunk is finished
+    auto step = [&](auto kc, int ra) -> bool {
+      constexpr int k = decltype(kc)::value;         // phase of row ra (even); rb has k + 1
+      if (ra > rlastp) return false;
+      const int rb = ra + 1;
+      while (!mbar_try_wait(&full[k], parb)) {}
+      while (!mbar_try_wait(&full[k + 1], parb)) {}
+      const RowPtrs Ra = rowptrs(IC<k>{}), Rb = rowptrs(IC<k + 1>{});
+      double qa[1] = {Ra.q[0]}, qb[1] = {Rb.q[0]};
+      if (a.apply_corr && jint) {                    // pending MF-PR term on the own interior cells
+        if (ra >= g.lo && ra < g.hi) {
+          qa[0] = fma(Ra.sgc0[0], corr, qa[0]);
+          ringS[(k % DS) * SSLOT + S_Q * RW + e] = qa[0];
+        }
+        if (rb >= g.lo && rb < g.hi) {
+          qb[0] = fma(Rb.sgc0[0], corr, qb[0]);
+          ringS[((k + 1) % DS) * SSLOT + S_Q * RW + e] = qb[0];
+        }
+      }
+      // ---------------- phase 1: own column, both rows
+      XEdge Xa, Xb;
+      double qxa[1], qxb[1];
+      phase_x_inner<RECON, SPLIT, MASK, k, W>(L, Xa, Ra, qa, cdx, qxa);
+      phase_x_inner<RECON, SPLIT, MASK, k + 1, W>(L, Xb, Rb, qb, cdx, qxb);
+      sX[e] = qxa[0];
+      sXb[e] = qxb[0];
+      __syncthreads();                                   // barrier A
+      // ---------------- phase 2: y-fluxes at edge j: inner on Q rows ra, rb, outer on Qx rows ra-3, rb-3
+      double Fa[1], Ga[1], CFa[1] = {0.0}, CGa[1], Fb[1], Gb[1], CFb[1] = {0.0}, CGb[1];
+      yflux_pair<RECON, SPLIT, MASK, k>(Ra.v0, Ra.vm0, Ra.sgv0, Ra.sgc0, Ra.q, cdy, Fa, CFa);
+      yflux_pair<RECON, SPLIT, MASK, k>(Rb.v0, Rb.vm0, Rb.sgv0, Rb.sgc0, Rb.q, cdy, Fb, CFb);
+      yflux_pair<RECON, SPLIT, MASK, k>(Ra.v3, Ra.vm3, Ra.sgv3, Ra.sgc3, sX + e, cdy, Ga, CGa);
+      yflux_pair<RECON, SPLIT, MASK, k>(Rb.v3, Rb.vm3, Rb.sgv3, Rb.sgc3, sXb + e, cdy, Gb, CGb);
+      sF[e] = Fa[0];
+      sG[e] = Ga[0];
+      sFb[e] = Fb[0];
+      sGb[e] = Gb[0];
+      if (SPLIT != 1) { sC[e] = CFa[0]; sCb[e] = CFb[0]; }
+      __syncthreads();                                   // barrier B
+      if (warp_u == 0 && ra + 4 <= rlastp) {             // the TMA copies of step s+2 (rows ra+4, ra+5)
+        if (elect_one()) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          issue_k(IC<(k + 4) % DL>{}, o0 - ld8, o0 - 2 * ld8);
+        }
+        o0 += ld8;
+        if (elect_one()) issue_k(IC<(k + 5) % DL>{}, o0 - ld8, o0 - 2 * ld8);
+        o0 += ld8;
+      }
+      // ---------------- phase 3: Qy rows ra, rb, outer x-fluxes, output rows ra-3, rb-3
+      double Fn[1], Gn[1], CFn[1] = {0.0}, out[1], sdiv[1];
+      Fn[0] = sF[e + 1];
+      Gn[0] = sG[e + 1];
+      if (SPLIT != 1) CFn[0] = sC[e + 1];
+      phase_x_outer<RECON, SPLIT, k, W>(L, Xa, Ra, Fa, Fn, Ga, Gn, CFa, CFn, out, sdiv);
+      if (ra >= r0 + 3) {
+        if (out_lane) {
+          *QN = out[0];
+          L.psum += sdiv[0];
+        }
+        QN += g.ld;
+      }
+      Fn[0] = sFb[e + 1];
+      Gn[0] = sGb[e + 1];
+      if (SPLIT != 1) CFn[0] = sCb[e + 1];
+      phase_x_outer<RECON, SPLIT, k + 1, W>(L, Xb, Rb, Fb, Fn, Gb, Gn, CFb, CFn, out, sdiv);
+      if (rb >= r0 + 3 && rb <= rlast) {
+        if (out_lane) {
+          *QN = out[0];
+          L.psum += sdiv[0];
+        }
+        QN += g.ld;
+      }
+      return true;
+    };
+    for (int rb0 = rfirst;; rb0 += DL, parb ^= 1u) {
+      if (!step(IC<0>{}, rb0)) break;
+      if (!step(IC<2>{}, rb0 + 2)) break;
+      if (!step(IC<4>{}, rb0 + 4)) break;
+      if (!step(IC<6>{}, rb0 + 6)) break;
+    }
+    psum_cta = L.psum;
+  } else if constexpr (CS) {
     static_assert(PF == 2, "const-slot march: rings of 3 and 6 rows, windows of 6 registers");
     static_assert(DL == WLEN && DL % DS == 0, "const-slot march: one period for rings and windows");
     const long long ld8 = (long long)g.ld * 8;
@@ -445,16 +611,18 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   }
 }
 
-template <int TB, int PF, int MASK>
+template <int TB, int PF, int MASK, int MINB>
 constexpr size_t smem_bytes() {
-  return sizeof(double) * (size_t)(TB + 6) * ((PF + 1) * ((MASK & 1) ? 4 : 3) + (PF + 4) * ((MASK & 1) ? 5 : 4) + 4) +
-         sizeof(uint64_t) * (PF + 4) + 16;
+  constexpr bool PAIR = (MINB >= 50);
+  constexpr int DS = PAIR ? 4 : PF + 1, DL = PAIR ? 8 : PF + 4, NWORK = PAIR ? 8 : 4;
+  return sizeof(double) * (size_t)(TB + 6) * (DS * ((MASK & 1) ? 4 : 3) + DL * ((MASK & 1) ? 5 : 4) + NWORK) +
+         sizeof(uint64_t) * DL + 16;
 }
 
 template <int TB, int RECON, int SPLIT, int MASK, int PF, int MINB, int MG>
 cudaError_t launch_mg(const FusedArgs& a, int nblocks, cudaStream_t st, int* resident) {
   static bool configured = false;
-  const size_t smem = smem_bytes<TB, PF, MASK>();
+  const size_t smem = smem_bytes<TB, PF, MASK, MG ? 0 : MINB>();
   auto kern = fused2b_kernel<TB, RECON, SPLIT, MASK, PF, MINB, MG>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -504,7 +672,7 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb,
   if (tb == T && pf == P && minb == M) return launch_mask<T, 3, 1, P, M>(a, mask, nblocks, st, resident)
     // (threads, rows in flight, MINB): measured points worth keeping, see profiles/r1_sweep_v2b.log
     TUNE(160, 2, 14); TUNE(160, 1, 14); TUNE(160, 2, 4); TUNE(160, 1, 4); TUNE(160, 2, 24); TUNE(128, 2, 15);
-    TUNE(128, 2, 5); TUNE(160, 2, 34); TUNE(128, 2, 35); TUNE(160, 2, 44); TUNE(128, 2, 45);
+    TUNE(128, 2, 5); TUNE(160, 2, 34); TUNE(128, 2, 35); TUNE(160, 2, 44); TUNE(128, 2, 45); TUNE(160, 2, 53); TUNE(160, 2, 54);
 #undef TUNE
     return cudaErrorInvalidValue;
   }
@@ -526,7 +694,7 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb,
 bool pycs_fused2b_has(int recon, int split, int tb, int pf, int minb) {
   if (recon != 1 && recon != 3) return false;
   if (recon == 3 && split == 1) {
-    const int t[][3] = {{160, 2, 14}, {160, 1, 14}, {160, 2, 4}, {160, 1, 4}, {160, 2, 24}, {128, 2, 15}, {128, 2, 5}, {160, 2, 34}, {128, 2, 35}, {160, 2, 44}, {128, 2, 45}};
+    const int t[][3] = {{160, 2, 14}, {160, 1, 14}, {160, 2, 4}, {160, 1, 4}, {160, 2, 24}, {128, 2, 15}, {128, 2, 5}, {160, 2, 34}, {128, 2, 35}, {160, 2, 44}, {128, 2, 45}, {160, 2, 53}, {160, 2, 54}};
     for (auto& x : t)
       if (x[0] == tb && x[1] == pf && x[2] == minb) return true;
     return false;

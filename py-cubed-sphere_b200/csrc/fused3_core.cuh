@@ -123,16 +123,18 @@ PYCS_HD double inner_update(double q, double d, double rg, double cdv) {
 }
 
 // The five-row windows come in two forms.  K < 0 (default): elements 0..4 hold rows r-4..r and
-// shift every row (free when the march is unrolled by 5).  K >= 0: circular buffer of WLEN = 6
-// registers, row r lives in element K = (r - first row) % 6, so a march unrolled by 6 -- the
+// shift every row (free when the march is unrolled by 5).  K >= 0: circular buffer of W
+// registers, row r lives in element K = (r - first row) % W, so a march unrolled by W -- the
 // period of the staged-row rings -- touches statically named registers and never moves one.
+// W = 6 for the one-row march (rings of 3 and 6 slots), W = 8 for the two-row march (4 and 8).
 constexpr int WLEN = 6;
-template <int K, int I> PYCS_HD constexpr int widx() { return K < 0 ? I : (K + 2 + I) % WLEN; }
+constexpr int WMAX = 8;
+template <int K, int I, int W = WLEN> PYCS_HD constexpr int widx() { return K < 0 ? I : (K + W - 4 + I) % W; }
 
 // Rolling state of one lane: everything is per column c of the lane's NC columns.
 struct Lane {
-  double qw[NC][WLEN];    // Q   rows r-4 .. r (see widx)
-  double yw[NC][WLEN];    // Qy  rows r-4 .. r
+  double qw[NC][WMAX];    // Q   rows r-4 .. r (see widx)
+  double yw[NC][WMAX];    // Qy  rows r-4 .. r
   double pl[NC], pr[NC];  // edge values of Q,  cell r-3
   double yl[NC], yr[NC];  // edge values of Qy, cell r-3
   double fin_prev[NC], fout_prev[NC];   // x-fluxes (inner on Q, outer on Qy) at edge r-3
@@ -148,7 +150,7 @@ struct XEdge {            // x-edge r-2 quantities computed in phase 1, reused i
 
 PYCS_HD void lane_init(Lane& L) {
   for (int c = 0; c < NC; ++c) {
-    for (int k = 0; k < WLEN; ++k) { L.qw[c][k] = 0.0; L.yw[c][k] = 0.0; }
+    for (int k = 0; k < WMAX; ++k) { L.qw[c][k] = 0.0; L.yw[c][k] = 0.0; }
     L.pl[c] = L.pr[c] = L.yl[c] = L.yr[c] = 0.0;
     L.fin_prev[c] = L.fout_prev[c] = 0.0;
     L.su2[c] = L.su3[c] = 0.0;
@@ -161,7 +163,7 @@ PYCS_HD void lane_init(Lane& L) {
 // qnew[c]: Q of row r in the lane's columns (the caller loads it, and patches it when a
 // projection term is pending).
 // cdxw = dt/dx times the time factor of a separable wind (1 otherwise).
-template <int RECON, int SPLIT, int MASK, int K = -1>
+template <int RECON, int SPLIT, int MASK, int K = -1, int W = WLEN>
 PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, const double qnew[NC], double cdxw, double qx[NC]) {
   constexpr int MT = (SPLIT == 3) ? 2 : 1;
 #pragma unroll
@@ -169,9 +171,9 @@ PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, const double qne
     const int o = c * CSTEP;
     double* q = L.qw[c];
     if (K < 0) { q[0] = q[1]; q[1] = q[2]; q[2] = q[3]; q[3] = q[4]; }
-    q[widx<K, 4>()] = qnew[c];
+    q[widx<K, 4, W>()] = qnew[c];
     double l2, r2;                                   // cell r-2
-    edge_values<RECON, (K >= 0)>(q[widx<K, 0>()], q[widx<K, 1>()], q[widx<K, 2>()], q[widx<K, 3>()], q[widx<K, 4>()], l2, r2);
+    edge_values<RECON, (K >= 0)>(q[widx<K, 0, W>()], q[widx<K, 1, W>()], q[widx<K, 2, W>()], q[widx<K, 3, W>()], q[widx<K, 4, W>()], l2, r2);
     const double cc = R.u[o] * cdxw;                // CFL number at edge r-2
     const bool up = ((MASK & 1) ? R.um[o] : cc) >= 0.0;
     const double su1c = R.su1[o];
@@ -182,7 +184,7 @@ PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, const double qne
     const double rg = R.rg3[o];
     double WE, WO, WG;
     edge_weights<MT, !(MASK & 1)>(cc, up, gE, gO, gC, WE, WO, WG);
-    const double E = up ? L.pr[c] : l2, O = up ? L.pl[c] : r2, qc = up ? q[widx<K, 1>()] : q[widx<K, 2>()];
+    const double E = up ? L.pr[c] : l2, O = up ? L.pl[c] : r2, qc = up ? q[widx<K, 1, W>()] : q[widx<K, 2, W>()];
     const double fin = fma(WE, E, fma(WO, O, WG * qc));
     double cdv = 0.0;
     if (SPLIT != 1) {
@@ -190,7 +192,7 @@ PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, const double qne
       cdv = cmx - L.cmx_prev[c];
       L.cmx_prev[c] = cmx;
     }
-    qx[c] = inner_update<SPLIT>(q[widx<K, 1>()], L.fin_prev[c] - fin, rg, cdv);
+    qx[c] = inner_update<SPLIT>(q[widx<K, 1, W>()], L.fin_prev[c] - fin, rg, cdv);
     L.pl[c] = l2; L.pr[c] = r2;
     L.fin_prev[c] = fin;
     L.su3[c] = gE; L.su2[c] = su1c;
@@ -246,7 +248,7 @@ PYCS_HD void yflux_pair(const double* v, const double* vm, const double* sgv, co
 // F, Fn: inner y-fluxes (row r) at the lane's columns and at the columns right of them;
 // G, Gn likewise the outer y-fluxes of row r-3; CM, CMn sqrtg_pv*cy of row r (SPLIT != 1).
 // out[c] = new Q of row r-3, sdiv[c] = pxdF + pydF of that cell.
-template <int RECON, int SPLIT, int K = -1>
+template <int RECON, int SPLIT, int K = -1, int W = WLEN>
 PYCS_HD void phase_x_outer(Lane& L, const XEdge& X, const RowPtrs& R, const double F[NC], const double Fn[NC],
                            const double G[NC], const double Gn[NC], const double CM[NC], const double CMn[NC],
                            double out[NC], double sdiv[NC]) {
@@ -254,16 +256,16 @@ PYCS_HD void phase_x_outer(Lane& L, const XEdge& X, const RowPtrs& R, const doub
   for (int c = 0; c < NC; ++c) {
     double* y = L.yw[c];
     const double cdv = (SPLIT != 1) ? CMn[c] - CM[c] : 0.0;
-    const double qy = inner_update<SPLIT>(L.qw[c][widx<K, 4>()], F[c] - Fn[c], R.rg0[c * CSTEP], cdv);
+    const double qy = inner_update<SPLIT>(L.qw[c][widx<K, 4, W>()], F[c] - Fn[c], R.rg0[c * CSTEP], cdv);
     if (K < 0) { y[0] = y[1]; y[1] = y[2]; y[2] = y[3]; y[3] = y[4]; }
-    y[widx<K, 4>()] = qy;
+    y[widx<K, 4, W>()] = qy;
     double l2, r2;                                   // Qy cell r-2
-    edge_values<RECON, (K >= 0)>(y[widx<K, 0>()], y[widx<K, 1>()], y[widx<K, 2>()], y[widx<K, 3>()], y[widx<K, 4>()], l2, r2);
+    edge_values<RECON, (K >= 0)>(y[widx<K, 0, W>()], y[widx<K, 1, W>()], y[widx<K, 2, W>()], y[widx<K, 3, W>()], y[widx<K, 4, W>()], l2, r2);
     const bool up = X.up[c];
-    const double E = up ? L.yr[c] : l2, O = up ? L.yl[c] : r2, qc = up ? y[widx<K, 1>()] : y[widx<K, 2>()];
+    const double E = up ? L.yr[c] : l2, O = up ? L.yl[c] : r2, qc = up ? y[widx<K, 1, W>()] : y[widx<K, 2, W>()];
     const double fo = fma(X.WE[c], E, fma(X.WO[c], O, X.WG[c] * qc));
     const double s = (L.fout_prev[c] - fo) + (G[c] - Gn[c]);
-    out[c] = fma(s, X.rg3[c], L.qw[c][widx<K, 1>()]);
+    out[c] = fma(s, X.rg3[c], L.qw[c][widx<K, 1, W>()]);
     sdiv[c] = s;
     L.yl[c] = l2; L.yr[c] = r2;
     L.fout_prev[c] = fo;

@@ -145,30 +145,34 @@ void run(const Args& a) {
 
 // ---- v2b (csrc/fused2b.cu): one column per thread, CTA = strip of TB-6 columns -------------
 // compile-time row phase k = (r - first row) % 6 of the circular-window march
-template <int RECON, int SPLIT, int MASK>
+template <int RECON, int SPLIT, int MASK, int W = f1::WLEN>
 void x_inner_k(int k, f1::Lane& L, f1::XEdge& X, const f1::RowPtrs& R, const double* qnew, double cdxw, double* qx) {
   using namespace f1;
   switch (k) {
-    case 0: phase_x_inner<RECON, SPLIT, MASK, 0>(L, X, R, qnew, cdxw, qx); break;
-    case 1: phase_x_inner<RECON, SPLIT, MASK, 1>(L, X, R, qnew, cdxw, qx); break;
-    case 2: phase_x_inner<RECON, SPLIT, MASK, 2>(L, X, R, qnew, cdxw, qx); break;
-    case 3: phase_x_inner<RECON, SPLIT, MASK, 3>(L, X, R, qnew, cdxw, qx); break;
-    case 4: phase_x_inner<RECON, SPLIT, MASK, 4>(L, X, R, qnew, cdxw, qx); break;
-    case 5: phase_x_inner<RECON, SPLIT, MASK, 5>(L, X, R, qnew, cdxw, qx); break;
+    case 0: phase_x_inner<RECON, SPLIT, MASK, 0, W>(L, X, R, qnew, cdxw, qx); break;
+    case 1: phase_x_inner<RECON, SPLIT, MASK, 1, W>(L, X, R, qnew, cdxw, qx); break;
+    case 2: phase_x_inner<RECON, SPLIT, MASK, 2, W>(L, X, R, qnew, cdxw, qx); break;
+    case 3: phase_x_inner<RECON, SPLIT, MASK, 3, W>(L, X, R, qnew, cdxw, qx); break;
+    case 4: phase_x_inner<RECON, SPLIT, MASK, 4, W>(L, X, R, qnew, cdxw, qx); break;
+    case 5: phase_x_inner<RECON, SPLIT, MASK, 5, W>(L, X, R, qnew, cdxw, qx); break;
+    case 6: phase_x_inner<RECON, SPLIT, MASK, 6, f1::WMAX>(L, X, R, qnew, cdxw, qx); break;
+    case 7: phase_x_inner<RECON, SPLIT, MASK, 7, f1::WMAX>(L, X, R, qnew, cdxw, qx); break;
     default: phase_x_inner<RECON, SPLIT, MASK>(L, X, R, qnew, cdxw, qx);
   }
 }
-template <int RECON, int SPLIT>
+template <int RECON, int SPLIT, int W = f1::WLEN>
 void x_outer_k(int k, f1::Lane& L, const f1::XEdge& X, const f1::RowPtrs& R, const double* f, const double* fn,
                const double* g, const double* gn, const double* cf, const double* cfn, double* out, double* sdiv) {
   using namespace f1;
   switch (k) {
-    case 0: phase_x_outer<RECON, SPLIT, 0>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
-    case 1: phase_x_outer<RECON, SPLIT, 1>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
-    case 2: phase_x_outer<RECON, SPLIT, 2>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
-    case 3: phase_x_outer<RECON, SPLIT, 3>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
-    case 4: phase_x_outer<RECON, SPLIT, 4>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
-    case 5: phase_x_outer<RECON, SPLIT, 5>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
+    case 0: phase_x_outer<RECON, SPLIT, 0, W>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
+    case 1: phase_x_outer<RECON, SPLIT, 1, W>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
+    case 2: phase_x_outer<RECON, SPLIT, 2, W>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
+    case 3: phase_x_outer<RECON, SPLIT, 3, W>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
+    case 4: phase_x_outer<RECON, SPLIT, 4, W>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
+    case 5: phase_x_outer<RECON, SPLIT, 5, W>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
+    case 6: phase_x_outer<RECON, SPLIT, 6, f1::WMAX>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
+    case 7: phase_x_outer<RECON, SPLIT, 7, f1::WMAX>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv); break;
     default: phase_x_outer<RECON, SPLIT>(L, X, R, f, fn, g, gn, cf, cfn, out, sdiv);
   }
 }
@@ -279,8 +283,139 @@ void run_block(const Args& a, int TB) {
   }
 }
 
+// ---- v2b, two rows per pair of barriers (csrc/fused2b.cu, MINB >= 50): rings of 4 and 8 slots, the copies of
+// step s+2 issued after barrier B of step s, circular windows of 8 registers, rows of a pair interleaved
+// phase by phase exactly as in the kernel.
+template <int RECON, int SPLIT, int MASK>
+void run_block_pair(const Args& a, int TB) {
+  using namespace f1;
+  const double cdxw = a.cdx * ((MASK & 2) ? a.ws : 1.0), cdyw = a.cdy * ((MASK & 2) ? a.ws : 1.0);
+  const int RW = TB + 6;
+  const int NS = (MASK & 1) ? 4 : 3, NL = (MASK & 1) ? 5 : 4;
+  const int SSLOT = NS * RW, LSLOT = NL * RW;
+  const int DS = 4, DL = 8;
+  const int wmax = TB - 6;
+  const int nstrips = (a.N + wmax - 1) / wmax;
+  int wcols = (a.N + nstrips - 1) / nstrips;
+  wcols += wcols & 1;
+  const int nchunks = (a.N + a.rows_per_chunk - 1) / a.rows_per_chunk;
+  std::vector<double> buf((size_t)DS * SSLOT + (size_t)DL * LSLOT + 8 * RW);
+  double* ringS = buf.data();
+  double* ringL = ringS + DS * SSLOT;
+  double* sX[2] = {ringL + DL * LSLOT, ringL + DL * LSLOT + 4 * RW};
+  double* sF[2] = {sX[0] + RW, sX[1] + RW};
+  double* sG[2] = {sF[0] + RW, sF[1] + RW};
+  double* sC[2] = {sG[0] + RW, sG[1] + RW};
+  std::vector<Lane> L(TB);
+  std::vector<XEdge> X[2] = {std::vector<XEdge>(TB), std::vector<XEdge>(TB)};
+  std::vector<RowPtrs> R[2] = {std::vector<RowPtrs>(TB), std::vector<RowPtrs>(TB)};
+  std::vector<double> F[2] = {std::vector<double>(TB), std::vector<double>(TB)}, G[2] = {F[0], F[0]}, CF[2] = {F[0], F[0]};
+  for (int blk = 0; blk < 6 * nstrips * nchunks; ++blk) {
+    int b = blk;
+    const int p = b % 6;
+    b /= 6;
+    const int strip = b % nstrips, chunk = b / nstrips;
+    const int jbase = a.lo + strip * wcols;
+    const int jend = std::min(jbase + wcols, a.hi);
+    const int r0 = a.lo + chunk * a.rows_per_chunk;
+    const int r1 = std::min(r0 + a.rows_per_chunk, a.hi);
+    const int rfirst = r0 - 3, rlast = r1 + 2;
+    const int rlastp = rlast + ((rlast - rfirst + 1) & 1);
+    const int c0 = jbase - 6;
+    const int len = std::min(RW, a.ld - JOFF - c0) & ~1;
+    const long long colb = (long long)p * a.ps + JOFF + c0, colm = JOFF + c0;
+    std::fill(buf.begin(), buf.end(), 0.0);
+    for (int t = 0; t < TB; ++t) lane_init(L[t]);
+    auto issue = [&](int r) {     // TMA row copies of row r
+      const int k = (r - rfirst) % DL;
+      double* dS = ringS + (k % DS) * SSLOT;
+      double* dL = ringL + k * LSLOT;
+      const long long rr = (long long)r * a.ld, rm1 = (long long)std::max(r - 1, 0) * a.ld,
+                      rm2 = (long long)std::max(r - 2, 0) * a.ld;
+      auto cp = [&](double* dst, const double* src) { std::memcpy(dst, src, sizeof(double) * len); };
+      cp(dS + S_Q * RW, a.q + colb + rr); cp(dL + L_V * RW, a.va + colb + rr);
+      cp(dL + L_SGC * RW, a.sgc + colm + rr); cp(dL + L_SGV * RW, a.sgv + colm + rr);
+      cp(dL + L_RGC * RW, a.rgc + colm + rr); cp(dS + S_SGU * RW, a.sgu + colm + rm1);
+      cp(dS + S_U * RW, a.ua + colb + rm2);
+      if (MASK & 1) { cp(dL + L_VM * RW, a.vm + colb + rr); cp(dS + S_UM * RW, a.um + colb + rm2); }
+    };
+    for (int r = rfirst; r < rfirst + 4 && r <= rlastp; ++r) issue(r);
+    double psum = 0.0;
+    for (int ra = rfirst; ra <= rlastp; ra += 2) {
+      const int rows[2] = {ra, ra + 1};
+      for (int t = 0; t < TB; ++t) {               // patch + phase 1 of both rows
+        const int e = t + 3, j = jbase - 3 + t;
+        for (int h = 0; h < 2; ++h) {
+          const int r = rows[h], k = (r - rfirst) % DL;
+          const int oS = (k % DS) * SSLOT, oL0 = k * LSLOT, oL2 = ((k + DL - 2) % DL) * LSLOT, oL3 = ((k + DL - 3) % DL) * LSLOT;
+          RowPtrs& P = R[h][t];
+          P.q = ringS + oS + S_Q * RW + e; P.u = ringS + oS + S_U * RW + e;
+          P.um = ringS + oS + S_UM * RW + e; P.su1 = ringS + oS + S_SGU * RW + e;
+          P.v0 = ringL + oL0 + L_V * RW + e; P.vm0 = ringL + oL0 + L_VM * RW + e;
+          P.sgv0 = ringL + oL0 + L_SGV * RW + e; P.sgc0 = ringL + oL0 + L_SGC * RW + e;
+          P.rg0 = ringL + oL0 + L_RGC * RW + e; P.sgc2 = ringL + oL2 + L_SGC * RW + e;
+          P.v3 = ringL + oL3 + L_V * RW + e; P.vm3 = ringL + oL3 + L_VM * RW + e;
+          P.sgv3 = ringL + oL3 + L_SGV * RW + e; P.sgc3 = ringL + oL3 + L_SGC * RW + e;
+          P.rg3 = ringL + oL3 + L_RGC * RW + e;
+        }
+        double qn[2][1];
+        for (int h = 0; h < 2; ++h) {
+          const int r = rows[h], k = (r - rfirst) % DL;
+          RowPtrs& P = R[h][t];
+          qn[h][0] = P.q[0];
+          if (a.apply_corr && j >= a.lo && j < a.hi && r >= a.lo && r < a.hi) {
+            qn[h][0] = fma(P.sgc0[0], a.corr, qn[h][0]);
+            ringS[(k % DS) * SSLOT + S_Q * RW + e] = qn[h][0];
+          }
+        }
+        for (int h = 0; h < 2; ++h) {
+          const int k = (rows[h] - rfirst) % DL;
+          double qx[1];
+          x_inner_k<RECON, SPLIT, MASK, WMAX>(k, L[t], X[h][t], R[h][t], qn[h], cdxw, qx);
+          sX[h][e] = qx[0];
+        }
+      }
+      for (int t = 0; t < TB; ++t) {               // barrier A; phase 2
+        const int e = t + 3;
+        for (int h = 0; h < 2; ++h) {
+          double f[1], g[1], cf[1] = {0.0}, cg[1];
+          yflux_pair<RECON, SPLIT, MASK, 0>(R[h][t].v0, R[h][t].vm0, R[h][t].sgv0, R[h][t].sgc0, R[h][t].q, cdyw, f, cf);
+          yflux_pair<RECON, SPLIT, MASK, 0>(R[h][t].v3, R[h][t].vm3, R[h][t].sgv3, R[h][t].sgc3, sX[h] + e, cdyw, g, cg);
+          F[h][t] = f[0]; G[h][t] = g[0]; CF[h][t] = cf[0];
+        }
+      }
+      for (int h = 0; h < 2; ++h)
+        for (int t = 0; t < TB; ++t) { sF[h][t + 3] = F[h][t]; sG[h][t + 3] = G[h][t]; sC[h][t + 3] = CF[h][t]; }
+      // barrier B; the copies of step s+2 overwrite the slots of this step and of rows ra-4, ra-3
+      if (ra + 4 <= rlastp) { issue(ra + 4); issue(ra + 5); }
+      for (int t = 0; t < TB; ++t) {               // phase 3 of both rows
+        const int e = t + 3, j = jbase - 3 + t;
+        for (int h = 0; h < 2; ++h) {
+          const int r = rows[h], k = (r - rfirst) % DL;
+          double f[1] = {F[h][t]}, g[1] = {G[h][t]}, cf[1] = {CF[h][t]};
+          double fn[1] = {sF[h][e + 1]}, gn[1] = {sG[h][e + 1]}, cfn[1] = {sC[h][e + 1]}, out[1], sdiv[1];
+          x_outer_k<RECON, SPLIT, WMAX>(k, L[t], X[h][t], R[h][t], f, fn, g, gn, cf, cfn, out, sdiv);
+          if (r >= r0 + 3 && r <= rlast && t >= 3 && j < jend) {
+            a.qn[(long long)p * a.ps + JOFF + j + (long long)(r - 3) * a.ld] = out[0];
+            L[t].psum += sdiv[0];
+          }
+        }
+      }
+    }
+    for (int t = 0; t < TB; ++t) psum += L[t].psum;
+    a.part[blk] = psum;
+  }
+}
+
 template <int RECON, int SPLIT>
 int run_block_mask(const Args& a, int mask, int TB) {
+  if (a.circ == 2) {
+    if (mask == 0) run_block_pair<RECON, SPLIT, 0>(a, TB);
+    else if (mask == 1) run_block_pair<RECON, SPLIT, 1>(a, TB);
+    else if (mask == 2) run_block_pair<RECON, SPLIT, 2>(a, TB);
+    else return -1;
+    return 0;
+  }
   if (mask == 0) run_block<RECON, SPLIT, 0>(a, TB);
   else if (mask == 1) run_block<RECON, SPLIT, 1>(a, TB);
   else if (mask == 2) run_block<RECON, SPLIT, 2>(a, TB);
@@ -350,6 +485,8 @@ int f3_emul_step_block_circ(STEP_BLOCK_ARGS) {
   if (depth != 2) return -2;
   return f3_emul_step_block_impl(1, STEP_BLOCK_PASS);
 }
+// the two-row march (MINB >= 50); depth is ignored (rings of 4 and 8 slots)
+int f3_emul_step_block_pair(STEP_BLOCK_ARGS) { return f3_emul_step_block_impl(2, STEP_BLOCK_PASS); }
 int f3_emul_block_grid(int N, int TB, int rows_per_chunk) {
   const int wmax = TB - 6;
   return 6 * ((N + wmax - 1) / wmax) * ((N + rows_per_chunk - 1) / rows_per_chunk);

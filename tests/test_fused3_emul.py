@@ -35,6 +35,8 @@ def emul():
     lib.f3_emul_step_block.restype = C.c_int
     lib.f3_emul_step_block_circ.argtypes = lib.f3_emul_step.argtypes
     lib.f3_emul_step_block_circ.restype = C.c_int
+    lib.f3_emul_step_block_pair.argtypes = lib.f3_emul_step.argtypes
+    lib.f3_emul_step_block_pair.restype = C.c_int
     lib.f3_emul_block_grid.argtypes = [C.c_int] * 3
     lib.f3_emul_block_grid.restype = C.c_int
     lib.f3_emul_grid.argtypes = [C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 3
@@ -103,7 +105,8 @@ def one_step(emul, N, vf, tup, pre_steps, nw=3, depth=3, rows=None, pending=Fals
     rows = rows or N
     if block_tb:        # v2b decomposition (csrc/fused2b.cu)
         part = np.zeros(emul.f3_emul_block_grid(N, block_tb, rows))
-        fn = emul.f3_emul_step_block_circ if circ else emul.f3_emul_step_block
+        fn = {False: emul.f3_emul_step_block, True: emul.f3_emul_step_block_circ,
+              "pair": emul.f3_emul_step_block_pair}[circ]
         rc = fn(N, recon, split, mask, block_tb, depth, rows, ptr(q), ptr(qn),
                 *[ptr(a) for a in arrs], ptr(part), corr, 1 if pending else 0, dt / g.dx, dt / g.dy, ws)
     else:               # v3 decomposition (csrc/fused3.cu)
@@ -203,3 +206,24 @@ def test_emulated_v2b_circular_windows_against_shifting(emul):
     a, _ = one_step(emul, 50, 3, TUPLES["default"], 3, depth=2, rows=11, block_tb=64, circ=True)
     b, _ = one_step(emul, 50, 3, TUPLES["default"], 3, depth=2, rows=11, block_tb=64, circ=False)
     assert 0 < np.max(np.abs(a - b)) <= 1e-14 * np.max(np.abs(b))
+
+
+# ---- v2b, two rows per pair of barriers (MINB >= 50): rings of 4 / 8 slots, windows of 8 registers --
+@pytest.mark.parametrize("N,vf,name,pre", CASES)
+def test_emulated_v2b_two_row_march_matches_oracle(emul, N, vf, name, pre):
+    got, want = one_step(emul, N, vf, TUPLES[name], pre, depth=2, block_tb=32 if N < 100 else 160, circ="pair")
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("tb,rows,kw", [(32, 7, {}), (64, 16, {"pending": True}), (160, 50, {"separable": True}),
+                                        (128, 9, {"pending": True}), (160, 6, {}), (64, 12, {}), (64, 25, {})])
+def test_emulated_v2b_two_row_march_chunk_lengths(emul, tb, rows, kw):
+    """odd and even numbers of marched rows, every exit phase of the eight-row group, copies issued two steps ahead."""
+    got, want = one_step(emul, 50, 3, TUPLES["default"], 3, depth=2, rows=rows, block_tb=tb, circ="pair", **kw)
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+
+
+def test_emulated_v2b_two_row_march_same_bits_as_const_slot(emul):
+    a, _ = one_step(emul, 50, 3, TUPLES["default"], 3, depth=2, rows=11, block_tb=64, circ="pair")
+    b, _ = one_step(emul, 50, 3, TUPLES["default"], 3, depth=2, rows=11, block_tb=64, circ=True)
+    assert np.array_equal(a, b)

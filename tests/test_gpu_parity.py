@@ -324,17 +324,19 @@ def test_fused_matches_operator_path(mods, N, vf, name):
     b.dev.close()
 
 
-@pytest.mark.parametrize("impl", ["2", "3", "4", "4g", "4s"])
+@pytest.mark.parametrize("impl", ["2", "3", "4", "4g", "4s", "4p"])
 @pytest.mark.parametrize("N,vf,name", [(16, 1, "default"), (50, 3, "default"), (130, 2, "AVLT-RK2-DG-PR"),
                                        (130, 1, "PL07-RK1-DG-PR"), (200, 4, "default"), (1536, 3, "default")])
 def test_fused_kernel_variants_match_operator_path(mods, N, vf, name, impl, monkeypatch):
     """Every fused step kernel -- v2 block-synchronous (csrc/fused.cu, PYCS_FUSED_IMPL=2), v3
     warp-autonomous (csrc/fused3.cu, 3), v2b block-synchronous with the lean core
     (csrc/fused2b.cu, 4 = default const-slot march; 4g with the ghost prologue, 4s the
-    shifting-window march MINB=14 / 4) -- against
+    shifting-window march MINB=14 / 4, 4p the two-row march MINB=53) -- against
     the operator path, over several run calls (separable wind and pending projection carried
     across calls)."""
     monkeypatch.setenv("PYCS_FUSED_IMPL", impl[0])
+    if impl.endswith("p"):        # two rows per pair of barriers (3 CTAs/SM); schemes without it fall back
+        monkeypatch.setenv("PYCS_FUSED_MINB", "53")
     if impl.endswith("s"):
         monkeypatch.setenv("PYCS_FUSED_MINB", "4" if name.startswith("PL07") else "14")
     monkeypatch.setenv("PYCS_GHOST_FUSED", "1" if impl.endswith("g") else "0")   # 4g: ghost fill inside v2b
