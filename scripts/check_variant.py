@@ -41,7 +41,7 @@ for N in sizes:
         b.dev.close()
 
 g = cs_datastruct.cubed_sphere(1536)
-for mb in ("34", minb, "34", minb):
+for mb in (minb, "34", minb):
     os.environ["PYCS_FUSED_MINB"] = mb
     s = sim_of(g, 3)
     ms = C.c_float()
