@@ -66,10 +66,6 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   constexpr bool CS = (MINB >= 30) && (MINB < 50) && !MG;
   // MINB >= 50: two rows per pair of block barriers (rings of 4 and 8 slots, windows of 8 registers)
   constexpr bool PAIR = (MINB >= 50) && !MG;
-  // MINB >= 40: every warp issues its share of a row's TMA copies (one mbarrier arrival per warp)
-  // instead of warp 0 carrying all of them into barrier B
-  constexpr bool DI = CS && (MINB >= 40);
-  constexpr int NWARP = TB / 32;
   constexpr int RW = TB + 6;                 // staged row: columns jbase-6 .. jbase+TB-1
   constexpr int NS = (MASK & 1) ? 4 : 3, NL = (MASK & 1) ? 5 : 4;
   constexpr int DS = PAIR ? 4 : PF + 1, DL = PAIR ? 8 : PF + 4;
@@ -108,7 +104,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
 
   for (int k = tid; k < DS * SSLOT + DL * LSLOT + NWORK * RW; k += TB) ringS[k] = 0.0;
   if (tid == 0) {
-    for (int s = 0; s < DL; ++s) mbar_init(&full[s], DI ? NWARP : 1);
+    for (int s = 0; s < DL; ++s) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -166,12 +162,10 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
                  "l"(src), "r"(row_bytes), "r"(bar)
                  : "memory");
   };
-  // The copies of a row are issued in two halves (MINB >= 20: the second half after barrier B),
-  // which halves the extra work warp 0 carries into either barrier.
-  constexpr bool SPLIT_ISSUE = (MINB >= 20);
-  auto issue_a = [&](int r) {                // elected lane of warp 0
+  auto issue = [&](int r) {                  // elected lane of warp 0 (shifting-window march)
     const uint32_t dS = ringS_a + (uint32_t)iS, dL = ringL_a + (uint32_t)iL, bar = full_a + 8u * (uint32_t)ib;
-    const long long rr = (long long)r * g.ld;
+    const long long rr = (long long)r * g.ld, r1_ = (long long)max(r - 1, 0) * g.ld,
+                    r2_ = (long long)max(r - 2, 0) * g.ld;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * (NS + NL))
                  : "memory");
     tma(dS + 8u * S_Q * RW, gq + rr, bar);
@@ -179,19 +173,10 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
     tma(dL + 8u * L_SGC * RW, gsgc + rr, bar);
     tma(dL + 8u * L_SGV * RW, gsgv + rr, bar);
     if (MASK & 1) tma(dL + 8u * L_VM * RW, gvm + rr, bar);
-  };
-  auto issue_b = [&](int r, int jS, int jL, int jb) {
-    const uint32_t dS = ringS_a + (uint32_t)jS, dL = ringL_a + (uint32_t)jL, bar = full_a + 8u * (uint32_t)jb;
-    const long long rr = (long long)r * g.ld, r1_ = (long long)max(r - 1, 0) * g.ld,
-                    r2_ = (long long)max(r - 2, 0) * g.ld;
     tma(dL + 8u * L_RGC * RW, grgc + rr, bar);
     tma(dS + 8u * S_SGU * RW, gsgu + r1_, bar);
     tma(dS + 8u * S_U * RW, gu + r2_, bar);
     if (MASK & 1) tma(dS + 8u * S_UM * RW, gum + r2_, bar);
-  };
-  auto issue = [&](int r) {
-    issue_a(r);
-    issue_b(r, iS, iL, ib);
   };
   double psum_cta = 0.0;
   if constexpr (PAIR) {
@@ -367,29 +352,27 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
     };
     // k = (row - rfirst) % DL is a compile-time constant everywhere below; o1, o2: offsets of the
     // rows staged one and two rows late (sqrtg_pu, u)
-    // copy c of a row is issued by warp c % NWARP when the issue is distributed, else by warp 0
     constexpr int NCOPY = NS + NL;
-    auto mine = [&](int c) { return !DI || warp_u == c % NWARP; };
-    const uint32_t my_bytes = DI ? row_bytes * (uint32_t)((NCOPY - warp_u + NWARP - 1) / NWARP) : row_bytes * NCOPY;
-    auto issue_k = [&](auto kc, long long o1, long long o2) {   // elected lane of an issuing warp
+    auto issue_k = [&](auto kc, long long o1, long long o2) {   // elected lane of warp 0
       constexpr int k = decltype(kc)::value;
       const uint32_t dS = ringS_a + 8u * (uint32_t)((k % DS) * SSLOT), dL = ringL_a + 8u * (uint32_t)(k * LSLOT),
                      bar = full_a + 8u * (uint32_t)k;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(my_bytes) : "memory");
-      if (mine(0)) tma(dS + 8u * S_Q * RW, at(gq, o0), bar);
-      if (mine(1)) tma(dL + 8u * L_V * RW, at(gv, o0), bar);
-      if (mine(2)) tma(dL + 8u * L_SGC * RW, at(gsgc, o0), bar);
-      if (mine(3)) tma(dL + 8u * L_SGV * RW, at(gsgv, o0), bar);
-      if (mine(4)) tma(dL + 8u * L_RGC * RW, at(grgc, o0), bar);
-      if (mine(5)) tma(dS + 8u * S_SGU * RW, at(gsgu, o1), bar);
-      if (mine(6)) tma(dS + 8u * S_U * RW, at(gu, o2), bar);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * NCOPY)
+                   : "memory");
+      tma(dS + 8u * S_Q * RW, at(gq, o0), bar);
+      tma(dL + 8u * L_V * RW, at(gv, o0), bar);
+      tma(dL + 8u * L_SGC * RW, at(gsgc, o0), bar);
+      tma(dL + 8u * L_SGV * RW, at(gsgv, o0), bar);
+      tma(dL + 8u * L_RGC * RW, at(grgc, o0), bar);
+      tma(dS + 8u * S_SGU * RW, at(gsgu, o1), bar);
+      tma(dS + 8u * S_U * RW, at(gu, o2), bar);
       if (MASK & 1) {
-        if (mine(7)) tma(dL + 8u * L_VM * RW, at(gvm, o0), bar);
-        if (mine(8)) tma(dS + 8u * S_UM * RW, at(gum, o2), bar);
+        tma(dL + 8u * L_VM * RW, at(gvm, o0), bar);
+        tma(dS + 8u * S_UM * RW, at(gum, o2), bar);
       }
     };
-    if (DI || warp_u == 0) {                   // rows rfirst, rfirst + 1 (rfirst >= 1: only row -1 is clamped)
+    if (warp_u == 0) {                         // rows rfirst, rfirst + 1 (rfirst >= 1: only row -1 is clamped)
       if (elect_one()) issue_k(IC<0>{}, o0 - ld8, (long long)max(rfirst - 2, 0) * ld8);
       o0 += ld8;
       if (rfirst + 1 <= rlast) {
@@ -437,7 +420,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
       phase_x_inner<RECON, SPLIT, MASK, k>(L, X, R, qnew, cdx, qx);
       sX[e] = qx[0];
       __syncthreads();                                   // barrier A
-      if ((DI || warp_u == 0) && r + PF <= rlast) {      // the TMA copies of row r+PF
+      if (warp_u == 0 && r + PF <= rlast) {              // warp 0 issues the TMA copies of row r+PF
         if (elect_one()) issue_k(IC<(k + PF) % DL>{}, o0 - ld8, o0 - 2 * ld8);
         o0 += ld8;
       }
@@ -524,12 +507,10 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
       phase_x_inner<RECON, SPLIT, MASK>(L, X, R, qnew, cdx, qx);
       sX[e] = qx[0];
       __syncthreads();                                   // barrier A
-      int jS = iS, jL = iL, jb = ib;                     // slots of row r+PF (for the second half)
       if (warp_u == 0 && r + PF <= rlast) {              // warp 0 issues the TMA copies of row r+PF
         if (elect_one()) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          if (SPLIT_ISSUE) issue_a(r + PF);
-          else issue(r + PF);
+          issue(r + PF);
         }
         iS = (iS + 8 * SSLOT == 8 * DS * SSLOT) ? 0 : iS + 8 * SSLOT;
         iL = (iL + 8 * LSLOT == 8 * DL * LSLOT) ? 0 : iL + 8 * LSLOT;
@@ -543,9 +524,6 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
       sG[e] = G[0];
       if (SPLIT != 1) sC[e] = CF[0];
       __syncthreads();                                   // barrier B
-      if (SPLIT_ISSUE && warp_u == 0 && r + PF <= rlast) {
-        if (elect_one()) issue_b(r + PF, jS, jL, jb);
-      }
       // ---------------- phase 3: Qy row r, outer x-flux on Qy, output row r-3
       double Fn[1], Gn[1], CFn[1] = {0.0}, out[1], sdiv[1];
       Fn[0] = sF[e + 1];
@@ -671,8 +649,8 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb,
 #define TUNE(T, P, M) \
   if (tb == T && pf == P && minb == M) return launch_mask<T, 3, 1, P, M>(a, mask, nblocks, st, resident)
     // (threads, rows in flight, MINB): measured points worth keeping, see profiles/r1_sweep_v2b.log
-    TUNE(160, 2, 14); TUNE(160, 1, 14); TUNE(160, 2, 4); TUNE(160, 1, 4); TUNE(160, 2, 24); TUNE(128, 2, 15);
-    TUNE(128, 2, 5); TUNE(160, 2, 34); TUNE(128, 2, 35); TUNE(160, 2, 44); TUNE(128, 2, 45); TUNE(160, 2, 53); TUNE(160, 2, 54);
+    TUNE(160, 2, 14); TUNE(160, 1, 14); TUNE(160, 2, 4); TUNE(160, 1, 4); TUNE(128, 2, 15);
+    TUNE(128, 2, 5); TUNE(160, 2, 34); TUNE(128, 2, 35); TUNE(160, 2, 53);
 #undef TUNE
     return cudaErrorInvalidValue;
   }
@@ -694,7 +672,7 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb,
 bool pycs_fused2b_has(int recon, int split, int tb, int pf, int minb) {
   if (recon != 1 && recon != 3) return false;
   if (recon == 3 && split == 1) {
-    const int t[][3] = {{160, 2, 14}, {160, 1, 14}, {160, 2, 4}, {160, 1, 4}, {160, 2, 24}, {128, 2, 15}, {128, 2, 5}, {160, 2, 34}, {128, 2, 35}, {160, 2, 44}, {128, 2, 45}, {160, 2, 53}, {160, 2, 54}};
+    const int t[][3] = {{160, 2, 14}, {160, 1, 14}, {160, 2, 4}, {160, 1, 4}, {128, 2, 15}, {128, 2, 5}, {160, 2, 34}, {128, 2, 35}, {160, 2, 53}};
     for (auto& x : t)
       if (x[0] == tb && x[1] == pf && x[2] == minb) return true;
     return false;
