@@ -9,8 +9,8 @@ R_p, which is exact in floating point, so the arrays equal the reference's.
 """
 import numpy as np
 
-from .constants import pio4, nbfaces
-from .sphgeo import point
+from .constants import pi, pio2, pio4, nbfaces
+from .sphgeo import point, sph2cart
 
 # R_p as (source component, sign) for X, Y, Z: panel p position = R_p (v0, v1, v2)
 # with (v0, v1, v2) the panel-0 position (src/cs_transform.py:64-92, :163-191).
@@ -104,6 +104,17 @@ class cubed_sphere:
             setattr(self, "prod_ey_elon_" + pos, eylon)
             setattr(self, "prod_ey_elat_" + pos, eylat)
             setattr(self, "determinant_ll2contra_" + pos, exlon * eylat - eylon * exlat)
+
+
+class latlon_grid:
+    """Regular lat-lon grid used for plots and the .npy error dumps (src/cs_datastruct.py:569-582);
+    `ix, jy, mask` are filled by interpolation.ll2cs."""
+
+    def __init__(self, Nlat, Nlon):
+        self.Nlat, self.Nlon = Nlat, Nlon
+        self.lat, self.lon = np.meshgrid(np.linspace(-pio2, pio2, Nlat), np.linspace(-pi, pi, Nlon))
+        self.X, self.Y, self.Z = sph2cart(self.lon, self.lat)
+        self.ix, self.jy, self.mask = [], [], []
 
 
 class scalar_field:

@@ -1,19 +1,21 @@
 """Driver with the reference's main.py structure (main.py:30-99) for the accelerated test cases:
 read par/configuration.par, build the grid, dispatch on test_case.  Test case 5 (advection,
-par/advection.par) and 4 (one-step divergence test) run on the GPU; 1-3 (grid plots, grid
+par/advection.par) and 4 (divergence convergence, src/operator_accuracy.py) run on the GPU; 1-3 (grid plots, grid
 quality, interpolation experiments) are not part of this library.
 
     python -m pycs_b200.main [pardir]        # from the repository root (pycs_b200.py shim on sys.path)
 """
 import sys
 
-import numpy as np
 
 
 def main(pardir=None):
     from .configuration import get_parameters, get_advection_parameters
-    from .cs_datastruct import cubed_sphere
-    from .advection_ic import adv_simulation_par, div_exact
+    from .cs_datastruct import cubed_sphere, latlon_grid
+    from .constants import Nlat, Nlon
+    from .interpolation import ll2cs
+    from .operator_accuracy import error_analysis_div
+    from .advection_ic import adv_simulation_par
     from .advection_sphere import adv_sphere
     from .advection_error import error_analysis_adv
     N, transformation, showonscreen, gridload, test_case, map_projection = get_parameters(pardir)
@@ -27,21 +29,17 @@ def main(pardir=None):
     cs_grid = cubed_sphere(N, transformation, showonscreen, gridload)
     dt, Tf, tc, ic, vf, recon, dp, opsplit, et, mt, mf = get_advection_parameters(pardir)
     if test_case == 4:
-        # src/operator_accuracy.py:29-110: Q = 1, one step, div against div_exact
+        # src/operator_accuracy.py:29-147: convergence of div for Q = 1 over N = 16 ... 1024
         print("Test case 4: Divergence test case.\n")
-        simulation = adv_simulation_par(cs_grid, dt, Tf, 1, vf, 1, recon, dp, opsplit, et, mt, mf)
-        adv_sphere(cs_grid, None, simulation, map_projection, False, True)
-        I = np.s_[cs_grid.i0:cs_grid.iend, cs_grid.j0:cs_grid.jend, :]
-        d = np.asarray(simulation.div)[I]
-        e = np.abs(d - div_exact(cs_grid.pc.lon[I], cs_grid.pc.lat[I], simulation))
-        print("Divergence error (Linf, L1, L2):", "{:.2e}".format(np.max(e)), "{:.2e}".format(np.mean(e)),
-              "{:.2e}".format(np.sqrt(np.mean(e * e))))
-        return simulation
+        return error_analysis_div(vf, map_projection, False, transformation, showonscreen, gridload, pardir=pardir)
+    # lat-lon grid of the error dump (main.py:57-60 of the reference)
+    ll_grid = latlon_grid(Nlat, Nlon)
+    ll_grid.ix, ll_grid.jy, ll_grid.mask = ll2cs(cs_grid, ll_grid)
     print("Test case 5: Advection test case.\n")
     simulation = adv_simulation_par(cs_grid, dt, Tf, ic, vf, tc, recon, dp, opsplit, et, mt, mf)
     if simulation.tc == 1:
         simulation.fused = True
-        adv_sphere(cs_grid, None, simulation, map_projection, False, False)
+        adv_sphere(cs_grid, ll_grid, simulation, map_projection, False, False)
     elif simulation.tc == 2:
         error_analysis_adv(simulation, map_projection, False, transformation, showonscreen, gridload)
     else:

@@ -1,15 +1,48 @@
-"""Diagnostics part of output_adv (src/output.py:22-50); plots and file dumps are out of scope."""
+"""Diagnostics and data files of output_adv (src/output.py:22-184); the plots are out of scope.
+
+What a run leaves behind in the reference besides figures -- and what this module writes when the
+caller passes a lat-lon grid (`ll_grid`, with `ix, jy, mask` from interpolation.ll2cs):
+  data/<grid name>_adv_Q_error_ic*_vf*_<scheme names>_interp<d>.npy   error field on the lat-lon grid
+  data/<grid name>_adv_Q_error_ic*_vf*_<scheme names>_interp<d>        seven numbers, one per line:
+        Linf, L1, L2 error, CFL, mass change, dt, Tf                    (src/output.py:136-150)
+"""
+import os
+
 import numpy as np
 
+from .constants import datadir
+from .cs_datastruct import scalar_field
 from .errors import compute_errors
-from .advection_ic import qexact_adv
+from .advection_ic import qexact_adv, div_exact
 from .diagnostics import mass_computation
+from .interpolation import nearest_neighbour
 
 
 def print_diagnostics_adv(error_linf, error_l1, error_l2, mass_change, t, Nsteps):
     print('\nStep', t, 'from', Nsteps)
     print('Error (Linf, L1, L2) :', "{:.2e}".format(error_linf), "{:.2e}".format(error_l1), "{:.2e}".format(error_l2))
     print('Total mass variation:', "{:.2e}".format(mass_change))
+
+
+def _scheme_tag(simulation, with_mf):
+    names = [simulation.opsplit_name, simulation.recon_name, simulation.dp_name, simulation.et_name, simulation.mt_name]
+    if with_mf:
+        names.append(simulation.mf_name)
+    return "_".join(names)
+
+
+def save_error_files(cs_grid, ll_grid, simulation, q, q_exact, k):
+    """The .npy / text pair of src/output.py:136-150 for the final step."""
+    fq, fe = scalar_field(cs_grid, 'q', 'center'), scalar_field(cs_grid, 'q_exact', 'center')
+    fq.f[:, :, :], fe.f[:, :, :] = q, q_exact
+    err_ll = nearest_neighbour(fe, cs_grid, ll_grid) - nearest_neighbour(fq, cs_grid, ll_grid)
+    base = datadir + cs_grid.name + '_adv_Q_error_ic' + str(simulation.ic) + '_vf' + str(simulation.vf) + '_' + \
+        _scheme_tag(simulation, True) + '_interp' + str(simulation.degree)
+    os.makedirs(os.path.dirname(base) or ".", exist_ok=True)
+    np.save(base, err_ll, allow_pickle=False)
+    np.savetxt(base, np.array([simulation.error_linf[k], simulation.error_l1[k], simulation.error_l2[k],
+                               simulation.CFL, simulation.mass_change, simulation.dt, simulation.Tf]))
+    return base
 
 
 def output_adv(cs_grid, ll_grid, simulation, plot, k, t, Nsteps, plotstep, map_projection, divtest_flag):
@@ -28,3 +61,12 @@ def output_adv(cs_grid, ll_grid, simulation, plot, k, t, Nsteps, plotstep, map_p
         if k > 0 and (not divtest_flag):
             print_diagnostics_adv(simulation.error_linf[k], simulation.error_l1[k], simulation.error_l2[k],
                                   simulation.mass_change, k, Nsteps)
+        if k % plotstep == 0 or k == 0 or k == Nsteps:
+            if divtest_flag:
+                # divergence test: the norms are those of div against the exact divergence
+                # (src/output.py:152-169)
+                d = np.asarray(simulation.div)[I]
+                dex = div_exact(cs_grid.pc.lon[I], cs_grid.pc.lat[I], simulation)
+                simulation.error_linf[k], simulation.error_l1[k], simulation.error_l2[k] = compute_errors(d, dex)
+            elif t > 0 and k == Nsteps and ll_grid is not None and len(np.shape(ll_grid.mask)) == 2:
+                save_error_files(cs_grid, ll_grid, simulation, q, q_exact, k)

@@ -10,6 +10,8 @@ Usage:  python tests/golden/make_golden.py small|kmin|norms|big384|big768|big153
   big384   config 2: N=384 default scheme, full period, sub-sampled Q + norms (~50 min)
   big768   config 3: N=768 vf=2 RK2, first 50 steps, sub-sampled Q
   big1536  config 4: N=1536 vf=3, first 20 steps, sub-sampled Q (needs ~15 GB RAM)
+  regrid   lat-lon -> cubed-sphere index maps (ll2cs), nearest-neighbour regridding and the
+           one-step divergence-test errors (drivers / output row of SURVEY s8 f4)
 """
 import json
 import os
@@ -244,6 +246,37 @@ def make_big(N, vf, tup_name, checkpoints, S):
         save("config_N%d_vf%d.npz" % (N, vf), **out)
 
 
+def make_regrid():
+    """src/interpolation.py:38-149 (ll2cs, nearest_neighbour) and the divergence test of
+    src/operator_accuracy.py / src/output.py:152-169, for small grids."""
+    rint.ll2cs_netcdf = lambda *a, **k: None          # the netCDF cache writer (netCDF4 is a stub here)
+    out = {}
+    rng = np.random.default_rng(11)
+    for proj in ("gnomonic_equiangular", "gnomonic_equidistant"):
+        for N in (16, 21):
+            g = cs.cubed_sphere(N, proj, False, False)
+            ll = cs.latlon_grid(36, 72)
+            ix, jy, mask = rint.ll2cs(g, ll)
+            ll.ix, ll.jy, ll.mask = ix, jy, mask
+            key = "%s_N%d" % (proj.split("_")[1], N)
+            out["ix_" + key], out["jy_" + key], out["mask_" + key] = ix, jy, mask
+            q = cs.scalar_field(g, "q", "center")
+            q.f[:, :, :] = rng.standard_normal(q.f.shape)
+            out["field_" + key] = q.f.copy()
+            out["regrid_" + key] = rint.nearest_neighbour(q, g, ll)
+    out["ll_lon"], out["ll_lat"] = ll.lon, ll.lat
+    # divergence test: Q = 1, one step, div against div_exact (src/operator_accuracy.py:29-110)
+    g = grid(16)
+    I = np.s_[g.i0:g.iend, g.j0:g.jend, :]
+    for vf in (1, 2, 3, 4):
+        for name in ("PL07-RK1", "PL07-RK1-DG-PR", "AVLT-RK2-DG-AF", "AVLT-RK2-DG-PR"):
+            sim = new_sim(g, vf, TUPLES[name], ic=1)
+            rts.adv_time_step(g, sim, 1, sim.dt)
+            dex = ric.div_exact(g.pc.lon[I], g.pc.lat[I], sim)
+            out["diverr_vf%d_%s" % (vf, name)] = np.array(rerr.compute_errors(sim.div[I], dex))
+    save("regrid_N16.npz", **out)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "small"
     if what in ("small", "all"):
@@ -252,6 +285,8 @@ if __name__ == "__main__":
         make_kmin()
     if what in ("norms", "all"):
         make_norms()
+    if what in ("regrid", "all"):
+        make_regrid()
     if what in ("big384", "all"):
         make_big(384, 1, "default", [1, 10, 100, 1000, 4800], 8)
     if what in ("big768", "all"):

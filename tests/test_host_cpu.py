@@ -112,3 +112,54 @@ def test_par_readers_follow_the_reference_format(tmp_path, capsys):
     with pytest.raises(SystemExit):
         configuration.get_interpolation_parameters(str(tmp_path))      # missing file: print + exit
     capsys.readouterr()
+
+
+# ---- output / regridding row: host numpy, pinned by the reference's own results
+@pytest.mark.skipif(not have("regrid_N16.npz"), reason="fixture not generated")
+@pytest.mark.parametrize("proj", ["gnomonic_equiangular", "gnomonic_equidistant"])
+@pytest.mark.parametrize("N", [16, 21])
+def test_ll2cs_index_maps_and_regridding_bit_exact(proj, N):
+    from pycs_b200 import interpolation
+    ref = load("regrid_N16.npz")
+    g = cs_datastruct.cubed_sphere(N, proj, centres_only=True)
+    ll = cs_datastruct.latlon_grid(36, 72)
+    assert np.array_equal(ll.lon, ref["ll_lon"]) and np.array_equal(ll.lat, ref["ll_lat"])
+    ll.ix, ll.jy, ll.mask = interpolation.ll2cs(g, ll)
+    key = "%s_N%d" % (proj.split("_")[1], N)
+    for mine, name in ((ll.ix, "ix_"), (ll.jy, "jy_"), (ll.mask, "mask_")):
+        assert mine.dtype == ref[name + key].dtype and np.array_equal(mine, ref[name + key]), name
+    assert set(np.unique(ll.mask)) == set(range(6)) and ll.ix.max() < N and ll.jy.max() < N
+    q = cs_datastruct.scalar_field(g, "q", "center")
+    q.f[...] = ref["field_" + key]
+    assert np.array_equal(interpolation.nearest_neighbour(q, g, ll), ref["regrid_" + key])
+
+
+def test_error_files_of_the_final_step(tmp_path, monkeypatch):
+    """data/<grid>_adv_Q_error_...{.npy, text}: names and contents of src/output.py:136-150."""
+    import types
+    from pycs_b200 import interpolation, output
+    monkeypatch.chdir(tmp_path)
+    g = cs_datastruct.cubed_sphere(16, centres_only=True)
+    ll = cs_datastruct.latlon_grid(12, 24)
+    ll.ix, ll.jy, ll.mask = interpolation.ll2cs(g, ll)
+    rng = np.random.default_rng(3)
+    q, qe = rng.standard_normal((16, 16, 6)), rng.standard_normal((16, 16, 6))
+    sim = types.SimpleNamespace(ic=2, vf=3, degree=3, opsplit_name="SP-AVLT", recon_name="PPM-PL07", dp_name="RK1",
+                                et_name="ET-DG", mt_name="MT-0", mf_name="MF-PR", CFL=0.31, mass_change=-2e-16,
+                                dt=0.00625, Tf=5.0, error_linf=[0, 1e-2], error_l1=[0, 2e-3], error_l2=[0, 3e-3])
+    base = output.save_error_files(g, ll, sim, q, qe, 1)
+    assert base == "data/gnomonic_equiangular_cs_16_adv_Q_error_ic2_vf3_SP-AVLT_PPM-PL07_RK1_ET-DG_MT-0_MF-PR_interp3"
+    err = np.load(base + ".npy")
+    assert err.shape == (24, 12)
+    assert np.array_equal(err, (qe - q)[ll.ix, ll.jy, ll.mask])
+    assert np.allclose(np.loadtxt(base), [1e-2, 2e-3, 3e-3, 0.31, -2e-16, 0.00625, 5.0], rtol=0, atol=0)
+
+
+def test_print_errors_simul_lines(capsys):
+    from pycs_b200.errors import print_errors_simul
+    print_errors_simul([1e-2, 2.5e-3], [1e-3, 2.5e-4], [2e-3, 5e-4], 0)
+    print_errors_simul([1e-2, 2.5e-3], [1e-3, 2.5e-4], [2e-3, 5e-4], 1)
+    out = capsys.readouterr().out.splitlines()
+    assert out[0] == "Error(Linf, L1, L2) : 1.00e-02 1.00e-03 2.00e-03"
+    assert out[2] == "Error E_1    : 2.50e-03 2.50e-04 5.00e-04"
+    assert out[3] == "Ratio E_1/E_0: 4.00e+00 4.00e+00 4.00e+00"

@@ -107,3 +107,22 @@ def test_full_period_norms_n16():
         e = ost.final_errors(g, sim, r["steps"])
         for a, b in zip(e, (r["linf"], r["l1"], r["l2"])):
             assert abs(a - b) <= 1e-13 * abs(b), r["scheme"]
+
+
+@pytest.mark.skipif(not have("regrid_N16.npz"), reason="fixture not generated")
+@pytest.mark.parametrize("vf", [1, 2, 3, 4])
+def test_divergence_test_errors(g16, vf):
+    """src/operator_accuracy.py: Q = 1, one step, norms of div - div_exact, against the reference's numbers
+    (the oracle's div is the reference's bit for bit; div_exact is the product's host function)."""
+    import pycs_b200  # noqa: F401
+    from pycs_b200.advection_ic import div_exact
+    from pycs_b200.errors import compute_errors
+    ref = load("regrid_N16.npz")
+    I = np.s_[4:20, 4:20, :]
+    for name in ("PL07-RK1", "PL07-RK1-DG-PR", "AVLT-RK2-DG-AF", "AVLT-RK2-DG-PR"):
+        recon, dp, split, et, mt, mf = TUPLES[name]
+        sim = ost.Simulation(g16, DT16[vf], 5, 1, vf, 1, recon, dp, split, et, mt, mf)
+        ost.init_vars_adv(g16, sim)
+        ost.adv_time_step(g16, sim, 1, sim.dt)
+        got = np.array(compute_errors(sim.div[I], div_exact(g16.pc.lon[I], g16.pc.lat[I], sim)))
+        assert np.array_equal(got, ref["diverr_vf%d_%s" % (vf, name)]), (vf, name)
