@@ -1,7 +1,8 @@
 """Driver with the reference's main.py structure (main.py:30-99) for the accelerated test cases:
-read par/configuration.par, build the grid, dispatch on test_case.  Test case 5 (advection,
-par/advection.par) and 4 (divergence convergence, src/operator_accuracy.py) run on the GPU; 1-3 (grid plots, grid
-quality, interpolation experiments) are not part of this library.
+read par/configuration.par, build the grid, dispatch on test_case.  Test cases 5 (advection,
+par/advection.par), 4 (divergence convergence, src/operator_accuracy.py) and 3 (ghost-cell
+interpolation experiment, par/interpolation.par) run on the GPU; 1 and 2 (grid plots, grid quality)
+are not part of this library.
 
     python -m pycs_b200.main [pardir]        # from the repository root (pycs_b200.py shim on sys.path)
 """
@@ -19,10 +20,12 @@ def main(pardir=None):
     from .advection_sphere import adv_sphere
     from .advection_error import error_analysis_adv
     N, transformation, showonscreen, gridload, test_case, map_projection = get_parameters(pardir)
-    if test_case in (1, 2, 3):
-        print("Test case %d (grid plots / grid quality / interpolation experiments) is outside the "
-              "accelerated advection path." % test_case)
+    if test_case in (1, 2):
+        print("Test case %d (grid plots / grid quality) is outside the accelerated advection path." % test_case)
         raise SystemExit(1)
+    if test_case == 3:
+        from .interpolation_test import interpolation_test
+        return interpolation_test(map_projection, transformation, showonscreen, True, pardir=pardir)
     if test_case not in (4, 5):
         print("ERROR: invalid testcase.")
         raise SystemExit(1)

@@ -248,6 +248,21 @@ def test_divergence_test_driver_vs_reference(mods, g16, vf):
         sim.dev.close()
 
 
+def test_interpolation_experiment_driver(mods):
+    """par/interpolation.par path (src/interpolation_test.py:104-176): Linf of the ghost-cell fill per degree
+    at N = 16 against the reference's numbers, and 4th-order decay for degree 3 at N = 32."""
+    from pycs_b200.interpolation_test import error_analysis_sf_interpolation
+    ref = load("halofill_N16.npz")
+    for ic in (1, 2):
+        Nc, err = error_analysis_sf_interpolation(ic, "mercator", "gnomonic_equiangular", False, False, Ntest=2)
+        assert list(Nc) == [16, 32]
+        for d in range(5):
+            want = float(ref["linf_ic%d_deg%d" % (ic, d)])
+            assert abs(err[0, d] - want) <= 1e-12 * max(want, 1.0), (ic, d, err[0, d], want)
+        if ic == 1:                 # SURVEY s8c: 2.605e-3 -> 2.799e-4
+            assert err[1, 3] < err[0, 3] / 8.0
+
+
 # ------------------------------------------------------------------ configs of BASELINE.json
 @pytest.mark.skipif(not have("config1_N48_final.npz"), reason="fixture not generated")
 @pytest.mark.parametrize("fused", [False, True])

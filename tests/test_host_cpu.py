@@ -163,3 +163,17 @@ def test_print_errors_simul_lines(capsys):
     assert out[0] == "Error(Linf, L1, L2) : 1.00e-02 1.00e-03 2.00e-03"
     assert out[2] == "Error E_1    : 2.50e-03 2.50e-04 5.00e-04"
     assert out[3] == "Ratio E_1/E_0: 4.00e+00 4.00e+00 4.00e+00"
+
+
+def test_interpolation_experiment_fields_and_dispatch(tmp_path, capsys):
+    """the analytic fields of the ghost-cell experiment equal the reference's bits; test cases 2-4 are refused."""
+    from pycs_b200.interpolation_test import q_scalar_field, interpolation_simulation_par, interpolation_test
+    ref = load("halofill_N16.npz")
+    g = cs_datastruct.cubed_sphere(16, centres_only=True)
+    for ic in (1, 2):
+        q = q_scalar_field(g.pc.lon, g.pc.lat, interpolation_simulation_par(ic, 3))
+        assert np.array_equal(q[4:20, 4:20, :], ref["ic%d_deg3" % ic][4:20, 4:20, :])
+    (tmp_path / "interpolation.par").write_text("#tc\n2\n#ic\n1\n#vf\n2\n")
+    with pytest.raises(SystemExit):
+        interpolation_test("mercator", "gnomonic_equiangular", False, True, pardir=str(tmp_path))
+    assert "not provided" in capsys.readouterr().out
