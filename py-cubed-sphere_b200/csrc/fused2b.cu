@@ -63,13 +63,19 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   // MINB >= 30: the march runs in groups of DL rows with every ring slot a compile-time constant
   // (all staged-row loads become [one base register + immediate]) and the TMA issue path keeps
   // running byte offsets instead of recomputing row * ld (see profiles/r1_sass_static.md)
-  constexpr bool CS = (MINB >= 30) && (MINB < 50) && !MG;
+  constexpr bool CS = ((MINB >= 30 && MINB < 50) || (MINB >= 60 && MINB < 70)) && !MG;
+  // MINB >= 60 (const-slot march only; written without GPU access, NOT yet measured or parity-run):
+  // barrier B of a row replaced by producer/consumer named barriers between neighbouring warps --
+  // warp w only needs lane 0 of warp w+1 for F/G[e+1] -- with the work rows double-buffered by row
+  // parity; barrier A (block-wide, once per row) still bounds the skew between warps to one row
+  constexpr bool PB = CS && (MINB >= 60);
+  constexpr int NWARP = TB / 32;
   // MINB >= 50: two rows per pair of block barriers (rings of 4 and 8 slots, windows of 8 registers)
-  constexpr bool PAIR = (MINB >= 50) && !MG;
+  constexpr bool PAIR = (MINB >= 50) && (MINB < 60) && !MG;
   constexpr int RW = TB + 6;                 // staged row: columns jbase-6 .. jbase+TB-1
   constexpr int NS = (MASK & 1) ? 4 : 3, NL = (MASK & 1) ? 5 : 4;
   constexpr int DS = PAIR ? 4 : PF + 1, DL = PAIR ? 8 : PF + 4;
-  constexpr int NWORK = PAIR ? 8 : 4;        // work rows: Qx, inner / outer y-flux, sqrtg_pv*cy (per row of a pair)
+  constexpr int NWORK = (PAIR || PB) ? 8 : 4;        // work rows: Qx, inner / outer y-flux, sqrtg_pv*cy (per row of a pair)
   constexpr int SSLOT = NS * RW, LSLOT = NL * RW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* ringS = reinterpret_cast<double*>(smem_raw);           // [DS][NS][RW]
@@ -392,6 +398,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
       if (r > rlast) return false;
       constexpr int kS = (k % DS) * SSLOT, kL0 = k * LSLOT, kL2 = ((k + DL - 2) % DL) * LSLOT,
                     kL3 = ((k + DL - 3) % DL) * LSLOT;
+      constexpr int WO = PB ? (k & 1) * 4 * RW : 0;      // work rows of this row's parity
       while (!mbar_try_wait(&full[k], parb)) {}
       RowPtrs R;
       R.q = eS + kS + S_Q * RW;
@@ -418,7 +425,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
       XEdge X;
       double qx[1];
       phase_x_inner<RECON, SPLIT, MASK, k>(L, X, R, qnew, cdx, qx);
-      sX[e] = qx[0];
+      sX[WO + e] = qx[0];
       __syncthreads();                                   // barrier A
       if (warp_u == 0 && r + PF <= rlast) {              // warp 0 issues the TMA copies of row r+PF
         if (elect_one()) issue_k(IC<(k + PF) % DL>{}, o0 - ld8, o0 - 2 * ld8);
@@ -427,16 +434,23 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
       // ---------------- phase 2: y-fluxes at edge j: inner on Q row r, outer on Qx row r-3
       double F[1], G[1], CF[1] = {0.0}, CG[1];
       yflux_pair<RECON, SPLIT, MASK, k>(R.v0, R.vm0, R.sgv0, R.sgc0, R.q, cdy, F, CF);
-      yflux_pair<RECON, SPLIT, MASK, k>(R.v3, R.vm3, R.sgv3, R.sgc3, sX + e, cdy, G, CG);
-      sF[e] = F[0];
-      sG[e] = G[0];
-      if (SPLIT != 1) sC[e] = CF[0];
-      __syncthreads();                                   // barrier B
+      yflux_pair<RECON, SPLIT, MASK, k>(R.v3, R.vm3, R.sgv3, R.sgc3, sX + WO + e, cdy, G, CG);
+      sF[WO + e] = F[0];
+      sG[WO + e] = G[0];
+      if (SPLIT != 1) sC[WO + e] = CF[0];
+      if constexpr (PB) {
+        // named barrier w+1 pairs warp w (consumer: bar.sync) with warp w+1 (producer: bar.arrive)
+        if (warp_u > 0) asm volatile("bar.arrive %0, 64;" ::"r"(warp_u) : "memory");
+        if (warp_u < NWARP - 1) asm volatile("bar.sync %0, 64;" ::"r"(warp_u + 1) : "memory");
+        else __syncwarp();
+      } else {
+        __syncthreads();                                 // barrier B
+      }
       // ---------------- phase 3: Qy row r, outer x-flux on Qy, output row r-3
       double Fn[1], Gn[1], CFn[1] = {0.0}, out[1], sdiv[1];
-      Fn[0] = sF[e + 1];
-      Gn[0] = sG[e + 1];
-      if (SPLIT != 1) CFn[0] = sC[e + 1];
+      Fn[0] = sF[WO + e + 1];
+      Gn[0] = sG[WO + e + 1];
+      if (SPLIT != 1) CFn[0] = sC[WO + e + 1];
       phase_x_outer<RECON, SPLIT, k>(L, X, R, F, Fn, G, Gn, CF, CFn, out, sdiv);
       if (r >= r0 + 3) {
         if (out_lane) {
@@ -591,8 +605,8 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
 
 template <int TB, int PF, int MASK, int MINB>
 constexpr size_t smem_bytes() {
-  constexpr bool PAIR = (MINB >= 50);
-  constexpr int DS = PAIR ? 4 : PF + 1, DL = PAIR ? 8 : PF + 4, NWORK = PAIR ? 8 : 4;
+  constexpr bool PAIR = (MINB >= 50) && (MINB < 60);
+  constexpr int DS = PAIR ? 4 : PF + 1, DL = PAIR ? 8 : PF + 4, NWORK = (MINB >= 50) ? 8 : 4;
   return sizeof(double) * (size_t)(TB + 6) * (DS * ((MASK & 1) ? 4 : 3) + DL * ((MASK & 1) ? 5 : 4) + NWORK) +
          sizeof(uint64_t) * DL + 16;
 }
@@ -650,7 +664,7 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb,
   if (tb == T && pf == P && minb == M) return launch_mask<T, 3, 1, P, M>(a, mask, nblocks, st, resident)
     // (threads, rows in flight, MINB): measured points worth keeping, see profiles/r1_sweep_v2b.log
     TUNE(160, 2, 14); TUNE(160, 1, 14); TUNE(160, 2, 4); TUNE(160, 1, 4); TUNE(128, 2, 15);
-    TUNE(128, 2, 5); TUNE(160, 2, 34); TUNE(128, 2, 35); TUNE(160, 2, 53);
+    TUNE(128, 2, 5); TUNE(160, 2, 34); TUNE(128, 2, 35); TUNE(160, 2, 53); TUNE(128, 2, 54); TUNE(160, 2, 64);
 #undef TUNE
     return cudaErrorInvalidValue;
   }
@@ -672,7 +686,7 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb,
 bool pycs_fused2b_has(int recon, int split, int tb, int pf, int minb) {
   if (recon != 1 && recon != 3) return false;
   if (recon == 3 && split == 1) {
-    const int t[][3] = {{160, 2, 14}, {160, 1, 14}, {160, 2, 4}, {160, 1, 4}, {128, 2, 15}, {128, 2, 5}, {160, 2, 34}, {128, 2, 35}, {160, 2, 53}};
+    const int t[][3] = {{160, 2, 14}, {160, 1, 14}, {160, 2, 4}, {160, 1, 4}, {128, 2, 15}, {128, 2, 5}, {160, 2, 34}, {128, 2, 35}, {160, 2, 53}, {128, 2, 54}, {160, 2, 64}};
     for (auto& x : t)
       if (x[0] == tb && x[1] == pf && x[2] == minb) return true;
     return false;

@@ -61,7 +61,7 @@ def output_adv(cs_grid, ll_grid, simulation, plot, k, t, Nsteps, plotstep, map_p
         if k > 0 and (not divtest_flag):
             print_diagnostics_adv(simulation.error_linf[k], simulation.error_l1[k], simulation.error_l2[k],
                                   simulation.mass_change, k, Nsteps)
-        if k % plotstep == 0 or k == 0 or k == Nsteps:
+        if k == 0 or k == Nsteps or (plotstep > 0 and k % plotstep == 0):
             if divtest_flag:
                 # divergence test: the norms are those of div against the exact divergence
                 # (src/output.py:152-169)
