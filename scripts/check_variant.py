@@ -1,6 +1,6 @@
 """One-shot check of a step-kernel tuning point on the GPU: parity against the operator path at small N
 (several run calls: separable wind, pending projection), then ms per launch at N=1536 next to the default.
-Usage: python scripts/check_variant.py MINB [N_parity ...]"""
+Usage: python scripts/check_variant.py MINB [N_parity ...] [--no-time]"""
 import ctypes as C
 import os
 import sys
@@ -11,8 +11,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pycs_b200  # noqa
 from pycs_b200 import cs_datastruct, advection_ic, advection_vars, advection_timestep
 
-minb = sys.argv[1] if len(sys.argv) > 1 else "53"
-sizes = [int(x) for x in sys.argv[2:]] or [130]
+args = [x for x in sys.argv[1:] if x != "--no-time"]
+timing = "--no-time" not in sys.argv
+minb = args[0] if args else "53"
+sizes = [int(x) for x in args[1:]] or [130]
 tup = (3, 1, 1, 3, 1, 3)
 
 
@@ -40,6 +42,8 @@ for N in sizes:
         a.dev.close()
         b.dev.close()
 
+if not timing:
+    sys.exit(0)
 g = cs_datastruct.cubed_sphere(1536)
 for mb in (minb, "34", minb):
     os.environ["PYCS_FUSED_MINB"] = mb
