@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   // (all staged-row loads become [one base register + immediate]) and the TMA issue path keeps
   // running byte offsets instead of recomputing row * ld (see profiles/r1_sass_static.md)
   constexpr bool CS = ((MINB >= 30 && MINB < 50) || (MINB >= 60 && MINB < 70)) && !MG;
-  // MINB >= 60 (const-slot march only; written without GPU access, NOT yet measured or parity-run):
+  // MINB >= 60 (const-slot march only; parity-checked at N=50 with the last GPU seconds of round 1, NOT yet timed):
   // barrier B of a row replaced by producer/consumer named barriers between neighbouring warps --
   // warp w only needs lane 0 of warp w+1 for F/G[e+1] -- with the work rows double-buffered by row
   // parity; barrier A (block-wide, once per row) still bounds the skew between warps to one row
