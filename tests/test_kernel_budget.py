@@ -1,0 +1,46 @@
+"""CPU: static budget of the default step kernel, read from the compiled object (no GPU needed).
+
+The const-slot march of csrc/fused2b.cu was tuned on its instruction mix (profiles/r1_sass_static.md):
+these checks keep a refactor from silently giving the gains back -- register spills, a register count
+that no longer allows 4 CTAs/SM, ring-slot arithmetic creeping back into the march loop."""
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OBJ = os.path.join(ROOT, "py-cubed-sphere_b200", "build", "fused2b.o")
+LOG = os.path.join(ROOT, "py-cubed-sphere_b200", "build", "fused2b.cu.ptxas.log")
+DEFAULT = "Li160ELi3ELi1ELi%dELi2ELi34ELi0E"      # fused2b_kernel<160, 3, 1, MASK, 2, 34, 0>
+
+pytestmark = pytest.mark.skipif(not (os.path.exists(OBJ) and os.path.exists(LOG) and shutil.which("cuobjdump")),
+                                reason="needs the in-tree build (python __graft_entry__.py) and cuobjdump")
+
+
+def test_no_step_kernel_spills_and_default_fits_four_ctas():
+    txt = open(LOG).read()
+    entries = re.findall(r"Compiling entry function '(\S+)'.*?\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, "
+                         r"(\d+) bytes spill loads\nptxas info\s+: Used (\d+) registers", txt)
+    assert len(entries) >= 30
+    for name, stack, st, ld, regs in entries:
+        assert (int(stack), int(st), int(ld)) == (0, 0, 0), name
+    for mask in (0, 1, 2):
+        regs = [int(r) for n, _, _, _, r in entries if DEFAULT % mask in n]
+        assert regs and regs[0] * 160 * 4 <= 65536, (mask, regs)
+
+
+@pytest.mark.parametrize("mask", [0, 2])
+def test_default_march_loop_instruction_mix(mask):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "sass_stats.py"), OBJ, DEFAULT % mask],
+                         capture_output=True, text=True, check=True).stdout
+    rows = int(re.search(r"(\d+) rows per trip", out).group(1))
+    assert rows == 6                                   # the six-row group of the const-slot march
+    common = out.split("elected lane")[0]              # the part every warp executes
+    per = {m.group(1): float(m.group(2)) for m in re.finditer(r"^\s+(\S+)\s+\d+\s+([\d.]+) / row", common, re.M)}
+    every = float(re.search(r"every warp: \d+ instructions = ([\d.]+) per row", out).group(1))
+    assert every <= 200.0, out                         # 232.6 for the shifting-window march
+    assert per["fp64"] <= 97.0 and per["lds"] <= 28.5 and per["int"] <= 20.0, out
+    assert per["bar"] == 2.0
