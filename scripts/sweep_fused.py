@@ -14,7 +14,7 @@ tup = (3, 1, 1, 3, 1, 3)
 if which == "v2":
     configs = [dict(IMPL=2, TB=tb, DEPTH=d, ROWS=rows) for tb in (128, 160) for d in (5, 6) for rows in (0, 48, 96)]
 elif which == "cs":      # const-slot march against the default point
-    configs = [dict(IMPL=4, TB=tb, PF=2, MINB=mb, ROWS=0) for tb, mb in ((160, 14), (160, 34), (128, 35), (160, 53), (128, 54), (160, 64), (160, 34), (160, 64))]
+    configs = [dict(IMPL=4, TB=tb, PF=2, MINB=mb, ROWS=0) for tb, mb in ((160, 14), (160, 34), (128, 35), (160, 53), (128, 54), (160, 64), (160, 33), (160, 34), (160, 64))]
 elif which == "v2b":
     pts = ((160, 2, 14), (160, 1, 14), (160, 2, 4), (160, 1, 4), (128, 2, 15), (128, 2, 5), (160, 2, 34), (128, 2, 35), (160, 2, 53))
     configs = [dict(IMPL=4, TB=tb, PF=pf, MINB=mb, ROWS=rows) for tb, pf, mb in pts for rows in (0, 96)]
