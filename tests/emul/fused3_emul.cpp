@@ -216,21 +216,24 @@ void run_block(const Args& a, int TB) {
     for (int t = 0; t < TB; ++t) lane_init(L[t]);
     int oS = 0, oL0 = 0, oL1 = (DL - 1) * LSLOT, oL2 = (DL - 2) * LSLOT, oL3 = (DL - 3) * LSLOT;
     double psum = 0.0;
+    // TMA row copies are made when the kernel issues them: rows rfirst .. rfirst+PF-1 before the march, row
+    // r+PF right after barrier A of row r -- a slot that is overwritten too early shows up as a parity failure
+    auto issue = [&](int r) {
+      const int k = r - rfirst;
+      double* dS = ringS + (k % DS) * SSLOT;
+      double* dL = ringL + (k % DL) * LSLOT;
+      const long long rr = (long long)r * a.ld, rm1 = (long long)std::max(r - 1, 0) * a.ld,
+                      rm2 = (long long)std::max(r - 2, 0) * a.ld;
+      auto cp = [&](double* dst, const double* src) { std::memcpy(dst, src, sizeof(double) * len); };
+      cp(dS + S_Q * RW, a.q + colb + rr); cp(dL + L_V * RW, a.va + colb + rr);
+      cp(dL + L_SGC * RW, a.sgc + colm + rr); cp(dL + L_SGV * RW, a.sgv + colm + rr);
+      cp(dL + L_RGC * RW, a.rgc + colm + rr); cp(dS + S_SGU * RW, a.sgu + colm + rm1);
+      cp(dS + S_U * RW, a.ua + colb + rm2);
+      if (MASK & 1) { cp(dL + L_VM * RW, a.vm + colb + rr); cp(dS + S_UM * RW, a.um + colb + rm2); }
+    };
+    for (int r = rfirst; r < rfirst + PF && r <= rlast; ++r) issue(r);
     for (int r = rfirst; r <= rlast; ++r) {
       const int kc = a.circ ? (r - rfirst) % WLEN : -1;
-      {   // TMA row copies of row r
-        const int k = r - rfirst;
-        double* dS = ringS + (k % DS) * SSLOT;
-        double* dL = ringL + (k % DL) * LSLOT;
-        const long long rr = (long long)r * a.ld, rm1 = (long long)std::max(r - 1, 0) * a.ld,
-                        rm2 = (long long)std::max(r - 2, 0) * a.ld;
-        auto cp = [&](double* dst, const double* src) { std::memcpy(dst, src, sizeof(double) * len); };
-        cp(dS + S_Q * RW, a.q + colb + rr); cp(dL + L_V * RW, a.va + colb + rr);
-        cp(dL + L_SGC * RW, a.sgc + colm + rr); cp(dL + L_SGV * RW, a.sgv + colm + rr);
-        cp(dL + L_RGC * RW, a.rgc + colm + rr); cp(dS + S_SGU * RW, a.sgu + colm + rm1);
-        cp(dS + S_U * RW, a.ua + colb + rm2);
-        if (MASK & 1) { cp(dL + L_VM * RW, a.vm + colb + rr); cp(dS + S_UM * RW, a.um + colb + rm2); }
-      }
       for (int t = 0; t < TB; ++t) {               // patch + phase 1
         const int e = t + 3, j = jbase - 3 + t;
         RowPtrs& P = R[t];
@@ -251,6 +254,7 @@ void run_block(const Args& a, int TB) {
         x_inner_k<RECON, SPLIT, MASK>(kc, L[t], X[t], P, qnew, cdxw, qx);
         sX[e] = qx[0];
       }
+      if (r + PF <= rlast) issue(r + PF);          // barrier A passed: warp 0 issues the copies of row r+PF
       for (int t = 0; t < TB; ++t) {               // barrier A; phase 2
         const int e = t + 3;
         double f[1], g[1], cf[1] = {0.0}, cg[1];
