@@ -184,6 +184,57 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
     tma(dS + 8u * S_U * RW, gu + r2_, bar);
     if (MASK & 1) tma(dS + 8u * S_UM * RW, gum + r2_, bar);
   };
+  // pointers to the staged rows of the row with (compile-time) phase k, for the const-slot marches
+  const double* const eS = ringS + e;          // the thread's element in slot 0 of either ring
+  const double* const eL = ringL + e;
+  auto rowptrs = [&](auto kc) {
+    constexpr int k = decltype(kc)::value;
+    constexpr int kS = (k % DS) * SSLOT, kL0 = k * LSLOT, kL2 = ((k + DL - 2) % DL) * LSLOT,
+                  kL3 = ((k + DL - 3) % DL) * LSLOT;
+    RowPtrs R;
+    R.q = eS + kS + S_Q * RW;
+    R.u = eS + kS + S_U * RW;
+    R.um = eS + kS + S_UM * RW;
+    R.su1 = eS + kS + S_SGU * RW;
+    R.v0 = eL + kL0 + L_V * RW;
+    R.vm0 = eL + kL0 + L_VM * RW;
+    R.sgv0 = eL + kL0 + L_SGV * RW;
+    R.sgc0 = eL + kL0 + L_SGC * RW;
+    R.rg0 = eL + kL0 + L_RGC * RW;
+    R.sgc2 = eL + kL2 + L_SGC * RW;
+    R.v3 = eL + kL3 + L_V * RW;
+    R.vm3 = eL + kL3 + L_VM * RW;
+    R.sgv3 = eL + kL3 + L_SGV * RW;
+    R.sgc3 = eL + kL3 + L_SGC * RW;
+    R.rg3 = eL + kL3 + L_RGC * RW;
+    return R;
+  };
+  const long long ld8 = (long long)g.ld * 8;
+  long long o0 = (long long)rfirst * ld8;    // byte offset of the next row to issue
+  auto at = [](const double* base, long long off) {
+    return reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + off);
+  };
+  constexpr int NCOPY = NS + NL;
+  // the TMA copies of the row with phase k (elected lane of warp 0, after its fence.proxy.async); o0, o1, o2:
+  // byte offsets of that row and of the rows staged one (sqrtg_pu) and two (u) rows late
+  auto issue_k = [&](auto kc, long long o1, long long o2) {
+    constexpr int k = decltype(kc)::value;
+    const uint32_t dS = ringS_a + 8u * (uint32_t)((k % DS) * SSLOT), dL = ringL_a + 8u * (uint32_t)(k * LSLOT),
+                   bar = full_a + 8u * (uint32_t)k;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * NCOPY)
+                 : "memory");
+    tma(dS + 8u * S_Q * RW, at(gq, o0), bar);
+    tma(dL + 8u * L_V * RW, at(gv, o0), bar);
+    tma(dL + 8u * L_SGC * RW, at(gsgc, o0), bar);
+    tma(dL + 8u * L_SGV * RW, at(gsgv, o0), bar);
+    tma(dL + 8u * L_RGC * RW, at(grgc, o0), bar);
+    tma(dS + 8u * S_SGU * RW, at(gsgu, o1), bar);
+    tma(dS + 8u * S_U * RW, at(gu, o2), bar);
+    if (MASK & 1) {
+      tma(dL + 8u * L_VM * RW, at(gvm, o0), bar);
+      tma(dS + 8u * S_UM * RW, at(gum, o2), bar);
+    }
+  };
   double psum_cta = 0.0;
   if constexpr (PAIR) {
     // ---- two rows per pair of barriers.  Step s marches rows (ra, rb) = rfirst + 2s, + 1:
@@ -199,30 +250,6 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
     double* sXb = sX + 4 * RW;                 // second row of a pair: Qx, F, G, C
     double *sFb = sXb + RW, *sGb = sFb + RW, *sCb = sGb + RW;
     const int rlastp = rlast + ((rlast - rfirst + 1) & 1);   // even number of rows (row r1+3 <= P-1 exists; its output is dropped)
-    const long long ld8 = (long long)g.ld * 8;
-    long long o0 = (long long)rfirst * ld8;    // byte offset of the next row to issue
-    auto at = [](const double* base, long long off) {
-      return reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + off);
-    };
-    constexpr int NCOPY = NS + NL;
-    auto issue_k = [&](auto kc, long long o1, long long o2) {   // elected lane of warp 0
-      constexpr int k = decltype(kc)::value;
-      const uint32_t dS = ringS_a + 8u * (uint32_t)((k % DS) * SSLOT), dL = ringL_a + 8u * (uint32_t)(k * LSLOT),
-                     bar = full_a + 8u * (uint32_t)k;
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * NCOPY)
-                   : "memory");
-      tma(dS + 8u * S_Q * RW, at(gq, o0), bar);
-      tma(dL + 8u * L_V * RW, at(gv, o0), bar);
-      tma(dL + 8u * L_SGC * RW, at(gsgc, o0), bar);
-      tma(dL + 8u * L_SGV * RW, at(gsgv, o0), bar);
-      tma(dL + 8u * L_RGC * RW, at(grgc, o0), bar);
-      tma(dS + 8u * S_SGU * RW, at(gsgu, o1), bar);
-      tma(dS + 8u * S_U * RW, at(gu, o2), bar);
-      if (MASK & 1) {
-        tma(dL + 8u * L_VM * RW, at(gvm, o0), bar);
-        tma(dS + 8u * S_UM * RW, at(gum, o2), bar);
-      }
-    };
     if (warp_u == 0) {                         // steps 0 and 1: rows rfirst .. rfirst+3 (rfirst >= 1: only row -1 is clamped)
       const bool el = elect_one();
       if (el) {
@@ -242,31 +269,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
     double* __restrict__ QN = a.qn + (long long)p * g.ps + PYCS_JOFF + min(j, g.P - 1) + (long long)r0 * g.ld;
     Lane L;
     lane_init(L);
-    const double* const eS = ringS + e;
-    const double* const eL = ringL + e;
     uint32_t parb = 0;
-    auto rowptrs = [&](auto kc) {
-      constexpr int k = decltype(kc)::value;
-      constexpr int kS = (k % DS) * SSLOT, kL0 = k * LSLOT, kL2 = ((k + DL - 2) % DL) * LSLOT,
-                    kL3 = ((k + DL - 3) % DL) * LSLOT;
-      RowPtrs R;
-      R.q = eS + kS + S_Q * RW;
-      R.u = eS + kS + S_U * RW;
-      R.um = eS + kS + S_UM * RW;
-      R.su1 = eS + kS + S_SGU * RW;
-      R.v0 = eL + kL0 + L_V * RW;
-      R.vm0 = eL + kL0 + L_VM * RW;
-      R.sgv0 = eL + kL0 + L_SGV * RW;
-      R.sgc0 = eL + kL0 + L_SGC * RW;
-      R.rg0 = eL + kL0 + L_RGC * RW;
-      R.sgc2 = eL + kL2 + L_SGC * RW;
-      R.v3 = eL + kL3 + L_V * RW;
-      R.vm3 = eL + kL3 + L_VM * RW;
-      R.sgv3 = eL + kL3 + L_SGV * RW;
-      R.sgc3 = eL + kL3 + L_SGC * RW;
-      R.rg3 = eL + kL3 + L_RGC * RW;
-      return R;
-    };
     // one step = two marched rows; false once the chunk is finished
     auto step = [&](auto kc, int ra) -> bool {
       constexpr int k = decltype(kc)::value;         // phase of row ra (even); rb has k + 1
@@ -351,71 +354,32 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   } else if constexpr (CS) {
     static_assert(PF == 2, "const-slot march: rings of 3 and 6 rows, windows of 6 registers");
     static_assert(DL == WLEN && DL % DS == 0, "const-slot march: one period for rings and windows");
-    const long long ld8 = (long long)g.ld * 8;
-    long long o0 = (long long)rfirst * ld8;    // byte offset of the next row to issue
-    auto at = [](const double* base, long long off) {
-      return reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + off);
-    };
-    // k = (row - rfirst) % DL is a compile-time constant everywhere below; o1, o2: offsets of the
-    // rows staged one and two rows late (sqrtg_pu, u)
-    constexpr int NCOPY = NS + NL;
-    auto issue_k = [&](auto kc, long long o1, long long o2) {   // elected lane of warp 0
-      constexpr int k = decltype(kc)::value;
-      const uint32_t dS = ringS_a + 8u * (uint32_t)((k % DS) * SSLOT), dL = ringL_a + 8u * (uint32_t)(k * LSLOT),
-                     bar = full_a + 8u * (uint32_t)k;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * NCOPY)
-                   : "memory");
-      tma(dS + 8u * S_Q * RW, at(gq, o0), bar);
-      tma(dL + 8u * L_V * RW, at(gv, o0), bar);
-      tma(dL + 8u * L_SGC * RW, at(gsgc, o0), bar);
-      tma(dL + 8u * L_SGV * RW, at(gsgv, o0), bar);
-      tma(dL + 8u * L_RGC * RW, at(grgc, o0), bar);
-      tma(dS + 8u * S_SGU * RW, at(gsgu, o1), bar);
-      tma(dS + 8u * S_U * RW, at(gu, o2), bar);
-      if (MASK & 1) {
-        tma(dL + 8u * L_VM * RW, at(gvm, o0), bar);
-        tma(dS + 8u * S_UM * RW, at(gum, o2), bar);
-      }
-    };
     if (warp_u == 0) {                         // rows rfirst, rfirst + 1 (rfirst >= 1: only row -1 is clamped)
-      if (elect_one()) issue_k(IC<0>{}, o0 - ld8, (long long)max(rfirst - 2, 0) * ld8);
+      if (elect_one()) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue_k(IC<0>{}, o0 - ld8, (long long)max(rfirst - 2, 0) * ld8);
+      }
       o0 += ld8;
       if (rfirst + 1 <= rlast) {
-        if (elect_one()) issue_k(IC<1>{}, o0 - ld8, o0 - 2 * ld8);
+        if (elect_one()) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          issue_k(IC<1>{}, o0 - ld8, o0 - 2 * ld8);
+        }
         o0 += ld8;
       }
     }
     double* __restrict__ QN = a.qn + (long long)p * g.ps + PYCS_JOFF + min(j, g.P - 1) + (long long)r0 * g.ld;
     Lane L;
     lane_init(L);
-    const double* const eS = ringS + e;        // the thread's element in slot 0 of either ring
-    const double* const eL = ringL + e;
     uint32_t parb = 0;
     // one marched row; false once the chunk is finished
     auto row = [&](auto kc, int r) -> bool {
       constexpr int k = decltype(kc)::value;
       if (r > rlast) return false;
-      constexpr int kS = (k % DS) * SSLOT, kL0 = k * LSLOT, kL2 = ((k + DL - 2) % DL) * LSLOT,
-                    kL3 = ((k + DL - 3) % DL) * LSLOT;
+      constexpr int kS = (k % DS) * SSLOT;
       constexpr int WO = PB ? (k & 1) * 4 * RW : 0;      // work rows of this row's parity
       while (!mbar_try_wait(&full[k], parb)) {}
-      RowPtrs R;
-      R.q = eS + kS + S_Q * RW;
-      R.u = eS + kS + S_U * RW;
-      R.um = eS + kS + S_UM * RW;
-      R.su1 = eS + kS + S_SGU * RW;
-      R.v0 = eL + kL0 + L_V * RW;
-      R.vm0 = eL + kL0 + L_VM * RW;
-      R.sgv0 = eL + kL0 + L_SGV * RW;
-      R.sgc0 = eL + kL0 + L_SGC * RW;
-      R.rg0 = eL + kL0 + L_RGC * RW;
-      R.sgc2 = eL + kL2 + L_SGC * RW;
-      R.v3 = eL + kL3 + L_V * RW;
-      R.vm3 = eL + kL3 + L_VM * RW;
-      R.sgv3 = eL + kL3 + L_SGV * RW;
-      R.sgc3 = eL + kL3 + L_SGC * RW;
-      R.rg3 = eL + kL3 + L_RGC * RW;
+      const RowPtrs R = rowptrs(IC<k>{});
       double qnew[1] = {R.q[0]};
       if (a.apply_corr && jint && r >= g.lo && r < g.hi) {
         qnew[0] = fma(R.sgc0[0], corr, qnew[0]);
@@ -428,7 +392,10 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
       sX[WO + e] = qx[0];
       __syncthreads();                                   // barrier A
       if (warp_u == 0 && r + PF <= rlast) {              // warp 0 issues the TMA copies of row r+PF
-        if (elect_one()) issue_k(IC<(k + PF) % DL>{}, o0 - ld8, o0 - 2 * ld8);
+        if (elect_one()) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          issue_k(IC<(k + PF) % DL>{}, o0 - ld8, o0 - 2 * ld8);
+        }
         o0 += ld8;
       }
       // ---------------- phase 2: y-fluxes at edge j: inner on Q row r, outer on Qx row r-3
