@@ -177,3 +177,29 @@ def test_interpolation_experiment_fields_and_dispatch(tmp_path, capsys):
     with pytest.raises(SystemExit):
         interpolation_test("mercator", "gnomonic_equiangular", False, True, pardir=str(tmp_path))
     assert "not provided" in capsys.readouterr().out
+
+
+def test_divergence_sweep_follows_the_reference_table(monkeypatch, capsys):
+    """error_analysis_div: N = 16, 32, ... with dt halved each time, Q = 1 (ic = 1), the four scheme tuples of
+    src/operator_accuracy.py:57-62 in the reference's order; device work replaced by fakes."""
+    import types
+    from pycs_b200 import operator_accuracy as oa
+    calls = []
+
+    def fake_sim(grid, dt, Tf, ic, vf, tc, recon, dp, opsplit, et, mt, mf):
+        calls.append((grid.N, dt, ic, vf, (recon, dp, opsplit, et, mt, mf)))
+        return types.SimpleNamespace(recon_name="r", opsplit_name="s", dp_name="d", et_name="e",
+                                     dev=types.SimpleNamespace(close=lambda: None))
+
+    monkeypatch.setattr(oa, "cubed_sphere", lambda N, *a, **k: types.SimpleNamespace(N=N))
+    monkeypatch.setattr(oa, "adv_simulation_par", fake_sim)
+    monkeypatch.setattr(oa, "adv_sphere", lambda g, ll, sim, mp, plot, divtest: (1.0 / g.N, 2.0 / g.N, 3.0 / g.N)
+                        if divtest and not plot else None)
+    Nc, err = oa.error_analysis_div(3, "mercator", False, "gnomonic_equiangular", False, False, Ntest=3)
+    assert list(Nc) == [16, 32, 64] and err.shape == (3, 3, 4)
+    assert [c[0] for c in calls] == [16, 32, 64] * 4
+    assert [c[1] for c in calls[:3]] == [0.00625, 0.003125, 0.0015625]
+    assert all(c[2] == 1 and c[3] == 3 for c in calls)
+    assert [c[4] for c in calls[::3]] == [(3, 1, 3, 2, 2, 1), (3, 1, 3, 3, 2, 3), (3, 2, 1, 3, 1, 2), (3, 2, 1, 3, 1, 3)]
+    assert np.allclose(err[0, :, 0], [1 / 16, 1 / 32, 1 / 64])
+    assert "Ratio E_1/E_0: 2.00e+00 2.00e+00 2.00e+00" in capsys.readouterr().out
