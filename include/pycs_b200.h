@@ -183,6 +183,13 @@ int pycs_mgpu_row_range(pycs_handle h, int32_t* row_lo, int32_t* row_hi);
 int pycs_mgpu_plan(int32_t N, int32_t world, int32_t rank, int32_t* row_lo, int32_t* row_hi,
                    int32_t* jobs5, int32_t max_jobs, int32_t* njobs);
 
+/* Host-only: CTA sets of a split fused step (PYCS_SPLIT=1).  The step kernel's grid is
+ * nstrips x nchunks x 6 CTAs, CTA = (chunk * nstrips + strip) * 6 + panel; `interior` receives the CTAs
+ * that read no ghost cell (they can run beside the ghost fill of src/advection_timestep.py:28),
+ * `boundary` the rest.  Both arrays need 6 * nstrips * nchunks entries; *n_interior = 0 when the grid
+ * is too small to split. */
+int pycs_split_plan(int32_t nstrips, int32_t nchunks, int32_t* interior, int32_t* boundary, int32_t* n_interior);
+
 /* ---- diagnostics (next row f2) -------------------------------------------------- */
 /* compute_errors (src/errors.py:99-113) of Q against a host reference field
  * qexact given on the interior (N,N,6): out = {Linf, L1, L2}. */

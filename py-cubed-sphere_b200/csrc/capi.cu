@@ -6,6 +6,7 @@
 #include <new>
 #include <vector>
 #include "pycs_common.cuh"
+#include "fused_args.cuh"
 #include "mgpu.cuh"
 
 static thread_local std::string g_err;
@@ -565,6 +566,15 @@ extern "C" int pycs_mgpu_plan(int32_t N, int32_t world, int32_t rank, int32_t* r
     jobs5[5 * k] = jobs[k].peer; jobs5[5 * k + 1] = jobs[k].i0; jobs5[5 * k + 2] = jobs[k].i1;
     jobs5[5 * k + 3] = jobs[k].j0; jobs5[5 * k + 4] = jobs[k].j1;
   }
+  return 0;
+}
+
+extern "C" int pycs_split_plan(int32_t nstrips, int32_t nchunks, int32_t* interior, int32_t* boundary,
+                               int32_t* n_interior) {
+  if (nstrips < 1 || nchunks < 1 || !interior || !boundary || !n_interior) return arg_fail("bad split-plan arguments");
+  *n_interior = pycs_split_sets(nstrips, nchunks, interior, boundary);
+  if (*n_interior == 0)                     // no split: everything is boundary
+    for (int b = 0; b < 6 * nstrips * nchunks; ++b) boundary[b] = b;
   return 0;
 }
 

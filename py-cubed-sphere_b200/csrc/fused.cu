@@ -593,6 +593,14 @@ struct FusedState {
   int tb = 160, depth = 6, rows = 0, nstrips = 0, wcols = 0, nchunks = 0;
   int impl = 0;                // 2: block-synchronous kernel (this file), 3: warp-autonomous kernel (fused3.cu)
   int nw = 3, pf = 3, minb = 3; // v3: consumer warps per CTA, rows in flight, register cap (CTAs/SM)
+  // PYCS_SPLIT=1 (single GPU, default v2b march, steps without wind kernels): a step = interior CTAs on
+  // the handle's stream + ghost fill and boundary CTAs on a second stream (FusedArgs::blk_map)
+  int split = 0;
+  int* map_i = nullptr;        // CTA indices of the interior / boundary launch
+  int* map_b = nullptr;
+  int n_i = 0, n_b = 0;
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t e_fork = nullptr, e_join = nullptr;
 };
 
 static std::map<pycs_handle, FusedState> g_fused;
@@ -713,6 +721,26 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
     fs.npart_cap = nb;
   }
   fs.npart = nb;
+  if (fs.split == 0) {
+    const char* es = getenv("PYCS_SPLIT");
+    fs.split = (es && atoi(es) && fs.impl == 4 && fs.tb == 160 && fs.pf == 2 && fs.minb == 34 && !h->mg) ? 1 : -1;
+    if (fs.split == 1) {
+      std::vector<int> in(nb), bd(nb);
+      fs.n_i = pycs_split_sets(fs.nstrips, fs.nchunks, in.data(), bd.data());
+      fs.n_b = nb - fs.n_i;
+      if (fs.n_i == 0) {
+        fs.split = -1;           // too few strips / chunks: nothing is ghost-free
+      } else {
+        CK(cudaMalloc(&fs.map_i, sizeof(int) * fs.n_i));
+        CK(cudaMalloc(&fs.map_b, sizeof(int) * fs.n_b));
+        CK(cudaMemcpy(fs.map_i, in.data(), sizeof(int) * fs.n_i, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(fs.map_b, bd.data(), sizeof(int) * fs.n_b, cudaMemcpyHostToDevice));
+        CK(cudaStreamCreateWithFlags(&fs.s2, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&fs.e_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&fs.e_join, cudaEventDisableTiming));
+      }
+    }
+  }
   if (!fs.counter) {
     CK(cudaMalloc(&fs.counter, sizeof(unsigned)));
     CK(cudaMemsetAsync(fs.counter, 0, sizeof(unsigned), h->stream));
@@ -792,6 +820,11 @@ void k_fused_release(pycs_handle h) {
   if (it->second.counter) cudaFree(it->second.counter);
   if (it->second.bu) cudaFree(it->second.bu);
   if (it->second.bv) cudaFree(it->second.bv);
+  if (it->second.map_i) cudaFree(it->second.map_i);
+  if (it->second.map_b) cudaFree(it->second.map_b);
+  if (it->second.e_fork) cudaEventDestroy(it->second.e_fork);
+  if (it->second.e_join) cudaEventDestroy(it->second.e_join);
+  if (it->second.s2) cudaStreamDestroy(it->second.s2);
   g_fused.erase(it);
 }
 
@@ -811,7 +844,14 @@ int k_dg_fill_single(pycs_handle h, double* q) {
 }
 
 // the rows this handle updates changed (pycs_mgpu_init): recompute the launch geometry
-void k_fused_reset_grid(pycs_handle h) { g_fused[h].rows = 0; }
+void k_fused_reset_grid(pycs_handle h) {
+  FusedState& fs = g_fused[h];
+  fs.rows = 0;
+  if (fs.map_i) cudaFree(fs.map_i);      // CTA sets of the split step belong to the old grid
+  if (fs.map_b) cudaFree(fs.map_b);
+  fs.map_i = fs.map_b = nullptr;
+  if (fs.split == 1) fs.split = -1;      // row slabs (several GPUs): no split step
+}
 
 // geometry was re-uploaded: 1/sqrtg and the t = 0 winds must be rebuilt
 void k_fused_invalidate(pycs_handle h) {
@@ -891,8 +931,10 @@ static int ensure_gs(pycs_handle h, FusedState& fs) {
   return 0;
 }
 
+// map / nmap / st: one launch of a split step (CTA subset on stream st); default: the whole grid on the handle's stream
 static int launch_step_kernel(pycs_handle h, FusedState& fs, const double* qcur, double* qnext, int pend,
-                              int mask, double ws) {
+                              int mask, double ws, const int* map = nullptr, int nmap = 0, cudaStream_t st = nullptr) {
+  if (!st) st = h->stream;
   const Geo& g = h->g;
   double *sgc, *sgu, *sgv, *ua, *va, *um, *vm;
   TRY(pycs_field_ptr(h, PYCS_F_SQRTG_PC, &sgc));
@@ -917,6 +959,13 @@ static int launch_step_kernel(pycs_handle h, FusedState& fs, const double* qcur,
   a.mg.world = 0;
   a.pdl = fs.pdl;
   a.gf.enable = 0;
+  a.blk_map = map;
+  a.nblk_total = fs.npart;
+  if (map) {                      // the kernel forms the projection coefficient itself
+    a.gf.sums = h->red_out + 9;
+    a.gf.nsums = 1;
+    a.gf.inv_a2 = pend ? 1.0 / h->a2 : 0.0;
+  }
   if (fs.impl == 4 && fs.ghost_fused && !h->mg) {
     a.gf.enable = 1;
     a.gf.order = h->order;
@@ -936,7 +985,7 @@ static int launch_step_kernel(pycs_handle h, FusedState& fs, const double* qcur,
   if (fs.impl == 3)
     CK(pycs_launch_fused3(a, h->prm.recon, h->prm.opsplit, mask, fs.nw, fs.pf, fs.minb, fs.npart / fs.nw, h->stream));
   else if (fs.impl == 4)
-    CK(pycs_launch_fused2b(a, h->prm.recon, h->prm.opsplit, mask, fs.tb, fs.pf, fs.minb, fs.npart, h->stream));
+    CK(pycs_launch_fused2b(a, h->prm.recon, h->prm.opsplit, mask, fs.tb, fs.pf, fs.minb, map ? nmap : fs.npart, st));
   else
     CK(launch_fused(a, h->prm.recon, h->prm.opsplit, mask, fs.npart, fs.tb, fs.depth, h->stream));
   CKL(h);
@@ -1038,6 +1087,30 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   // 1. ghost cells of Q (src/advection_timestep.py:28), folding in the pending MF-PR term
   int pend = fs.pending;
   const bool ghost_in_kernel = fs.impl == 4 && fs.ghost_fused && !h->mg;
+  // split step: no wind kernel may sit between the ghost fill and the step kernel
+  const bool split = fs.split == 1 && !ghost_in_kernel && !fs.pdl && !h->mg && (h->prm.vf < 2 || separable);
+  if (split) {
+    const int mask = separable ? 2 : ((h->prm.dp == 2) ? 1 : 0);
+    const double ws = separable ? cos(3.141592653589793 * ((double)(k - 1) * g.dt) / 5.0) : 1.0;
+    const int nbx = (g.N + 127) / 128;
+    CK(cudaEventRecord(fs.e_fork, h->stream));            // everything before this step
+    CK(cudaStreamWaitEvent(fs.s2, fs.e_fork, 0));
+    dg_fill_fused_kernel<<<nbx * 4 * 24 + 3, 128, 0, fs.s2>>>(g, h->maps, qcur, h->kminE, h->wE, h->order, fs.gs, sums,
+                                                             pend ? nsums : 0, pend ? 1.0 / h->a2 : 0.0, h->red_out + 8,
+                                                             nullptr, 0, 0, nbx, nullptr);
+    CKL(h);
+    TRY(launch_step_kernel(h, fs, qcur, qnext, pend, mask, ws, fs.map_b, fs.n_b, fs.s2));     // needs the ghost cells
+    CK(cudaEventRecord(fs.e_join, fs.s2));
+    TRY(launch_step_kernel(h, fs, qcur, qnext, pend, mask, ws, fs.map_i, fs.n_i, h->stream)); // reads no ghost cell
+    CK(cudaStreamWaitEvent(h->stream, fs.e_join, 0));
+    mark();
+    h->last_step_kernel_launches++;
+    h->qcur ^= 1;
+    fs.last_pend = pend;
+    fs.pending = (h->prm.mf == 3) ? 1 : 0;
+    fs.ring_pending = 1;
+    return 0;
+  }
   if (!ghost_in_kernel) {
     const int nbx = (g.N + 127) / 128;
     if (fs.pdl && fs.impl == 4) {

@@ -27,6 +27,8 @@ __constant__ double f2b_ppm_coef[5] = {2.0 / 60.0, -13.0 / 60.0, 47.0 / 60.0, 27
 #include "fused3_core.cuh"
 #undef F3_COEF_BANK
 
+#define F2B_CS_MINB 34     // the default march (const-slot, 4 CTAs/SM)
+
 namespace {
 
 using namespace f1;
@@ -55,15 +57,18 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// MG: multi-GPU build -- the kernel stores boundary cells to the peers and publishes sum + flags
-// (kept out of the single-GPU instantiation: the extra code in the unrolled march loop costs ~7 %)
+// MG = 1: multi-GPU build -- the kernel stores boundary cells to the peers and publishes sum + flags
+// (kept out of the single-GPU instantiation: the extra code in the unrolled march loop costs ~7 %).
+// MG = 2: split-launch build (FusedArgs::blk_map): CTA index through the map, projection
+// coefficient formed from the previous step's sum (no dependence on the ghost-fill kernel),
+// partials / ticket shared with the other launch of the step.
 template <int TB, int RECON, int SPLIT, int MASK, int PF, int MINB, int MG>
 __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   // MINB >= 10: register cap of MINB % 10 CTAs/SM and the march loop unrolled by the window length;
   // MINB >= 30: the march runs in groups of DL rows with every ring slot a compile-time constant
   // (all staged-row loads become [one base register + immediate]) and the TMA issue path keeps
   // running byte offsets instead of recomputing row * ld (see profiles/r1_sass_static.md)
-  constexpr bool CS = ((MINB >= 30 && MINB < 50) || (MINB >= 60 && MINB < 70)) && !MG;
+  constexpr bool CS = ((MINB >= 30 && MINB < 50) || (MINB >= 60 && MINB < 70)) && MG != 1;
   // MINB >= 60 (const-slot march only; parity-checked at N=50 with the last GPU seconds of round 1, NOT yet timed):
   // barrier B of a row replaced by producer/consumer named barriers between neighbouring warps --
   // warp w only needs lane 0 of warp w+1 for F/G[e+1] -- with the work rows double-buffered by row
@@ -71,7 +76,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   constexpr bool PB = CS && (MINB >= 60);
   constexpr int NWARP = TB / 32;
   // MINB >= 50: two rows per pair of block barriers (rings of 4 and 8 slots, windows of 8 registers)
-  constexpr bool PAIR = (MINB >= 50) && (MINB < 60) && !MG;
+  constexpr bool PAIR = (MINB >= 50) && (MINB < 60) && MG != 1;
   constexpr int RW = TB + 6;                 // staged row: columns jbase-6 .. jbase+TB-1
   constexpr int NS = (MASK & 1) ? 4 : 3, NL = (MASK & 1) ? 5 : 4;
   constexpr int DS = PAIR ? 4 : PF + 1, DL = PAIR ? 8 : PF + 4;
@@ -87,7 +92,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   uint64_t* full = reinterpret_cast<uint64_t*>(sX + NWORK * RW);   // [DL]
 
   const Geo& g = a.g;
-  int b = blockIdx.x;
+  int b = (MG == 2) ? a.blk_map[blockIdx.x] : (int)blockIdx.x;   // CTA index in the full grid
   const int p = b % 6;
   b /= 6;
   const int strip = b % a.nstrips, chunk = b / a.nstrips;
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   const bool out_lane = (tid >= 3) && (j < jend);
   const bool jint = (j >= g.lo) && (j < g.hi);
   const double cdx = a.cdx * ((MASK & 2) ? a.ws : 1.0), cdy = a.cdy * ((MASK & 2) ? a.ws : 1.0);   // time factor folded in
-  const int mgw = MG ? a.mg.world : 0;
+  const int mgw = (MG == 1) ? a.mg.world : 0;
   const int c0 = jbase - 6;                  // 16-byte aligned: JOFF and wcols are even
   const int len = min(RW, g.ld - PYCS_JOFF - c0) & ~1;
   const uint32_t row_bytes = (uint32_t)len * 8u;
@@ -119,7 +124,13 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   double corr = 0.0;
-  if (a.gf.enable) {
+  if (MG == 2) {
+    if (a.apply_corr) {         // same expression as the ghost-fill kernel: same bits
+      double sm = 0.0;
+      for (int k = 0; k < a.gf.nsums; ++k) sm += a.gf.sums[k];
+      corr = -sm * a.gf.inv_a2;
+    }
+  } else if (a.gf.enable) {
     // ---- ghost prologue: the Lagrange ghost cells of the rectangle this CTA stages (rows
     // rfirst..rlast, columns jbase-3..jend+2), written in place before the TMA copies read them.
     // Neighbouring CTAs compute the ghost cells they share; the values are identical.
@@ -457,7 +468,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
     int oL0 = 0, oL1 = (DL - 1) * LSLOT, oL2 = (DL - 2) * LSLOT, oL3 = (DL - 3) * LSLOT;
     int sb = 0;
     uint32_t parb = 0;
-  #pragma unroll((MINB >= 10 && !MG) ? 5 : 1)   // MINB 1x / 2x: unrolled by the window length
+  #pragma unroll((MINB >= 10 && MG != 1) ? 5 : 1)   // MINB 1x / 2x: unrolled by the window length
     for (int r = rfirst; r <= rlast; ++r) {
       while (!mbar_try_wait(&full[sb], parb)) {}
       RowPtrs R;
@@ -548,17 +559,17 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   if (tid == 0) {
     double t = 0.0;
     for (int w = 0; w < TB / 32; ++w) t += sF[w];
-    a.part[blockIdx.x] = t;
-    sF[40] = fused_last_writer(a.counter, gridDim.x, mgw > 1) ? 1.0 : 0.0;
+    a.part[(MG == 2) ? a.blk_map[blockIdx.x] : (int)blockIdx.x] = t;   // re-read: not worth a register across the march
+    sF[40] = fused_last_writer(a.counter, (MG == 2) ? (unsigned)a.nblk_total : gridDim.x, mgw > 1) ? 1.0 : 0.0;
   }
   __syncthreads();
   if (sF[40] != 0.0 && tid < 32) {            // last CTA of the launch: total in a fixed order
-    double tot = fused_warp_sum(a.part, (int)gridDim.x, tid);
+    double tot = fused_warp_sum(a.part, (MG == 2) ? a.nblk_total : (int)gridDim.x, tid);
     if (tid == 0) {
       *a.sum_out = tot;
       *a.counter = 0u;
     }
-    if (MG && mgw > 1) {                      // publish this rank's sum, then raise its flag everywhere
+    if (MG == 1 && mgw > 1) {                 // publish this rank's sum, then raise its flag everywhere
       tot = __shfl_sync(0xffffffffu, tot, 0);
       if (tid < mgw) {
         MgSync* sy = a.mg.peer_sync[tid];
@@ -581,7 +592,7 @@ constexpr size_t smem_bytes() {
 template <int TB, int RECON, int SPLIT, int MASK, int PF, int MINB, int MG>
 cudaError_t launch_mg(const FusedArgs& a, int nblocks, cudaStream_t st, int* resident) {
   static bool configured = false;
-  const size_t smem = smem_bytes<TB, PF, MASK, MG ? 0 : MINB>();
+  const size_t smem = smem_bytes<TB, PF, MASK, (MG == 1) ? 0 : MINB>();
   auto kern = fused2b_kernel<TB, RECON, SPLIT, MASK, PF, MINB, MG>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -610,6 +621,12 @@ template <int TB, int RECON, int SPLIT, int MASK, int PF, int MINB>
 cudaError_t launch_one(const FusedArgs& a, int nblocks, cudaStream_t st, int* resident) {
   // the multi-GPU build is never unrolled: one instantiation per register cap
   if (a.mg.world > 1) return launch_mg<TB, RECON, SPLIT, MASK, PF, MINB % 10, 1>(a, nblocks, st, resident);
+  if (a.blk_map) {               // split launches: built for the default march only
+    if constexpr (TB == 160 && PF == 2 && MINB == F2B_CS_MINB)
+      return launch_mg<TB, RECON, SPLIT, MASK, PF, MINB, 2>(a, nblocks, st, resident);
+    else
+      return cudaErrorInvalidValue;
+  }
   return launch_mg<TB, RECON, SPLIT, MASK, PF, MINB, 0>(a, nblocks, st, resident);
 }
 
@@ -623,7 +640,6 @@ cudaError_t launch_mask(const FusedArgs& a, int mask, int nblocks, cudaStream_t 
 #define F2B_DEFAULT_TB 160
 #define F2B_DEFAULT_PF 2
 #define F2B_DEFAULT_MINB 4
-#define F2B_CS_MINB 34
 cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb, int pf, int minb, int nblocks,
                      cudaStream_t st, int* resident) {
   if (recon == 3 && split == 1) {
@@ -649,6 +665,21 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb,
 }
 
 }  // namespace
+
+int pycs_split_sets(int nstrips, int nchunks, int* interior, int* boundary) {
+  if (nstrips < 3 || nchunks < 3) return 0;
+  int ni = 0, nb = 0;
+  for (int chunk = 0; chunk < nchunks; ++chunk)
+    for (int strip = 0; strip < nstrips; ++strip) {
+      const bool in = strip >= 1 && strip <= nstrips - 2 && chunk >= 1 && chunk <= nchunks - 2;
+      for (int p = 0; p < 6; ++p) {
+        const int b = (chunk * nstrips + strip) * 6 + p;
+        if (in) interior[ni++] = b;
+        else boundary[nb++] = b;
+      }
+    }
+  return ni;
+}
 
 bool pycs_fused2b_has(int recon, int split, int tb, int pf, int minb) {
   if (recon != 1 && recon != 3) return false;

@@ -46,7 +46,18 @@ struct FusedArgs {
   FusedMg mg;                 // world <= 1: single GPU
   int pdl;                    // launch with programmatic stream serialization (v2b)
   FusedGhost gf;
+  // split launches (v2b, PYCS_SPLIT=1): a step is two launches over disjoint CTA sets -- the
+  // interior CTAs, which read no ghost cell, start at once; the boundary CTAs follow the ghost
+  // fill on a second stream.  blk_map[blockIdx.x] = CTA index in the full grid; both launches
+  // share part[], the ticket counter and nblk_total, so the later one totals the MF-PR sum.
+  const int* blk_map;         // nullptr: one launch over the whole grid
+  int nblk_total;
 };
+
+// CTA sets of a split step: strips x chunks x 6 panels, CTA = (chunk * nstrips + strip) * 6 + panel.
+// Interior: strips 1 .. nstrips-2 and chunks 1 .. nchunks-2 (their staged rows / columns hold no
+// ghost cell and no row of another slab).  Returns the number of interior CTAs (0: no split).
+int pycs_split_sets(int nstrips, int nchunks, int* interior, int* boundary);
 
 #ifdef __CUDACC__
 // The writer of the last partial of a launch adds them all up: consumers of the MF-PR sum

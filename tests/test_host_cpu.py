@@ -203,3 +203,26 @@ def test_divergence_sweep_follows_the_reference_table(monkeypatch, capsys):
     assert [c[4] for c in calls[::3]] == [(3, 1, 3, 2, 2, 1), (3, 1, 3, 3, 2, 3), (3, 2, 1, 3, 1, 2), (3, 2, 1, 3, 1, 3)]
     assert np.allclose(err[0, :, 0], [1 / 16, 1 / 32, 1 / 64])
     assert "Ratio E_1/E_0: 2.00e+00 2.00e+00 2.00e+00" in capsys.readouterr().out
+
+
+@pytest.mark.parametrize("ns,nch", [(10, 19), (3, 3), (5, 7), (2, 9), (9, 2)])
+def test_split_step_cta_sets(ns, nch):
+    """PYCS_SPLIT: interior + boundary CTA sets partition the grid; an interior CTA's staged rows and columns
+    (chunk rows -3..+2, strip columns -3..+2) never reach the first / last chunk or strip, i.e. no ghost cell."""
+    lib = device.load_library()
+    ip = ctypes.POINTER(ctypes.c_int32)
+    lib.pycs_split_plan.argtypes = [ctypes.c_int32, ctypes.c_int32, ip, ip, ip]
+    lib.pycs_split_plan.restype = ctypes.c_int
+    n = 6 * ns * nch
+    inner, outer, cnt = (ctypes.c_int32 * n)(), (ctypes.c_int32 * n)(), ctypes.c_int32()
+    assert lib.pycs_split_plan(ns, nch, inner, outer, ctypes.byref(cnt)) == 0
+    ni = cnt.value
+    if ns < 3 or nch < 3:
+        assert ni == 0 and list(outer) == list(range(n))
+        return
+    assert ni == 6 * (ns - 2) * (nch - 2)
+    a, b = list(inner[:ni]), list(outer[:n - ni])
+    assert sorted(a + b) == list(range(n)) and a == sorted(a) and b == sorted(b)
+    for blk in a:
+        strip, chunk = (blk // 6) % ns, blk // (6 * ns)
+        assert 1 <= strip <= ns - 2 and 1 <= chunk <= nch - 2

@@ -52,3 +52,28 @@ def test_interpolation_experiment_driver(mods):
             assert abs(err[0, d] - want) <= 1e-12 * max(want, 1.0), (ic, d, err[0, d], want)
         if ic == 1:                 # 2.605e-3 -> 2.799e-4
             assert err[1, 3] < err[0, 3] / 8.0
+
+
+@pytest.mark.parametrize("N,vf", [(320, 3), (320, 1), (1536, 3)])
+def test_split_step_matches_operator_path(mods, N, vf, monkeypatch):
+    """PYCS_SPLIT=1 (DESIGN s7.1): interior CTAs beside the ghost fill, boundary CTAs after it, two streams;
+    several run calls (separable wind, pending projection) against the operator path."""
+    from pycs_b200 import advection_vars, advection_timestep
+    monkeypatch.setenv("PYCS_SPLIT", "1")
+    g = mods.cs_datastruct.cubed_sphere(N)
+
+    def sim_of():
+        s = mods.advection_ic.adv_simulation_par(g, DT16[vf] * 16 / N, 5, 2, vf, 1, *TUPLES["default"])
+        advection_vars.init_vars_adv(g, s)
+        return s
+
+    a, b = sim_of(), sim_of()
+    k = 0
+    for n in ((1, 4, 7) if N < 1000 else (3,)):
+        advection_timestep.run_steps(g, a, k, n, fused=True)
+        k += n
+    advection_timestep.run_steps(g, b, 0, k, fused=False)
+    qa, qb = np.asarray(a.Q), np.asarray(b.Q)
+    assert np.max(np.abs(qa - qb)) / np.max(np.abs(qb)) <= 1e-12
+    a.dev.close()
+    b.dev.close()
