@@ -645,9 +645,9 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int tb,
   if (recon == 3 && split == 1) {
 #define TUNE(T, P, M) \
   if (tb == T && pf == P && minb == M) return launch_mask<T, 3, 1, P, M>(a, mask, nblocks, st, resident)
-    // (threads, rows in flight, MINB): measured points worth keeping, see profiles/r1_sweep_v2b.log
-    TUNE(160, 2, 14); TUNE(160, 1, 14); TUNE(160, 2, 4); TUNE(160, 1, 4); TUNE(128, 2, 15);
-    TUNE(128, 2, 5); TUNE(160, 2, 34); TUNE(128, 2, 35); TUNE(160, 2, 53); TUNE(128, 2, 54); TUNE(160, 2, 64); TUNE(160, 2, 33);
+    // (threads, rows in flight, MINB): the default, the earlier marches it is tested against and the
+    // candidates of the next sweep; measured-and-dropped points are in profiles/r1_sweep_v2b*.log
+    TUNE(160, 2, 14); TUNE(160, 2, 4); TUNE(160, 2, 34); TUNE(128, 2, 35); TUNE(160, 2, 53); TUNE(128, 2, 54); TUNE(160, 2, 64); TUNE(160, 2, 33);
 #undef TUNE
     return cudaErrorInvalidValue;
   }
@@ -684,7 +684,7 @@ int pycs_split_sets(int nstrips, int nchunks, int* interior, int* boundary) {
 bool pycs_fused2b_has(int recon, int split, int tb, int pf, int minb) {
   if (recon != 1 && recon != 3) return false;
   if (recon == 3 && split == 1) {
-    const int t[][3] = {{160, 2, 14}, {160, 1, 14}, {160, 2, 4}, {160, 1, 4}, {128, 2, 15}, {128, 2, 5}, {160, 2, 34}, {128, 2, 35}, {160, 2, 53}, {128, 2, 54}, {160, 2, 64}, {160, 2, 33}};
+    const int t[][3] = {{160, 2, 14}, {160, 2, 4}, {160, 2, 34}, {128, 2, 35}, {160, 2, 53}, {128, 2, 54}, {160, 2, 64}, {160, 2, 33}};
     for (auto& x : t)
       if (x[0] == tb && x[1] == pf && x[2] == minb) return true;
     return false;

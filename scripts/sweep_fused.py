@@ -16,7 +16,7 @@ if which == "v2":
 elif which == "cs":      # const-slot march against the default point
     configs = [dict(IMPL=4, TB=tb, PF=2, MINB=mb, ROWS=0) for tb, mb in ((160, 14), (160, 34), (128, 35), (160, 53), (128, 54), (160, 64), (160, 33), (160, 34), (160, 64))]
 elif which == "v2b":
-    pts = ((160, 2, 14), (160, 1, 14), (160, 2, 4), (160, 1, 4), (128, 2, 15), (128, 2, 5), (160, 2, 34), (128, 2, 35), (160, 2, 53))
+    pts = ((160, 2, 14), (160, 2, 4), (160, 2, 34), (128, 2, 35), (160, 2, 53), (160, 2, 33), (160, 2, 64))
     configs = [dict(IMPL=4, TB=tb, PF=pf, MINB=mb, ROWS=rows) for tb, pf, mb in pts for rows in (0, 96)]
 else:
     pts = ((3, 3, 3), (3, 2, 3), (3, 4, 3), (3, 2, 4), (3, 3, 4), (3, 3, 13), (3, 4, 13), (2, 3, 4), (2, 4, 4), (2, 4, 5),
