@@ -144,6 +144,9 @@ void run(const Args& a) {
 }
 
 // ---- v2b (csrc/fused2b.cu): one column per thread, CTA = strip of TB-6 columns -------------
+// optional CTA subset of the next v2b runs (the split step of FusedArgs::blk_map): nullptr = whole grid
+static const int* g_blk_list = nullptr;
+static int g_blk_count = 0;
 // compile-time row phase k = (r - first row) % 6 of the circular-window march
 template <int RECON, int SPLIT, int MASK, int W = f1::WLEN>
 void x_inner_k(int k, f1::Lane& L, f1::XEdge& X, const f1::RowPtrs& R, const double* qnew, double cdxw, double* qx) {
@@ -199,7 +202,8 @@ void run_block(const Args& a, int TB) {
   std::vector<XEdge> X(TB);
   std::vector<RowPtrs> R(TB);
   std::vector<double> F(TB), G(TB), CF(TB);
-  for (int blk = 0; blk < 6 * nstrips * nchunks; ++blk) {
+  for (int idx = 0; idx < (g_blk_list ? g_blk_count : 6 * nstrips * nchunks); ++idx) {
+    const int blk = g_blk_list ? g_blk_list[idx] : idx;
     int b = blk;
     const int p = b % 6;
     b /= 6;
@@ -314,7 +318,8 @@ void run_block_pair(const Args& a, int TB) {
   std::vector<XEdge> X[2] = {std::vector<XEdge>(TB), std::vector<XEdge>(TB)};
   std::vector<RowPtrs> R[2] = {std::vector<RowPtrs>(TB), std::vector<RowPtrs>(TB)};
   std::vector<double> F[2] = {std::vector<double>(TB), std::vector<double>(TB)}, G[2] = {F[0], F[0]}, CF[2] = {F[0], F[0]};
-  for (int blk = 0; blk < 6 * nstrips * nchunks; ++blk) {
+  for (int idx = 0; idx < (g_blk_list ? g_blk_count : 6 * nstrips * nchunks); ++idx) {
+    const int blk = g_blk_list ? g_blk_list[idx] : idx;
     int b = blk;
     const int p = b % 6;
     b /= 6;
@@ -491,6 +496,8 @@ int f3_emul_step_block_circ(STEP_BLOCK_ARGS) {
 }
 // the two-row march (MINB >= 50); depth is ignored (rings of 4 and 8 slots)
 int f3_emul_step_block_pair(STEP_BLOCK_ARGS) { return f3_emul_step_block_impl(2, STEP_BLOCK_PASS); }
+// run only these CTAs (indices in the full grid) in the following f3_emul_step_block* calls; n = 0 resets
+void f3_emul_set_block_list(const int* list, int n) { g_blk_list = n > 0 ? list : nullptr; g_blk_count = n; }
 int f3_emul_block_grid(int N, int TB, int rows_per_chunk) {
   const int wmax = TB - 6;
   return 6 * ((N + wmax - 1) / wmax) * ((N + rows_per_chunk - 1) / rows_per_chunk);

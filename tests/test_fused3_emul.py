@@ -37,6 +37,8 @@ def emul():
     lib.f3_emul_step_block_circ.restype = C.c_int
     lib.f3_emul_step_block_pair.argtypes = lib.f3_emul_step.argtypes
     lib.f3_emul_step_block_pair.restype = C.c_int
+    lib.f3_emul_set_block_list.argtypes = [C.POINTER(C.c_int), C.c_int]
+    lib.f3_emul_set_block_list.restype = None
     lib.f3_emul_block_grid.argtypes = [C.c_int] * 3
     lib.f3_emul_block_grid.restype = C.c_int
     lib.f3_emul_grid.argtypes = [C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 3
@@ -63,7 +65,7 @@ def ptr(a):
 
 
 def one_step(emul, N, vf, tup, pre_steps, nw=3, depth=3, rows=None, pending=False, separable=False, block_tb=0,
-             circ=False):
+             circ=False, split_sets=None):
     from oracle.grid import LeanGrid
     from oracle import step as ost, wind as owind
     recon, dp, split, et, mt, mf = tup
@@ -107,8 +109,21 @@ def one_step(emul, N, vf, tup, pre_steps, nw=3, depth=3, rows=None, pending=Fals
         part = np.zeros(emul.f3_emul_block_grid(N, block_tb, rows))
         fn = {False: emul.f3_emul_step_block, True: emul.f3_emul_step_block_circ,
               "pair": emul.f3_emul_step_block_pair}[circ]
-        rc = fn(N, recon, split, mask, block_tb, depth, rows, ptr(q), ptr(qn),
-                *[ptr(a) for a in arrs], ptr(part), corr, 1 if pending else 0, dt / g.dx, dt / g.dy, ws)
+        if split_sets is None:
+            rc = fn(N, recon, split, mask, block_tb, depth, rows, ptr(q), ptr(qn),
+                    *[ptr(a) for a in arrs], ptr(part), corr, 1 if pending else 0, dt / g.dx, dt / g.dy, ws)
+        else:
+            # split step: the interior CTAs run while the ghost cells are still being written -- here: NaN
+            inner, outer = [np.ascontiguousarray(x, dtype=np.int32) for x in split_sets]
+            qbad = q.copy()
+            qbad[:, :4, :] = qbad[:, N + 4:, :] = np.nan
+            qbad[:, :, :JOFF + 4] = qbad[:, :, JOFF + N + 4:] = np.nan
+            for lst, src in ((inner, qbad), (outer, q)):
+                emul.f3_emul_set_block_list(lst.ctypes.data_as(C.POINTER(C.c_int)), len(lst))
+                rc = fn(N, recon, split, mask, block_tb, depth, rows, ptr(src), ptr(qn),
+                        *[ptr(a) for a in arrs], ptr(part), corr, 1 if pending else 0, dt / g.dx, dt / g.dy, ws)
+                emul.f3_emul_set_block_list(None, 0)
+                assert rc == 0
     else:               # v3 decomposition (csrc/fused3.cu)
         ns, wc, nch = C.c_int(), C.c_int(), C.c_int()
         npart = emul.f3_emul_grid(N, nw, rows, C.byref(ns), C.byref(wc), C.byref(nch))
@@ -227,3 +242,26 @@ def test_emulated_v2b_two_row_march_same_bits_as_const_slot(emul):
     a, _ = one_step(emul, 50, 3, TUPLES["default"], 3, depth=2, rows=11, block_tb=64, circ="pair")
     b, _ = one_step(emul, 50, 3, TUPLES["default"], 3, depth=2, rows=11, block_tb=64, circ=True)
     assert np.array_equal(a, b)
+
+
+# ---- split step (PYCS_SPLIT, FusedArgs::blk_map): interior CTAs must not depend on any ghost cell -----
+@pytest.mark.parametrize("vf,kw", [(3, {"pending": True}), (1, {}), (3, {"separable": True})])
+def test_emulated_split_step_interior_reads_no_ghost_cell(emul, vf, kw):
+    """The CTA sets of pycs_split_plan: the interior set runs on a Q whose ghost cells are NaN, the boundary set
+    on the ghost-filled Q; together they must give the oracle's step (a NaN would show a ghost dependence)."""
+    import ctypes
+    import pycs_b200  # noqa: F401
+    from pycs_b200 import device
+    N, tb, rows = 130, 32, 20
+    ns, nch = -(-N // (tb - 6)), -(-N // rows)
+    lib = device.load_library()
+    ip = ctypes.POINTER(ctypes.c_int32)
+    lib.pycs_split_plan.argtypes = [ctypes.c_int32, ctypes.c_int32, ip, ip, ip]
+    n = 6 * ns * nch
+    inner, outer, cnt = (ctypes.c_int32 * n)(), (ctypes.c_int32 * n)(), ctypes.c_int32()
+    assert lib.pycs_split_plan(ns, nch, inner, outer, ctypes.byref(cnt)) == 0 and cnt.value == 6 * (ns - 2) * (nch - 2)
+    sets = (list(inner[:cnt.value]), list(outer[:n - cnt.value]))
+    got, want = one_step(emul, N, vf, TUPLES["default"], 2, depth=2, rows=rows, block_tb=tb, circ=True,
+                         split_sets=sets, **kw)
+    assert np.all(np.isfinite(got))
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
