@@ -2,19 +2,24 @@
 src/interpolation_test.py:65-176): the Lagrange duo-grid fill of an analytic scalar field for
 degrees 0..4 on N = 16, 32, ..., error in the ghost cells against the field itself.
 
-Only the scalar test (tc = 1) is on the accelerated path; the vector-field and reconstruction
-experiments (tc = 2, 3, 4) and all plots are not provided.  The fill runs on the GPU
-(`pycs_halo_fill_dg`); the tables are the host set-up of `lagrange.py`."""
+Test case 4 (:506-617) is the reconstruction experiment: ghost fill (ET-S72 / ET-PL07 / ET-DG) + PPM edge values
+(PPM-PL07, PPM-L04) of the same analytic fields against the field at the cell edges.
+
+The scalar test (tc = 1) and the reconstruction test (tc = 4) run on the GPU operators
+(`pycs_halo_fill_*`, `pycs_ppm_reconstruction`); the vector-field experiments (tc = 2, 3) and all plots
+are not provided.  The tables are the host set-up of `lagrange.py`."""
 import types
 
 import numpy as np
 
 from .advection_ic import div_exact
 from .configuration import get_interpolation_parameters
-from .cs_datastruct import cubed_sphere
+from .cs_datastruct import cubed_sphere, ppm_parabola
 from .device import Device
 from .errors import compute_errors, print_errors_simul
+from .edges_treatment import edges_ghost_cell_treatment_scalar
 from .interpolation import ghost_cell_pc_lagrange_interpolation
+from .reconstruction_1d import ppm_reconstruction
 from .lagrange import lagrange_poly_ghostcell_pc
 from .sphgeo import sph2cart
 
@@ -66,13 +71,75 @@ def error_analysis_sf_interpolation(ic, map_projection, transformation, showonsc
     return Nc, error_linf
 
 
+class recon_simulation_par:
+    """src/interpolation_test.py:660-702; `attach` creates the device handle for one grid."""
+    _RECON = {1: 'PPM-0', 2: 'PPM-CW84', 3: 'PPM-PL07', 4: 'PPM-L04'}
+    _ET = {1: 'ET-S72', 2: 'ET-PL07', 3: 'ET-DG'}
+
+    def __init__(self, ic, recon, et):
+        if ic not in (1, 2, 3):
+            print("Error - invalid scalar field")
+            raise SystemExit(1)
+        if et not in self._ET:
+            print('ERROR in recon_simulation_par: invalid ET')
+            raise SystemExit(1)
+        self.ic, self.recon, self.edge_treatment = ic, recon, et
+        self.recon_name, self.et_name = self._RECON.get(recon), self._ET[et]
+        self.degree = 3
+        self.title = 'Reconstruction'
+        self.dev = None
+
+    def attach(self, cs_grid):
+        self.dev = Device(cs_grid.N, cs_grid.dx, cs_grid.dy, 0.01, recon=self.recon, et=self.edge_treatment,
+                          mf=1, ic=min(self.ic, 2))
+        return self
+
+
+def error_analysis_recon(ic, map_projection, transformation, showonscreen, gridload, Ntest=7, recons=(3, 4)):
+    """Error norms [Ntest, len(ets), len(recons), 3] of the reconstructed edge values
+    (src/interpolation_test.py:506-617); ET-DG only on the equiangular grid."""
+    ets = (1, 2, 3) if transformation == 'gnomonic_equiangular' else (1, 2)
+    Nc = 16 * 2 ** np.arange(Ntest)
+    errors = np.zeros((Ntest, len(ets), len(recons), 3))
+    for e, et in enumerate(ets):
+        for r, recon in enumerate(recons):
+            for i in range(Ntest):
+                N = int(Nc[i])
+                cs_grid = cubed_sphere(N, transformation, False, True)
+                simulation = recon_simulation_par(ic, recon, et).attach(cs_grid)
+                i0, iend, j0, jend = cs_grid.i0, cs_grid.iend, cs_grid.j0, cs_grid.jend
+                Q = np.zeros((N + cs_grid.ng, N + cs_grid.ng, 6))
+                Qexact = q_scalar_field(cs_grid.pc.lon, cs_grid.pc.lat, simulation)
+                q_pu = q_scalar_field(cs_grid.pu.lon, cs_grid.pu.lat, simulation)
+                q_pv = q_scalar_field(cs_grid.pv.lon, cs_grid.pv.lat, simulation)
+                Q[i0:iend, j0:jend, :] = Qexact[i0:iend, j0:jend, :]
+                print('\nParameters: N = ' + str(N) + ', et = ' + str(et) + ' , recon = ', recon)
+                if cs_grid.projection == 'gnomonic_equiangular':
+                    lagrange_poly_ghostcell_pc(cs_grid, simulation)
+                edges_ghost_cell_treatment_scalar(Q, Q, cs_grid, simulation)
+                px, py = ppm_parabola(cs_grid, simulation, 'x'), ppm_parabola(cs_grid, simulation, 'y')
+                ppm_reconstruction(Q, Q, px, py, cs_grid, simulation)
+                I = np.s_[i0:iend, j0:jend, :]
+                err = abs(q_pu[i0:iend, j0:jend, :] - np.asarray(px.q_L)[I])
+                err = np.maximum(err, abs(q_pu[i0 + 1:iend + 1, j0:jend, :] - np.asarray(px.q_R)[I]))
+                err = np.maximum(err, abs(q_pv[i0:iend, j0:jend, :] - np.asarray(py.q_L)[I]))
+                err = np.maximum(err, abs(q_pv[i0:iend, j0 + 1:jend + 1, :] - np.asarray(py.q_R)[I]))
+                errors[i, e, r] = compute_errors(err, 0 * err)
+                print_errors_simul(errors[:, e, r, 0], errors[:, e, r, 1], errors[:, e, r, 2], i)
+                simulation.dev.close()
+    return Nc, errors
+
+
 def interpolation_test(map_projection, transformation, showonscreen, gridload, pardir=None, Ntest=6):
     tc, ic, vf = get_interpolation_parameters(pardir)
     if tc == 1:
         print("Test case 1: Interpolation of scalar field test case.\n")
         return error_analysis_sf_interpolation(ic, map_projection, transformation, showonscreen, gridload, Ntest)
-    if tc in (2, 3, 4):
-        print("Interpolation test case %d (vector field / reconstruction experiments) is not provided." % tc)
+    if tc == 4:
+        print("Test case 4: Reconstruction test case.\n")
+        return error_analysis_recon(ic, map_projection, transformation, showonscreen, gridload, Ntest)
+    if tc in (2, 3):
+        print("Interpolation test case %d (vector field experiments) is not provided." % tc)
         raise SystemExit(1)
     print('ERROR in interpolation_test: invalid test case ', tc)
     raise SystemExit(1)

@@ -10,6 +10,7 @@ Usage:  python tests/golden/make_golden.py small|kmin|norms|big384|big768|big153
   big384   config 2: N=384 default scheme, full period, sub-sampled Q + norms (~50 min)
   big768   config 3: N=768 vf=2 RK2, first 50 steps, sub-sampled Q
   big1536  config 4: N=1536 vf=3, first 20 steps, sub-sampled Q (needs ~15 GB RAM)
+  recon    the reconstruction experiment of interpolation_test (tc 4): error norms per ET x recon at N=16, 32
   regrid   lat-lon -> cubed-sphere index maps (ll2cs), nearest-neighbour regridding and the
            one-step divergence-test errors (drivers / output row of SURVEY s8 f4)
 """
@@ -277,6 +278,36 @@ def make_regrid():
     save("regrid_N16.npz", **out)
 
 
+def make_recon():
+    """Reconstruction experiment (src/interpolation_test.py:506-617): ghost fill + PPM edge values of an
+    analytic field against the field at the edges, per edge treatment x reconstruction."""
+    redge = R.ref("edges_treatment")
+    rrec = R.ref("reconstruction_1d")
+    out = {}
+    for N in (16, 32):
+        g = grid(N)
+        i0, iend, j0, jend = g.i0, g.iend, g.j0, g.jend
+        for ic in (1, 2):
+            for et in (1, 2, 3):
+                for recon in (3, 4):
+                    sim = rtest.recon_simulation_par(ic, recon, et)
+                    Q = np.zeros((N + g.ng, N + g.ng, 6))
+                    Qe = rtest.q_scalar_field(g.pc.lon, g.pc.lat, sim)
+                    q_pu = rtest.q_scalar_field(g.pu.lon, g.pu.lat, sim)
+                    q_pv = rtest.q_scalar_field(g.pv.lon, g.pv.lat, sim)
+                    Q[i0:iend, j0:jend, :] = Qe[i0:iend, j0:jend, :]
+                    rlag.lagrange_poly_ghostcell_pc(g, sim)
+                    redge.edges_ghost_cell_treatment_scalar(Q, Q, g, sim)
+                    px, py = cs.ppm_parabola(g, sim, 'x'), cs.ppm_parabola(g, sim, 'y')
+                    rrec.ppm_reconstruction(Q, Q, px, py, g, sim)
+                    e = abs(q_pu[i0:iend, j0:jend, :] - px.q_L[i0:iend, j0:jend, :])
+                    e = np.maximum(e, abs(q_pu[i0 + 1:iend + 1, j0:jend, :] - px.q_R[i0:iend, j0:jend, :]))
+                    e = np.maximum(e, abs(q_pv[i0:iend, j0:jend, :] - py.q_L[i0:iend:, j0:jend, :]))
+                    e = np.maximum(e, abs(q_pv[i0:iend, j0 + 1:jend + 1, :] - py.q_R[i0:iend:, j0:jend, :]))
+                    out["err_N%d_ic%d_et%d_recon%d" % (N, ic, et, recon)] = np.array(rerr.compute_errors(e, 0 * e))
+    save("recon_experiment.npz", **out)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "small"
     if what in ("small", "all"):
@@ -287,6 +318,8 @@ if __name__ == "__main__":
         make_norms()
     if what in ("regrid", "all"):
         make_regrid()
+    if what in ("recon", "all"):
+        make_recon()
     if what in ("big384", "all"):
         make_big(384, 1, "default", [1, 10, 100, 1000, 4800], 8)
     if what in ("big768", "all"):

@@ -126,3 +126,36 @@ def test_divergence_test_errors(g16, vf):
         ost.adv_time_step(g16, sim, 1, sim.dt)
         got = np.array(compute_errors(sim.div[I], div_exact(g16.pc.lon[I], g16.pc.lat[I], sim)))
         assert np.array_equal(got, ref["diverr_vf%d_%s" % (vf, name)]), (vf, name)
+
+
+@pytest.mark.skipif(not have("recon_experiment.npz"), reason="fixture not generated")
+@pytest.mark.parametrize("N", [16, 32])
+def test_reconstruction_experiment_errors(N):
+    """src/interpolation_test.py:506-617 with the oracle's ghost fills and PPM edge values: the reference's error
+    norms per edge treatment x reconstruction, bit for bit."""
+    from oracle import ppm as oppm
+    ref = load("recon_experiment.npz")
+    g = LeanGrid(N)
+    i0, iend = g.i0, g.iend
+    I = np.s_[i0:iend, i0:iend, :]
+    for ic in (1, 2):
+        Qe = ost.q_scalar_field(g.pc.lon, g.pc.lat, ic)
+        q_pu = ost.q_scalar_field(g.pu.lon, g.pu.lat, ic)
+        q_pv = ost.q_scalar_field(g.pv.lon, g.pv.lat, ic)
+        for et in (1, 2, 3):
+            for recon in (3, 4):
+                sim = ost.Simulation(g, 0.01, 5, 1, 1, 1, recon, 1, 1, et, 1, 1)
+                ost.init_vars_adv(g, sim)
+                Q = np.zeros_like(Qe)
+                Q[I] = Qe[I]
+                ost.ghost_fill_scalar(Q, Q, g, sim)
+                oppm.reconstruct(Q, sim.px, sim.recon_name, i0, iend)
+                oppm.reconstruct(np.swapaxes(Q, 0, 1), sim.py, sim.recon_name, i0, iend)
+                if sim.et_name == "ET-PL07":
+                    ost.edges_extrapolation(Q, Q, sim.px, sim.py, g, sim)
+                e = abs(q_pu[i0:iend, i0:iend, :] - sim.px.q_L[I])
+                e = np.maximum(e, abs(q_pu[i0 + 1:iend + 1, i0:iend, :] - sim.px.q_R[I]))
+                e = np.maximum(e, abs(q_pv[i0:iend, i0:iend, :] - sim.py.q_L[I]))
+                e = np.maximum(e, abs(q_pv[i0:iend, i0 + 1:iend + 1, :] - sim.py.q_R[I]))
+                got = np.array(ost.compute_errors(e, 0 * e))
+                assert np.array_equal(got, ref["err_N%d_ic%d_et%d_recon%d" % (N, ic, et, recon)]), (ic, et, recon)

@@ -78,3 +78,19 @@ def test_split_step_matches_operator_path(mods, N, vf, monkeypatch):
     assert np.max(np.abs(qa - qb)) / np.max(np.abs(qb)) <= 1e-12
     a.dev.close()
     b.dev.close()
+
+
+@pytest.mark.skipif(not have("recon_experiment.npz"), reason="fixture not generated")
+def test_reconstruction_experiment_driver(mods):
+    """interpolation_test tc 4 (src/interpolation_test.py:506-617): ghost fill + PPM edge values on the GPU
+    operators, error norms per edge treatment x reconstruction against the reference's numbers."""
+    from pycs_b200.interpolation_test import error_analysis_recon
+    ref = load("recon_experiment.npz")
+    for ic in (1, 2):
+        Nc, err = error_analysis_recon(ic, "mercator", "gnomonic_equiangular", False, False, Ntest=2)
+        assert list(Nc) == [16, 32] and err.shape == (2, 3, 2, 3)
+        for i, N in enumerate((16, 32)):
+            for e, et in enumerate((1, 2, 3)):
+                for r, recon in enumerate((3, 4)):
+                    want = ref["err_N%d_ic%d_et%d_recon%d" % (N, ic, et, recon)]
+                    assert np.max(np.abs(err[i, e, r] - want) / want) <= 1e-10, (N, ic, et, recon, err[i, e, r], want)
