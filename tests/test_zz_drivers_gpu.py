@@ -1,11 +1,14 @@
-"""GPU: the reference's experiment drivers (main.py test cases 3 and 4) run through the product modules.
-Sorted after the parity files on purpose: these drivers were added after the last GPU minute of round 1."""
+"""GPU: the reference's experiment drivers (main.py test cases 3 and 4) run through the product modules, and the
+opt-in split step.  Everything here was written after the last GPU minute of round 1 and has not run on a GPU yet
+(the CPU halves -- oracle against the same fixtures, host logic, the kernel emulator -- are green), hence the
+non-strict xfail marks: a first-run failure must not mask the parity suite; remove the marks after the first run."""
 import numpy as np
 import pytest
 
 from golden_common import TUPLES, DT16, load, have
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(reason="first GPU run pending (written after the round-1 GPU budget ran out)", strict=False)]
 
 
 @pytest.fixture(scope="module")
@@ -54,7 +57,6 @@ def test_interpolation_experiment_driver(mods):
             assert err[1, 3] < err[0, 3] / 8.0
 
 
-@pytest.mark.xfail(reason="opt-in path written after the GPU budget of round 1 ran out: first run pending", strict=False)
 @pytest.mark.parametrize("N,vf", [(320, 3), (320, 1), (1536, 3)])
 def test_split_step_matches_operator_path(mods, N, vf, monkeypatch):
     """PYCS_SPLIT=1 (DESIGN s7.1): interior CTAs beside the ghost fill, boundary CTAs after it, two streams;
