@@ -5,14 +5,19 @@ degrees 0..4 on N = 16, 32, ..., error in the ghost cells against the field itse
 Test case 4 (:506-617) is the reconstruction experiment: ghost fill (ET-S72 / ET-PL07 / ET-DG) + PPM edge values
 (PPM-PL07, PPM-L04) of the same analytic fields against the field at the cell edges.
 
-The scalar test (tc = 1) and the reconstruction test (tc = 4) run on the GPU operators
-(`pycs_halo_fill_*`, `pycs_ppm_reconstruction`); the vector-field experiments (tc = 2, 3) and all plots
-are not provided.  The tables are the host set-up of `lagrange.py`."""
+Test case 3 (:354-470) is the vector-field ghost-cell experiment: wind at the cell edges -> centres (cubic) ->
+Lagrange ghost fill of the lat-lon wind -> ghost edges, relative Linf error of the contravariant wind there.
+
+The scalar test (tc = 1), the ghost-edge wind test (tc = 3) and the reconstruction test (tc = 4) run on the
+GPU operators (`pycs_halo_fill_*`, `pycs_halo_fill_vector`, `pycs_ppm_reconstruction`); tc = 2 (error at the
+centres: the reference's own routine only fills the ring next to the cube edges, src/interpolation.py:359-418,
+so its interior error is the field itself) and all plots are not provided.  The tables are the host set-up of `lagrange.py`."""
 import types
 
 import numpy as np
 
-from .advection_ic import div_exact
+from .advection_ic import div_exact, velocity_adv, adv_simulation_par
+from .advection_vars import init_vars_adv
 from .configuration import get_interpolation_parameters
 from .cs_datastruct import cubed_sphere, ppm_parabola
 from .device import Device
@@ -21,7 +26,7 @@ from .edges_treatment import edges_ghost_cell_treatment_scalar
 from .interpolation import ghost_cell_pc_lagrange_interpolation
 from .reconstruction_1d import ppm_reconstruction
 from .lagrange import lagrange_poly_ghostcell_pc
-from .sphgeo import sph2cart
+from .sphgeo import sph2cart, latlon_to_contravariant
 
 
 class interpolation_simulation_par:
@@ -65,6 +70,52 @@ def error_analysis_sf_interpolation(ic, map_projection, transformation, showonsc
             lagrange_poly_ghostcell_pc(cs_grid, simulation)
             ghost_cell_pc_lagrange_interpolation(Q_numerical, cs_grid, simulation)
             error_linf[i, d], _, _ = compute_errors(Q_numerical, Q_exact)
+            print_errors_simul(error_linf[:, d], error_linf[:, d], error_linf[:, d], i)
+            simulation.dev.close()
+        print()
+    return Nc, error_linf
+
+
+def ghost_edge_wind_errors(cs_grid, simulation):
+    """The eight relative errors of src/interpolation_test.py:441-456 (east u, v; west; north; south) of the
+    device-resident winds of `simulation` against the analytic wind at t = 0."""
+    i0, iend, j0, jend = cs_grid.i0, cs_grid.iend, cs_grid.j0, cs_grid.jend
+    exact = {}
+    for pos in ("pu", "pv"):
+        pts = getattr(cs_grid, pos)
+        ulon, vlat = velocity_adv(pts.lon, pts.lat, 0.0, simulation)
+        exact[pos] = latlon_to_contravariant(ulon, vlat, getattr(cs_grid, "prod_ex_elon_" + pos),
+                                             getattr(cs_grid, "prod_ex_elat_" + pos),
+                                             getattr(cs_grid, "prod_ey_elon_" + pos),
+                                             getattr(cs_grid, "prod_ey_elat_" + pos),
+                                             getattr(cs_grid, "determinant_ll2contra_" + pos))
+    got = {"pu": (np.asarray(simulation.U_pu.ucontra), np.asarray(simulation.U_pu.vcontra)),
+           "pv": (np.asarray(simulation.U_pv.ucontra), np.asarray(simulation.U_pv.vcontra))}
+    regions = (("pv", np.s_[iend:, j0 - 1:jend + 2, :]), ("pv", np.s_[:i0, j0 - 1:jend + 2, :]),
+               ("pu", np.s_[i0 - 1:iend + 2, jend:, :]), ("pu", np.s_[i0 - 1:iend + 2, :j0, :]))
+    errs = []
+    for pos, R in regions:
+        for c in (0, 1):
+            errs.append(np.amax(abs(got[pos][c][R] - exact[pos][c][R])) / np.amax(abs(exact[pos][c][R])))
+    return np.array(errs)
+
+
+def error_analysis_vf_interpolation_ghost_cells(vf, map_projection, transformation, showonscreen, gridload, Ntest=7,
+                                                degrees=(0, 1, 2, 3, 4)):
+    """Linf error [Ntest, len(degrees)] of the wind on the ghost edges (src/interpolation_test.py:354-470).  The
+    reference sets the edge winds and calls the two interpolation routines; here init_vars_adv does exactly that
+    on the device (RK2 build, so that the lines next to the panel are filled as well)."""
+    Nc = 16 * 2 ** np.arange(Ntest)
+    error_linf = np.zeros((Ntest, len(degrees)))
+    for d, degree in enumerate(degrees):
+        for i in range(Ntest):
+            N = int(Nc[i])
+            print('\nParameters: N = ' + str(N) + ', degree = ' + str(degree))
+            cs_grid = cubed_sphere(N, transformation, False, gridload)
+            simulation = adv_simulation_par(cs_grid, 0.01, 5.0, 1, vf, 1, 3, 2, 1, 3, 1, 1)
+            simulation.degree = degree
+            init_vars_adv(cs_grid, simulation)
+            error_linf[i, d] = np.max(ghost_edge_wind_errors(cs_grid, simulation))
             print_errors_simul(error_linf[:, d], error_linf[:, d], error_linf[:, d], i)
             simulation.dev.close()
         print()
@@ -138,8 +189,12 @@ def interpolation_test(map_projection, transformation, showonscreen, gridload, p
     if tc == 4:
         print("Test case 4: Reconstruction test case.\n")
         return error_analysis_recon(ic, map_projection, transformation, showonscreen, gridload, Ntest)
-    if tc in (2, 3):
-        print("Interpolation test case %d (vector field experiments) is not provided." % tc)
+    if tc == 3:
+        print("Test case 3: Interpolation of vector field at ghost cells test case.\n")
+        return error_analysis_vf_interpolation_ghost_cells(vf, map_projection, transformation, showonscreen, gridload,
+                                                           Ntest)
+    if tc == 2:
+        print("Interpolation test case 2 (vector field at the centres) is not provided.")
         raise SystemExit(1)
     print('ERROR in interpolation_test: invalid test case ', tc)
     raise SystemExit(1)

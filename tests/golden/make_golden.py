@@ -10,6 +10,7 @@ Usage:  python tests/golden/make_golden.py small|kmin|norms|big384|big768|big153
   big384   config 2: N=384 default scheme, full period, sub-sampled Q + norms (~50 min)
   big768   config 3: N=768 vf=2 RK2, first 50 steps, sub-sampled Q
   big1536  config 4: N=1536 vf=3, first 20 steps, sub-sampled Q (needs ~15 GB RAM)
+  vfinterp the vector-field ghost-cell experiment of interpolation_test (tc 3), per degree at N=16, 32
   recon    the reconstruction experiment of interpolation_test (tc 4): error norms per ET x recon at N=16, 32
   regrid   lat-lon -> cubed-sphere index maps (ll2cs), nearest-neighbour regridding and the
            one-step divergence-test errors (drivers / output row of SURVEY s8 f4)
@@ -308,6 +309,46 @@ def make_recon():
     save("recon_experiment.npz", **out)
 
 
+def make_vfinterp():
+    """Vector-field ghost-cell experiment (src/interpolation_test.py:354-470): wind from the cell edges to the
+    centres (cubic), Lagrange ghost fill of the lat-lon wind, centres to ghost edges; relative Linf error of the
+    contravariant wind on the ghost edges, per interpolation degree."""
+    sg = R.ref("sphgeo")
+    out = {}
+    for N in (16, 32):
+        g = grid(N)
+        i0, iend, j0, jend = g.i0, g.iend, g.j0, g.jend
+        for vf in (1, 2, 3):
+            ex = {}
+            for pos in ("pu", "pv"):
+                pts = getattr(g, pos)
+                sim0 = rtest.interpolation_simulation_par(vf, 3)
+                ulon, vlat = ric.velocity_adv(pts.lon, pts.lat, 0.0, sim0)
+                ex[pos] = sg.latlon_to_contravariant(ulon, vlat, getattr(g, "prod_ex_elon_" + pos),
+                                                     getattr(g, "prod_ex_elat_" + pos), getattr(g, "prod_ey_elon_" + pos),
+                                                     getattr(g, "prod_ey_elat_" + pos),
+                                                     getattr(g, "determinant_ll2contra_" + pos))
+            for degree in (0, 1, 2, 3, 4):
+                sim = rtest.interpolation_simulation_par(vf, degree)
+                U_pu, U_pv, U_pc = cs.velocity(g, 'pu'), cs.velocity(g, 'pv'), cs.velocity(g, 'pc')
+                U_pu.ucontra[i0:iend + 1, j0:jend, :] = ex["pu"][0][i0:iend + 1, j0:jend, :]
+                U_pv.vcontra[i0:iend, j0:jend + 1, :] = ex["pv"][1][i0:iend, j0:jend + 1, :]
+                rlag.lagrange_poly_ghostcell_pc(g, sim)
+                rint.wind_edges2center_cubic_interpolation(U_pc, U_pu, U_pv, g, sim)
+                rint.wind_center2ghostedge_cubic_interpolation(U_pc, U_pu, U_pv, g, sim)
+                rel = lambda a, b: np.amax(abs(a - b)) / np.amax(abs(b))
+                E = np.s_[iend:, j0 - 1:jend + 2, :]
+                W = np.s_[:i0, j0 - 1:jend + 2, :]
+                Nn = np.s_[i0 - 1:iend + 2, jend:, :]
+                S = np.s_[i0 - 1:iend + 2, :j0, :]
+                errs = [rel(U_pv.ucontra[E], ex["pv"][0][E]), rel(U_pv.vcontra[E], ex["pv"][1][E]),
+                        rel(U_pv.ucontra[W], ex["pv"][0][W]), rel(U_pv.vcontra[W], ex["pv"][1][W]),
+                        rel(U_pu.ucontra[Nn], ex["pu"][0][Nn]), rel(U_pu.vcontra[Nn], ex["pu"][1][Nn]),
+                        rel(U_pu.ucontra[S], ex["pu"][0][S]), rel(U_pu.vcontra[S], ex["pu"][1][S])]
+                out["err_N%d_vf%d_deg%d" % (N, vf, degree)] = np.array(errs)
+    save("vfinterp_experiment.npz", **out)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "small"
     if what in ("small", "all"):
@@ -320,6 +361,8 @@ if __name__ == "__main__":
         make_regrid()
     if what in ("recon", "all"):
         make_recon()
+    if what in ("vfinterp", "all"):
+        make_vfinterp()
     if what in ("big384", "all"):
         make_big(384, 1, "default", [1, 10, 100, 1000, 4800], 8)
     if what in ("big768", "all"):

@@ -226,3 +226,23 @@ def test_split_step_cta_sets(ns, nch):
     for blk in a:
         strip, chunk = (blk // 6) % ns, blk // (6 * ns)
         assert 1 <= strip <= ns - 2 and 1 <= chunk <= nch - 2
+
+
+@pytest.mark.parametrize("vf", [1, 2, 3, 4])
+def test_host_exact_contravariant_wind_matches_oracle_bits(vf):
+    """the analytic wind of the ghost-edge experiment (host numpy of the product) against the oracle's."""
+    import types
+    from oracle.grid import LeanGrid
+    from oracle import wind as owind
+    from pycs_b200.advection_ic import velocity_adv
+    from pycs_b200.sphgeo import latlon_to_contravariant
+    g, og = cs_datastruct.cubed_sphere(16), LeanGrid(16)
+    sim = types.SimpleNamespace(vf=vf, ic=1)
+    for pos in ("pu", "pv"):
+        pts = getattr(g, pos)
+        ulon, vlat = velocity_adv(pts.lon, pts.lat, 0.0, sim)
+        u, v = latlon_to_contravariant(ulon, vlat, *[getattr(g, n + pos) for n in (
+            "prod_ex_elon_", "prod_ex_elat_", "prod_ey_elon_", "prod_ey_elat_", "determinant_ll2contra_")])
+        opts = getattr(og, pos)
+        ou, ov = owind.ll2contra(*owind.velocity_adv(opts.lon, opts.lat, 0.0, vf), og, pos)
+        assert np.array_equal(u, ou) and np.array_equal(v, ov), pos

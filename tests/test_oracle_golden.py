@@ -159,3 +159,30 @@ def test_reconstruction_experiment_errors(N):
                 e = np.maximum(e, abs(q_pv[i0:iend, i0 + 1:iend + 1, :] - sim.py.q_R[I]))
                 got = np.array(ost.compute_errors(e, 0 * e))
                 assert np.array_equal(got, ref["err_N%d_ic%d_et%d_recon%d" % (N, ic, et, recon)]), (ic, et, recon)
+
+
+@pytest.mark.skipif(not have("vfinterp_experiment.npz"), reason="fixture not generated")
+@pytest.mark.parametrize("N", [16, 32])
+def test_ghost_edge_wind_experiment_errors(N):
+    """src/interpolation_test.py:354-470 with the oracle's wind ghost fill: the eight relative errors per
+    wind field and interpolation degree, bit for bit."""
+    from oracle import wind as owind
+    ref = load("vfinterp_experiment.npz")
+    g = LeanGrid(N)
+    i0, iend = g.i0, g.iend
+    regions = (("pv", np.s_[iend:, i0 - 1:iend + 2, :]), ("pv", np.s_[:i0, i0 - 1:iend + 2, :]),
+               ("pu", np.s_[i0 - 1:iend + 2, iend:, :]), ("pu", np.s_[i0 - 1:iend + 2, :i0, :]))
+    for vf in (1, 2, 3):
+        exact = {}
+        for pos in ("pu", "pv"):
+            pts = getattr(g, pos)
+            ulon, vlat = owind.velocity_adv(pts.lon, pts.lat, 0.0, vf)
+            exact[pos] = owind.ll2contra(ulon, vlat, g, pos)
+        for degree in (0, 1, 2, 3, 4):
+            sim = ost.Simulation(g, 0.01, 5, 1, vf, 1, 3, 2, 1, 3, 1, 1)
+            sim.degree = degree
+            ost.init_vars_adv(g, sim)
+            got = {"pu": (sim.U_pu.ucontra, sim.U_pu.vcontra), "pv": (sim.U_pv.ucontra, sim.U_pv.vcontra)}
+            errs = [np.amax(abs(got[pos][c][R] - exact[pos][c][R])) / np.amax(abs(exact[pos][c][R]))
+                    for pos, R in regions for c in (0, 1)]
+            assert np.array_equal(np.array(errs), ref["err_N%d_vf%d_deg%d" % (N, vf, degree)]), (vf, degree)

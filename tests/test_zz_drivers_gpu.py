@@ -96,3 +96,25 @@ def test_reconstruction_experiment_driver(mods):
                 for r, recon in enumerate((3, 4)):
                     want = ref["err_N%d_ic%d_et%d_recon%d" % (N, ic, et, recon)]
                     assert np.max(np.abs(err[i, e, r] - want) / want) <= 1e-10, (N, ic, et, recon, err[i, e, r], want)
+
+
+@pytest.mark.skipif(not have("vfinterp_experiment.npz"), reason="fixture not generated")
+@pytest.mark.parametrize("vf", [1, 2, 3])
+def test_ghost_edge_wind_experiment_driver(mods, vf):
+    """interpolation_test tc 3 (src/interpolation_test.py:354-470) on the device wind ghost fill: the eight
+    relative errors per degree at N = 16 against the reference's numbers."""
+    from pycs_b200 import advection_vars
+    from pycs_b200.interpolation_test import ghost_edge_wind_errors, error_analysis_vf_interpolation_ghost_cells
+    ref = load("vfinterp_experiment.npz")
+    g = mods.cs_datastruct.cubed_sphere(16)
+    for degree in (0, 1, 2, 3, 4):
+        sim = mods.advection_ic.adv_simulation_par(g, 0.01, 5.0, 1, vf, 1, 3, 2, 1, 3, 1, 1)
+        sim.degree = degree
+        advection_vars.init_vars_adv(g, sim)
+        got = ghost_edge_wind_errors(g, sim)
+        want = ref["err_N16_vf%d_deg%d" % (vf, degree)]
+        assert np.max(np.abs(got - want) / want) <= 1e-9, (vf, degree, got, want)
+        sim.dev.close()
+    Nc, err = error_analysis_vf_interpolation_ghost_cells(vf, "mercator", "gnomonic_equiangular", False, False,
+                                                          Ntest=2, degrees=(3,))
+    assert abs(err[1, 0] - np.max(ref["err_N32_vf%d_deg3" % vf])) <= 1e-9 * err[1, 0]
