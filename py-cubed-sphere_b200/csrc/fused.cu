@@ -723,7 +723,7 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
   fs.npart = nb;
   if (fs.split == 0) {
     const char* es = getenv("PYCS_SPLIT");
-    fs.split = (es && atoi(es) && fs.impl == 4 && fs.tb == 160 && fs.pf == 2 && fs.minb == 34 && !h->mg) ? 1 : -1;
+    fs.split = (es && atoi(es) && fs.impl == 4 && fs.tb == 160 && fs.pf == 2 && fs.minb == 34) ? 1 : -1;
     if (fs.split == 1) {
       std::vector<int> in(nb), bd(nb);
       fs.n_i = pycs_split_sets(fs.nstrips, fs.nchunks, in.data(), bd.data());
@@ -735,9 +735,11 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
         CK(cudaMalloc(&fs.map_b, sizeof(int) * fs.n_b));
         CK(cudaMemcpy(fs.map_i, in.data(), sizeof(int) * fs.n_i, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(fs.map_b, bd.data(), sizeof(int) * fs.n_b, cudaMemcpyHostToDevice));
-        CK(cudaStreamCreateWithFlags(&fs.s2, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&fs.e_fork, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&fs.e_join, cudaEventDisableTiming));
+        if (!fs.s2) {
+          CK(cudaStreamCreateWithFlags(&fs.s2, cudaStreamNonBlocking));
+          CK(cudaEventCreateWithFlags(&fs.e_fork, cudaEventDisableTiming));
+          CK(cudaEventCreateWithFlags(&fs.e_join, cudaEventDisableTiming));
+        }
       }
     }
   }
@@ -850,7 +852,7 @@ void k_fused_reset_grid(pycs_handle h) {
   if (fs.map_i) cudaFree(fs.map_i);      // CTA sets of the split step belong to the old grid
   if (fs.map_b) cudaFree(fs.map_b);
   fs.map_i = fs.map_b = nullptr;
-  if (fs.split == 1) fs.split = -1;      // row slabs (several GPUs): no split step
+  if (fs.split == 1) fs.split = 0;       // rebuilt for the new grid (row slabs of several GPUs) by fused_setup
 }
 
 // geometry was re-uploaded: 1/sqrtg and the t = 0 winds must be rebuilt
@@ -933,7 +935,8 @@ static int ensure_gs(pycs_handle h, FusedState& fs) {
 
 // map / nmap / st: one launch of a split step (CTA subset on stream st); default: the whole grid on the handle's stream
 static int launch_step_kernel(pycs_handle h, FusedState& fs, const double* qcur, double* qnext, int pend,
-                              int mask, double ws, const int* map = nullptr, int nmap = 0, cudaStream_t st = nullptr) {
+                              int mask, double ws, const int* map = nullptr, int nmap = 0, cudaStream_t st = nullptr,
+                              bool wait_flags = false) {
   if (!st) st = h->stream;
   const Geo& g = h->g;
   double *sgc, *sgu, *sgv, *ua, *va, *um, *vm;
@@ -961,10 +964,18 @@ static int launch_step_kernel(pycs_handle h, FusedState& fs, const double* qcur,
   a.gf.enable = 0;
   a.blk_map = map;
   a.nblk_total = fs.npart;
+  a.wait_flags = nullptr;
+  a.wait_world = 0;
+  a.wait_epoch = 0;
   if (map) {                      // the kernel forms the projection coefficient itself
-    a.gf.sums = h->red_out + 9;
-    a.gf.nsums = 1;
+    a.gf.sums = h->mg ? k_mg_sums(h) : h->red_out + 9;
+    a.gf.nsums = h->mg ? h->mg->world : 1;
     a.gf.inv_a2 = pend ? 1.0 / h->a2 : 0.0;
+    if (h->mg && wait_flags) {    // interior launch on several GPUs: the peers' sums arrive with their flags
+      a.wait_flags = h->mg->sync->flag;
+      a.wait_world = h->mg->world;
+      a.wait_epoch = h->mg->epoch;
+    }
   }
   if (fs.impl == 4 && fs.ghost_fused && !h->mg) {
     a.gf.enable = 1;
@@ -1088,21 +1099,25 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   int pend = fs.pending;
   const bool ghost_in_kernel = fs.impl == 4 && fs.ghost_fused && !h->mg;
   // split step: no wind kernel may sit between the ghost fill and the step kernel
-  const bool split = fs.split == 1 && !ghost_in_kernel && !fs.pdl && !h->mg && (h->prm.vf < 2 || separable);
+  const bool split = fs.split == 1 && !ghost_in_kernel && !fs.pdl && !(h->mg && fs.mg_fused) &&
+                     (h->prm.vf < 2 || separable);
   if (split) {
     const int mask = separable ? 2 : ((h->prm.dp == 2) ? 1 : 0);
     const double ws = separable ? cos(3.141592653589793 * ((double)(k - 1) * g.dt) / 5.0) : 1.0;
     const int nbx = (g.N + 127) / 128;
     CK(cudaEventRecord(fs.e_fork, h->stream));            // everything before this step
     CK(cudaStreamWaitEvent(fs.s2, fs.e_fork, 0));
+    mark();                                               // (four marks per step: the ghost fill has no interval of its own here)
     dg_fill_fused_kernel<<<nbx * 4 * 24 + 3, 128, 0, fs.s2>>>(g, h->maps, qcur, h->kminE, h->wE, h->order, fs.gs, sums,
                                                              pend ? nsums : 0, pend ? 1.0 / h->a2 : 0.0, h->red_out + 8,
-                                                             nullptr, 0, 0, nbx, nullptr);
+                                                             mgflags, mgworld, mgepoch, nbx, nullptr);
     CKL(h);
     TRY(launch_step_kernel(h, fs, qcur, qnext, pend, mask, ws, fs.map_b, fs.n_b, fs.s2));     // needs the ghost cells
     CK(cudaEventRecord(fs.e_join, fs.s2));
-    TRY(launch_step_kernel(h, fs, qcur, qnext, pend, mask, ws, fs.map_i, fs.n_i, h->stream)); // reads no ghost cell
+    TRY(launch_step_kernel(h, fs, qcur, qnext, pend, mask, ws, fs.map_i, fs.n_i, h->stream, true)); // reads no ghost cell
     CK(cudaStreamWaitEvent(h->stream, fs.e_join, 0));
+    mark();
+    if (h->mg) TRY(k_mg_exchange(h, qnext, h->red_out + 9, 1));   // after both launches: boundary cells + the sum
     mark();
     h->last_step_kernel_launches++;
     h->qcur ^= 1;

@@ -125,7 +125,18 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   double corr = 0.0;
   if (MG == 2) {
-    if (a.apply_corr) {         // same expression as the ghost-fill kernel: same bits
+    if (a.wait_flags) {         // same wait as dg_fill_fused_kernel (csrc/fused.cu)
+      if (tid < a.wait_world) {
+        const volatile long long* f = a.wait_flags + tid;
+        for (unsigned n = 0; *f < a.wait_epoch; ++n) {
+          if (n > (1u << 26)) __trap();          // a lost peer must not hang the GPU
+          __nanosleep(40);
+        }
+        __threadfence_system();
+      }
+      __syncthreads();
+    }
+    if (a.apply_corr) {         // single GPU: same expression as the ghost-fill kernel, same bits
       double sm = 0.0;
       for (int k = 0; k < a.gf.nsums; ++k) sm += a.gf.sums[k];
       corr = -sm * a.gf.inv_a2;

@@ -52,6 +52,11 @@ struct FusedArgs {
   // share part[], the ticket counter and nblk_total, so the later one totals the MF-PR sum.
   const int* blk_map;         // nullptr: one launch over the whole grid
   int nblk_total;
+  // several GPUs: the peers' MF-PR sums (gf.sums) are valid once every flag has reached wait_epoch; the
+  // interior launch waits for them itself (the boundary launch follows the ghost fill, which has waited)
+  const long long* wait_flags;
+  int wait_world;
+  long long wait_epoch;
 };
 
 // CTA sets of a split step: strips x chunks x 6 panels, CTA = (chunk * nstrips + strip) * 6 + panel.

@@ -35,9 +35,12 @@ def main():
     worst = 0.0
     # 4 = default kernel + exchange kernel; 4f = same kernel with the exchange fused into it
     # (PYCS_MG_FUSED=1); 2, 3 = older kernels (separate exchange launch)
-    for impl in ("4", "4f", "2", "3"):
+    # 4x (only with PYCS_TEST_SPLIT=1: not yet run on GPUs) = split step, interior CTAs beside ghost fill + boundary CTAs
+    impls = ("4", "4f", "2", "3") + (("4x",) if os.environ.get("PYCS_TEST_SPLIT") else ())
+    for impl in impls:
         os.environ["PYCS_FUSED_IMPL"] = impl[0]
         os.environ["PYCS_MG_FUSED"] = "1" if impl.endswith("f") else "0"
+        os.environ["PYCS_SPLIT"] = "1" if impl.endswith("x") else "0"
         for N, vf, name, calls in cases:
             g = cs_datastruct.cubed_sphere(N)
             a = make(g, vf, TUPLES[name], local)
