@@ -95,6 +95,25 @@ static int wind_sync(pycs_handle h) {
   return k_wind_catch_up(h, k);
 }
 
+// The fused step leaves Q in whichever of the two ping-pong buffers it wrote last, with the MF-PR
+// projection term of the last step still pending and a stale ghost ring (fused.cu).  pycs_run does
+// not pay for that at the end of every call (the reference's loop has no per-run epilogue either,
+// src/advection_sphere.py:45-57): every other entry point that reads or writes Q calls this first.
+static int normalize_q(pycs_handle h) {
+  TRY(k_fused_flush(h));
+  if (h->qcur == 1) {
+    double* t = h->f[PYCS_F_Q];
+    h->f[PYCS_F_Q] = h->f[PYCS_F_Q_NEXT];
+    h->f[PYCS_F_Q_NEXT] = t;
+    h->qcur = 0;
+  }
+  return 0;
+}
+static int state_sync(pycs_handle h) {
+  TRY(wind_sync(h));
+  return normalize_q(h);
+}
+
 // --------------------------------------------------------------------------- lifetime
 extern "C" const char* pycs_last_error(void) { return g_err.c_str(); }
 
@@ -134,6 +153,8 @@ extern "C" int pycs_create(const pycs_params* prm, pycs_handle* out) {
   h->row_lo = g.lo;
   h->row_hi = g.hi;
   h->wind_stale_k = -1;
+  h->no_separable = getenv("PYCS_NO_SEPARABLE") ? 1 : 0;     // environment knobs are read once per handle
+  h->dg_two_phase = getenv("PYCS_DG_TWO_PHASE") ? 1 : 0;
   cudaDeviceProp dp;
   CK(cudaGetDeviceProperties(&dp, prm->device));
   h->sm_count = dp.multiProcessorCount;
@@ -183,7 +204,7 @@ extern "C" int pycs_device_info(pycs_handle h, int32_t* sm_count, char* name, in
 
 extern "C" int pycs_synchronize(pycs_handle h) {
   CK(cudaStreamSynchronize(h->stream));
-  return 0;
+  return k_mg_check(h);
 }
 
 extern "C" int pycs_set_dt(pycs_handle h, double dt) {
@@ -218,9 +239,10 @@ extern "C" int pycs_upload_field(pycs_handle h, int32_t field, const double* hos
   TRY(wind_sync(h));
   if (!host) return arg_fail("null host pointer");
   CK(cudaSetDevice(h->device));
+  if (field == PYCS_F_Q) TRY(k_fused_discard(h));   // a new state: nothing of the old one is pending
+  else if (field == PYCS_F_Q_NEXT) TRY(normalize_q(h));
   TRY(upload_from(h, field, host, false));
   CK(cudaStreamSynchronize(h->stream));
-  if (field == PYCS_F_Q) h->qcur = 0;
   if (field == PYCS_F_SQRTG_PC) h->a2_valid = 0;
   if (field >= PYCS_F_SQRTG_PC && field <= PYCS_F_PV_LAT) k_fused_invalidate(h);
   return 0;
@@ -241,16 +263,16 @@ static int download_to(pycs_handle h, int field, double* host) {
 }
 
 extern "C" int pycs_download_field(pycs_handle h, int32_t field, double* host) {
-  TRY(wind_sync(h));
+  TRY(state_sync(h));
   if (!host) return arg_fail("null host pointer");
   CK(cudaSetDevice(h->device));
   TRY(download_to(h, field, host));
   CK(cudaStreamSynchronize(h->stream));
-  return 0;
+  return k_mg_check(h);
 }
 
 extern "C" int pycs_copy_field(pycs_handle h, int32_t dst, int32_t src) {
-  TRY(wind_sync(h));
+  TRY(state_sync(h));
   double *d, *s;
   TRY(pycs_field_ptr(h, dst, &d));
   TRY(pycs_field_ptr(h, src, &s));
@@ -261,7 +283,7 @@ extern "C" int pycs_copy_field(pycs_handle h, int32_t dst, int32_t src) {
 }
 
 extern "C" int pycs_fill_field(pycs_handle h, int32_t field, double value) {
-  TRY(wind_sync(h));
+  TRY(state_sync(h));
   double* d;
   TRY(pycs_field_ptr(h, field, &d));
   long long n = (long long)(pycs_field_single_panel(field) ? 1 : 6) * h->g.ps;
@@ -274,6 +296,7 @@ extern "C" int pycs_upload_lagrange(pycs_handle h, int32_t degree, const int32_t
                                     const double* weights_east) {
   if (degree < 0 || degree > 7 || !kmin_east || !weights_east) return arg_fail("bad Lagrange table");
   CK(cudaSetDevice(h->device));
+  TRY(normalize_q(h));                   // a pending projection term was defined with the old tables' ghost(sqrtg)
   int order = degree + 1, P = h->g.P;
   // validate the stencil range here: the kernels index neighbour strips with it
   for (int k = 0; k < 4 * P; ++k)
@@ -288,12 +311,14 @@ extern "C" int pycs_upload_lagrange(pycs_handle h, int32_t degree, const int32_t
   CK(cudaMemcpy(h->wE, weights_east, sizeof(double) * 4 * P * order, cudaMemcpyHostToDevice));
   h->degree = degree;
   h->order = order;
+  k_fused_invalidate_ghost_metric(h);    // ghost(sqrtg) was filled with the old tables
   return 0;
 }
 
 // --------------------------------------------------------------------------- halo API
 extern "C" int pycs_halo_gather(pycs_handle h, int32_t fx, int32_t fy, double* east, double* west,
                                 double* north, double* south) {
+  TRY(normalize_q(h));
   double *x, *y;
   TRY(pycs_field_ptr(h, fx, &x));
   TRY(pycs_field_ptr(h, fy, &y));
@@ -310,13 +335,15 @@ extern "C" int pycs_halo_gather(pycs_handle h, int32_t fx, int32_t fy, double* e
 }
 
 extern "C" int pycs_halo_fill_dg(pycs_handle h, int32_t field) {
+  TRY(normalize_q(h));
   double* q;
   TRY(pycs_field_ptr(h, field, &q));
-  if (getenv("PYCS_DG_TWO_PHASE")) return k_dg_fill(h, q);     // the reference's two phases as two launches
+  if (h->dg_two_phase) return k_dg_fill(h, q);     // the reference's two phases as two launches
   return k_dg_fill_single(h, q);
 }
 
 extern "C" int pycs_halo_fill_copy(pycs_handle h, int32_t fx, int32_t fy) {
+  TRY(normalize_q(h));
   double *x, *y;
   TRY(pycs_field_ptr(h, fx, &x));
   TRY(pycs_field_ptr(h, fy, &y));
@@ -349,6 +376,7 @@ extern "C" int pycs_cfl(pycs_handle h, int32_t dst, int32_t src, int32_t dir) {
 }
 
 extern "C" int pycs_ppm_reconstruction(pycs_handle h, int32_t fx, int32_t fy) {
+  TRY(normalize_q(h));
   double *x, *y;
   TRY(pycs_field_ptr(h, fx, &x));
   TRY(pycs_field_ptr(h, fy, &y));
@@ -358,7 +386,7 @@ extern "C" int pycs_ppm_reconstruction(pycs_handle h, int32_t fx, int32_t fy) {
 }
 
 extern "C" int pycs_numerical_flux(pycs_handle h, int32_t fx, int32_t fy) {
-  TRY(wind_sync(h));
+  TRY(state_sync(h));
   double *x, *y;
   TRY(pycs_field_ptr(h, fx, &x));
   TRY(pycs_field_ptr(h, fy, &y));
@@ -377,7 +405,7 @@ extern "C" int pycs_average_flux_cube_edges(pycs_handle h) { return k_average_fl
 
 // divergence, operator by operator (src/discrete_operators.py:18-101)
 extern "C" int pycs_divergence(pycs_handle h) {
-  TRY(wind_sync(h));
+  TRY(state_sync(h));
   double *Q, *gQ, *cx, *cy, *ua, *va;
   TRY(pycs_field_ptr(h, PYCS_F_Q, &Q));
   TRY(pycs_field_ptr(h, PYCS_F_GQ, &gQ));
@@ -398,18 +426,6 @@ extern "C" int pycs_divergence(pycs_handle h) {
   TRY(k_flux_diff(h, 0));                                       // :89-90
   TRY(k_flux_diff(h, 1));
   return k_div_and_fix(h);                                      // :95-101
-}
-
-// make PYCS_F_Q the current state if the fused path left it in Q_NEXT
-static int normalize_q(pycs_handle h) {
-  TRY(k_fused_flush(h));
-  if (h->qcur == 1) {
-    double* t = h->f[PYCS_F_Q];
-    h->f[PYCS_F_Q] = h->f[PYCS_F_Q_NEXT];
-    h->f[PYCS_F_Q_NEXT] = t;
-    h->qcur = 0;
-  }
-  return 0;
 }
 
 extern "C" int pycs_adv_time_step(pycs_handle h, int64_t k, double t) {
@@ -439,27 +455,32 @@ extern "C" int pycs_convert_wind_interior(pycs_handle h) {
   return k_wind_interior(h, 0.0, 1, 0);
 }
 
+// Is the wind of this handle U(0) * f(t) with the step able to apply f(t) itself?  Wind field 3 with RK1:
+// U(t) = U(0) cos(pi t / T) exactly (src/advection_ic.py:301-305); the fused step then scales a private
+// copy of the t = 0 contravariant winds in-kernel and no wind kernel runs.
+static bool separable_wind(pycs_handle h) { return h->prm.vf == 3 && h->prm.dp == 1 && !h->no_separable; }
+
 static int run_steps(pycs_handle h, int64_t k0, int64_t nsteps, int fused) {
   CK(cudaSetDevice(h->device));
-  TRY(wind_sync(h));
   if (fused && !k_fused_supported(h)) return arg_fail("no fused step kernel for this scheme tuple");
   if (h->mg && !fused) return arg_fail("multi-GPU handles run the fused step only");
-  // wind field 3 + RK1 is U(0)*cos(pi t/T): all but the last step of a fused run scale
-  // the t = 0 winds inside the step kernel; the last step runs the wind kernels after a
-  // resync so that U_pu / U_pv / U_pc end up as the reference leaves them.
-  bool separable = fused && h->prm.vf == 3 && h->prm.dp == 1 && nsteps >= 2 && !getenv("PYCS_NO_SEPARABLE");
+  if (nsteps <= 0) return 0;
+  // Separable wind: the steps never touch U_pu / U_pv / U_pc, so those arrays are left behind and
+  // caught up lazily (wind_sync) by whatever reads them next -- like pycs_adv_time_step_host, and
+  // like the reference's loop, a run has no epilogue.  Stale arrays from an earlier run stay stale.
+  const bool separable = fused && separable_wind(h);
+  if (!separable) TRY(wind_sync(h));
   for (int64_t k = k0 + 1; k <= k0 + nsteps; ++k) {
-    double t = (double)k * h->g.dt;                             // t = k*dt, src/advection_sphere.py:47
+    const double t = (double)k * h->g.dt;                       // t = k*dt, src/advection_sphere.py:47
     if (fused) {
-      bool last = (k == k0 + nsteps);
-      if (separable && last) TRY(k_wind_resync(h, k - 1));
-      TRY(k_fused_step(h, k, t, (separable && !last) ? 1 : 0));
+      TRY(k_fused_step(h, k, t, separable ? 1 : 0));
     } else {
       TRY(pycs_adv_time_step(h, k, t));
       TRY(k_update_adv(h, t));
     }
   }
-  if (fused) TRY(normalize_q(h));
+  if (separable) h->wind_stale_k = k0 + nsteps;
+  if (fused) k_fused_profile_report(h);
   return 0;
 }
 
@@ -481,7 +502,7 @@ extern "C" int pycs_run_timed(pycs_handle h, int64_t k0, int64_t nsteps, int32_t
   CK(cudaEventSynchronize(h->ev1));
   if (r) return r;
   CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
-  return 0;
+  return k_mg_check(h);
 }
 
 extern "C" int pycs_time_step_kernel(pycs_handle h, int32_t reps, int32_t separable, float* ms) {
@@ -514,7 +535,7 @@ extern "C" int pycs_adv_time_step_host(pycs_handle h, double* Q, int64_t k, doub
     if (!k_fused_supported(h)) return arg_fail("no fused step kernel for this scheme tuple");
     // wind field 3 + RK1 is U(0)*cos(pi t/T): the step scales the t = 0 winds in-kernel and the
     // exposed wind arrays are caught up lazily (wind_sync) when something reads them
-    const bool separable = h->prm.vf == 3 && h->prm.dp == 1 && !getenv("PYCS_NO_SEPARABLE") &&
+    const bool separable = separable_wind(h) &&
                            fabs(t - (double)k * h->g.dt) <= 1e-12 * (1.0 + fabs(t));   // t = k*dt as in adv_sphere
     if (separable) {
       TRY(k_fused_step(h, k, t, 1));
@@ -579,7 +600,16 @@ extern "C" int pycs_split_plan(int32_t nstrips, int32_t nchunks, int32_t* interi
 }
 
 // --------------------------------------------------------------------------- diagnostics
+// The whole-sphere reductions need every row: a sharded handle holds only its slab (the other rows are stale).
+static int whole_sphere_only(pycs_handle h, const char* what) {
+  if (!h->mg) return 0;
+  g_err = std::string(what) + ": this handle is sharded (pycs_mgpu_init) and holds only rows [row_lo, row_hi); "
+          "gather the field (parallel.gather_field) and reduce on an unsharded handle or on the host";
+  return PYCS_ERR_STATE;
+}
+
 extern "C" int pycs_errors(pycs_handle h, const double* qexact_interior, double* out3) {
+  TRY(whole_sphere_only(h, "pycs_errors"));
   // stage the (N,N,6) exact field into the interior of USER_B
   const Geo& g = h->g;
   TRY(normalize_q(h));
@@ -594,6 +624,7 @@ extern "C" int pycs_errors(pycs_handle h, const double* qexact_interior, double*
 }
 
 extern "C" int pycs_mass(pycs_handle h, double* mass) {
+  TRY(whole_sphere_only(h, "pycs_mass"));
   TRY(normalize_q(h));
   return k_mass(h, mass);
 }

@@ -427,7 +427,8 @@ __global__ void dg_fill_fused_kernel(Geo g, HaloMaps maps, double* __restrict__ 
                                      const double* __restrict__ wE, int order, const double* __restrict__ gs,
                                      const double* __restrict__ part, int npart, double inv_a2,
                                      double* __restrict__ corr_out, const long long* __restrict__ flags, int world,
-                                     long long epoch, int nbx, const double* __restrict__ corr_in) {
+                                     long long epoch, int nbx, const double* __restrict__ corr_in, int* mg_err,
+                                     unsigned long long mg_timeout_ns) {
   __shared__ double sh[32];
   // programmatic dependent launch (no-ops otherwise): this grid may start while the previous
   // step kernel drains; nothing of it is read before this point
@@ -435,11 +436,7 @@ __global__ void dg_fill_fused_kernel(Geo g, HaloMaps maps, double* __restrict__ 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (flags) {
     if (threadIdx.x < world) {
-      const volatile long long* f = flags + threadIdx.x;
-      for (unsigned n = 0; *f < epoch; ++n) {
-        if (n > (1u << 26)) __trap();          // a lost peer must not hang the GPU
-        __nanosleep(40);
-      }
+      mg_wait_flag(flags + threadIdx.x, epoch, mg_err, mg_timeout_ns);     // bounded, see mgpu.cuh
       __threadfence_system();
     }
     __syncthreads();
@@ -750,34 +747,55 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
   return 0;
 }
 
+// PYCS_STEP_PROFILE: per-kernel device time of the run that just ended
+void k_fused_profile_report(pycs_handle h) {
+  auto it = g_fused.find(h);
+  if (it == g_fused.end()) return;
+  FusedState& fs = it->second;
+  if (fs.prof <= 0 || fs.ev.size() < 8) return;
+  cudaStreamSynchronize(h->stream);
+  const size_t ns = fs.ev.size() / 4, skip = ns > 8 ? 4 : 0;
+  double t[4] = {0, 0, 0, 0};
+  for (size_t k = skip; k < ns; ++k) {
+    float ms;
+    for (int j = 0; j < 3; ++j) {
+      cudaEventElapsedTime(&ms, fs.ev[4 * k + j], fs.ev[4 * k + j + 1]);
+      t[j] += ms;
+    }
+    if (k + 1 < ns) {
+      cudaEventElapsedTime(&ms, fs.ev[4 * k + 3], fs.ev[4 * k + 4]);
+      t[3] += ms;
+    }
+  }
+  const double n = (double)(ns - skip);
+  fprintf(stderr, "[pycs step profile] rank %d: %zu steps; ghost fill (+flag wait) %.2f us, winds+step kernel %.2f us, "
+                  "exchange %.2f us, gap to next step %.2f us\n",
+          h->mg ? h->mg->rank : 0, ns - skip, 1e3 * t[0] / n, 1e3 * t[1] / n, 1e3 * t[2] / n, 1e3 * t[3] / n);
+  for (auto e : fs.ev) cudaEventDestroy(e);
+  fs.ev.clear();
+}
+
+// A new Q was uploaded into PYCS_F_Q: whatever the fused path had pending belonged to the old state.
+int k_fused_discard(pycs_handle h) {
+  if (h->qcur == 1) {
+    double* t = h->f[PYCS_F_Q];
+    h->f[PYCS_F_Q] = h->f[PYCS_F_Q_NEXT];
+    h->f[PYCS_F_Q_NEXT] = t;
+    h->qcur = 0;
+  }
+  auto it = g_fused.find(h);
+  if (it == g_fused.end()) return 0;
+  it->second.pending = 0;
+  it->second.ring_pending = 0;
+  return 0;
+}
+
 // apply the pending projection term to the current Q so that every other code
 // path (download, operator kernels, diagnostics) sees the reference's Q
 int k_fused_flush(pycs_handle h) {
   auto it = g_fused.find(h);
   if (it == g_fused.end()) return 0;
   FusedState& fs = it->second;
-  if (fs.prof > 0 && fs.ev.size() >= 8) {      // PYCS_STEP_PROFILE: per-kernel device time of this run
-    cudaStreamSynchronize(h->stream);
-    const size_t ns = fs.ev.size() / 4, skip = ns > 8 ? 4 : 0;
-    double t[4] = {0, 0, 0, 0};
-    for (size_t k = skip; k < ns; ++k) {
-      float ms;
-      for (int j = 0; j < 3; ++j) {
-        cudaEventElapsedTime(&ms, fs.ev[4 * k + j], fs.ev[4 * k + j + 1]);
-        t[j] += ms;
-      }
-      if (k + 1 < ns) {
-        cudaEventElapsedTime(&ms, fs.ev[4 * k + 3], fs.ev[4 * k + 4]);
-        t[3] += ms;
-      }
-    }
-    const double n = (double)(ns - skip);
-    fprintf(stderr, "[pycs step profile] rank %d: %zu steps; ghost fill (+flag wait) %.2f us, winds+step kernel %.2f us, "
-                    "exchange %.2f us, gap to next step %.2f us\n",
-            h->mg ? h->mg->rank : 0, ns - skip, 1e3 * t[0] / n, 1e3 * t[1] / n, 1e3 * t[2] / n, 1e3 * t[3] / n);
-    for (auto e : fs.ev) cudaEventDestroy(e);
-    fs.ev.clear();
-  }
   const Geo& g = h->g;
   double *sgc, *q, *qo;
   TRY(pycs_field_ptr(h, PYCS_F_SQRTG_PC, &sgc));
@@ -802,7 +820,7 @@ int k_fused_flush(pycs_handle h) {
     const int nbx = (g.N + 127) / 128;
     dg_fill_fused_kernel<<<nbx * 4 * 24 + 3, 128, 0, h->stream>>>(
         g, h->maps, qo, h->kminE, h->wE, h->order, fs.last_pend ? fs.gs : nullptr, nullptr, 0, 0.0, h->red_out + 10,
-        nullptr, 0, 0, nbx, fs.last_pend ? h->red_out + 8 : nullptr);
+        nullptr, 0, 0, nbx, fs.last_pend ? h->red_out + 8 : nullptr, nullptr, 0ull);
     CKL(h);
   }
   if (fs.ring_pending) {
@@ -840,7 +858,7 @@ int k_dg_fill_single(pycs_handle h, double* q) {
   }
   const int nbx = (h->g.N + 127) / 128;
   dg_fill_fused_kernel<<<nbx * 4 * 24 + 3, 128, 0, h->stream>>>(h->g, h->maps, q, h->kminE, h->wE, h->order, nullptr,
-                                                                nullptr, 0, 0.0, h->red_out + 10, nullptr, 0, 0, nbx, nullptr);
+                                                                nullptr, 0, 0.0, h->red_out + 10, nullptr, 0, 0, nbx, nullptr, nullptr, 0ull);
   CKL(h);
   return 0;
 }
@@ -864,6 +882,13 @@ void k_fused_invalidate(pycs_handle h) {
   if (it->second.gs) cudaFree(it->second.gs);
   it->second.gs = nullptr;
   it->second.base_valid = 0;
+}
+
+void k_fused_invalidate_ghost_metric(pycs_handle h) {
+  auto it = g_fused.find(h);
+  if (it == g_fused.end()) return;
+  if (it->second.gs) cudaFree(it->second.gs);
+  it->second.gs = nullptr;
 }
 
 // Separable wind (vf = 3, RK1): the step kernel scales the contravariant wind of t = 0
@@ -928,7 +953,7 @@ static int ensure_gs(pycs_handle h, FusedState& fs) {
   const int nbx = (g.N + 127) / 128;
   dg_fill_fused_kernel<<<nbx * 4 * 24 + 3, 128, 0, h->stream>>>(g, h->maps, fs.gs, h->kminE, h->wE, h->order, nullptr,
                                                                 nullptr, 0, 0.0, h->red_out + 10, nullptr, 0, 0, nbx,
-                                                                nullptr);
+                                                                nullptr, nullptr, 0ull);
   CKL(h);
   return 0;
 }
@@ -967,6 +992,8 @@ static int launch_step_kernel(pycs_handle h, FusedState& fs, const double* qcur,
   a.wait_flags = nullptr;
   a.wait_world = 0;
   a.wait_epoch = 0;
+  a.mg_err = nullptr;
+  a.mg_timeout_ns = 0;
   if (map) {                      // the kernel forms the projection coefficient itself
     a.gf.sums = h->mg ? k_mg_sums(h) : h->red_out + 9;
     a.gf.nsums = h->mg ? h->mg->world : 1;
@@ -975,6 +1002,8 @@ static int launch_step_kernel(pycs_handle h, FusedState& fs, const double* qcur,
       a.wait_flags = h->mg->sync->flag;
       a.wait_world = h->mg->world;
       a.wait_epoch = h->mg->epoch;
+      a.mg_err = &h->mg->sync->err;
+      a.mg_timeout_ns = h->mg->timeout_ns;
     }
   }
   if (fs.impl == 4 && fs.ghost_fused && !h->mg) {
@@ -1079,7 +1108,11 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   const long long* mgflags = nullptr;
   int mgworld = 0;
   long long mgepoch = 0;
-  if (h->mg) {                       // the wait is folded into the ghost-fill kernel
+  int* mgerr = nullptr;
+  unsigned long long mgtimeout = 0;
+  if (h->mg) {
+    mgerr = &h->mg->sync->err;
+    mgtimeout = h->mg->timeout_ns;                       // the wait is folded into the ghost-fill kernel
     sums = k_mg_sums(h);
     nsums = h->mg->world;
     mgflags = h->mg->sync->flag;
@@ -1103,14 +1136,14 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
                      (h->prm.vf < 2 || separable);
   if (split) {
     const int mask = separable ? 2 : ((h->prm.dp == 2) ? 1 : 0);
-    const double ws = separable ? cos(3.141592653589793 * ((double)(k - 1) * g.dt) / 5.0) : 1.0;
+    const double ws = separable ? cos(PYCS_PI * ((double)(k - 1) * g.dt) / PYCS_WIND_PERIOD) : 1.0;
     const int nbx = (g.N + 127) / 128;
     CK(cudaEventRecord(fs.e_fork, h->stream));            // everything before this step
     CK(cudaStreamWaitEvent(fs.s2, fs.e_fork, 0));
     mark();                                               // (four marks per step: the ghost fill has no interval of its own here)
     dg_fill_fused_kernel<<<nbx * 4 * 24 + 3, 128, 0, fs.s2>>>(g, h->maps, qcur, h->kminE, h->wE, h->order, fs.gs, sums,
                                                              pend ? nsums : 0, pend ? 1.0 / h->a2 : 0.0, h->red_out + 8,
-                                                             mgflags, mgworld, mgepoch, nbx, nullptr);
+                                                             mgflags, mgworld, mgepoch, nbx, nullptr, mgerr, mgtimeout);
     CKL(h);
     TRY(launch_step_kernel(h, fs, qcur, qnext, pend, mask, ws, fs.map_b, fs.n_b, fs.s2));     // needs the ghost cells
     CK(cudaEventRecord(fs.e_join, fs.s2));
@@ -1140,11 +1173,11 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
       cfg.numAttrs = 1;
       CK(cudaLaunchKernelEx(&cfg, dg_fill_fused_kernel, g, h->maps, qcur, (const int*)h->kminE, (const double*)h->wE,
                             h->order, (const double*)fs.gs, sums, pend ? nsums : 0, pend ? 1.0 / h->a2 : 0.0,
-                            h->red_out + 8, mgflags, mgworld, mgepoch, nbx, (const double*)nullptr));
+                            h->red_out + 8, mgflags, mgworld, mgepoch, nbx, (const double*)nullptr, mgerr, mgtimeout));
     } else {
       dg_fill_fused_kernel<<<nbx * 4 * 24 + 3, 128, 0, h->stream>>>(
           g, h->maps, qcur, h->kminE, h->wE, h->order, fs.gs, sums, pend ? nsums : 0, pend ? 1.0 / h->a2 : 0.0,
-          h->red_out + 8, mgflags, mgworld, mgepoch, nbx, nullptr);
+          h->red_out + 8, mgflags, mgworld, mgepoch, nbx, nullptr, mgerr, mgtimeout);
     }
     CKL(h);
   }
@@ -1156,7 +1189,7 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   }
   // 3. divergence + Q update
   int mask = separable ? 2 : ((h->prm.dp == 2) ? 1 : 0);    // RK1: averaged wind == instantaneous wind
-  double ws = separable ? cos(3.141592653589793 * ((double)(k - 1) * g.dt) / 5.0) : 1.0;
+  double ws = separable ? cos(PYCS_PI * ((double)(k - 1) * g.dt) / PYCS_WIND_PERIOD) : 1.0;
   TRY(launch_step_kernel(h, fs, qcur, qnext, pend, mask, ws));
   mark();
   if (h->mg && !(fs.impl == 4 && fs.mg_fused)) TRY(k_mg_exchange(h, qnext, h->red_out + 9, 1));

@@ -127,11 +127,7 @@ __global__ void __launch_bounds__(TB, MINB % 10) fused2b_kernel(FusedArgs a) {
   if (MG == 2) {
     if (a.wait_flags) {         // same wait as dg_fill_fused_kernel (csrc/fused.cu)
       if (tid < a.wait_world) {
-        const volatile long long* f = a.wait_flags + tid;
-        for (unsigned n = 0; *f < a.wait_epoch; ++n) {
-          if (n > (1u << 26)) __trap();          // a lost peer must not hang the GPU
-          __nanosleep(40);
-        }
+        mg_wait_flag(a.wait_flags + tid, a.wait_epoch, a.mg_err, a.mg_timeout_ns);   // bounded, see mgpu.cuh
         __threadfence_system();
       }
       __syncthreads();

@@ -57,6 +57,8 @@ struct FusedArgs {
   const long long* wait_flags;
   int wait_world;
   long long wait_epoch;
+  int* mg_err;                       // bounded wait: see mg_wait_flag (mgpu.cuh)
+  unsigned long long mg_timeout_ns;
 };
 
 // CTA sets of a split step: strips x chunks x 6 panels, CTA = (chunk * nstrips + strip) * 6 + panel.

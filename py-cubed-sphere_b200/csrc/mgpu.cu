@@ -14,6 +14,7 @@
 // Everything is stream ordered on the handle's stream: there is no host synchronisation in
 // the step loop.  Flags are epoch counters, so buffers (the two ping-pong Q arrays) are
 // reused without resets; a peer can be at most one step ahead.
+#include <cstdlib>
 #include <cstring>
 #include "pycs_common.cuh"
 #include "mgpu.cuh"
@@ -21,16 +22,10 @@
 
 namespace {
 
-__global__ void mg_wait_kernel(const MgSync* sync, int world, long long epoch) {
+__global__ void mg_wait_kernel(MgSync* sync, int world, long long epoch, unsigned long long timeout_ns) {
   const int d = threadIdx.x;
   if (d >= world) return;
-  const volatile long long* f = &sync->flag[d];
-  for (unsigned n = 0;; ++n) {
-    long long v = *f;
-    if (v >= epoch) break;
-    if (n > (1u << 26)) __trap();      // a lost peer must not hang the GPU
-    __nanosleep(40);
-  }
+  mg_wait_flag(&sync->flag[d], epoch, &sync->err, timeout_ns);
   __threadfence_system();
 }
 
@@ -130,6 +125,9 @@ int k_mg_init(pycs_handle h, int rank, int world, unsigned char* handles_out) {
   memset(mg, 0, sizeof *mg);
   mg->rank = rank;
   mg->world = world;
+  const char* et = getenv("PYCS_MG_TIMEOUT_S");
+  const double tsec = et ? atof(et) : 30.0;
+  mg->timeout_ns = (unsigned long long)((tsec > 0.001 ? tsec : 30.0) * 1e9);
   TRY(pycs_field_ptr(h, PYCS_F_Q, &mg->alloc[0]));
   TRY(pycs_field_ptr(h, PYCS_F_Q_NEXT, &mg->alloc[1]));
   CK(cudaMalloc(&mg->sync, sizeof(MgSync)));
@@ -199,8 +197,22 @@ void k_mg_release(pycs_handle h) {
 // wait until every rank has delivered the data of exchange `epoch` (stream ordered)
 int k_mg_wait(pycs_handle h) {
   MgpuState* mg = h->mg;
-  mg_wait_kernel<<<1, 32, 0, h->stream>>>(mg->sync, mg->world, mg->epoch);
+  mg_wait_kernel<<<1, 32, 0, h->stream>>>(mg->sync, mg->world, mg->epoch, mg->timeout_ns);
   CKL(h);
+  return 0;
+}
+
+// Host side of the bounded wait: call after the stream has been synchronised.
+int k_mg_check(pycs_handle h) {
+  MgpuState* mg = h->mg;
+  if (!mg) return 0;
+  int e = 0;
+  CK(cudaMemcpy(&e, &mg->sync->err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (e) {
+    pycs_set_error("multi-GPU step: a peer's flag did not arrive within PYCS_MG_TIMEOUT_S (a rank is gone or "
+                   "never entered the run); the state of this handle is undefined");
+    return PYCS_ERR_STATE;
+  }
   return 0;
 }
 

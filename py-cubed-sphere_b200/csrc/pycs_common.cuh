@@ -13,6 +13,10 @@
 
 #define PYCS_JOFF 12
 #define PYCS_NG 4          // ngl = ngr = 4  (src/cs_datastruct.py:225-231)
+// Period T of the Nair-Lauritzen wind fields 2 and 3: a literal of velocity_adv (src/advection_ic.py:295,302),
+// NOT the run length Tf.  wind.cu evaluates the fields with it, fused.cu the separable time factor cos(pi t / T).
+#define PYCS_WIND_PERIOD 5.0
+#define PYCS_PI 3.141592653589793
 
 struct Geo {
   int N, P, ld, lo, hi;    // lo = i0 = j0 = 4, hi = iend = jend = N + 4
@@ -71,6 +75,8 @@ struct pycs_handle_s {
   // >= 0: U_pu / U_pv / U_pc still hold an older step's winds; they must be brought to the state
   // after update_adv(t_k), k = wind_stale_k, before anything reads them (capi.cu: wind_sync)
   long long wind_stale_k;
+  int no_separable;     // PYCS_NO_SEPARABLE: refresh the wind of field 3 every step instead of scaling it in-kernel
+  int dg_two_phase;     // PYCS_DG_TWO_PHASE: pycs_halo_fill_dg as the reference's two phases (two launches)
   struct MgpuState* mg;   // multi-GPU state (mgpu.cu), null on a single GPU
 };
 
@@ -143,6 +149,9 @@ int k_fused_time_kernel(pycs_handle h, int reps, int separable, float* ms);
 int k_fused_grid_info(pycs_handle h, int* tb, int* rows, int* nblocks);
 int k_fused_kernel_name(pycs_handle h, char* out, int len);
 int k_fused_flush(pycs_handle h);
+int k_fused_discard(pycs_handle h);                 // a new Q was uploaded: drop what the fused path had pending
+void k_fused_profile_report(pycs_handle h);         // PYCS_STEP_PROFILE: print and reset the per-kernel device times
 void k_fused_release(pycs_handle h);
 void k_fused_invalidate(pycs_handle h);
+void k_fused_invalidate_ghost_metric(pycs_handle h); // the Lagrange tables changed
 // layout.cu (in capi.cu)

@@ -15,7 +15,7 @@
 namespace {
 
 constexpr int BX = 128;
-#define PI_ 3.141592653589793
+#define PI_ PYCS_PI
 
 struct Conv { const double *exlon, *exlat, *eylon, *eylat, *det; };
 
@@ -37,13 +37,13 @@ __device__ __forceinline__ void velocity_point(int vf, double t, double lo_, dou
     u = u0 * (cos(la) * cos(alpha) + sin(la) * cos(lo_) * sin(alpha));
     v = -u0 * sin(lo_) * sin(alpha);
   } else if (vf == 2) {
-    double T = 5.0, k = 2.0;
+    double T = PYCS_WIND_PERIOD, k = 2.0;
     double lonp = lo_ - 2 * pi * t / T;
     double s1 = sin((lonp + pi));
     u = k * (s1 * s1) * (sin(2. * la)) * (cos(pi * t / T)) + 2. * pi * cos(la) / T;
     v = k * (sin(2 * (lonp + pi))) * (cos(la)) * (cos(pi * t / T));
   } else if (vf == 3) {
-    double T = 5.0, k = 1.0;
+    double T = PYCS_WIND_PERIOD, k = 1.0;
     double s1 = sin((lo_ + pi) / 2.0), c1 = cos(la);
     u = -k * (s1 * s1) * (sin(2.0 * la)) * (c1 * c1) * (cos(pi * t / T));
     v = (k / 2.0) * (sin((lo_ + pi))) * (pow(c1, 3.0)) * (cos(pi * t / T));

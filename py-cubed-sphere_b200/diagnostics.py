@@ -5,8 +5,9 @@ from .device import DeviceArray
 
 
 def mass_computation(Q, cs_grid, total_mass0):
-    if not isinstance(Q, DeviceArray):
-        raise TypeError("mass_computation expects the device-resident simulation.Q")
+    from .device import F
+    if not isinstance(Q, DeviceArray) or Q.fid != F["Q"]:
+        raise TypeError("mass_computation expects the device-resident simulation.Q (the reduction runs on F_Q)")
     m = C.c_double()
     Q.dev.call("pycs_mass", C.byref(m))
     total_mass = m.value

@@ -29,14 +29,14 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
     cases = [(48, 1, "default", (1, 4, 7)), (130, 3, "default", (2, 9)), (130, 2, "AVLT-RK2-DG-PR", (3, 5)),
-             (64, 1, "PL07-RK1-DG-PR", (6,)), (384, 3, "default", (10,))]
+             (64, 1, "PL07-RK1-DG-PR", (6,)), (384, 3, "default", (10,)), (1536, 3, "default", (3, 4))]
     if len(sys.argv) > 1:
         cases = [(int(sys.argv[1]), 3, "default", (10,))]
     worst = 0.0
     # 4 = default kernel + exchange kernel; 4f = same kernel with the exchange fused into it
     # (PYCS_MG_FUSED=1); 2, 3 = older kernels (separate exchange launch)
-    # 4x (only with PYCS_TEST_SPLIT=1: not yet run on GPUs) = split step, interior CTAs beside ghost fill + boundary CTAs
-    impls = ("4", "4f", "2", "3") + (("4x",) if os.environ.get("PYCS_TEST_SPLIT") else ())
+    # 4x = split step, interior CTAs beside ghost fill + boundary CTAs
+    impls = ("4", "4x", "4f", "2", "3")
     for impl in impls:
         os.environ["PYCS_FUSED_IMPL"] = impl[0]
         os.environ["PYCS_MG_FUSED"] = "1" if impl.endswith("f") else "0"
