@@ -170,20 +170,24 @@ int pycs_synchronize(pycs_handle h);
 
 /* ---- multi-GPU (the reference is single process) ------------------------ */
 /* One process per GPU.  Rank `rank` of `world` (2..8) owns a slab of rows of every panel;
- * after each fused step it stores its boundary rows / strips straight into the peers' Q
- * arrays (CUDA IPC over NVLink) and raises a flag the peers' next step waits on.
- * pycs_mgpu_init: after the state upload; returns 3 cudaIpcMemHandle_t (192 bytes).  The
+ * in each fused step it stores the cells its peers read (halo rows, sources of their ghost cells)
+ * straight into the peers' Q arrays (CUDA IPC over NVLink) beside its interior update and raises
+ * flags the peers' kernels wait on.
+ * pycs_mgpu_init: after the state and the Lagrange tables are uploaded; returns 3 cudaIpcMemHandle_t (192 bytes).  The
  * caller all-gathers them (torch.distributed) and passes the world*192 bytes to
  * pycs_mgpu_connect.  Afterwards pycs_run(fused=1) advances the own slab; pycs_download_field
  * returns an array whose rows [row_lo,row_hi) (pycs_mgpu_row_range, padded-panel index) are valid. */
 int pycs_mgpu_init(pycs_handle h, int32_t rank, int32_t world, unsigned char* handles_out);
 int pycs_mgpu_connect(pycs_handle h, const unsigned char* all_handles);
 int pycs_mgpu_row_range(pycs_handle h, int32_t* row_lo, int32_t* row_hi);
-/* Host-only: the slab and the scatter jobs (peer, i0, i1, j0, j1) of one rank. */
-int pycs_mgpu_plan(int32_t N, int32_t world, int32_t rank, int32_t* row_lo, int32_t* row_hi,
-                   int32_t* jobs5, int32_t max_jobs, int32_t* njobs);
+/* Host-only: the slab of one rank and the rectangles (peer, panel, i0, i1, j0, j1) it stores into its
+ * peers after every step -- the 3 rows next to their slabs and the interior cells their ghost cells are
+ * interpolated from, derived from the halo index maps (src/halo_data.py:15-185) and the Lagrange stencil
+ * table kmin_east (4, P) of the given degree (src/lagrange.py:28-163).  *nrects may exceed max_rects. */
+int pycs_mgpu_plan(int32_t N, int32_t world, int32_t rank, int32_t degree, const int32_t* kmin_east,
+                   int32_t* row_lo, int32_t* row_hi, int32_t* rects6, int32_t max_rects, int32_t* nrects);
 
-/* Host-only: CTA sets of a split fused step (PYCS_SPLIT=1).  The step kernel's grid is
+/* Host-only: CTA sets of a split fused step (several GPUs, or PYCS_SPLIT=1).  The step kernel's grid is
  * nstrips x nchunks x 6 CTAs, CTA = (chunk * nstrips + strip) * 6 + panel; `interior` receives the CTAs
  * that read no ghost cell (they can run beside the ghost fill of src/advection_timestep.py:28),
  * `boundary` the rest.  Both arrays need 6 * nstrips * nchunks entries; *n_interior = 0 when the grid

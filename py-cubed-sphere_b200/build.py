@@ -24,8 +24,8 @@ UNITS = {
     "ppm.cu": ["-fmad=false"],
     "wind.cu": ["-fmad=false"],
     "fused.cu": [],
-    "fused3.cu": [],
     "fused2b.cu": [],
+    "stepper.cu": [],
     "mgpu.cu": [],
 }
 

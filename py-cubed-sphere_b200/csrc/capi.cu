@@ -179,6 +179,7 @@ extern "C" int pycs_destroy(pycs_handle h) {
     if (h->f[k]) cudaFree(h->f[k]);
   if (h->kminE) cudaFree(h->kminE);
   if (h->wE) cudaFree(h->wE);
+  free(h->kmin_host);
   if (h->halo_buf) cudaFree(h->halo_buf);
   if (h->red_part) cudaFree(h->red_part);
   if (h->red_out) cudaFree(h->red_out);
@@ -211,6 +212,7 @@ extern "C" int pycs_set_dt(pycs_handle h, double dt) {
   TRY(wind_sync(h));
   h->g.dt = dt;
   h->prm.dt = dt;
+  k_fused_invalidate_graphs(h);
   return 0;
 }
 
@@ -309,10 +311,14 @@ extern "C" int pycs_upload_lagrange(pycs_handle h, int32_t degree, const int32_t
   CK(cudaMalloc(&h->wE, sizeof(double) * 4 * P * order));
   CK(cudaMemcpy(h->kminE, kmin_east, sizeof(int) * 4 * P, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->wE, weights_east, sizeof(double) * 4 * P * order, cudaMemcpyHostToDevice));
+  free(h->kmin_host);
+  h->kmin_host = (int*)malloc(sizeof(int) * 4 * P);
+  if (!h->kmin_host) return PYCS_ERR_NOMEM;
+  memcpy(h->kmin_host, kmin_east, sizeof(int) * 4 * P);
   h->degree = degree;
   h->order = order;
   k_fused_invalidate_ghost_metric(h);    // ghost(sqrtg) was filled with the old tables
-  return 0;
+  return k_mg_replan(h);                 // the exchange plan follows the stencils
 }
 
 // --------------------------------------------------------------------------- halo API
@@ -573,19 +579,24 @@ extern "C" int pycs_mgpu_row_range(pycs_handle h, int32_t* row_lo, int32_t* row_
   *row_hi = h->row_hi;
   return 0;
 }
-extern "C" int pycs_mgpu_plan(int32_t N, int32_t world, int32_t rank, int32_t* row_lo, int32_t* row_hi,
-                              int32_t* jobs5, int32_t max_jobs, int32_t* njobs) {
-  if (N < 8 || world < 1 || world > MG_MAX_WORLD || rank < 0 || rank >= world) return arg_fail("bad plan arguments");
+extern "C" int pycs_mgpu_plan(int32_t N, int32_t world, int32_t rank, int32_t degree, const int32_t* kmin_east,
+                              int32_t* row_lo, int32_t* row_hi, int32_t* rects6, int32_t max_rects, int32_t* nrects) {
+  if (N < 8 || world < 1 || world > MG_MAX_WORLD || rank < 0 || rank >= world || degree < 0 || degree > 7 || !kmin_east)
+    return arg_fail("bad plan arguments");
+  const int P = N + 2 * PYCS_NG;
+  for (int k = 0; k < 4 * P; ++k)
+    if (kmin_east[k] < 0 || kmin_east[k] + degree + 1 > P) return arg_fail("Kmin outside [0, P-order]");
   int a, b;
   pycs_mgpu_rows(N, world, rank, &a, &b);
   *row_lo = a;
   *row_hi = b;
-  MgJob jobs[MG_MAX_JOBS];
-  int n = world > 1 ? pycs_mgpu_plan_jobs(N, world, rank, jobs, MG_MAX_JOBS) : 0;
-  *njobs = n;
-  for (int k = 0; k < n && k < max_jobs && k < MG_MAX_JOBS; ++k) {
-    jobs5[5 * k] = jobs[k].peer; jobs5[5 * k + 1] = jobs[k].i0; jobs5[5 * k + 2] = jobs[k].i1;
-    jobs5[5 * k + 3] = jobs[k].j0; jobs5[5 * k + 4] = jobs[k].j1;
+  std::vector<MgRect> rects;
+  if (world > 1) pycs_mgpu_plan_rects(N, world, rank, kmin_east, degree + 1, &rects);
+  *nrects = (int)rects.size();
+  for (int k = 0; k < (int)rects.size() && k < max_rects; ++k) {
+    const MgRect& r = rects[k];
+    int32_t* o = rects6 + 6 * k;
+    o[0] = r.peer; o[1] = r.panel; o[2] = r.i0; o[3] = r.i1; o[4] = r.j0; o[5] = r.j1;
   }
   return 0;
 }

@@ -1,64 +1,70 @@
-// Arguments of the fused step kernels (fused.cu: v2 block-synchronous kernel;
-// fused3.cu: v3 warp-autonomous kernel).
+// Arguments of the fused step kernels (fused2b.cu: the production kernel; fused.cu: the first-generation
+// kernel that still serves the limited reconstructions PPM-CW84 / PPM-L04).
 #pragma once
 #include "pycs_common.cuh"
 
-// Multi-GPU part of a fused launch (csrc/mgpu.cu): with world > 1 the step kernel itself stores
-// the cells its peers need (boundary strips, halo rows) into their Q arrays over NVLink and its
-// last CTA publishes the MF-PR sum and raises the flags -- compute and exchange in ONE kernel.
 struct MgSync;
-struct FusedMg {
-  int world, rank, parity;
-  long long epoch;
-  double* peer_qn[8];         // the peers' output arrays (same layout, same positions)
-  MgSync* peer_sync[8];
+
+// Device-side control block of the fused step loop (one per handle, device memory).  Everything that
+// changes from step to step lives here instead of in kernel parameters, so that the launches of a step
+// are identical from one step to the next and can be replayed from a CUDA graph:
+//   * steps      -- fused steps completed; read by every CTA of a step at its start, advanced by the
+//                   step's last CTA.  It indexes the separable-wind time factors (ws_tab) and is the
+//                   epoch of the multi-GPU MF-PR sums (flag `sflag`, mgpu.cuh);
+//   * xcount     -- multi-GPU halo exchanges delivered by this rank (epoch of `dflag`);
+//   * pend       -- the MF-PR sum(s) of the last step still have to be applied to what it wrote;
+//   * corr_applied -- the projection coefficient the last step applied to what it read (ring restore);
+//   * sum        -- single GPU: total of the last step's partial sums of pxdF + pydF.
+struct StepCtl {
+  long long steps;
+  long long xcount;
+  int pend;
+  int pad_;
+  double corr_applied;
+  double sum;
 };
 
-// Ghost fill fused into the step kernel (fused2b.cu, single GPU): every CTA computes the ghost
-// cells its own rows / columns touch before it stages them, so the stand-alone ghost-fill launch
-// disappears from the step.
-struct FusedGhost {
-  int enable, order, nsums;
-  const int* kminE;
-  const double* wE;
-  const double* gs;           // ghost(sqrtg), see dg_fill_fused_kernel
-  const double* sums;         // MF-PR sums of the previous step (nsums of them)
-  double inv_a2;
-  double* corr_out;           // the projection coefficient of this launch, for the ring restore
-  HaloMaps maps;
+// Multi-GPU: where the last CTA of a step publishes this rank's MF-PR sum and raises `sflag`.
+struct FusedMgPub {
+  int world, rank;            // world <= 1: single GPU
+  MgSync* peer_sync[8];       // peer_sync[rank] is this rank's own block
 };
 
 struct FusedArgs {
   Geo g;
   const double* q;
   double* qn;
-  const double *ua, *va;      // U_pu.ucontra_averaged, U_pv.vcontra_averaged
+  const double *ua, *va;      // U_pu.ucontra_averaged, U_pv.vcontra_averaged (MASK & 2: the t = 0 winds)
   const double *um, *vm;      // mask sources (U_pu.ucontra, U_pv.vcontra)
   const double *sgc, *rgc, *sgu, *sgv;
-  double* part;               // per-CTA (v3: per-warp) partial sums of pxdF + pydF
-  double* sum_out;            // their total, written by the last CTA of the launch (fixed order)
-  unsigned* counter;          // CTAs (warps) that have written their partial; reset by the last one
-  const double* corr;         // device scalar: pending projection coefficient -sum(s)/a2
-  int rows_per_chunk, nstrips, wcols, apply_corr;
+  double* part;               // per-CTA partial sums of pxdF + pydF
+  unsigned* counter;          // CTAs that have written their partial; reset by the last one
+  StepCtl* ctl;
+  const double* ws_tab;       // separable wind (MASK & 2): U(t_k) = U(0) * ws_tab[steps & ws_mask]
+  int ws_mask;
+  // pending MF-PR projection term of the previous step, added to Q as it is loaded:
+  //   corr_ptr != null: coefficient written by the ghost-fill kernel of this step (serial path);
+  //   else formed here from the previous step's sum(s): -sum / a2 (same expression, same bits)
+  int apply_corr;             // the scheme has MF-PR
+  const double* corr_ptr;
+  double inv_a2;
+  const double* gs;           // GH = 1: ghost(sqrtg) for the projection term on ghost cells (raw ghost fill)
+  int rows_per_chunk, nstrips, wcols;
   int row_lo, row_hi;         // rows this launch updates (the whole interior, or this rank's slab)
   double cdx, cdy;            // dt/dx, dt/dy
-  double ws;                  // separable wind: U(t) = U(0) * ws (MASK & 2)
-  FusedMg mg;                 // world <= 1: single GPU
-  int pdl;                    // launch with programmatic stream serialization (v2b)
-  FusedGhost gf;
-  // split launches (v2b, PYCS_SPLIT=1): a step is two launches over disjoint CTA sets -- the
-  // interior CTAs, which read no ghost cell, start at once; the boundary CTAs follow the ghost
-  // fill on a second stream.  blk_map[blockIdx.x] = CTA index in the full grid; both launches
-  // share part[], the ticket counter and nblk_total, so the later one totals the MF-PR sum.
+  // split step: a step is two launches over disjoint CTA sets -- boundary CTAs (everything a ghost cell or
+  // a peer reads, launched first on a high-priority stream, followed by the exchange and the next ghost
+  // fill) and interior CTAs.  blk_map[blockIdx.x] = CTA index in the full grid; both launches share
+  // part[], the ticket counter and nblk_total, so whichever finishes last closes the step.
   const int* blk_map;         // nullptr: one launch over the whole grid
   int nblk_total;
-  // several GPUs: the peers' MF-PR sums (gf.sums) are valid once every flag has reached wait_epoch; the
-  // interior launch waits for them itself (the boundary launch follows the ghost fill, which has waited)
+  // several GPUs: the peers' sums (and the right to overwrite their buffers) arrive with sflag >= steps
   const long long* wait_flags;
   int wait_world;
-  long long wait_epoch;
-  int* mg_err;                       // bounded wait: see mg_wait_flag (mgpu.cuh)
+  int* mg_err;                // bounded wait: see mg_wait_flag (mgpu.cuh)
   unsigned long long mg_timeout_ns;
+  FusedMgPub pub;
+  int timing;                 // roofline timing launches: leave the control block alone
 };
 
 // CTA sets of a split step: strips x chunks x 6 panels, CTA = (chunk * nstrips + strip) * 6 + panel.
@@ -84,14 +90,14 @@ __device__ __forceinline__ double fused_warp_sum(const double* part, int n, int 
 }
 #endif
 
-// v3 launcher: nw consumer warps, pf rows in flight, minb = register cap as CTAs per SM
-cudaError_t pycs_launch_fused3(const FusedArgs& a, int recon, int split, int mask, int nw, int pf, int minb,
-                               int nblocks, cudaStream_t st);
-// resident CTAs per SM of the v3 kernel for this template point (occupancy API); < 0 on error
-int pycs_fused3_resident(int recon, int split, int mask, int nw, int pf, int minb);
-bool pycs_fused3_has(int recon, int split, int nw, int pf, int minb);
-// v2b launcher (fused2b.cu): tb threads per CTA, pf rows in flight, minb = register cap as CTAs per SM
-cudaError_t pycs_launch_fused2b(const FusedArgs& a, int recon, int split, int mask, int tb, int pf, int minb,
-                                int nblocks, cudaStream_t st);
-int pycs_fused2b_resident(int recon, int split, int mask, int tb, int pf, int minb);
-bool pycs_fused2b_has(int recon, int split, int tb, int pf, int minb);
+// v2b launcher (fused2b.cu): gh = 1 launches the flavour that adds the projection term on ghost cells itself
+cudaError_t pycs_launch_fused2b(const FusedArgs& a, int recon, int split, int mask, int gh, int nblocks, cudaStream_t st);
+// resident CTAs per SM of that instantiation (occupancy API; also sets its shared-memory attribute, which
+// must not happen inside a stream capture); < 0 on error
+int pycs_fused2b_resident(int recon, int split, int mask, int gh = 0);
+bool pycs_fused2b_has(int recon, int split);
+int pycs_fused2b_threads();
+// v2 launcher (fused.cu): limited reconstructions, single GPU, serial path only
+cudaError_t pycs_launch_fused_v2(const FusedArgs& a, int recon, int split, int mask, int nblocks, cudaStream_t st);
+int pycs_fused_v2_threads();
+int pycs_fused_v2_resident();

@@ -1,43 +1,55 @@
 // Multi-GPU state of a handle (see mgpu.cu).
 #pragma once
+#include <vector>
 #include "pycs_common.cuh"
 
 #define MG_MAX_WORLD 8
-#define MG_MAX_JOBS 40
 
+// One block per rank, exported to every peer through CUDA IPC.  All flags are epoch counters, never reset:
+//   sflag[d] = fused steps rank d has completed (its MF-PR sum of that step is in psum[steps & 1][d]);
+//   dflag[d] = halo exchanges rank d has delivered into this rank's Q arrays.
 struct MgSync {
-  long long flag[MG_MAX_WORLD];      // flag[d] = last exchange epoch rank d delivered to this rank
-  double psum[2][MG_MAX_WORLD];      // per-rank MF-PR sums, slot = epoch & 1
+  long long sflag[MG_MAX_WORLD];
+  long long dflag[MG_MAX_WORLD];
+  double psum[2][MG_MAX_WORLD];
   int err;                           // != 0: a flag wait of this rank gave up (a peer is gone); the host turns it
                                      // into PYCS_ERR_STATE at the next synchronisation point (k_mg_check)
 };
-struct MgJob { int peer, i0, i1, j0, j1; };   // rectangle of every panel to store into rank `peer`
+// rectangle [i0,i1) x [j0,j1) of one panel that this rank stores into rank `peer` after every step
+struct MgRect { int peer, panel, i0, i1, j0, j1; };
+struct MgScatterJob { double* dst; int panel, i0, i1, j0, j1; };
 
+struct StepCtl;
 struct MgpuState {
   int rank, world, connected;
   double* alloc[2];                  // this rank's two Q allocations, in export order
   double* peer_q[2][MG_MAX_WORLD];   // peer_q[i][d]: allocation i of rank d, mapped here
   MgSync* sync;
-  unsigned* counter;                 // blocks of the exchange kernel that have finished
+  unsigned* counter;                 // CTAs of the exchange kernel that have finished
   MgSync* peer_sync[MG_MAX_WORLD];
-  long long epoch;                   // exchanges issued so far
   unsigned long long timeout_ns;     // wall-clock bound of a flag wait (PYCS_MG_TIMEOUT_S, default 30 s)
+  std::vector<MgRect>* rects;        // what this rank sends (host copy of the plan)
+  MgScatterJob* jobs_dev[2];         // the same with the destination pointers of allocation 0 / 1 resolved
   int njobs;
-  MgJob jobs[MG_MAX_JOBS];
+  int gf_lo, gf_hi;                  // rows whose ghost cells this rank needs: [row_lo - 3, row_hi + 3)
 };
 
+// Host-side plan (no GPU needed: exercised by the CPU tests).
 void pycs_mgpu_rows(int N, int world, int rank, int* row_lo, int* row_hi);
-int pycs_mgpu_plan_jobs(int N, int world, int rank, MgJob* jobs, int max_jobs);
+// Rectangles rank `rank` must send after every step so that every peer holds what its next step reads:
+// the 3 rows next to its slab and the sources of the Lagrange ghost cells it needs (derived from the
+// halo index maps and the stencil table kmin_east (4, P), degree = order - 1).
+void pycs_mgpu_plan_rects(int N, int world, int rank, const int* kmin_east, int order, std::vector<MgRect>* out);
+
 int k_mg_init(pycs_handle h, int rank, int world, unsigned char* handles_out);
 int k_mg_connect(pycs_handle h, const unsigned char* all_handles);
+int k_mg_replan(pycs_handle h);      // after the Lagrange tables changed
 void k_mg_release(pycs_handle h);
-int k_mg_wait(pycs_handle h);
+int k_mg_wait_steps(pycs_handle h, cudaStream_t st);  // until every rank has completed as many steps as this one
 int k_mg_check(pycs_handle h);       // after a stream synchronisation: did a flag wait time out?
-const double* k_mg_sums(pycs_handle h);
-int k_mg_exchange(pycs_handle h, const double* qnext, const double* part, int npart);
+// after the boundary CTAs of a step wrote `qnext`: deliver the rectangles, then raise dflag on every peer
+int k_mg_exchange(pycs_handle h, const double* qnext, StepCtl* ctl, cudaStream_t st);
 void k_fused_reset_grid(pycs_handle h);
-struct FusedMg;
-int k_mg_fill_args(pycs_handle h, const double* qnext, FusedMg* out);
 
 #ifdef __CUDACC__
 // Wait until *f >= epoch.  A peer that is merely late (host work between runs, a slow rank) is waited

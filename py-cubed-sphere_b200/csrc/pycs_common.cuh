@@ -49,6 +49,7 @@ struct pycs_handle_s {
   int degree, order;
   int* kminE;
   double* wE;
+  int* kmin_host;       // host copy of the stencil table: the multi-GPU exchange plan is derived from it
   HaloMaps maps;
   // halo gather buffers for the copy fill: E, W (4,P,6 each) then N, S (P,4,6)
   double* halo_buf;
@@ -120,7 +121,7 @@ void pycs_build_halo_maps(const Geo& g, HaloMaps* maps);
 int k_halo_gather(pycs_handle h, const double* fx, const double* fy, double* buf);
 int k_halo_scatter_copy(pycs_handle h, double* fx, double* fy, const double* buf);
 int k_dg_fill(pycs_handle h, double* q);          // two launches (halo.cu)
-int k_dg_fill_single(pycs_handle h, double* q);   // one launch (fused.cu)
+int k_dg_fill_single(pycs_handle h, double* q);   // one launch (stepper.cu)
 // ppm.cu
 int k_cfl(pycs_handle h, double* dst, const double* src, int dir);
 int k_mul_metric(pycs_handle h, double* gq, const double* q);
@@ -140,10 +141,9 @@ int k_time_averaged_velocity(pycs_handle h);
 int k_wind_ghost_fill(pycs_handle h);
 int k_update_adv(pycs_handle h, double t);
 int k_wind_interior(pycs_handle h, double t, int convert_interior_only, int do_velocity);
-// fused.cu
+// stepper.cu
 int k_fused_supported(pycs_handle h);
 int k_fused_step(pycs_handle h, long long k, double t, int separable);
-int k_wind_resync(pycs_handle h, long long kprev);
 int k_wind_catch_up(pycs_handle h, long long k);
 int k_fused_time_kernel(pycs_handle h, int reps, int separable, float* ms);
 int k_fused_grid_info(pycs_handle h, int* tb, int* rows, int* nblocks);
@@ -154,4 +154,5 @@ void k_fused_profile_report(pycs_handle h);         // PYCS_STEP_PROFILE: print 
 void k_fused_release(pycs_handle h);
 void k_fused_invalidate(pycs_handle h);
 void k_fused_invalidate_ghost_metric(pycs_handle h); // the Lagrange tables changed
+void k_fused_invalidate_graphs(pycs_handle h);       // dt changed: it is baked into the captured launches
 // layout.cu (in capi.cu)

@@ -106,7 +106,7 @@ def load_library():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int
-    lib.pycs_mgpu_plan.argtypes = [C.c_int32] * 3 + [C.POINTER(C.c_int32)] * 3 + [C.c_int32, C.POINTER(C.c_int32)]
+    lib.pycs_mgpu_plan.argtypes = [C.c_int32] * 4 + [C.POINTER(C.c_int32)] * 4 + [C.c_int32, C.POINTER(C.c_int32)]
     lib.pycs_mgpu_plan.restype = C.c_int
     lib.pycs_last_error.restype = C.c_char_p
     lib.pycs_last_error.argtypes = []
@@ -213,15 +213,22 @@ class Device:
         return n.value
 
 
-def mgpu_plan(N, world, rank):
-    """Host-only view of the decomposition: (row_lo, row_hi, [(peer, i0, i1, j0, j1), ...])."""
+def mgpu_plan(N, world, rank, kmin_east, degree=3):
+    """Host-only view of the decomposition: (row_lo, row_hi, [(peer, panel, i0, i1, j0, j1), ...]) -- the
+    rectangles `rank` stores into its peers after every step.  kmin_east: the (4, P) stencil-start table
+    of lagrange_poly_ghostcell_pc (simulation.stencil_ghost_pc[0][0])."""
     lib = load_library()
+    km = np.ascontiguousarray(kmin_east, dtype=np.int32)
     a, b, n = C.c_int32(), C.c_int32(), C.c_int32()
-    jobs = (C.c_int32 * (5 * 40))()
-    rc = lib.pycs_mgpu_plan(N, world, rank, C.byref(a), C.byref(b), jobs, 40, C.byref(n))
+    cap = 4096
+    rects = (C.c_int32 * (6 * cap))()
+    rc = lib.pycs_mgpu_plan(N, world, rank, degree, km.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(a), C.byref(b),
+                            rects, cap, C.byref(n))
     if rc != 0:
         raise PycsError(lib.pycs_last_error().decode())
-    return a.value, b.value, [tuple(jobs[5 * k:5 * k + 5]) for k in range(n.value)]
+    if n.value > cap:
+        raise PycsError("mgpu_plan: %d rectangles" % n.value)
+    return a.value, b.value, [tuple(rects[6 * k:6 * k + 6]) for k in range(n.value)]
 
 
 class DeviceArray:

@@ -33,14 +33,9 @@ def main():
     if len(sys.argv) > 1:
         cases = [(int(sys.argv[1]), 3, "default", (10,))]
     worst = 0.0
-    # 4 = default kernel + exchange kernel; 4f = same kernel with the exchange fused into it
-    # (PYCS_MG_FUSED=1); 2, 3 = older kernels (separate exchange launch)
-    # 4x = split step, interior CTAs beside ghost fill + boundary CTAs
-    impls = ("4", "4x", "4f", "2", "3")
-    for impl in impls:
-        os.environ["PYCS_FUSED_IMPL"] = impl[0]
-        os.environ["PYCS_MG_FUSED"] = "1" if impl.endswith("f") else "0"
-        os.environ["PYCS_SPLIT"] = "1" if impl.endswith("x") else "0"
+    # the multi-GPU step is always the split step; replayed from CUDA graphs (default) or launched directly
+    for impl in ("graph", "nograph"):
+        os.environ["PYCS_GRAPH"] = "1" if impl == "graph" else "0"
         for N, vf, name, calls in cases:
             g = cs_datastruct.cubed_sphere(N)
             a = make(g, vf, TUPLES[name], local)

@@ -281,7 +281,11 @@ def _check_big(mods, fname, fused, max_k=None):
         assert abs(np.sum(Q[I]) - float(ref["sumQ_k%d" % k])) <= TOL * abs(float(ref["sumQ_k%d" % k]))
         qe = mods.advection_ic.qexact_adv(g.pc.lon[I], g.pc.lat[I], k * sim.dt, sim)
         for a, b in zip(ost.compute_errors(Q[I], qe), ref["err_k%d" % k]):
-            assert abs(a - b) <= TOL * abs(b), (fname, k, a, b)
+            # a norm is a mean / max of |Q - Qexact|: a 1-ulp difference of Q (2.2e-16 max|Q|) moves it by up to
+            # that much, so below E ~ 2e-4 max|Q| a purely relative 1e-12 is finer than fp64 resolves on the
+            # field itself (measured: |dE| = 1.1e-16 on E = 1.57e-6 at k = 1, N = 384).  Hence the floor of
+            # 4 ulp of the field scale next to the 1e-12 relative bound.
+            assert abs(a - b) <= TOL * abs(b) + 4 * np.finfo(float).eps * float(np.max(np.abs(Q[I]))), (fname, k, a, b)
     sim.dev.close()
 
 
@@ -324,22 +328,19 @@ def test_fused_matches_operator_path(mods, N, vf, name):
     b.dev.close()
 
 
-@pytest.mark.parametrize("impl", ["2", "3", "4", "4g", "4s", "4p"])
+@pytest.mark.parametrize("mode", ["serial", "serial-nograph", "split", "split-nograph"])
 @pytest.mark.parametrize("N,vf,name", [(16, 1, "default"), (50, 3, "default"), (130, 2, "AVLT-RK2-DG-PR"),
-                                       (130, 1, "PL07-RK1-DG-PR"), (200, 4, "default"), (1536, 3, "default")])
-def test_fused_kernel_variants_match_operator_path(mods, N, vf, name, impl, monkeypatch):
-    """Every fused step kernel -- v2 block-synchronous (csrc/fused.cu, PYCS_FUSED_IMPL=2), v3
-    warp-autonomous (csrc/fused3.cu, 3), v2b block-synchronous with the lean core
-    (csrc/fused2b.cu, 4 = default const-slot march; 4g with the ghost prologue, 4s the
-    shifting-window march MINB=14 / 4, 4p the two-row march MINB=53) -- against
-    the operator path, over several run calls (separable wind and pending projection carried
-    across calls)."""
-    monkeypatch.setenv("PYCS_FUSED_IMPL", impl[0])
-    if impl.endswith("p"):        # two rows per pair of barriers (3 CTAs/SM); schemes without it fall back
-        monkeypatch.setenv("PYCS_FUSED_MINB", "53")
-    if impl.endswith("s"):
-        monkeypatch.setenv("PYCS_FUSED_MINB", "4" if name.startswith("PL07") else "14")
-    monkeypatch.setenv("PYCS_GHOST_FUSED", "1" if impl.endswith("g") else "0")   # 4g: ghost fill inside v2b
+                                       (130, 1, "PL07-RK1-DG-PR"), (200, 4, "default"), (130, 3, "L04-AVLT-DG-PR"),
+                                       (320, 3, "default"), (1536, 3, "default")])
+def test_fused_step_shapes_match_operator_path(mods, N, vf, name, mode, monkeypatch):
+    """Both shapes of the fused step (csrc/stepper.cu) -- serial: ghost fill with the projection term folded
+    in, then one launch; split (PYCS_SPLIT=1, the shape every multi-GPU run uses): boundary CTAs with the
+    in-kernel projection term on ghost cells + early raw ghost fill on a second stream beside the interior
+    CTAs -- replayed from CUDA graphs or launched directly (PYCS_GRAPH=0), against the operator path, over
+    several run calls (separable wind, pending projection and ghost state carried across calls).  The
+    PPM-L04 tuple runs on the first-generation kernel (csrc/fused.cu)."""
+    monkeypatch.setenv("PYCS_SPLIT", "1" if mode.startswith("split") else "0")
+    monkeypatch.setenv("PYCS_GRAPH", "0" if mode.endswith("nograph") else "1")
     g = mods.cs_datastruct.cubed_sphere(N)
     a = make_sim(mods, g, vf, TUPLES[name])
     b = make_sim(mods, g, vf, TUPLES[name])
@@ -347,6 +348,8 @@ def test_fused_kernel_variants_match_operator_path(mods, N, vf, name, impl, monk
     for n in ((1, 4, 7) if N < 1000 else (3,)):
         mods.advection_timestep.run_steps(g, a, k, n, fused=True)
         k += n
+        if n == 4:       # something else reads Q between two runs: flush, ring restore, ghost state reset
+            assert np.all(np.isfinite(np.asarray(a.Q)))
     mods.advection_timestep.run_steps(g, b, 0, k, fused=False)
     assert relerr(np.asarray(a.Q), np.asarray(b.Q)) <= TOL
     a.dev.close()

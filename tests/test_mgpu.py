@@ -1,4 +1,4 @@
-"""Multi-GPU tests.  CPU part: the decomposition plan (host-only C ABI call) and the
+"""Multi-GPU tests.  CPU part: the exchange plan (host-only C ABI call) against the oracle's ghost fill, and the
 torch.distributed rendezvous helper under gloo, world_size 2.  GPU part: the sharded fused
 step against an unsharded replica, torchrun with 2 ranks (skipped on a 1-GPU box)."""
 import os
@@ -11,32 +11,64 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("N,world", [(16, 2), (48, 4), (50, 3), (1536, 8), (130, 8)])
-def test_plan_covers_what_every_rank_reads(N, world):
-    """Own rows + received rectangles must contain: own rows, 3 halo rows on each side, and the
-    four 4-wide boundary strips of the panel (the sources of the Lagrange ghost fill)."""
+def _tables(N):
+    from oracle.grid import LeanGrid
+    from oracle import halo as ohalo
+    og = LeanGrid.centres_only(N)
+    return og, ohalo, ohalo.lagrange_tables(og, 3)
+
+
+@pytest.mark.parametrize("N,world", [(16, 2), (48, 4), (50, 3), (130, 8), (96, 8)])
+def test_plan_delivers_every_cell_a_rank_reads(N, world):
+    """The exchange plan against the oracle's ghost fill: a rank that holds ONLY its own rows plus the
+    rectangles the plan delivers (everything else NaN) must end up, after the reference's two-phase
+    Lagrange fill, with exactly the values of the whole-sphere fill on every cell its step reads: the rows
+    of its slab +- 3 (with the W / E ghost rows at the ends), all columns, ghost cells and corners included."""
     import pycs_b200  # noqa: F401
     from pycs_b200.device import mgpu_plan
-    lo, hi = 4, N + 4
-    plans = [mgpu_plan(N, world, r) for r in range(world)]
+    og, ohalo, tables = _tables(N)
+    kminE = tables[0][0][0]
+    lo, hi, P = 4, N + 4, N + 8
+    plans = [mgpu_plan(N, world, r, kminE, 3) for r in range(world)]
     assert plans[0][0] == lo and plans[-1][1] == hi
     for r in range(world - 1):
         assert plans[r][1] == plans[r + 1][0]
-    have = [np.zeros((N + 8, N + 8), bool) for _ in range(world)]
-    for r, (a, b, jobs) in enumerate(plans):
-        have[r][a:b, lo:hi] = True
-    for r, (a, b, jobs) in enumerate(plans):
-        for peer, i0, i1, j0, j1 in jobs:
-            assert peer != r and a <= i0 < i1 <= b and lo <= j0 < j1 <= hi      # a rank only sends its own cells
-            have[peer][i0:i1, j0:j1] = True
-    for r, (a, b, jobs) in enumerate(plans):
-        need = np.zeros((N + 8, N + 8), bool)
-        need[max(a - 3, lo):min(b + 3, hi), lo:hi] = True
-        need[lo:hi, lo:lo + 4] = True
-        need[lo:hi, hi - 4:hi] = True
-        need[lo:lo + 4, lo:hi] = True
-        need[hi - 4:hi, lo:hi] = True
-        assert not np.any(need & ~have[r]), r
+    rng = np.random.default_rng(N * 10 + world)
+    full = np.zeros((P, P, 6))
+    full[lo:hi, lo:hi, :] = rng.standard_normal((N, N, 6))
+    want = full.copy()
+    ohalo.dg_fill(want, og, tables)
+    sent = 0
+    for r, (a, b, _) in enumerate(plans):
+        mine = np.full((P, P, 6), np.nan)
+        mine[a:b, lo:hi, :] = full[a:b, lo:hi, :]
+        for s, (sa, sb, rects) in enumerate(plans):
+            for peer, panel, i0, i1, j0, j1 in rects:
+                assert peer != s and sa <= i0 < i1 <= sb and lo <= j0 < j1 <= hi      # a rank only sends its own cells
+                if peer == r:
+                    mine[i0:i1, j0:j1, panel] = full[i0:i1, j0:j1, panel]
+                    sent += (i1 - i0) * (j1 - j0) if r == 0 else 0
+        ohalo.dg_fill(mine, og, tables)
+        ia = 0 if a - 3 < lo else a - 3
+        ib = P if b + 3 > hi else b + 3
+        got, exp = mine[ia:ib], want[ia:ib]
+        assert not np.any(np.isnan(got)), (r, np.argwhere(np.isnan(got))[:5])
+        assert np.array_equal(got, exp), r
+    # nothing is broadcast: what rank 0 receives is a small multiple of its halo rows + strip pieces
+    assert sent <= 6 * (3 * N + 16 * (N // world + 16) + 8 * N + 64 * world)
+
+
+def test_plan_is_targeted_at_bench_size():
+    """N = 1536 on 8 ranks: a few hundred rectangles in total, each rank sends a few hundred KB."""
+    import pycs_b200  # noqa: F401
+    from pycs_b200.device import mgpu_plan
+    og, ohalo, tables = _tables(1536)
+    kminE = tables[0][0][0]
+    for r in (0, 3, 7):
+        a, b, rects = mgpu_plan(1536, 8, r, kminE, 3)
+        cells = sum((i1 - i0) * (j1 - j0) for _, _, i0, i1, j0, j1 in rects)
+        assert len(rects) <= 400, len(rects)
+        assert cells * 8 <= 1.5e6, cells
 
 
 def _gloo_worker(rank, world, port, q):
