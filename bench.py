@@ -171,7 +171,9 @@ def run_gpu(args):
     cfg = workload(N)
     dt = cfg["dt"]
     t_setup = time.time()
-    g = cs_datastruct.cubed_sphere(N)
+    # lean grid: geometry, wind, initial condition and diagnostics are generated on the device (csrc/grid.cu);
+    # --host-grid builds the reference's numpy arrays instead (10-15 s at N=1536)
+    g = cs_datastruct.cubed_sphere(N, lean=not args.host_grid)
     sim = advection_ic.adv_simulation_par(g, dt, 5, IC, VF, 1, *TUPLE, device=local)
     advection_vars.init_vars_adv(g, sim)
     dev = sim.dev
@@ -332,7 +334,7 @@ def run_gpu(args):
                 "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "parity": parity, "parity_relerr": parity["relerr"] if parity else None,
                 "gpu_launches": int(launches), "clocks": clocks, "device": name, "sm_count": sm,
-                "setup_s": setup_s,
+                "setup_s": setup_s, "grid": "host numpy" if args.host_grid else "device-generated (lean)",
                 "parallelism": "single GPU" if world == 1 else
                 "%d row slabs per panel, peer-mapped halo stores over NVLink (csrc/mgpu.cu)" % world,
                 "wind_path": "separable (U(t)=U(0)cos(pi t/T) scaled in-kernel; the exposed wind arrays are "
@@ -354,6 +356,7 @@ def main():
                     help="N of the CPU sample (0: reference arm 1536 if steps + warmup <= 8 else 768; cpu_baseline leg 768)")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--host-grid", action="store_true", help="build the grid with host numpy like the reference")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -109,6 +109,20 @@ int pycs_upload_lagrange(pycs_handle h, int32_t degree, const int32_t* kmin_east
                          const double* weights_east);
 int pycs_set_dt(pycs_handle h, double dt);
 
+/* ---- device-side set-up ("next" rows f2 / f3) ---------------------------------- */
+/* The grid fields the path reads -- sqrt(g) at pc / pu / pv (src/cs_datastruct.py:407-446), the lat-lon <->
+ * contravariant coefficients and determinant (:448-493) and the point coordinates lon / lat (:240-324,
+ * src/cs_transform.py:41-96) -- generated on the device from the 1-D coordinate arrays of the equiangular
+ * grid: xc = centres (P values), xe = edges (P + 1 values), as np.linspace gives them.  Replaces the 24
+ * pycs_upload_field calls of the host-built grid; agrees with it to the last one or two ulps. */
+int pycs_generate_geometry(pycs_handle h, const double* xc, const double* xe);
+/* q0_adv / qexact_adv (src/advection_ic.py:215-281) at time t into the interior of a centre field
+ * (ghost cells zero), evaluated on the device from pc.lon / pc.lat. */
+int pycs_init_tracer(pycs_handle h, int32_t field, double t);
+/* max over [i0,i1) x [j0,j1) x panels of a field, e.g. the CFL number of init_vars_adv
+ * (src/advection_vars.py:89-98: amax of cx[i0:iend+1,:,:], no abs inside). */
+int pycs_field_max(pycs_handle h, int32_t field, int32_t i0, int32_t i1, int32_t j0, int32_t j1, double* out);
+
 /* ---- halo / edges (L1 of SURVEY.md s1) -------------------------------------- */
 /* get_halo_data_interpolation (src/halo_data.py:15-185): out_* are (4,P,6),
  * (4,P,6), (P,4,6), (P,4,6) host arrays.  With fx != fy it is the _WE/_NS pair
@@ -187,17 +201,22 @@ int pycs_mgpu_row_range(pycs_handle h, int32_t* row_lo, int32_t* row_hi);
 int pycs_mgpu_plan(int32_t N, int32_t world, int32_t rank, int32_t degree, const int32_t* kmin_east,
                    int32_t* row_lo, int32_t* row_hi, int32_t* rects6, int32_t max_rects, int32_t* nrects);
 
-/* Host-only: CTA sets of a split fused step (several GPUs, or PYCS_SPLIT=1).  The step kernel's grid is
- * nstrips x nchunks x 6 CTAs, CTA = (chunk * nstrips + strip) * 6 + panel; `interior` receives the CTAs
- * that read no ghost cell (they can run beside the ghost fill of src/advection_timestep.py:28),
- * `boundary` the rest.  Both arrays need 6 * nstrips * nchunks entries; *n_interior = 0 when the grid
- * is too small to split. */
-int pycs_split_plan(int32_t nstrips, int32_t nchunks, int32_t* interior, int32_t* boundary, int32_t* n_interior);
+/* Host-only: the CTA table of a split fused step (several GPUs, or PYCS_SPLIT=1) over the rows
+ * [row_lo, row_hi) of every panel cut into nstrips column strips.  Entries (r0, r1, strip, panel); the
+ * first *n_boundary are the boundary CTAs -- bands of `band` rows at both ends of the slab over all strips,
+ * then the first and last strip in chunks of `edge_rows` rows: everything a ghost cell or a peer reads,
+ * launched first and done early -- the rest are the interior CTAs (chunks of `rows` rows), which stage no
+ * ghost cell and no row outside the slab and run beside the exchange and the ghost fill of
+ * src/advection_timestep.py:28.  *n_ctas may exceed max_ctas. */
+int pycs_split_plan(int32_t row_lo, int32_t row_hi, int32_t nstrips, int32_t band, int32_t edge_rows, int32_t rows,
+                    int32_t* ctas4, int32_t max_ctas, int32_t* n_ctas, int32_t* n_boundary);
 
 /* ---- diagnostics (next row f2) -------------------------------------------------- */
 /* compute_errors (src/errors.py:99-113) of Q against a host reference field
  * qexact given on the interior (N,N,6): out = {Linf, L1, L2}. */
 int pycs_errors(pycs_handle h, const double* qexact_interior, double* out3);
+/* The same against qexact_adv(t) evaluated on the device (no host field, no transfer). */
+int pycs_errors_exact(pycs_handle h, double t, double* out3);
 /* mass_computation (src/diagnostics.py:14-26): sum Q*sqrtg*dx*dy over the interior. */
 int pycs_mass(pycs_handle h, double* mass);
 /* Number of kernels launched by this handle since creation (bench bookkeeping). */

@@ -75,12 +75,20 @@ class adv_simulation_par:
 
         self.dev = Device(cs_grid.N, cs_grid.dx, cs_grid.dy, dt, recon, dp, opsplit, et, mt, mf, vf, ic, device)
         cs_grid.dev = self.dev
-        for fname, attr in _GEOM:
-            self.dev.upload(F[fname], getattr(cs_grid, attr))
-        for pos in ("pc", "pu", "pv"):
-            pts = getattr(cs_grid, pos)
-            self.dev.upload(F[pos.upper() + "_LON"], pts.lon)
-            self.dev.upload(F[pos.upper() + "_LAT"], pts.lat)
+        if getattr(cs_grid, "lean", False):
+            # geometry generated on the device from the 1-D coordinates (csrc/grid.cu)
+            import ctypes as C
+            xc = np.ascontiguousarray(cs_grid.x_centres, dtype=np.float64)
+            xe = np.ascontiguousarray(cs_grid.x_edges, dtype=np.float64)
+            dp = C.POINTER(C.c_double)
+            self.dev.call("pycs_generate_geometry", xc.ctypes.data_as(dp), xe.ctypes.data_as(dp))
+        else:
+            for fname, attr in _GEOM:
+                self.dev.upload(F[fname], getattr(cs_grid, attr))
+            for pos in ("pc", "pu", "pv"):
+                pts = getattr(cs_grid, pos)
+                self.dev.upload(F[pos.upper() + "_LON"], pts.lon)
+                self.dev.upload(F[pos.upper() + "_LAT"], pts.lat)
 
         self.px = None
         self.py = None

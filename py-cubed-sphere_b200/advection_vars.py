@@ -17,17 +17,24 @@ def init_vars_adv(cs_grid, simulation):
     simulation.U_pv = velocity(cs_grid, 'pv', simulation)
     simulation.U_pc = velocity(cs_grid, 'pc', simulation)
 
-    # winds at t = 0 on the interior edge points (:37-41), evaluated on the host so
-    # that the steady wind (vf = 1) enters the device bit-identical to the reference
-    for pos, idx, shape in (("pu", np.s_[i0:iend + 1, j0:jend, :], (P + 1, P, 6)),
-                            ("pv", np.s_[i0:iend, j0:jend + 1, :], (P, P + 1, 6))):
-        pts = getattr(cs_grid, pos)
-        ulon, vlat = np.zeros(shape), np.zeros(shape)
-        ulon[idx], vlat[idx] = velocity_adv(pts.lon[idx], pts.lat[idx], 0.0, simulation)
-        dev.upload(F[pos.upper() + "_ULON"], ulon)
-        dev.upload(F[pos.upper() + "_VLAT"], vlat)
-    # latlon -> contravariant on the interior (:44-53)
-    dev.call("pycs_convert_wind_interior")
+    lean = getattr(cs_grid, "lean", False)
+    if lean:
+        # lean grid: wind at t = 0 and its conversion on the device (the kernels of update_adv)
+        for f in ("PU_ULON", "PU_VLAT", "PV_ULON", "PV_VLAT"):
+            dev.call("pycs_fill_field", F[f], 0.0)
+        dev.call("pycs_init_wind")
+    else:
+        # winds at t = 0 on the interior edge points (:37-41), evaluated on the host so
+        # that the steady wind (vf = 1) enters the device bit-identical to the reference
+        for pos, idx, shape in (("pu", np.s_[i0:iend + 1, j0:jend, :], (P + 1, P, 6)),
+                                ("pv", np.s_[i0:iend, j0:jend + 1, :], (P, P + 1, 6))):
+            pts = getattr(cs_grid, pos)
+            ulon, vlat = np.zeros(shape), np.zeros(shape)
+            ulon[idx], vlat[idx] = velocity_adv(pts.lon[idx], pts.lat[idx], 0.0, simulation)
+            dev.upload(F[pos.upper() + "_ULON"], ulon)
+            dev.upload(F[pos.upper() + "_VLAT"], vlat)
+        # latlon -> contravariant on the interior (:44-53)
+        dev.call("pycs_convert_wind_interior")
 
     if cs_grid.projection == "gnomonic_equiangular":          # :76-77
         lagrange_poly_ghostcell_pc(cs_grid, simulation)
@@ -40,14 +47,17 @@ def init_vars_adv(cs_grid, simulation):
     # CFL (:89-98): cx, cy of the instantaneous wind, max WITHOUT abs inside
     dev.call("pycs_cfl", F["CX"], F["PU_UCONTRA"], 0)
     dev.call("pycs_cfl", F["CY"], F["PV_VCONTRA"], 1)
-    CFL_x = np.amax(np.asarray(simulation.cx)[i0:iend + 1, :, :])
-    CFL_y = np.amax(np.asarray(simulation.cy)[:, j0:jend + 1, :])
+    CFL_x = dev.field_max(F["CX"], i0, iend + 1, 0, P)            # reduced on the device (a max is exact)
+    CFL_y = dev.field_max(F["CY"], 0, P, j0, jend + 1)
     simulation.CFL = max(abs(CFL_x), abs(CFL_y))
 
     simulation.px = ppm_parabola(cs_grid, simulation, 'x')      # :101-102
     simulation.py = ppm_parabola(cs_grid, simulation, 'y')
 
-    Q = np.zeros((P, P, 6))                                      # :105
-    I = np.s_[i0:iend, j0:jend, :]
-    Q[I] = q0_adv(cs_grid.pc.lon[I], cs_grid.pc.lat[I], simulation)
-    simulation.Q[...] = Q
+    if lean:
+        dev.call("pycs_init_tracer", F["Q"], 0.0)                # :105 on the device
+    else:
+        Q = np.zeros((P, P, 6))                                  # :105
+        I = np.s_[i0:iend, j0:jend, :]
+        Q[I] = q0_adv(cs_grid.pc.lon[I], cs_grid.pc.lat[I], simulation)
+        simulation.Q[...] = Q

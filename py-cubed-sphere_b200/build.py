@@ -23,6 +23,7 @@ UNITS = {
     "halo.cu": ["-fmad=false"],
     "ppm.cu": ["-fmad=false"],
     "wind.cu": ["-fmad=false"],
+    "grid.cu": ["-fmad=false"],
     "fused.cu": [],
     "fused2b.cu": [],
     "stepper.cu": [],

@@ -34,10 +34,16 @@ def _rotate(vec0, shape):
 
 class cubed_sphere:
     def __init__(self, N, transformation="gnomonic_equiangular", showonscreen=False, gridload=False,
-                 centres_only=False):
+                 centres_only=False, lean=False):
         """centres_only (not in the reference): build only the cell-centre coordinates (pc), which is
         all the Lagrange ghost-cell tables and the standalone halo fill read (src/lagrange.py:60-69);
-        lets the interpolation.par path run at N = 3072 without the 50 GB full grid."""
+        lets the interpolation.par path run at N = 3072 without the 50 GB full grid.
+
+        lean (not in the reference; equiangular grid only): build nothing but the scalars and the two 1-D
+        coordinate arrays; the fields the path reads (sqrt(g), conversion coefficients, lon / lat) are then
+        generated on the device by adv_simulation_par (pycs_generate_geometry, csrc/grid.cu), and
+        init_vars_adv evaluates the wind and the initial condition there too.  The host arrays
+        (cs_grid.pc.lon, metric_tensor_pc ...) do not exist on a lean grid."""
         if transformation not in ("gnomonic_equiangular", "gnomonic_equidistant"):
             print("ERROR: invalid grid transformation.")
             raise SystemExit(1)
@@ -58,6 +64,13 @@ class cubed_sphere:
         edges = np.linspace(-a - 4 * dx, a + 4 * dx, N + 1 + 8)
         cents = np.linspace(-a + dx / 2.0 - 4 * dx, a - dx / 2.0 + 4 * dx, P)
         half = self.R / np.sqrt(3.0)
+        self.x_centres, self.x_edges = cents, edges
+        self.lean = bool(lean)
+        if lean:
+            if not equiang:
+                print("ERROR: the lean (device-generated) grid is equiangular only.")
+                raise SystemExit(1)
+            return
         positions = {"pc": (cents, cents), "pu": (edges, cents), "pv": (cents, edges)}
         if centres_only:
             positions = {"pc": (cents, cents)}

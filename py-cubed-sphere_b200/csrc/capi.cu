@@ -321,6 +321,38 @@ extern "C" int pycs_upload_lagrange(pycs_handle h, int32_t degree, const int32_t
   return k_mg_replan(h);                 // the exchange plan follows the stencils
 }
 
+// --------------------------------------------------------------------------- device-side set-up (f2 / f3)
+extern "C" int pycs_generate_geometry(pycs_handle h, const double* xc, const double* xe) {
+  if (!xc || !xe) return arg_fail("null coordinate array");
+  CK(cudaSetDevice(h->device));
+  TRY(state_sync(h));
+  TRY(k_generate_geometry(h, xc, xe));
+  h->a2_valid = 0;
+  k_fused_invalidate(h);
+  return 0;
+}
+
+extern "C" int pycs_init_tracer(pycs_handle h, int32_t field, double t) {
+  if (field < 0 || field >= PYCS_F_COUNT || pycs_field_is_u(field) || pycs_field_is_v(field) ||
+      pycs_field_single_panel(field))
+    return arg_fail("pycs_init_tracer: not a six-panel centre field");
+  CK(cudaSetDevice(h->device));
+  if (field == PYCS_F_Q) TRY(k_fused_discard(h));
+  else TRY(normalize_q(h));
+  return k_init_tracer(h, field, t);
+}
+
+extern "C" int pycs_field_max(pycs_handle h, int32_t field, int32_t i0, int32_t i1, int32_t j0, int32_t j1, double* out) {
+  int ni, nj, np;
+  TRY(pycs_field_shape(h->g, field, &ni, &nj, &np));
+  if (np != 6 || i0 < 0 || i1 > ni || j0 < 0 || j1 > nj || i0 >= i1 || j0 >= j1 || !out) return arg_fail("pycs_field_max: bad rectangle");
+  CK(cudaSetDevice(h->device));
+  TRY(state_sync(h));
+  double* f;
+  TRY(pycs_field_ptr(h, field, &f));
+  return k_rect_max(h, f, i0, i1, j0, j1, out);
+}
+
 // --------------------------------------------------------------------------- halo API
 extern "C" int pycs_halo_gather(pycs_handle h, int32_t fx, int32_t fy, double* east, double* west,
                                 double* north, double* south) {
@@ -601,12 +633,15 @@ extern "C" int pycs_mgpu_plan(int32_t N, int32_t world, int32_t rank, int32_t de
   return 0;
 }
 
-extern "C" int pycs_split_plan(int32_t nstrips, int32_t nchunks, int32_t* interior, int32_t* boundary,
-                               int32_t* n_interior) {
-  if (nstrips < 1 || nchunks < 1 || !interior || !boundary || !n_interior) return arg_fail("bad split-plan arguments");
-  *n_interior = pycs_split_sets(nstrips, nchunks, interior, boundary);
-  if (*n_interior == 0)                     // no split: everything is boundary
-    for (int b = 0; b < 6 * nstrips * nchunks; ++b) boundary[b] = b;
+extern "C" int pycs_split_plan(int32_t row_lo, int32_t row_hi, int32_t nstrips, int32_t band, int32_t edge_rows,
+                               int32_t rows, int32_t* ctas4, int32_t max_ctas, int32_t* n_ctas, int32_t* n_boundary) {
+  if (row_hi <= row_lo || nstrips < 1 || !ctas4 || !n_ctas || !n_boundary) return arg_fail("bad split-plan arguments");
+  std::vector<CtaDesc> tab;
+  *n_boundary = pycs_plan_split_ctas(row_lo, row_hi, nstrips, band, edge_rows, rows, &tab);
+  *n_ctas = (int)tab.size();
+  for (int k = 0; k < (int)tab.size() && k < max_ctas; ++k) {
+    ctas4[4 * k] = tab[k].r0; ctas4[4 * k + 1] = tab[k].r1; ctas4[4 * k + 2] = tab[k].strip; ctas4[4 * k + 3] = tab[k].panel;
+  }
   return 0;
 }
 
@@ -629,6 +664,16 @@ extern "C" int pycs_errors(pycs_handle h, const double* qexact_interior, double*
     memcpy(&full[(((size_t)(i + g.lo)) * g.P + g.lo) * 6], qexact_interior + (size_t)i * g.N * 6,
            sizeof(double) * g.N * 6);
   TRY(pycs_upload_field(h, PYCS_F_USER_B, full.data()));
+  double* qe;
+  TRY(pycs_field_ptr(h, PYCS_F_USER_B, &qe));
+  return k_errors(h, qe, out3);
+}
+
+extern "C" int pycs_errors_exact(pycs_handle h, double t, double* out3) {
+  TRY(whole_sphere_only(h, "pycs_errors_exact"));
+  CK(cudaSetDevice(h->device));
+  TRY(normalize_q(h));
+  TRY(k_init_tracer(h, PYCS_F_USER_B, t));
   double* qe;
   TRY(pycs_field_ptr(h, PYCS_F_USER_B, &qe));
   return k_errors(h, qe, out3);

@@ -90,19 +90,27 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
   uint64_t* full = reinterpret_cast<uint64_t*>(sX + NWORK * RW); // [DL]
 
   const Geo& g = a.g;
-  const int cta = a.blk_map ? a.blk_map[blockIdx.x] : (int)blockIdx.x;   // CTA index in the full grid
-  int b = cta;
-  const int p = b % 6;
-  b /= 6;
-  const int strip = b % a.nstrips, chunk = b / a.nstrips;
+  int cta, p, strip, r0, r1;
+  if (a.cta_tab) {                           // split step: the CTA's rows and strip come from the table
+    cta = a.cta_off + (int)blockIdx.x;
+    const int4 d = a.cta_tab[cta];
+    r0 = d.x; r1 = d.y; strip = d.z; p = d.w;
+  } else {                                   // uniform grid: strips x chunks x 6, panel fastest
+    cta = (int)blockIdx.x;
+    int b = cta;
+    p = b % 6;
+    b /= 6;
+    strip = b % a.nstrips;
+    const int chunk = b / a.nstrips;
+    r0 = a.row_lo + chunk * a.rows_per_chunk;
+    r1 = min(r0 + a.rows_per_chunk, a.row_hi);
+  }
   const int tid = threadIdx.x;
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp index, provably warp-uniform
   const int e = tid + 3;                     // own element in a staged row (the y-stencil reaches e-3 .. e+2)
   const int jbase = g.lo + strip * a.wcols;
   const int jend = min(jbase + a.wcols, g.hi);
   const int j = jbase - 3 + tid;
-  const int r0 = a.row_lo + chunk * a.rows_per_chunk;
-  const int r1 = min(r0 + a.rows_per_chunk, a.row_hi);
   const int rfirst = r0 - 3, rlast = r1 + 2;
   const bool out_lane = (tid >= 3) && (j < jend);
   const bool jint = (j >= g.lo) && (j < g.hi);
@@ -311,7 +319,7 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   if ((tid & 31) == 0) sF[tid >> 5] = v;
   __syncthreads();
-  const int ntot = a.blk_map ? a.nblk_total : (int)gridDim.x;
+  const int ntot = a.cta_tab ? a.nblk_total : (int)gridDim.x;
   const int mgw = a.pub.world;
   if (tid == 0) {
     double t = 0.0;
@@ -386,19 +394,34 @@ cudaError_t dispatch(const FusedArgs& a, int recon, int split, int mask, int gh,
 
 }  // namespace
 
-int pycs_split_sets(int nstrips, int nchunks, int* interior, int* boundary) {
-  if (nstrips < 3 || nchunks < 3) return 0;
-  int ni = 0, nb = 0;
-  for (int chunk = 0; chunk < nchunks; ++chunk)
-    for (int strip = 0; strip < nstrips; ++strip) {
-      const bool in = strip >= 1 && strip <= nstrips - 2 && chunk >= 1 && chunk <= nchunks - 2;
-      for (int p = 0; p < 6; ++p) {
-        const int b = (chunk * nstrips + strip) * 6 + p;
-        if (in) interior[ni++] = b;
-        else boundary[nb++] = b;
-      }
+int pycs_plan_split_ctas(int row_lo, int row_hi, int nstrips, int band, int edge_rows, int rows,
+                         std::vector<CtaDesc>* out) {
+  out->clear();
+  const int nrows = row_hi - row_lo;
+  if (band < 3) band = 3;
+  if (edge_rows < 4) edge_rows = 4;
+  if (rows < 4) rows = 4;
+  auto chunks = [&](int a, int b, int len, int s0, int s1) {        // rows [a, b) in chunks of <= len, strips [s0, s1)
+    if (b <= a) return;
+    const int n = (b - a + len - 1) / len, per = (b - a + n - 1) / n;
+    for (int c = 0; c < n; ++c) {
+      const int r0 = a + c * per, r1 = r0 + per < b ? r0 + per : b;
+      if (r0 >= r1) continue;
+      for (int st = s0; st < s1; ++st)
+        for (int p = 0; p < 6; ++p) out->push_back(CtaDesc{r0, r1, st, p});   // panel fastest: shared metric rows
     }
-  return ni;
+  };
+  if (nstrips < 3 || nrows < 2 * band + 8) {           // no interior: everything is boundary
+    chunks(row_lo, row_hi, edge_rows > band ? edge_rows : band, 0, nstrips);
+    return (int)out->size();
+  }
+  chunks(row_lo, row_lo + band, band, 0, nstrips);                                  // lower band
+  chunks(row_hi - band, row_hi, band, 0, nstrips);                                  // upper band
+  chunks(row_lo + band, row_hi - band, edge_rows, 0, 1);                            // first strip
+  chunks(row_lo + band, row_hi - band, edge_rows, nstrips - 1, nstrips);            // last strip
+  const int nb = (int)out->size();
+  chunks(row_lo + band, row_hi - band, rows, 1, nstrips - 1);                       // interior
+  return nb;
 }
 
 bool pycs_fused2b_has(int recon, int split) { return (recon == 1 || recon == 3) && split >= 1 && split <= 3; }

@@ -1,6 +1,7 @@
 // Arguments of the fused step kernels (fused2b.cu: the production kernel; fused.cu: the first-generation
 // kernel that still serves the limited reconstructions PPM-CW84 / PPM-L04).
 #pragma once
+#include <vector>
 #include "pycs_common.cuh"
 
 struct MgSync;
@@ -54,9 +55,13 @@ struct FusedArgs {
   double cdx, cdy;            // dt/dx, dt/dy
   // split step: a step is two launches over disjoint CTA sets -- boundary CTAs (everything a ghost cell or
   // a peer reads, launched first on a high-priority stream, followed by the exchange and the next ghost
-  // fill) and interior CTAs.  blk_map[blockIdx.x] = CTA index in the full grid; both launches share
-  // part[], the ticket counter and nblk_total, so whichever finishes last closes the step.
-  const int* blk_map;         // nullptr: one launch over the whole grid
+  // fill) and interior CTAs.  The CTAs are listed in a table (boundary CTAs first): CTA blockIdx.x of a
+  // launch is entry cta_off + blockIdx.x = (first row, end row, strip, panel).  The boundary CTAs march
+  // few rows each, so that they are done -- and the exchange under way -- long before the interior
+  // CTAs.  Both launches share part[], the ticket counter and nblk_total: whichever finishes last
+  // closes the step.
+  const int4* cta_tab;        // nullptr: one launch over the uniform grid strips x chunks x 6
+  int cta_off;
   int nblk_total;
   // several GPUs: the peers' sums (and the right to overwrite their buffers) arrive with sflag >= steps
   const long long* wait_flags;
@@ -67,10 +72,15 @@ struct FusedArgs {
   int timing;                 // roofline timing launches: leave the control block alone
 };
 
-// CTA sets of a split step: strips x chunks x 6 panels, CTA = (chunk * nstrips + strip) * 6 + panel.
-// Interior: strips 1 .. nstrips-2 and chunks 1 .. nchunks-2 (their staged rows / columns hold no
-// ghost cell and no row of another slab).  Returns the number of interior CTAs (0: no split).
-int pycs_split_sets(int nstrips, int nchunks, int* interior, int* boundary);
+// CTA table of a split step over the rows [row_lo, row_hi) of a panel of N x N cells cut into nstrips column
+// strips: boundary CTAs first (row bands of `band` rows at both ends of the slab over all strips, then the
+// first and last strip in chunks of `edge_rows` rows), then the interior CTAs (strips 1 .. nstrips-2 in
+// chunks of `rows` rows).  Interior CTAs stage neither a ghost cell nor a row of another slab (band >= 3).
+// Entries are (r0, r1, strip, panel).  Returns the number of boundary CTAs; a slab or panel too small to
+// have an interior yields boundary CTAs only.
+struct CtaDesc { int r0, r1, strip, panel; };
+int pycs_plan_split_ctas(int row_lo, int row_hi, int nstrips, int band, int edge_rows, int rows,
+                         std::vector<CtaDesc>* out);
 
 #ifdef __CUDACC__
 // The writer of the last partial of a launch adds them all up: consumers of the MF-PR sum

@@ -136,6 +136,10 @@ int k_q_update(pycs_handle h);
 int k_errors(pycs_handle h, const double* qexact_dev, double* out3_host);
 int k_mass(pycs_handle h, double* out_host);
 int k_sum_sq_metric(pycs_handle h, double* out_host);
+// grid.cu
+int k_generate_geometry(pycs_handle h, const double* xc, const double* xe);
+int k_init_tracer(pycs_handle h, int field, double t);
+int k_rect_max(pycs_handle h, const double* f, int i0, int i1, int j0, int j1, double* out_host);
 // wind.cu
 int k_time_averaged_velocity(pycs_handle h);
 int k_wind_ghost_fill(pycs_handle h);

@@ -245,9 +245,9 @@ struct FusedState {
   int impl = 0;                // 4: v2b (fused2b.cu), 2: v2 (fused.cu, limited reconstructions)
   // split step
   int split = 0;               // 0 undecided, 1 on, -1 off
-  int* map_i = nullptr;        // CTA indices of the interior / boundary launch
-  int* map_b = nullptr;
+  int4* cta_tab = nullptr;     // CTA table of the split step: n_b boundary CTAs, then n_i interior CTAs
   int n_i = 0, n_b = 0;
+  int band = 0, edge_rows = 0, irows = 0;
   cudaStream_t s2 = nullptr;
   cudaEvent_t e_fork = nullptr, e_join = nullptr;
   // graphs: one per ping-pong parity and wind mask
@@ -347,29 +347,47 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
     fs.nchunks = (nrows + rows - 1) / rows;
     drop_graphs(fs);
   }
-  const int nb = 6 * fs.nstrips * fs.nchunks;      // MF-PR partial sums
-  if (fs.npart_cap < nb) {
-    if (fs.part) cudaFree(fs.part);
-    CK(cudaMalloc(&fs.part, sizeof(double) * nb));
-    fs.npart_cap = nb;
-  }
-  fs.npart = nb;
   if (fs.split == 0) {
     const char* es = getenv("PYCS_SPLIT");
     const bool want = h->mg || (es && atoi(es));   // several GPUs always run the split step
     fs.split = (want && fs.impl == 4) ? 1 : -1;
     if (fs.split == 1) {
-      std::vector<int> in(nb), bd(nb);
-      fs.n_i = pycs_split_sets(fs.nstrips, fs.nchunks, in.data(), bd.data());
-      if (fs.n_i == 0)                              // too few strips / chunks: everything is boundary
-        for (int b = 0; b < nb; ++b) bd[b] = b;
-      fs.n_b = nb - fs.n_i;
-      if (fs.n_i) {
-        CK(cudaMalloc(&fs.map_i, sizeof(int) * fs.n_i));
-        CK(cudaMemcpy(fs.map_i, in.data(), sizeof(int) * fs.n_i, cudaMemcpyHostToDevice));
+      // Boundary CTAs march few rows each, so that they are done early and the exchange + ghost fill of
+      // the next step run beside the interior CTAs: bands of `band` rows at both ends of the slab, the
+      // first / last strip in chunks of `edge_rows`; the interior in chunks sized for the CTA slots left.
+      const char* eb = getenv("PYCS_SPLIT_BAND");
+      const char* ee = getenv("PYCS_SPLIT_EDGE_ROWS");
+      const char* ei = getenv("PYCS_SPLIT_ROWS");
+      const int nrows = h->row_hi - h->row_lo;
+      fs.band = eb ? atoi(eb) : 12;
+      fs.edge_rows = ee ? atoi(ee) : 16;
+      if (fs.band < 4) fs.band = 4;                // >= the 4-wide E / W strips and the 3 halo rows
+      int irows = ei ? atoi(ei) : 0;
+      if (irows <= 0) {
+        std::vector<CtaDesc> tmp;
+        const int nbnd = pycs_plan_split_ctas(h->row_lo, h->row_hi, fs.nstrips, fs.band, fs.edge_rows, nrows, &tmp);
+        const int per_sm = pycs_fused2b_resident(h->prm.recon, h->prm.opsplit, (h->prm.dp == 2) ? 1 : 0);
+        int slots = h->sm_count * (per_sm > 0 ? per_sm : 4) - nbnd;      // the boundary CTAs are resident too
+        if (slots < h->sm_count) slots = h->sm_count;
+        const int icols = 6 * (fs.nstrips - 2), inrows = nrows - 2 * fs.band;
+        int best = inrows > 0 ? inrows : 8;
+        double best_cost = 1e30;
+        for (int nch = 1; icols > 0 && nch <= inrows; ++nch) {
+          const int rr = (inrows + nch - 1) / nch;
+          if (rr < 8 && nch > 1) break;
+          const int waves = (icols * ((inrows + rr - 1) / rr) + slots - 1) / slots;
+          const double cost = (double)waves * (rr + 6);
+          if (cost < best_cost) { best_cost = cost; best = rr; }
+        }
+        irows = best;
       }
-      CK(cudaMalloc(&fs.map_b, sizeof(int) * fs.n_b));
-      CK(cudaMemcpy(fs.map_b, bd.data(), sizeof(int) * fs.n_b, cudaMemcpyHostToDevice));
+      fs.irows = irows;
+      std::vector<CtaDesc> tab;
+      fs.n_b = pycs_plan_split_ctas(h->row_lo, h->row_hi, fs.nstrips, fs.band, fs.edge_rows, irows, &tab);
+      fs.n_i = (int)tab.size() - fs.n_b;
+      static_assert(sizeof(CtaDesc) == sizeof(int4), "CTA table entries are int4");
+      CK(cudaMalloc(&fs.cta_tab, sizeof(int4) * tab.size()));
+      CK(cudaMemcpy(fs.cta_tab, tab.data(), sizeof(int4) * tab.size(), cudaMemcpyHostToDevice));
       if (!fs.s2) {
         int lo_pri = 0, hi_pri = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
@@ -379,13 +397,23 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
       }
     }
   }
+  // MF-PR partial sums: one per CTA
+  const int nb = (fs.split == 1) ? fs.n_b + fs.n_i : 6 * fs.nstrips * fs.nchunks;
+  if (fs.npart_cap < nb) {
+    if (fs.part) cudaFree(fs.part);
+    CK(cudaMalloc(&fs.part, sizeof(double) * nb));
+    fs.npart_cap = nb;
+  }
+  fs.npart = nb;
   if (!fs.counter) {
     CK(cudaMalloc(&fs.counter, sizeof(unsigned)));
     CK(cudaMemsetAsync(fs.counter, 0, sizeof(unsigned), h->stream));
   }
   if (fs.use_graph < 0) {
+    // replay from a CUDA graph: on by default for the serial step; the split step is launched directly
+    // unless PYCS_GRAPH=1 (measured at 2 GPUs, N = 1536: 0.131 ms per step replayed, 0.122 ms launched)
     const char* eg = getenv("PYCS_GRAPH");
-    fs.use_graph = (eg && !atoi(eg)) ? 0 : 1;
+    fs.use_graph = eg ? (atoi(eg) ? 1 : 0) : (fs.split == 1 ? 0 : 1);
   }
   if (fs.prof < 0) fs.prof = getenv("PYCS_STEP_PROFILE") ? 1 : 0;
   return 0;
@@ -553,8 +581,7 @@ void k_fused_release(pycs_handle h) {
   if (fs.ws_tab) cudaFree(fs.ws_tab);
   if (fs.bu) cudaFree(fs.bu);
   if (fs.bv) cudaFree(fs.bv);
-  if (fs.map_i) cudaFree(fs.map_i);
-  if (fs.map_b) cudaFree(fs.map_b);
+  if (fs.cta_tab) cudaFree(fs.cta_tab);
   if (fs.e_fork) cudaEventDestroy(fs.e_fork);
   if (fs.e_join) cudaEventDestroy(fs.e_join);
   if (fs.s2) cudaStreamDestroy(fs.s2);
@@ -567,9 +594,8 @@ void k_fused_release(pycs_handle h) {
 void k_fused_reset_grid(pycs_handle h) {
   FusedState& fs = g_fused[h];
   fs.rows = 0;
-  if (fs.map_i) cudaFree(fs.map_i);      // CTA sets of the split step belong to the old grid
-  if (fs.map_b) cudaFree(fs.map_b);
-  fs.map_i = fs.map_b = nullptr;
+  if (fs.cta_tab) cudaFree(fs.cta_tab);  // the CTA table of the split step belongs to the old grid
+  fs.cta_tab = nullptr;
   fs.n_i = fs.n_b = 0;
   fs.split = 0;                          // decided again by fused_setup
   fs.ghost_ready = 0;
@@ -696,7 +722,8 @@ static int step_args(pycs_handle h, FusedState& fs, const double* qcur, double* 
   a.rows_per_chunk = fs.rows; a.nstrips = fs.nstrips; a.wcols = fs.wcols;
   a.row_lo = h->row_lo; a.row_hi = h->row_hi;
   a.cdx = g.dt / g.dx; a.cdy = g.dt / g.dy;
-  a.blk_map = nullptr;
+  a.cta_tab = nullptr;
+  a.cta_off = 0;
   a.nblk_total = fs.npart;
   a.pub.world = 0;
   a.timing = 0;
@@ -735,7 +762,8 @@ int k_fused_time_kernel(pycs_handle h, int reps, int separable, float* ms) {
     a.ws_tab = fs.ws_tab + WS_CAP;
     a.ws_mask = 0;
     a.timing = 1;
-    TRY(launch_step(h, fs, a, mask, 0, fs.npart, h->stream));
+    a.nblk_total = 6 * fs.nstrips * fs.nchunks;
+    TRY(launch_step(h, fs, a, mask, 0, 6 * fs.nstrips * fs.nchunks, h->stream));
   }
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaEventSynchronize(h->ev1));
@@ -761,7 +789,7 @@ int k_fused_grid_info(pycs_handle h, int* tb, int* rows, int* nblocks) {
   TRY(fused_setup(h, fs));
   *tb = fs.tb;
   *rows = fs.rows;
-  *nblocks = fs.npart;
+  *nblocks = 6 * fs.nstrips * fs.nchunks;
   return 0;
 }
 
@@ -826,7 +854,8 @@ static int enqueue_split(pycs_handle h, FusedState& fs, double* qcur, double* qn
   CK(cudaEventRecord(fs.e_fork, h->stream));            // everything before this step
   CK(cudaStreamWaitEvent(fs.s2, fs.e_fork, 0));
   FusedArgs b = a;
-  b.blk_map = fs.map_b;
+  b.cta_tab = fs.cta_tab;
+  b.cta_off = 0;
   TRY(launch_step(h, fs, b, mask, 1, fs.n_b, fs.s2));   // reads ghost cells, feeds the peers
   if (h->mg) TRY(k_mg_exchange(h, qnext, fs.ctl, fs.s2));
   // the ghost cells the NEXT step reads: their sources are boundary cells of this step's output (own:
@@ -835,7 +864,8 @@ static int enqueue_split(pycs_handle h, FusedState& fs, double* qcur, double* qn
   CK(cudaEventRecord(fs.e_join, fs.s2));
   if (fs.n_i) {
     FusedArgs c = a;
-    c.blk_map = fs.map_i;
+    c.cta_tab = fs.cta_tab;
+    c.cta_off = fs.n_b;
     TRY(launch_step(h, fs, c, mask, 0, fs.n_i, h->stream));   // reads no ghost cell
   }
   CK(cudaStreamWaitEvent(h->stream, fs.e_join, 0));

@@ -93,6 +93,10 @@ def load_library():
         "pycs_adv_time_step_host": [h, dp, C.c_int64, C.c_double, C.c_int32],
         "pycs_synchronize": [h],
         "pycs_errors": [h, dp, dp],
+        "pycs_errors_exact": [h, C.c_double, dp],
+        "pycs_generate_geometry": [h, dp, dp],
+        "pycs_init_tracer": [h, C.c_int32, C.c_double],
+        "pycs_field_max": [h, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, dp],
         "pycs_mass": [h, dp],
         "pycs_launch_count": [h, C.POINTER(C.c_int64)],
         "pycs_time_step_kernel": [h, C.c_int32, C.c_int32, C.POINTER(C.c_float)],
@@ -173,6 +177,11 @@ class Device:
 
     def array(self, fid):
         return DeviceArray(self, fid)
+
+    def field_max(self, fid, i0, i1, j0, j1):
+        out = C.c_double()
+        self.call("pycs_field_max", fid, int(i0), int(i1), int(j0), int(j1), C.byref(out))
+        return out.value
 
     def sm_count(self):
         n = C.c_int32()

@@ -30,10 +30,24 @@ def ghost_tables(cs_grid, degree):
     i0, iend = cs_grid.i0, cs_grid.iend
     P = N + ng
     order = degree + 1
-    pc = cs_grid.pc
+    if getattr(cs_grid, "lean", False):
+        # lean grid: the two four-row strips of cell centres from the 1-D coordinates, with the expressions
+        # of cs_datastruct.cubed_sphere (src/cs_transform.py:41-96), hence the same bits as the full grid's
+        def strip(rows, panel):
+            x, y = np.meshgrid(cs_grid.x_centres[rows], cs_grid.x_centres, indexing="ij")
+            tx, ty = np.tan(x), np.tan(y)
+            invD = 1.0 / np.sqrt(1.0 + tx**2 + ty**2)
+            v0 = (invD, invD * tx, invD * ty)
+            return (v0[1], v0[2]) if panel == 0 else (v0[0], v0[2])     # (Y, Z): panel 1 has Y = invD
+        Yg, Zg = strip(slice(iend, iend + ngr), 0)
+        Y1, Z1 = strip(slice(i0, i0 + ngr), 1)
+    else:
+        pc = cs_grid.pc
+        Yg, Zg = pc.Y[iend:iend + ngr, :, 0], pc.Z[iend:iend + ngr, :, 0]
+        Y1, Z1 = pc.Y[i0:i0 + ngr, :, 1], pc.Z[i0:i0 + ngr, :, 1]
     # inverse equiangular map on panel 1: y = arctan(Z/Y) (src/cs_transform.py:105-107)
-    y_ghost = np.arctan(pc.Z[iend:iend + ngr, :, 0] / pc.Y[iend:iend + ngr, :, 0])
-    y = np.arctan(pc.Z[i0:i0 + ngr, :, 1] / pc.Y[i0:i0 + ngr, :, 1])
+    y_ghost = np.arctan(Zg / Yg)
+    y = np.arctan(Z1 / Y1)
     K = (y_ghost - y[:, 0:1]) / cs_grid.dy
     Kmax = K + ceil(order / 2)
     Kmin = Kmax - order + 1

@@ -45,13 +45,44 @@ def save_error_files(cs_grid, ll_grid, simulation, q, q_exact, k):
     return base
 
 
+def errors_device(simulation, q_exact):
+    """compute_errors (src/errors.py:99-113) of the device-resident Q against a host exact field (N,N,6)."""
+    import ctypes as C
+    qe = np.ascontiguousarray(q_exact, dtype=np.float64)
+    out = (C.c_double * 3)()
+    dp = C.POINTER(C.c_double)
+    simulation.dev.call("pycs_errors", qe.ctypes.data_as(dp), C.cast(out, dp))
+    return out[0], out[1], out[2]
+
+
+def errors_exact_device(simulation, t):
+    """The same against qexact_adv(t) evaluated on the device (csrc/grid.cu)."""
+    import ctypes as C
+    out = (C.c_double * 3)()
+    simulation.dev.call("pycs_errors_exact", float(t), C.cast(out, C.POINTER(C.c_double)))
+    return out[0], out[1], out[2]
+
+
 def output_adv(cs_grid, ll_grid, simulation, plot, k, t, Nsteps, plotstep, map_projection, divtest_flag):
     if plot or k == Nsteps:
         i0, iend, j0, jend = cs_grid.i0, cs_grid.iend, cs_grid.j0, cs_grid.jend
         I = np.s_[i0:iend, j0:jend, :]
-        q_exact = qexact_adv(cs_grid.pc.lon[I], cs_grid.pc.lat[I], t, simulation)
-        q = simulation.Q[I]
-        simulation.error_linf[k], simulation.error_l1[k], simulation.error_l2[k] = compute_errors(q, q_exact)
+        lean = getattr(cs_grid, "lean", False)
+        sharded = simulation.dev.row_range() != (i0, iend)
+        if lean and not sharded:
+            # exact solution and the three norms on the device: nothing is transferred
+            simulation.error_linf[k], simulation.error_l1[k], simulation.error_l2[k] = errors_exact_device(simulation, t)
+            q = q_exact = None
+        else:
+            q_exact = qexact_adv(cs_grid.pc.lon[I], cs_grid.pc.lat[I], t, simulation)
+            if sharded:
+                q = simulation.Q[I]
+                simulation.error_linf[k], simulation.error_l1[k], simulation.error_l2[k] = compute_errors(q, q_exact)
+            else:
+                # |Q - Qexact| reduced on the device (csrc/ppm.cu k_errors); only the exact field goes up
+                simulation.error_linf[k], simulation.error_l1[k], simulation.error_l2[k] = \
+                    errors_device(simulation, q_exact)
+                q = None
         if simulation.error_linf[k] > 100.0:
             print('Stopping due to large errors.')
             print('The CFL number is:', simulation.CFL)
@@ -68,5 +99,5 @@ def output_adv(cs_grid, ll_grid, simulation, plot, k, t, Nsteps, plotstep, map_p
                 d = np.asarray(simulation.div)[I]
                 dex = div_exact(cs_grid.pc.lon[I], cs_grid.pc.lat[I], simulation)
                 simulation.error_linf[k], simulation.error_l1[k], simulation.error_l2[k] = compute_errors(d, dex)
-            elif t > 0 and k == Nsteps and ll_grid is not None and len(np.shape(ll_grid.mask)) == 2:
-                save_error_files(cs_grid, ll_grid, simulation, q, q_exact, k)
+            elif t > 0 and k == Nsteps and ll_grid is not None and len(np.shape(ll_grid.mask)) == 2 and q_exact is not None:
+                save_error_files(cs_grid, ll_grid, simulation, simulation.Q[I] if q is None else q, q_exact, k)

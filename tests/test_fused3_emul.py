@@ -244,24 +244,3 @@ def test_emulated_v2b_two_row_march_same_bits_as_const_slot(emul):
     assert np.array_equal(a, b)
 
 
-# ---- split step (PYCS_SPLIT, FusedArgs::blk_map): interior CTAs must not depend on any ghost cell -----
-@pytest.mark.parametrize("vf,kw", [(3, {"pending": True}), (1, {}), (3, {"separable": True})])
-def test_emulated_split_step_interior_reads_no_ghost_cell(emul, vf, kw):
-    """The CTA sets of pycs_split_plan: the interior set runs on a Q whose ghost cells are NaN, the boundary set
-    on the ghost-filled Q; together they must give the oracle's step (a NaN would show a ghost dependence)."""
-    import ctypes
-    import pycs_b200  # noqa: F401
-    from pycs_b200 import device
-    N, tb, rows = 130, 32, 20
-    ns, nch = -(-N // (tb - 6)), -(-N // rows)
-    lib = device.load_library()
-    ip = ctypes.POINTER(ctypes.c_int32)
-    lib.pycs_split_plan.argtypes = [ctypes.c_int32, ctypes.c_int32, ip, ip, ip]
-    n = 6 * ns * nch
-    inner, outer, cnt = (ctypes.c_int32 * n)(), (ctypes.c_int32 * n)(), ctypes.c_int32()
-    assert lib.pycs_split_plan(ns, nch, inner, outer, ctypes.byref(cnt)) == 0 and cnt.value == 6 * (ns - 2) * (nch - 2)
-    sets = (list(inner[:cnt.value]), list(outer[:n - cnt.value]))
-    got, want = one_step(emul, N, vf, TUPLES["default"], 2, depth=2, rows=rows, block_tb=tb, circ=True,
-                         split_sets=sets, **kw)
-    assert np.all(np.isfinite(got))
-    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))

@@ -256,11 +256,11 @@ def test_config1_n48_full_revolution(mods, fused):
     sim.dev.close()
 
 
-def _check_big(mods, fname, fused, max_k=None):
+def _check_big(mods, fname, fused, max_k=None, lean=False):
     ref = load(fname)
     N, vf = int(ref["N"]), int(ref["vf"])
     tup = tuple(int(x) for x in ref["tuple"])
-    g = mods.cs_datastruct.cubed_sphere(N)
+    g = mods.cs_datastruct.cubed_sphere(N, lean=lean)
     sim = mods.advection_ic.adv_simulation_par(g, float(ref["dt"]), 5, 2, vf, 1, *tup)
     mods.advection_vars.init_vars_adv(g, sim)
     if fused and not sim.dev.fused_supported():
@@ -279,8 +279,13 @@ def _check_big(mods, fname, fused, max_k=None):
         Q = np.asarray(sim.Q)
         assert relerr(Q[np.ix_(idx, idx, np.arange(6))], ref["Q_k%d" % k]) <= TOL, (fname, k)
         assert abs(np.sum(Q[I]) - float(ref["sumQ_k%d" % k])) <= TOL * abs(float(ref["sumQ_k%d" % k]))
-        qe = mods.advection_ic.qexact_adv(g.pc.lon[I], g.pc.lat[I], k * sim.dt, sim)
-        for a, b in zip(ost.compute_errors(Q[I], qe), ref["err_k%d" % k]):
+        if lean:
+            from pycs_b200.output import errors_exact_device
+            errs = errors_exact_device(sim, k * sim.dt)
+        else:
+            qe = mods.advection_ic.qexact_adv(g.pc.lon[I], g.pc.lat[I], k * sim.dt, sim)
+            errs = ost.compute_errors(Q[I], qe)
+        for a, b in zip(errs, ref["err_k%d" % k]):
             # a norm is a mean / max of |Q - Qexact|: a 1-ulp difference of Q (2.2e-16 max|Q|) moves it by up to
             # that much, so below E ~ 2e-4 max|Q| a purely relative 1e-12 is finer than fp64 resolves on the
             # field itself (measured: |dE| = 1.1e-16 on E = 1.57e-6 at k = 1, N = 384).  Hence the floor of
@@ -308,6 +313,17 @@ def test_config3_n768_deformational(mods, fused):
 def test_config4_n1536_divergent(mods, fused):
     """Config 4: N=1536, divergent flow, first 20 steps."""
     _check_big(mods, "config_N1536_vf3.npz", fused)
+
+
+@pytest.mark.skipif(not have("config_N1536_vf3.npz"), reason="fixture not generated")
+def test_config4_n1536_lean_grid(mods):
+    """Config 4 the way bench.py runs it: geometry, wind, initial condition and error norms on the device."""
+    _check_big(mods, "config_N1536_vf3.npz", True, lean=True)
+
+
+@pytest.mark.skipif(not have("config_N768_vf2.npz"), reason="fixture not generated")
+def test_config3_n768_lean_grid(mods):
+    _check_big(mods, "config_N768_vf2.npz", True, lean=True)
 
 
 # ------------------------------------------------------------------ fused vs operator path
@@ -424,4 +440,76 @@ def test_full_size_properties_n1536(mods):
             _, dm = mods.diagnostics.mass_computation(sim.Q, g, m0)
             assert dm <= 1e-13
     assert relerr(outs[2], 2.0 * outs[0] - 3.0 * outs[1]) <= 1e-12
+    sim.dev.close()
+
+
+# ------------------------------------------------------------------ lean grid: geometry, IC, diagnostics on the device
+def test_lean_grid_device_geometry_matches_host(mods):
+    """cubed_sphere(N, lean=True): sqrt(g), the conversion coefficients and lon / lat generated on the device
+    (csrc/grid.cu) against the host numpy grid (= the reference's arrays): last-ulp agreement."""
+    from pycs_b200.device import F
+    N = 48
+    gh = mods.cs_datastruct.cubed_sphere(N)
+    gl = mods.cs_datastruct.cubed_sphere(N, lean=True)
+    a = make_sim(mods, gh, 3, TUPLES["default"])
+    b = make_sim(mods, gl, 3, TUPLES["default"])
+    names = ["SQRTG_PC", "SQRTG_PU", "SQRTG_PV"] + [p + "_" + c for p in ("PC", "PU", "PV")
+                                                    for c in ("EXLON", "EXLAT", "EYLON", "EYLAT", "DET", "LON", "LAT")]
+    for nm in names:
+        x, y = a.dev.download(F[nm]), b.dev.download(F[nm])
+        assert np.max(np.abs(x - y)) <= 4e-15 * max(1.0, float(np.max(np.abs(x)))), nm
+    assert np.array_equal(a.stencil_ghost_pc[0][0], b.stencil_ghost_pc[0][0])
+    assert np.array_equal(a.lagrange_poly_ghost_pc[0], b.lagrange_poly_ghost_pc[0])
+    assert abs(a.CFL - b.CFL) <= 1e-14 * a.CFL
+    assert relerr(np.asarray(b.Q), np.asarray(a.Q)) <= 1e-14         # initial condition evaluated on the device
+    assert relerr(np.asarray(b.U_pu.ucontra), np.asarray(a.U_pu.ucontra)) <= 1e-13
+    a.dev.close()
+    b.dev.close()
+
+
+@pytest.mark.parametrize("N,vf,name", [(50, 3, "default"), (130, 2, "AVLT-RK2-DG-PR"), (64, 1, "PL07-RK1-DG-PR")])
+def test_lean_grid_steps_match_host_grid(mods, N, vf, name):
+    gh = mods.cs_datastruct.cubed_sphere(N)
+    gl = mods.cs_datastruct.cubed_sphere(N, lean=True)
+    a = make_sim(mods, gh, vf, TUPLES[name])
+    b = make_sim(mods, gl, vf, TUPLES[name])
+    for fused in (True, False):
+        mods.advection_timestep.run_steps(gh, a, 0 if fused else 12, 12, fused=fused)
+        mods.advection_timestep.run_steps(gl, b, 0 if fused else 12, 12, fused=fused)
+        assert relerr(np.asarray(b.Q), np.asarray(a.Q)) <= TOL, (N, vf, name, fused)
+    a.dev.close()
+    b.dev.close()
+
+
+def test_lean_grid_config1_norms_and_device_diagnostics(mods):
+    """Config 1 through adv_sphere on a lean grid: exact solution, error norms and mass on the device
+    (pycs_errors_exact, pycs_mass), against the reference's numbers."""
+    rows = json.load(open(os.path.join(GOLDEN, "norms.json")))
+    row = [r for r in rows if r["N"] == 48][0]
+    g = mods.cs_datastruct.cubed_sphere(48, lean=True)
+    sim = mods.advection_ic.adv_simulation_par(g, row["dt"], 5, 2, 1, 2, *row["tuple"])
+    linf, l1, l2 = mods.advection_sphere.adv_sphere(g, None, sim, "sphere", False, False)
+    Q = np.asarray(sim.Q)
+    floor = 4 * np.finfo(float).eps * float(np.max(np.abs(Q)))
+    for x, y in zip((linf, l1, l2), (row["linf"], row["l1"], row["l2"])):
+        assert abs(x - y) <= TOL * abs(y) + floor, (x, y)
+    if have("config1_N48_final.npz"):
+        assert relerr(Q[4:52, 4:52, :], load("config1_N48_final.npz")["Q"]) <= TOL
+    assert sim.mass_change <= 1e-13
+    sim.dev.close()
+
+
+def test_device_error_norms_match_host(mods, g16):
+    """pycs_errors / pycs_errors_exact (device reductions) against errors.compute_errors on the host."""
+    from pycs_b200.output import errors_device, errors_exact_device
+    from pycs_b200.errors import compute_errors
+    sim = make_sim(mods, g16, 1, TUPLES["default"])
+    mods.advection_timestep.run_steps(g16, sim, 0, 7, fused=True)
+    I = np.s_[4:20, 4:20, :]
+    t = 7 * sim.dt
+    qe = mods.advection_ic.qexact_adv(g16.pc.lon[I], g16.pc.lat[I], t, sim)
+    want = compute_errors(np.asarray(sim.Q)[I], qe)
+    for got in (errors_device(sim, qe), errors_exact_device(sim, t)):
+        for x, y in zip(got, want):
+            assert abs(x - y) <= 1e-12 * abs(y) + 1e-15
     sim.dev.close()

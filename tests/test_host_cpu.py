@@ -205,27 +205,62 @@ def test_divergence_sweep_follows_the_reference_table(monkeypatch, capsys):
     assert "Ratio E_1/E_0: 2.00e+00 2.00e+00 2.00e+00" in capsys.readouterr().out
 
 
-@pytest.mark.parametrize("ns,nch", [(10, 19), (3, 3), (5, 7), (2, 9), (9, 2)])
-def test_split_step_cta_sets(ns, nch):
-    """PYCS_SPLIT: interior + boundary CTA sets partition the grid; an interior CTA's staged rows and columns
-    (chunk rows -3..+2, strip columns -3..+2) never reach the first / last chunk or strip, i.e. no ghost cell."""
+def _split_plan(row_lo, row_hi, ns, band, edge_rows, rows):
     lib = device.load_library()
     ip = ctypes.POINTER(ctypes.c_int32)
-    lib.pycs_split_plan.argtypes = [ctypes.c_int32, ctypes.c_int32, ip, ip, ip]
+    lib.pycs_split_plan.argtypes = [ctypes.c_int32] * 6 + [ip, ctypes.c_int32, ip, ip]
     lib.pycs_split_plan.restype = ctypes.c_int
-    n = 6 * ns * nch
-    inner, outer, cnt = (ctypes.c_int32 * n)(), (ctypes.c_int32 * n)(), ctypes.c_int32()
-    assert lib.pycs_split_plan(ns, nch, inner, outer, ctypes.byref(cnt)) == 0
-    ni = cnt.value
-    if ns < 3 or nch < 3:
-        assert ni == 0 and list(outer) == list(range(n))
-        return
-    assert ni == 6 * (ns - 2) * (nch - 2)
-    a, b = list(inner[:ni]), list(outer[:n - ni])
-    assert sorted(a + b) == list(range(n)) and a == sorted(a) and b == sorted(b)
-    for blk in a:
-        strip, chunk = (blk // 6) % ns, blk // (6 * ns)
-        assert 1 <= strip <= ns - 2 and 1 <= chunk <= nch - 2
+    cap = 1 << 16
+    tab, n, nb = (ctypes.c_int32 * (4 * cap))(), ctypes.c_int32(), ctypes.c_int32()
+    assert lib.pycs_split_plan(row_lo, row_hi, ns, band, edge_rows, rows, tab, cap, ctypes.byref(n), ctypes.byref(nb)) == 0
+    assert n.value <= cap
+    return [tuple(tab[4 * k:4 * k + 4]) for k in range(n.value)], nb.value
+
+
+@pytest.mark.parametrize("N,world,rank,band,edge_rows,rows", [(1536, 1, 0, 12, 16, 81), (1536, 8, 0, 12, 16, 28),
+                                                              (1536, 8, 3, 12, 12, 40), (1536, 2, 1, 8, 24, 90),
+                                                              (320, 1, 0, 12, 16, 60), (48, 1, 0, 12, 16, 48),
+                                                              (130, 8, 7, 4, 8, 8), (384, 4, 2, 12, 16, 30)])
+def test_split_step_cta_table(N, world, rank, band, edge_rows, rows):
+    """The CTA table of the split step: (1) the CTAs tile the slab exactly once per panel; (2) an interior
+    CTA stages no ghost cell and no row outside the slab (rows r0-3 .. r1+2, columns of its strip -3 .. +2);
+    (3) everything the exchange plan sends to a peer, and every source of a ghost cell this rank owns, is
+    written by a boundary CTA -- those finish first and the exchange / next ghost fill follow them."""
+    from pycs_b200.device import mgpu_plan
+    lo, hi = 4, N + 4
+    base, rem = divmod(N, world)
+    a = lo + rank * base + min(rank, rem)
+    b = a + base + (1 if rank < rem else 0)
+    wmax = 154
+    ns = (N + wmax - 1) // wmax
+    wcols = (N + ns - 1) // ns
+    wcols += wcols & 1
+    tab, nb = _split_plan(a, b, ns, band, edge_rows, rows)
+    cover = np.zeros((6, N + 8, N + 8), np.int32)
+    bnd = np.zeros((6, N + 8, N + 8), bool)
+    for k, (r0, r1, strip, panel) in enumerate(tab):
+        j0, j1 = lo + strip * wcols, min(lo + (strip + 1) * wcols, hi)
+        assert a <= r0 < r1 <= b and 0 <= strip < ns and 0 <= panel < 6
+        cover[panel, r0:r1, j0:j1] += 1
+        if k < nb:
+            bnd[panel, r0:r1, j0:j1] = True
+        else:
+            assert r0 - 3 >= a and r1 + 2 < b                  # no row of another slab, no W / E ghost row
+            assert j0 - 3 >= lo and j1 + 2 < hi                # no S / N ghost column
+    assert np.all(cover[:, a:b, lo:hi] == 1) and cover.sum() == 6 * (b - a) * N
+    # the 4-wide strips along all four panel edges and the 3 rows next to the neighbouring slabs
+    need = np.zeros((N + 8, N + 8), bool)
+    need[a:b, lo:lo + 4] = need[a:b, hi - 4:hi] = True
+    need[a:min(a + 4, b)] |= True
+    need[max(b - 4, a):b] |= True
+    need[:, :lo] = need[:, hi:] = False
+    assert np.all(bnd[:, need])
+    if world > 1 and N <= 400:
+        from oracle.grid import LeanGrid
+        from oracle import halo as ohalo
+        km = ohalo.lagrange_tables(LeanGrid.centres_only(N), 3)[0][0][0]
+        for peer, panel, i0, i1, j0, j1 in mgpu_plan(N, world, rank, km, 3)[2]:
+            assert np.all(bnd[panel, i0:i1, j0:j1]), (peer, panel, i0, i1, j0, j1)
 
 
 @pytest.mark.parametrize("vf", [1, 2, 3, 4])
