@@ -493,31 +493,35 @@ extern "C" int pycs_convert_wind_interior(pycs_handle h) {
   return k_wind_interior(h, 0.0, 1, 0);
 }
 
-// Is the wind of this handle U(0) * f(t) with the step able to apply f(t) itself?  Wind field 3 with RK1:
-// U(t) = U(0) cos(pi t / T) exactly (src/advection_ic.py:301-305); the fused step then scales a private
-// copy of the t = 0 contravariant winds in-kernel and no wind kernel runs.
-static bool separable_wind(pycs_handle h) { return h->prm.vf == 3 && h->prm.dp == 1 && !h->no_separable; }
+// How the fused step gets a time-dependent wind without the reference's per-step wind kernels (stepper.cu:
+// k_fused_step): 1 = wind field 3 with RK1 is U(0) cos(pi t / T) exactly (src/advection_ic.py:301-305),
+// scaled inside the step kernel; 2 = fields 2 and 3 are finite sums of static basis fields, combined by
+// one kernel per step; 0 = steady winds (fields 1, 4) or PYCS_NO_SEPARABLE (wind kernels every step).
+static int lazy_wind_mode(pycs_handle h) {
+  if (h->no_separable || !(h->prm.vf == 2 || h->prm.vf == 3) || h->prm.et != 3) return 0;
+  return (h->prm.vf == 3 && h->prm.dp == 1) ? 1 : 2;
+}
 
 static int run_steps(pycs_handle h, int64_t k0, int64_t nsteps, int fused) {
   CK(cudaSetDevice(h->device));
   if (fused && !k_fused_supported(h)) return arg_fail("no fused step kernel for this scheme tuple");
   if (h->mg && !fused) return arg_fail("multi-GPU handles run the fused step only");
   if (nsteps <= 0) return 0;
-  // Separable wind: the steps never touch U_pu / U_pv / U_pc, so those arrays are left behind and
+  // Lazy wind modes: the steps never touch U_pu / U_pv / U_pc, so those arrays are left behind and
   // caught up lazily (wind_sync) by whatever reads them next -- like pycs_adv_time_step_host, and
   // like the reference's loop, a run has no epilogue.  Stale arrays from an earlier run stay stale.
-  const bool separable = fused && separable_wind(h);
-  if (!separable) TRY(wind_sync(h));
+  const int wmode = fused ? lazy_wind_mode(h) : 0;
+  if (!wmode) TRY(wind_sync(h));
   for (int64_t k = k0 + 1; k <= k0 + nsteps; ++k) {
     const double t = (double)k * h->g.dt;                       // t = k*dt, src/advection_sphere.py:47
     if (fused) {
-      TRY(k_fused_step(h, k, t, separable ? 1 : 0));
+      TRY(k_fused_step(h, k, t, wmode));
     } else {
       TRY(pycs_adv_time_step(h, k, t));
       TRY(k_update_adv(h, t));
     }
   }
-  if (separable) h->wind_stale_k = k0 + nsteps;
+  if (wmode) h->wind_stale_k = k0 + nsteps;
   if (fused) k_fused_profile_report(h);
   return 0;
 }
@@ -573,10 +577,9 @@ extern "C" int pycs_adv_time_step_host(pycs_handle h, double* Q, int64_t k, doub
     if (!k_fused_supported(h)) return arg_fail("no fused step kernel for this scheme tuple");
     // wind field 3 + RK1 is U(0)*cos(pi t/T): the step scales the t = 0 winds in-kernel and the
     // exposed wind arrays are caught up lazily (wind_sync) when something reads them
-    const bool separable = separable_wind(h) &&
-                           fabs(t - (double)k * h->g.dt) <= 1e-12 * (1.0 + fabs(t));   // t = k*dt as in adv_sphere
-    if (separable) {
-      TRY(k_fused_step(h, k, t, 1));
+    const int wmode = fabs(t - (double)k * h->g.dt) <= 1e-12 * (1.0 + fabs(t)) ? lazy_wind_mode(h) : 0;   // t = k*dt as in adv_sphere
+    if (wmode) {
+      TRY(k_fused_step(h, k, t, wmode));
       h->wind_stale_k = k;
     } else {
       TRY(wind_sync(h));

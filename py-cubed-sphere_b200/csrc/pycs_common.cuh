@@ -144,7 +144,12 @@ int k_rect_max(pycs_handle h, const double* f, int i0, int i1, int j0, int j1, d
 int k_time_averaged_velocity(pycs_handle h);
 int k_wind_ghost_fill(pycs_handle h);
 int k_update_adv(pycs_handle h, double t);
-int k_wind_interior(pycs_handle h, double t, int convert_interior_only, int do_velocity);
+int k_wind_interior(pycs_handle h, double t, int convert_interior_only, int do_velocity, int basis = -1);
+int k_wind_basis_count(pycs_handle h);
+int k_wind_basis_build(pycs_handle h, int m);
+int k_wind_basis_combine(pycs_handle h, double* const* bu, double* const* bv, int nb, double* ua, double* um, double* va,
+                         double* vm, const double* coef, int cmask, const long long* steps);
+int k_wind_coef_fill(pycs_handle h, double* tab, int cmask, long long s0, long long k0, int n);
 // stepper.cu
 int k_fused_supported(pycs_handle h);
 int k_fused_step(pycs_handle h, long long k, double t, int separable);

@@ -236,6 +236,14 @@ struct FusedState {
   double* bu = nullptr;        // separable wind: ucontra(t = 0) incl. ghost edges
   double* bv = nullptr;        //                 vcontra(t = 0)
   int base_valid = 0;
+  // basis winds (wind mode 2): the contravariant wind incl. ghost edges of every basis field of the wind
+  // (wind.cu), the per-step combination (instantaneous + departure-point averaged) and its coefficients
+  double* basis_u[4] = {nullptr, nullptr, nullptr, nullptr};
+  double* basis_v[4] = {nullptr, nullptr, nullptr, nullptr};
+  int nbasis = 0, basis_valid = 0;
+  double *wua = nullptr, *wum = nullptr, *wva = nullptr, *wvm = nullptr;
+  double* wcoef = nullptr;     // [WS_CAP][8]
+  long long wc_off = 0, wc_until = -1;
   int pending = 0;             // the sum of the last step waits to be applied (mirror of ctl->pend)
   int ring_pending = 0;        // ghost ring of the current buffer is stale
   int ring_raw = 0;            // ... and the ring of the buffer the last step read carries no projection term
@@ -252,9 +260,9 @@ struct FusedState {
   cudaEvent_t e_fork = nullptr, e_join = nullptr;
   // graphs: one per ping-pong parity and wind mask
   int use_graph = -1;
-  cudaGraphExec_t gexec[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
-  const double* gq[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
-  int gnodes[2][3] = {{0, 0, 0}, {0, 0, 0}};
+  cudaGraphExec_t gexec[2][5] = {};
+  const double* gq[2][5] = {};
+  int gnodes[2][5] = {};
 };
 
 static std::map<pycs_handle, FusedState> g_fused;
@@ -263,7 +271,7 @@ StepCtl* k_fused_ctl(pycs_handle h) { return g_fused[h].ctl; }
 
 static void drop_graphs(FusedState& fs) {
   for (int a = 0; a < 2; ++a)
-    for (int b = 0; b < 3; ++b) {
+    for (int b = 0; b < 5; ++b) {
       if (fs.gexec[a][b]) cudaGraphExecDestroy(fs.gexec[a][b]);
       fs.gexec[a][b] = nullptr;
       fs.gq[a][b] = nullptr;
@@ -581,6 +589,12 @@ void k_fused_release(pycs_handle h) {
   if (fs.ws_tab) cudaFree(fs.ws_tab);
   if (fs.bu) cudaFree(fs.bu);
   if (fs.bv) cudaFree(fs.bv);
+  for (int m = 0; m < 4; ++m) {
+    if (fs.basis_u[m]) cudaFree(fs.basis_u[m]);
+    if (fs.basis_v[m]) cudaFree(fs.basis_v[m]);
+  }
+  for (double* p : {fs.wua, fs.wum, fs.wva, fs.wvm, fs.wcoef})
+    if (p) cudaFree(p);
   if (fs.cta_tab) cudaFree(fs.cta_tab);
   if (fs.e_fork) cudaEventDestroy(fs.e_fork);
   if (fs.e_join) cudaEventDestroy(fs.e_join);
@@ -605,6 +619,7 @@ void k_fused_reset_grid(pycs_handle h) {
     h->launches++;
     fs.steps_host = 0;
     fs.ws_until = -1;
+    fs.wc_until = -1;
   }
 }
 
@@ -618,6 +633,7 @@ void k_fused_invalidate(pycs_handle h) {
   if (fs.gs) cudaFree(fs.gs);
   fs.gs = nullptr;
   fs.base_valid = 0;
+  fs.basis_valid = 0;
   drop_graphs(fs);
 }
 
@@ -636,6 +652,7 @@ void k_fused_invalidate_graphs(pycs_handle h) {
   if (it == g_fused.end()) return;
   drop_graphs(it->second);
   it->second.ws_until = -1;
+  it->second.wc_until = -1;
 }
 
 // Separable wind (vf = 3, RK1): the step kernel scales the contravariant wind of t = 0
@@ -660,16 +677,63 @@ static int ensure_base_winds(pycs_handle h, FusedState& fs) {
   return 0;
 }
 
+// Basis winds (wind mode 2: field 2, or field 3 with RK2): every basis field of the wind pushed once
+// through the wind pipeline of init_vars_adv (wind.cu: k_wind_basis_build), kept as contravariant
+// fields incl. ghost edges.  Building them overwrites U_pu / U_pv / U_pc; the lazy catch-up restores them.
+static int ensure_basis_winds(pycs_handle h, FusedState& fs) {
+  if (fs.basis_valid) return 0;
+  const size_t bytes = sizeof(double) * 6 * (size_t)h->g.ps;
+  fs.nbasis = k_wind_basis_count(h);
+  double *u, *v;
+  TRY(pycs_field_ptr(h, PYCS_F_PU_UCONTRA, &u));
+  TRY(pycs_field_ptr(h, PYCS_F_PV_VCONTRA, &v));
+  for (int m = 0; m < fs.nbasis; ++m) {
+    if (!fs.basis_u[m]) CK(cudaMalloc(&fs.basis_u[m], bytes));
+    if (!fs.basis_v[m]) CK(cudaMalloc(&fs.basis_v[m], bytes));
+    TRY(k_wind_basis_build(h, m));
+    CK(cudaMemcpyAsync(fs.basis_u[m], u, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(fs.basis_v[m], v, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  for (double** p : {&fs.wua, &fs.wum, &fs.wva, &fs.wvm})
+    if (!*p) {
+      CK(cudaMalloc(p, bytes));
+      CK(cudaMemsetAsync(*p, 0, bytes, h->stream));
+    }
+  if (!fs.wcoef) CK(cudaMalloc(&fs.wcoef, sizeof(double) * 8 * WS_CAP));
+  fs.basis_valid = 1;
+  fs.wc_until = -1;
+  drop_graphs(fs);
+  return 0;
+}
+
 // Everything the reference's step k leaves in U_pu / U_pv / U_pc, rebuilt from the analytic wind
-// after one or more separable-wind steps that did not touch those arrays: wind(t_{k-1}) on the
-// interior, the ghost fill and the departure velocity of step k (src/advection_timestep.py:31-37),
-// then update_adv(t_k) (:48-75).
+// after one or more fused steps that did not touch those arrays: the wind of t_{k-1} with -- for
+// RK2 -- the wind of t_{k-2} in ucontra_old (src/advection_timestep.py:61-62), the ghost fill and the
+// departure velocity of step k (:31-37), then update_adv(t_k) (:48-75).
 int k_wind_catch_up(pycs_handle h, long long k) {
   if (k < 1 || h->prm.vf < 2) return 0;
-  TRY(k_wind_interior(h, (double)(k - 1) * h->g.dt, 1, 1));
+  const double dt = h->g.dt;
+  if (h->prm.dp == 2 && k >= 2) {
+    TRY(k_wind_interior(h, (double)(k - 2) * dt, 1, 1));
+    TRY(k_wind_ghost_fill(h));
+    TRY(k_update_adv(h, (double)(k - 1) * dt));       // old <- wind(t_{k-2}) incl. its ghost edges; wind(t_{k-1})
+  } else {
+    TRY(k_wind_interior(h, (double)(k - 1) * dt, 1, 1));
+    if (h->prm.dp == 2) {                              // first step: old = the wind of t = 0 after its ghost fill
+      TRY(k_wind_ghost_fill(h));
+      double *u, *v, *uo, *vo;
+      TRY(pycs_field_ptr(h, PYCS_F_PU_UCONTRA, &u));
+      TRY(pycs_field_ptr(h, PYCS_F_PV_VCONTRA, &v));
+      TRY(pycs_field_ptr(h, PYCS_F_PU_UOLD, &uo));
+      TRY(pycs_field_ptr(h, PYCS_F_PV_VOLD, &vo));
+      const size_t bytes = sizeof(double) * 6 * (size_t)h->g.ps;
+      CK(cudaMemcpyAsync(uo, u, bytes, cudaMemcpyDeviceToDevice, h->stream));
+      CK(cudaMemcpyAsync(vo, v, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    }
+  }
   TRY(k_wind_ghost_fill(h));
   TRY(k_time_averaged_velocity(h));
-  return k_update_adv(h, (double)k * h->g.dt);
+  return k_update_adv(h, (double)k * dt);
 }
 
 // ghost(sqrtg): the Lagrange fill applied to the metric field itself, once (see dg_fill_kernel)
@@ -693,7 +757,8 @@ static int ensure_gs(pycs_handle h, FusedState& fs) {
 }
 
 // arguments common to every launch of the step kernel
-static int step_args(pycs_handle h, FusedState& fs, const double* qcur, double* qnext, int mask, FusedArgs* out) {
+static int step_args(pycs_handle h, FusedState& fs, const double* qcur, double* qnext, int mask, FusedArgs* out,
+                     int wind_mode = 0) {
   const Geo& g = h->g;
   double *sgc, *sgu, *sgv, *ua, *va, *um, *vm;
   TRY(pycs_field_ptr(h, PYCS_F_SQRTG_PC, &sgc));
@@ -708,6 +773,7 @@ static int step_args(pycs_handle h, FusedState& fs, const double* qcur, double* 
   a.g = g;
   a.q = qcur; a.qn = qnext;
   if (mask == 2) { ua = fs.bu; va = fs.bv; }
+  if (wind_mode == 2) { ua = fs.wua; va = fs.wva; um = fs.wum; vm = fs.wvm; }
   a.ua = ua; a.va = va; a.um = um; a.vm = vm;
   a.sgc = sgc; a.rgc = fs.rgc; a.sgu = sgu; a.sgv = sgv;
   a.part = fs.part;
@@ -795,8 +861,19 @@ int k_fused_grid_info(pycs_handle h, int* tb, int* rows, int* nblocks) {
 
 // ---- one step, enqueued (or captured) on the handle's stream ----------------------------------------
 // serial: ghost fill with the projection term folded in, (wind kernels), step kernel over the whole grid
+static int step_winds(pycs_handle h, FusedState& fs, bool winds, int wind_mode) {
+  if (winds) {                    // the reference's wind kernels (src/advection_timestep.py:31-37)
+    TRY(k_wind_ghost_fill(h));
+    TRY(k_time_averaged_velocity(h));
+  } else if (wind_mode == 2) {    // the same winds combined from the basis fields, one launch
+    TRY(k_wind_basis_combine(h, fs.basis_u, fs.basis_v, fs.nbasis, fs.wua, fs.wum, fs.wva, fs.wvm, fs.wcoef,
+                             WS_CAP - 1, &fs.ctl->steps));
+  }
+  return 0;
+}
+
 static int enqueue_serial(pycs_handle h, FusedState& fs, double* qcur, double* qnext, int mask, bool winds,
-                          bool profile) {
+                          bool profile, int wind_mode) {
   auto mark = [&]() {
     if (!profile || fs.ev.size() >= 4 * 4096) return;
     cudaEvent_t e;
@@ -808,14 +885,11 @@ static int enqueue_serial(pycs_handle h, FusedState& fs, double* qcur, double* q
   // 1. ghost cells of Q (src/advection_timestep.py:28), folding in the pending MF-PR term
   TRY(launch_ghost_fill(h, qcur, h->stream, fs.gs, fs.ctl, h->prm.mf == 3 ? 1 : 0, h->red_out + 8, nullptr, false));
   // 2. winds (src/advection_timestep.py:31-37)
-  if (winds) {
-    TRY(k_wind_ghost_fill(h));
-    TRY(k_time_averaged_velocity(h));
-  }
+  TRY(step_winds(h, fs, winds, wind_mode));
   mark();
   // 3. divergence + Q update
   FusedArgs a;
-  TRY(step_args(h, fs, qcur, qnext, mask, &a));
+  TRY(step_args(h, fs, qcur, qnext, mask, &a, wind_mode));
   a.corr_ptr = (h->prm.mf == 3) ? h->red_out + 8 : nullptr;
   TRY(launch_step(h, fs, a, mask, 0, fs.npart, h->stream));
   mark();
@@ -826,7 +900,7 @@ static int enqueue_serial(pycs_handle h, FusedState& fs, double* qcur, double* q
 // split: boundary CTAs -> exchange -> ghost fill of the next step on the high-priority stream, interior
 // CTAs on the handle's stream.  Precondition: the ghost cells of qcur are (raw) filled.
 static int enqueue_split(pycs_handle h, FusedState& fs, double* qcur, double* qnext, int mask, bool winds,
-                         bool profile) {
+                         bool profile, int wind_mode) {
   auto mark = [&]() {
     if (!profile || fs.ev.size() >= 4 * 4096) return;
     cudaEvent_t e;
@@ -835,13 +909,10 @@ static int enqueue_split(pycs_handle h, FusedState& fs, double* qcur, double* qn
     fs.ev.push_back(e);
   };
   mark();
-  if (winds) {
-    TRY(k_wind_ghost_fill(h));
-    TRY(k_time_averaged_velocity(h));
-  }
+  TRY(step_winds(h, fs, winds, wind_mode));
   mark();
   FusedArgs a;
-  TRY(step_args(h, fs, qcur, qnext, mask, &a));
+  TRY(step_args(h, fs, qcur, qnext, mask, &a, wind_mode));
   if (h->mg) {
     a.wait_flags = h->mg->sync->sflag;
     a.wait_world = h->mg->world;
@@ -874,10 +945,15 @@ static int enqueue_split(pycs_handle h, FusedState& fs, double* qcur, double* qn
   return 0;
 }
 
-// separable != 0: wind field 3 with RK1 -- U(t) = U(0) cos(pi t / T) exactly
-// (src/advection_ic.py:301-305), so the step reads a private copy of the t = 0 winds and scales
-// them; no wind kernels run.
-int k_fused_step(pycs_handle h, long long k, double t, int separable) {
+// wind_mode: how the step gets its winds without the reference's per-step wind kernels
+//   0  none of the below: steady winds (fields 1 and 4) are read as init_vars_adv left them, time-dependent
+//      ones are refreshed by the wind kernels around the step kernel (PYCS_NO_SEPARABLE);
+//   1  separable: wind field 3 with RK1 is U(0) cos(pi t / T) exactly (src/advection_ic.py:301-305): the step
+//      kernel reads a private copy of the t = 0 winds and scales them;
+//   2  basis winds: the instantaneous and the departure-point averaged wind are combined from the static
+//      basis fields by one kernel (wind.cu: wind_basis_kernel).
+// In modes 1 and 2 U_pu / U_pv / U_pc are not touched; the caller marks them stale (capi.cu: wind_sync).
+int k_fused_step(pycs_handle h, long long k, double t, int wind_mode) {
   FusedState& fs = g_fused[h];
   TRY(fused_setup(h, fs));
   if (h->prm.mf == 3 && !h->a2_valid) {
@@ -897,21 +973,26 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   TRY(pycs_field_ptr(h, PYCS_F_Q_NEXT, &qb));
   double* qcur = h->qcur ? qb : qa;
   double* qnext = h->qcur ? qa : qb;
+  const bool separable = wind_mode == 1;
   if (separable) TRY(ensure_base_winds(h, fs));
+  if (wind_mode == 2) TRY(ensure_basis_winds(h, fs));
   TRY(ensure_gs(h, fs));
   const int mask = separable ? 2 : ((h->prm.dp == 2) ? 1 : 0);    // RK1: averaged wind == instantaneous wind
-  const bool winds = h->prm.vf >= 2 && !separable;
+  const bool winds = (h->prm.vf == 2 || h->prm.vf == 3) && wind_mode == 0;
   const bool split = fs.split == 1;
 
-  // time factors of the separable wind for this and the following steps
-  if (separable) {
-    const long long idx = fs.steps_host;
-    if (!(k - idx == fs.ws_off && idx < fs.ws_until)) {
-      ws_fill_kernel<<<(WS_BATCH + 255) / 256, 256, 0, h->stream>>>(fs.ws_tab, idx, k, WS_BATCH, h->g.dt);
-      CKL(h);
-      fs.ws_off = k - idx;
-      fs.ws_until = idx + WS_BATCH;
-    }
+  // per-step coefficients of the lazy wind modes for this and the following steps
+  const long long idx = fs.steps_host;
+  if (separable && !(k - idx == fs.ws_off && idx < fs.ws_until)) {
+    ws_fill_kernel<<<(WS_BATCH + 255) / 256, 256, 0, h->stream>>>(fs.ws_tab, idx, k, WS_BATCH, h->g.dt);
+    CKL(h);
+    fs.ws_off = k - idx;
+    fs.ws_until = idx + WS_BATCH;
+  }
+  if (wind_mode == 2 && !(k - idx == fs.wc_off && idx < fs.wc_until)) {
+    TRY(k_wind_coef_fill(h, fs.wcoef, WS_CAP - 1, idx, k, WS_BATCH));
+    fs.wc_off = k - idx;
+    fs.wc_until = idx + WS_BATCH;
   }
   if (split && !fs.ghost_ready) {
     // first step after something else touched Q: the raw ghost fill this step's boundary CTAs read
@@ -923,14 +1004,16 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
   if (graph) {
     // nothing may allocate or configure inside the capture: touch every field and kernel attribute first
     FusedArgs warm;
-    TRY(step_args(h, fs, qcur, qnext, mask, &warm));
-    if (fs.impl == 4 && pycs_fused2b_resident(h->prm.recon, h->prm.opsplit, mask, split ? 1 : 0) < 1) {
+    TRY(step_args(h, fs, qcur, qnext, mask, &warm, wind_mode));
+    if (fs.impl == 4 && (pycs_fused2b_resident(h->prm.recon, h->prm.opsplit, mask, 0) < 1 ||
+                         pycs_fused2b_resident(h->prm.recon, h->prm.opsplit, mask, split ? 1 : 0) < 1)) {
       pycs_set_error("fused2b kernel: occupancy query failed");
       return PYCS_ERR_CUDA;
     }
     const int par = (qcur == qa) ? 0 : 1;      // keyed by the buffer that is read (f[Q] / f[Q_NEXT] may have been swapped)
-    cudaGraphExec_t& ge = fs.gexec[par][mask];
-    if (ge && fs.gq[par][mask] != qcur) {
+    const int key = wind_mode == 2 ? 3 + mask : mask;
+    cudaGraphExec_t& ge = fs.gexec[par][key];
+    if (ge && fs.gq[par][key] != qcur) {
       cudaGraphExecDestroy(ge);
       ge = nullptr;
     }
@@ -938,23 +1021,23 @@ int k_fused_step(pycs_handle h, long long k, double t, int separable) {
       const long long l0 = h->launches;
       cudaGraph_t gr = nullptr;
       CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-      int r = split ? enqueue_split(h, fs, qcur, qnext, mask, false, false)
-                    : enqueue_serial(h, fs, qcur, qnext, mask, false, false);
+      int r = split ? enqueue_split(h, fs, qcur, qnext, mask, false, false, wind_mode)
+                    : enqueue_serial(h, fs, qcur, qnext, mask, false, false, wind_mode);
       cudaError_t ce = cudaStreamEndCapture(h->stream, &gr);
       if (r) return r;
       CK(ce);
       CK(cudaGraphInstantiate(&ge, gr, 0));
       cudaGraphDestroy(gr);
-      fs.gq[par][mask] = qcur;
-      fs.gnodes[par][mask] = (int)(h->launches - l0);
+      fs.gq[par][key] = qcur;
+      fs.gnodes[par][key] = (int)(h->launches - l0);
       h->launches = l0;                        // captured, not run
     }
     CK(cudaGraphLaunch(ge, h->stream));
-    h->launches += fs.gnodes[par][mask];
+    h->launches += fs.gnodes[par][key];
   } else if (split) {
-    TRY(enqueue_split(h, fs, qcur, qnext, mask, winds, profile));
+    TRY(enqueue_split(h, fs, qcur, qnext, mask, winds, profile, wind_mode));
   } else {
-    TRY(enqueue_serial(h, fs, qcur, qnext, mask, winds, profile));
+    TRY(enqueue_serial(h, fs, qcur, qnext, mask, winds, profile, wind_mode));
   }
   fs.steps_host += 1;
   h->last_step_kernel_launches++;

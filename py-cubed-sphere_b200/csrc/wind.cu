@@ -56,19 +56,115 @@ __device__ __forceinline__ void velocity_point(int vf, double t, double lo_, dou
   *vo = v;
 }
 
+// The time-dependent wind fields are finite sums  W(lon, lat, t) = sum_m f_m(t) B_m(lon, lat)  of static
+// lat-lon fields (angle addition on src/advection_ic.py:294-305, with c = cos(pi t / T), phi = 4 pi t / T):
+//   field 2:  B_0 = (2 pi cos(lat) / T, 0)                                  f_0 = 1
+//             B_1 = (k/2 sin(2 lat), 0)                                     f_1 = c
+//             B_2 = (-k/2 sin(2 lat) cos(2 lon),  k cos(lat) sin(2 lon))    f_2 = c cos(phi)
+//             B_3 = (-k/2 sin(2 lat) sin(2 lon), -k cos(lat) cos(2 lon))    f_3 = c sin(phi)
+//   field 3:  B_0 = W(lon, lat, 0)                                          f_0 = c
+// Everything between the lat-lon wind and the contravariant wind on the edges incl. the ghost edges is
+// linear (conversion, cubic interpolation, Lagrange fill), so the contravariant wind at any time is the
+// same combination of the basis fields pushed through that pipeline once (stepper.cu: basis winds).
+__host__ __device__ inline int wind_basis_count(int vf) { return vf == 2 ? 4 : (vf == 3 ? 1 : 0); }
+__device__ __forceinline__ void velocity_basis_point(int vf, int m, double lo_, double la, double* uo, double* vo) {
+  const double pi = PI_;
+  if (vf == 3) {
+    velocity_point(3, 0.0, lo_, la, uo, vo);
+    return;
+  }
+  const double T = PYCS_WIND_PERIOD, k = 2.0;
+  double u = 0.0, v = 0.0;
+  if (m == 0) u = 2. * pi * cos(la) / T;
+  else if (m == 1) u = 0.5 * k * sin(2. * la);
+  else if (m == 2) { u = -0.5 * k * sin(2. * la) * cos(2. * lo_); v = k * cos(la) * sin(2. * lo_); }
+  else { u = -0.5 * k * sin(2. * la) * sin(2. * lo_); v = -k * cos(la) * cos(2. * lo_); }
+  *uo = u;
+  *vo = v;
+}
+// coefficients f_m(t) of the basis fields
+__host__ __device__ inline void wind_basis_coef(int vf, double t, double* f) {
+  const double pi = PI_, T = PYCS_WIND_PERIOD;
+  const double c = cos(pi * t / T);
+  if (vf == 3) { f[0] = c; return; }
+  const double phi = 4.0 * pi * t / T;
+  f[0] = 1.0; f[1] = c; f[2] = c * cos(phi); f[3] = c * sin(phi);
+}
+
 // velocity_adv on the interior edge points of one position (pu: i in [lo,hi], j in [lo,hi);
-// pv: i in [lo,hi), j in [lo,hi])
+// pv: i in [lo,hi), j in [lo,hi]); basis >= 0: that basis field instead of the wind at time t
 __global__ void velocity_kernel(Geo g, int vf, double t, int is_pu, const double* __restrict__ lon,
                                 const double* __restrict__ lat, double* __restrict__ ulon,
-                                double* __restrict__ vlat) {
+                                double* __restrict__ vlat, int basis) {
   int j = g.lo + blockIdx.x * BX + threadIdx.x, i = g.lo + blockIdx.y, p = blockIdx.z;
   int ih = is_pu ? g.hi : g.hi - 1, jh = is_pu ? g.hi - 1 : g.hi;
   if (i > ih || j > jh) return;
   long long id = gidx(g, p, i, j);
   double u, v;
-  velocity_point(vf, t, lon[id], lat[id], &u, &v);
+  if (basis >= 0) velocity_basis_point(vf, basis, lon[id], lat[id], &u, &v);
+  else velocity_point(vf, t, lon[id], lat[id], &u, &v);
   ulon[id] = u;
   vlat[id] = v;
+}
+
+// Contravariant wind of a step from the basis fields, both directions in one launch (blockIdx.z = 6 dir + p):
+//   u  = sum_m f_m B_m           the instantaneous wind the step's upwind masks look at (src/averaged_velocity.py:21-27)
+//   u* = sum_m g_m B_m           g = 1.5 f(t_{k-1}) - 0.5 f(t_{k-2}): the time-extrapolated wind (:42)
+//   ubar = departure-point average of u* (:44-49, :54-62), or u itself for RK1
+// on the edges lo .. hi along the direction, all transversal indices (where time_averaged_velocity writes).
+struct WindBasisArgs {
+  Geo g;
+  const double* bu[4];
+  const double* bv[4];
+  double *ua, *um, *va, *vm;
+  const double* coef;         // [WS_CAP][8]: f_0..f_3, g_0..g_3 of a step
+  const long long* steps;     // StepCtl::steps: which row of the table
+  int cmask, nb, rk2;
+  double dto2;
+};
+__global__ void wind_basis_kernel(const __grid_constant__ WindBasisArgs a) {
+  const Geo& g = a.g;
+  const int dir = blockIdx.z / 6, p = blockIdx.z % 6;
+  const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y;
+  const int ni = dir == 0 ? g.P + 1 : g.P, nj = dir == 0 ? g.P : g.P + 1;
+  if (j >= nj || i >= ni) return;
+  const int s = dir == 0 ? i : j;
+  if (s < g.lo || s > g.hi) return;
+  const double* c = a.coef + 8 * (*a.steps & a.cmask);
+  const double* const* B = dir == 0 ? a.bu : a.bv;
+  const long long st = dir == 0 ? g.ld : 1;
+  const long long id = gidx(g, p, i, j);
+  double u = 0.0, us0 = 0.0, usm = 0.0, usp = 0.0;
+  for (int m = 0; m < a.nb; ++m) {
+    const double b0 = B[m][id];
+    u = fma(c[m], b0, u);
+    if (a.rk2) {
+      us0 = fma(c[4 + m], b0, us0);
+      usm = fma(c[4 + m], B[m][id - st], usm);
+      usp = fma(c[4 + m], B[m][id + st], usp);
+    }
+  }
+  double r = u;
+  if (a.rk2) {
+    const double aa = u * a.dto2 / (dir == 0 ? g.dx : g.dy);
+    r = (u >= 0) ? fma(aa, usm - us0, us0) : fma(aa, us0 - usp, us0);     // (1-a) u*_i + a u*_{i-1} | -a u*_{i+1} + (1+a) u*_i
+    (dir == 0 ? a.um : a.vm)[id] = u;
+  }
+  (dir == 0 ? a.ua : a.va)[id] = r;
+}
+__global__ void wind_coef_fill_kernel(double* tab, int cmask, long long s0, long long k0, int n, double dt, int vf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long k = k0 + i;                         // reference step k reads the wind of t_{k-1}, old = wind of t_{k-2}
+  const double tp = (double)(k - 1) * dt, tpp = (k >= 2) ? (double)(k - 2) * dt : tp;
+  double f[4] = {0, 0, 0, 0}, fo[4] = {0, 0, 0, 0};
+  wind_basis_coef(vf, tp, f);
+  wind_basis_coef(vf, tpp, fo);
+  double* row = tab + 8 * ((s0 + i) & cmask);
+  for (int m = 0; m < 4; ++m) {
+    row[m] = f[m];
+    row[4 + m] = 1.5 * f[m] - 0.5 * fo[m];
+  }
 }
 
 // update_adv for one position in ONE pass over the whole array (src/advection_timestep.py:48-75):
@@ -288,7 +384,7 @@ int k_wind_ghost_fill(pycs_handle h) {
 
 // velocity at time t on the interior edge points; convert_interior_only = 1 for the
 // init block (src/advection_vars.py:37-53), 0 for update_adv (whole arrays, :65-75)
-int k_wind_interior(pycs_handle h, double t, int convert_interior_only, int do_velocity) {
+int k_wind_interior(pycs_handle h, double t, int convert_interior_only, int do_velocity, int basis) {
   const Geo& g = h->g;
   double *ulon_ = nullptr, *ulat_ = nullptr, *vlon_ = nullptr, *vlat_ = nullptr;
   if (do_velocity) {
@@ -299,9 +395,9 @@ int k_wind_interior(pycs_handle h, double t, int convert_interior_only, int do_v
   F(h, PYCS_F_PV_ULON, vul); F(h, PYCS_F_PV_VLAT, vvl); F(h, PYCS_F_PV_UCONTRA, vuc); F(h, PYCS_F_PV_VCONTRA, vvc);
   dim3 gr((g.N + 1 + BX - 1) / BX, g.N + 1, 6);
   if (do_velocity) {
-    velocity_kernel<<<gr, BX, 0, h->stream>>>(g, h->prm.vf, t, 1, ulon_, ulat_, uul, uvl);
+    velocity_kernel<<<gr, BX, 0, h->stream>>>(g, h->prm.vf, t, 1, ulon_, ulat_, uul, uvl, basis);
     CKL(h);
-    velocity_kernel<<<gr, BX, 0, h->stream>>>(g, h->prm.vf, t, 0, vlon_, vlat_, vul, vvl);
+    velocity_kernel<<<gr, BX, 0, h->stream>>>(g, h->prm.vf, t, 0, vlon_, vlat_, vul, vvl, basis);
     CKL(h);
   }
   Conv cpu, cpv;
@@ -343,6 +439,44 @@ int k_update_adv(pycs_handle h, double t) {
   CKL(h);
   update_adv_kernel<<<grid_all(g.P, g.P + 1), BX, 0, h->stream>>>(g, h->prm.vf, t, 0, g.P, g.P + 1, vlon_, vlat_, cpv,
                                                                   vul, vvl, vuc, vvc, vo);
+  CKL(h);
+  return 0;
+}
+
+
+// ---- basis winds (stepper.cu) ------------------------------------------------------------------------
+int k_wind_basis_count(pycs_handle h) { return wind_basis_count(h->prm.vf); }
+
+// basis field m through the wind pipeline of init_vars_adv (interior conversion + ghost fill,
+// src/advection_vars.py:37-80): leaves it in U_pu.ucontra / U_pv.vcontra (and clobbers U_pu / U_pv / U_pc)
+int k_wind_basis_build(pycs_handle h, int m) {
+  TRY(k_wind_interior(h, 0.0, 1, 1, m));
+  return k_wind_ghost_fill(h);
+}
+
+int k_wind_basis_combine(pycs_handle h, double* const* bu, double* const* bv, int nb, double* ua, double* um, double* va,
+                         double* vm, const double* coef, int cmask, const long long* steps) {
+  const Geo& g = h->g;
+  WindBasisArgs a;
+  a.g = g;
+  for (int m = 0; m < 4; ++m) {
+    a.bu[m] = m < nb ? bu[m] : nullptr;
+    a.bv[m] = m < nb ? bv[m] : nullptr;
+  }
+  a.ua = ua; a.um = um; a.va = va; a.vm = vm;
+  a.coef = coef;
+  a.steps = steps;
+  a.cmask = cmask;
+  a.nb = nb;
+  a.rk2 = (h->prm.dp == 2) ? 1 : 0;
+  a.dto2 = g.dt * 0.5;
+  wind_basis_kernel<<<dim3((g.P + 1 + BX - 1) / BX, g.P + 1, 12), BX, 0, h->stream>>>(a);
+  CKL(h);
+  return 0;
+}
+
+int k_wind_coef_fill(pycs_handle h, double* tab, int cmask, long long s0, long long k0, int n) {
+  wind_coef_fill_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(tab, cmask, s0, k0, n, h->g.dt, h->prm.vf);
   CKL(h);
   return 0;
 }

@@ -390,6 +390,33 @@ def test_fused_separable_wind_across_run_calls(mods):
     b.dev.close()
 
 
+@pytest.mark.parametrize("vf,name", [(2, "AVLT-RK2-DG-PR"), (2, "default"), (3, "AVLT-RK2-DG-PR"), (4, "AVLT-RK2-DG-PR")])
+def test_fused_basis_winds_across_run_calls(mods, vf, name):
+    """Time-dependent winds as combinations of static basis fields (wind fields 2 and 3; csrc/wind.cu
+    wind_basis_kernel) and the steady field 4: Q after several fused run calls and the lazily caught-up
+    wind state (ucontra, ucontra_old of t_{k-2} for RK2, the averaged wind, U_pc) against the operator path."""
+    g = mods.cs_datastruct.cubed_sphere(50)
+    a = make_sim(mods, g, vf, TUPLES[name])
+    b = make_sim(mods, g, vf, TUPLES[name])
+    k = 0
+    for n in (1, 4, 15, 2, 9):
+        mods.advection_timestep.run_steps(g, a, k, n, fused=True)
+        k += n
+    mods.advection_timestep.run_steps(g, b, 0, k, fused=False)
+    assert relerr(np.asarray(a.Q), np.asarray(b.Q)) <= TOL
+    for obj, names in (("U_pu", ("ucontra", "ucontra_old", "ucontra_averaged", "ulon", "vlat")),
+                       ("U_pv", ("vcontra", "vcontra_old", "vcontra_averaged")), ("U_pc", ("ulon", "vlat"))):
+        for nm in names:
+            x, y = np.asarray(getattr(getattr(a, obj), nm)), np.asarray(getattr(getattr(b, obj), nm))
+            assert relerr(x, y) <= TOL, (obj, nm)
+    # and both can go on from there with either path
+    mods.advection_timestep.run_steps(g, a, k, 3, fused=False)
+    mods.advection_timestep.run_steps(g, b, k, 3, fused=True)
+    assert relerr(np.asarray(a.Q), np.asarray(b.Q)) <= TOL
+    a.dev.close()
+    b.dev.close()
+
+
 def test_host_step_keeps_wind_state_lazily(mods):
     """pycs_adv_time_step_host (numpy Q in, numpy Q out) advances with the separable wind and
     catches the exposed wind arrays up only when they are read: Q after every step and the
