@@ -309,9 +309,17 @@ def run_gpu(args):
         tt = torch.tensor([te], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         te = float(tt.item())
-    e2e = {"value": cells * e2e_steps / te, "unit": "cell-updates/s", "h2d_bytes_per_step": int(Q0.nbytes) * world,
-           "d2h_bytes_per_step": int(Q0.nbytes) * world, "ms_per_step": 1e3 * te / e2e_steps, "steps": e2e_steps,
-           "api": "pycs_adv_time_step_host (adv_time_step + update_adv on a host numpy Q)"}
+    # a sharded handle moves only its slab: rows [row_lo, row_hi) of the (P, P, 6) array, both ways
+    slab_bytes = int(Q0.nbytes) if world == 1 else (slab[1] - slab[0]) * Q0.shape[1] * Q0.shape[2] * 8
+    moved = slab_bytes
+    if world > 1:
+        tt = torch.tensor([float(slab_bytes)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        moved = int(tt.item())
+    e2e = {"value": cells * e2e_steps / te, "unit": "cell-updates/s", "h2d_bytes_per_step": moved,
+           "d2h_bytes_per_step": moved, "ms_per_step": 1e3 * te / e2e_steps, "steps": e2e_steps,
+           "api": "pycs_adv_time_step_host (adv_time_step + update_adv on a host numpy Q; every rank moves its own "
+                  "rows of Q over its own PCIe link)"}
 
     # ---- CPU baseline (rank 0, N=1 only): the numpy oracle on the same grid
     cpu = None

@@ -44,16 +44,16 @@ int pycs_field_ptr(pycs_handle h, int f, double** out) {
 // --------------------------------------------------------------------------- layout kernels
 namespace {
 // host reference layout [i][j][6] (staged on the device) -> panel-major padded
-__global__ void to_device_layout(Geo g, int ni, int nj, int np, const double* __restrict__ src,
+__global__ void to_device_layout(Geo g, int i0, int nj, int np, const double* __restrict__ src,
                                  double* __restrict__ dst) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  int j = blockIdx.x * blockDim.x + threadIdx.x, i = i0 + blockIdx.y;
   if (j >= nj) return;
   const double* s = src + ((long long)i * nj + j) * 6;
   for (int p = 0; p < np; ++p) dst[gidx(g, p, i, j)] = s[p];
 }
-__global__ void from_device_layout(Geo g, int ni, int nj, int np, const double* __restrict__ src,
+__global__ void from_device_layout(Geo g, int i0, int nj, int np, const double* __restrict__ src,
                                    double* __restrict__ dst) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  int j = blockIdx.x * blockDim.x + threadIdx.x, i = i0 + blockIdx.y;
   if (j >= nj) return;
   double* d = dst + ((long long)i * nj + j) * 6;
   for (int p = 0; p < 6; ++p) d[p] = src[gidx(g, np == 1 ? 0 : p, i, j)];
@@ -222,17 +222,18 @@ extern "C" int pycs_launch_count(pycs_handle h, int64_t* count) {
 }
 
 // --------------------------------------------------------------------------- transfers
-static int upload_from(pycs_handle h, int field, const double* host, bool pinned_src) {
+// rows [i0, i1) of a field (the reference layout keeps a row of all six panels contiguous); i1 < 0: all rows
+static int upload_from(pycs_handle h, int field, const double* host, int i0 = 0, int i1 = -1) {
   int ni, nj, np;
   TRY(pycs_field_shape(h->g, field, &ni, &nj, &np));
+  if (i1 < 0) i1 = ni;
   double* dst;
   TRY(pycs_field_ptr(h, field, &dst));
-  size_t bytes = (size_t)ni * nj * 6 * sizeof(double);
-  TRY(ensure_stage(h, bytes));
-  (void)pinned_src;
-  CK(cudaMemcpyAsync(h->stage_dev, host, bytes, cudaMemcpyHostToDevice, h->stream));
-  dim3 grid((nj + 127) / 128, ni);
-  to_device_layout<<<grid, 128, 0, h->stream>>>(h->g, ni, nj, np, h->stage_dev, dst);
+  const size_t row = (size_t)nj * 6, bytes = (size_t)(i1 - i0) * row * sizeof(double);
+  TRY(ensure_stage(h, (size_t)ni * row * sizeof(double)));
+  CK(cudaMemcpyAsync(h->stage_dev + i0 * row, host + i0 * row, bytes, cudaMemcpyHostToDevice, h->stream));
+  dim3 grid((nj + 127) / 128, i1 - i0);
+  to_device_layout<<<grid, 128, 0, h->stream>>>(h->g, i0, nj, np, h->stage_dev, dst);
   CKL(h);
   return 0;
 }
@@ -243,24 +244,25 @@ extern "C" int pycs_upload_field(pycs_handle h, int32_t field, const double* hos
   CK(cudaSetDevice(h->device));
   if (field == PYCS_F_Q) TRY(k_fused_discard(h));   // a new state: nothing of the old one is pending
   else if (field == PYCS_F_Q_NEXT) TRY(normalize_q(h));
-  TRY(upload_from(h, field, host, false));
+  TRY(upload_from(h, field, host));
   CK(cudaStreamSynchronize(h->stream));
   if (field == PYCS_F_SQRTG_PC) h->a2_valid = 0;
   if (field >= PYCS_F_SQRTG_PC && field <= PYCS_F_PV_LAT) k_fused_invalidate(h);
   return 0;
 }
 
-static int download_to(pycs_handle h, int field, double* host) {
+static int download_to(pycs_handle h, int field, double* host, int i0 = 0, int i1 = -1) {
   int ni, nj, np;
   TRY(pycs_field_shape(h->g, field, &ni, &nj, &np));
+  if (i1 < 0) i1 = ni;
   double* src;
   TRY(pycs_field_ptr(h, field, &src));
-  size_t bytes = (size_t)ni * nj * 6 * sizeof(double);
-  TRY(ensure_stage(h, bytes));
-  dim3 grid((nj + 127) / 128, ni);
-  from_device_layout<<<grid, 128, 0, h->stream>>>(h->g, ni, nj, np, src, h->stage_dev);
+  const size_t row = (size_t)nj * 6, bytes = (size_t)(i1 - i0) * row * sizeof(double);
+  TRY(ensure_stage(h, (size_t)ni * row * sizeof(double)));
+  dim3 grid((nj + 127) / 128, i1 - i0);
+  from_device_layout<<<grid, 128, 0, h->stream>>>(h->g, i0, nj, np, src, h->stage_dev);
   CKL(h);
-  CK(cudaMemcpyAsync(host, h->stage_dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(host + i0 * row, h->stage_dev + i0 * row, bytes, cudaMemcpyDeviceToHost, h->stream));
   return 0;
 }
 
@@ -571,12 +573,18 @@ extern "C" int pycs_step_kernel_name(pycs_handle h, char* name, int32_t name_len
 extern "C" int pycs_adv_time_step_host(pycs_handle h, double* Q, int64_t k, double t, int32_t fused) {
   if (!Q) return arg_fail("null Q");
   CK(cudaSetDevice(h->device));
-  TRY(normalize_q(h));
-  TRY(upload_from(h, PYCS_F_Q, Q, true));
+  if (h->mg && !fused) return arg_fail("multi-GPU handles run the fused step only");
+  TRY(k_fused_discard(h));                  // the caller's Q replaces the device state
+  // A sharded handle moves only its own slab: rows [row_lo, row_hi) of the caller's array go up, the
+  // cells the peers read from them (halo rows, ghost-fill sources) are delivered by one extra exchange,
+  // and the same rows come back.  The rest of the caller's array is neither read nor written.
+  const int i0 = h->mg ? h->row_lo : 0, i1 = h->mg ? h->row_hi : -1;
+  TRY(upload_from(h, PYCS_F_Q, Q, i0, i1));
+  if (h->mg) TRY(k_fused_share_slab(h));
   if (fused) {
     if (!k_fused_supported(h)) return arg_fail("no fused step kernel for this scheme tuple");
-    // wind field 3 + RK1 is U(0)*cos(pi t/T): the step scales the t = 0 winds in-kernel and the
-    // exposed wind arrays are caught up lazily (wind_sync) when something reads them
+    // lazy wind modes: the step does not touch the exposed wind arrays, they are caught up (wind_sync)
+    // when something reads them
     const int wmode = fabs(t - (double)k * h->g.dt) <= 1e-12 * (1.0 + fabs(t)) ? lazy_wind_mode(h) : 0;   // t = k*dt as in adv_sphere
     if (wmode) {
       TRY(k_fused_step(h, k, t, wmode));
@@ -591,9 +599,9 @@ extern "C" int pycs_adv_time_step_host(pycs_handle h, double* Q, int64_t k, doub
     TRY(pycs_adv_time_step(h, k, t));
     TRY(k_update_adv(h, t));
   }
-  TRY(download_to(h, PYCS_F_Q, Q));
+  TRY(download_to(h, PYCS_F_Q, Q, i0, i1));
   CK(cudaStreamSynchronize(h->stream));
-  return 0;
+  return k_mg_check(h);
 }
 
 // --------------------------------------------------------------------------- multi-GPU

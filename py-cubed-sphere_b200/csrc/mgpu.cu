@@ -38,6 +38,18 @@ __global__ void mg_wait_steps_kernel(MgSync* sync, const StepCtl* ctl, int world
 
 struct PeerSync { MgSync* s[MG_MAX_WORLD]; };
 
+__global__ void mg_quiesce_raise_kernel(PeerSync peers, int world, int rank, long long value) {
+  if ((int)threadIdx.x >= world) return;
+  __threadfence_system();
+  *((volatile long long*)&peers.s[threadIdx.x]->qflag[rank]) = value;
+}
+__global__ void mg_quiesce_wait_kernel(MgSync* sync, int world, long long value, unsigned long long timeout_ns) {
+  const int d = threadIdx.x;
+  if (d >= world) return;
+  mg_wait_flag(&sync->qflag[d], value, &sync->err, timeout_ns);
+  __threadfence_system();
+}
+
 // One launch per step, one CTA per rectangle: (1) copy the rectangle of one panel of src into the same
 // position of a peer's array; (2) system-scope fence, ticket; (3) the last CTA raises dflag on every
 // rank.  Latency, not bandwidth, is what matters here (a few hundred KB per rank and step).
@@ -352,6 +364,23 @@ int k_mg_exchange(pycs_handle h, const double* qnext, StepCtl* ctl, cudaStream_t
   for (int d = 0; d < MG_MAX_WORLD; ++d) ps.s[d] = d < mg->world ? mg->peer_sync[d] : nullptr;
   // (a rank always has something to send: at least the halo rows of its slab neighbours)
   mg_exchange_kernel<<<mg->njobs, 256, 0, st>>>(h->g, mg->jobs_dev[idx], qnext, ps, mg->world, mg->rank, ctl, mg->counter);
+  CKL(h);
+  return 0;
+}
+
+int k_mg_quiesce_raise(pycs_handle h, cudaStream_t st) {
+  MgpuState* mg = h->mg;
+  if (!mg->connected) return 0;
+  PeerSync ps;
+  for (int d = 0; d < MG_MAX_WORLD; ++d) ps.s[d] = d < mg->world ? mg->peer_sync[d] : nullptr;
+  mg->qcount += 1;
+  mg_quiesce_raise_kernel<<<1, 32, 0, st>>>(ps, mg->world, mg->rank, mg->qcount);
+  CKL(h);
+  return 0;
+}
+int k_mg_quiesce_wait(pycs_handle h, cudaStream_t st) {
+  MgpuState* mg = h->mg;
+  mg_quiesce_wait_kernel<<<1, 32, 0, st>>>(mg->sync, mg->world, mg->qcount, mg->timeout_ns);
   CKL(h);
   return 0;
 }

@@ -7,10 +7,12 @@
 
 // One block per rank, exported to every peer through CUDA IPC.  All flags are epoch counters, never reset:
 //   sflag[d] = fused steps rank d has completed (its MF-PR sum of that step is in psum[steps & 1][d]);
-//   dflag[d] = halo exchanges rank d has delivered into this rank's Q arrays.
+//   dflag[d] = halo exchanges rank d has delivered into this rank's Q arrays;
+//   qflag[d] = flushes rank d has completed (it has stopped modifying its current Q array: see k_mg_quiesce).
 struct MgSync {
   long long sflag[MG_MAX_WORLD];
   long long dflag[MG_MAX_WORLD];
+  long long qflag[MG_MAX_WORLD];
   double psum[2][MG_MAX_WORLD];
   int err;                           // != 0: a flag wait of this rank gave up (a peer is gone); the host turns it
                                      // into PYCS_ERR_STATE at the next synchronisation point (k_mg_check)
@@ -32,6 +34,7 @@ struct MgpuState {
   MgScatterJob* jobs_dev[2];         // the same with the destination pointers of allocation 0 / 1 resolved
   int njobs;
   int gf_lo, gf_hi;                  // rows whose ghost cells this rank needs: [row_lo - 3, row_hi + 3)
+  long long qcount;                  // flushes of this rank (every rank runs the same call sequence)
 };
 
 // Host-side plan (no GPU needed: exercised by the CPU tests).
@@ -46,6 +49,11 @@ int k_mg_connect(pycs_handle h, const unsigned char* all_handles);
 int k_mg_replan(pycs_handle h);      // after the Lagrange tables changed
 void k_mg_release(pycs_handle h);
 int k_mg_wait_steps(pycs_handle h, cudaStream_t st);  // until every rank has completed as many steps as this one
+// A flush rewrites the whole interior of the current Q array, peers' cells included.  Before a rank may
+// store into that array of a peer outside the step protocol (k_fused_share_slab), the peer's flush must be
+// over: every flush ends with k_mg_quiesce_raise, and the writer waits with k_mg_quiesce_wait.
+int k_mg_quiesce_raise(pycs_handle h, cudaStream_t st);
+int k_mg_quiesce_wait(pycs_handle h, cudaStream_t st);
 int k_mg_check(pycs_handle h);       // after a stream synchronisation: did a flag wait time out?
 // after the boundary CTAs of a step wrote `qnext`: deliver the rectangles, then raise dflag on every peer
 int k_mg_exchange(pycs_handle h, const double* qnext, StepCtl* ctl, cudaStream_t st);

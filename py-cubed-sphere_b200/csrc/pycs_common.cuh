@@ -158,6 +158,7 @@ int k_fused_time_kernel(pycs_handle h, int reps, int separable, float* ms);
 int k_fused_grid_info(pycs_handle h, int* tb, int* rows, int* nblocks);
 int k_fused_kernel_name(pycs_handle h, char* out, int len);
 int k_fused_flush(pycs_handle h);
+int k_fused_share_slab(pycs_handle h);              // multi-GPU: deliver the freshly uploaded slab's boundary cells to the peers
 int k_fused_discard(pycs_handle h);                 // a new Q was uploaded: drop what the fused path had pending
 void k_fused_profile_report(pycs_handle h);         // PYCS_STEP_PROFILE: print and reset the per-kernel device times
 void k_fused_release(pycs_handle h);

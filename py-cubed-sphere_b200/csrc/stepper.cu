@@ -537,6 +537,24 @@ int k_fused_discard(pycs_handle h) {
   return 0;
 }
 
+// Several GPUs, after every rank uploaded its own rows of a new state into PYCS_F_Q: one exchange of the
+// current buffer, so that each rank holds the peers' cells its first step reads (the regular exchange
+// only ever ships a step's output).
+int k_fused_share_slab(pycs_handle h) {
+  if (!h->mg) return 0;
+  FusedState& fs = g_fused[h];
+  TRY(fused_setup(h, fs));
+  double* q;
+  TRY(pycs_field_ptr(h, h->qcur ? PYCS_F_Q_NEXT : PYCS_F_Q, &q));
+  // nobody may still be reading or rewriting this buffer: every rank has finished the steps issued so far
+  // and the flush that followed them
+  TRY(k_mg_wait_steps(h, h->stream));
+  TRY(k_mg_quiesce_wait(h, h->stream));
+  TRY(k_mg_exchange(h, q, fs.ctl, h->stream));
+  fs.ghost_ready = 0;
+  return 0;
+}
+
 // apply the pending projection term to the current Q so that every other code
 // path (download, operator kernels, diagnostics) sees the reference's Q
 int k_fused_flush(pycs_handle h) {
@@ -544,6 +562,7 @@ int k_fused_flush(pycs_handle h) {
   if (it == g_fused.end()) return 0;
   FusedState& fs = it->second;
   if (!fs.pending && !fs.ring_pending) return 0;
+  const bool had_pending = fs.pending != 0;
   const Geo& g = h->g;
   double *sgc, *q, *qo;
   TRY(pycs_field_ptr(h, PYCS_F_SQRTG_PC, &sgc));
@@ -573,6 +592,7 @@ int k_fused_flush(pycs_handle h) {
     fs.ring_pending = 0;
   }
   fs.ghost_ready = 0;
+  if (h->mg && had_pending) TRY(k_mg_quiesce_raise(h, h->stream));
   return 0;
 }
 

@@ -107,7 +107,7 @@ __global__ void velocity_kernel(Geo g, int vf, double t, int is_pu, const double
   vlat[id] = v;
 }
 
-// Contravariant wind of a step from the basis fields, both directions in one launch (blockIdx.z = 6 dir + p):
+// Contravariant wind of a step from the basis fields (one launch per direction):
 //   u  = sum_m f_m B_m           the instantaneous wind the step's upwind masks look at (src/averaged_velocity.py:21-27)
 //   u* = sum_m g_m B_m           g = 1.5 f(t_{k-1}) - 0.5 f(t_{k-2}): the time-extrapolated wind (:42)
 //   ubar = departure-point average of u* (:44-49, :54-62), or u itself for RK1
@@ -122,35 +122,74 @@ struct WindBasisArgs {
   int cmask, nb, rk2;
   double dto2;
 };
-__global__ void wind_basis_kernel(const __grid_constant__ WindBasisArgs a) {
+// dir = 1 (v on the y-edges): the neighbours along the direction are the neighbouring threads' columns, i.e. the
+// same cache lines -- plain loads.  blockIdx.z = panel.
+__global__ void wind_basis_v_kernel(const __grid_constant__ WindBasisArgs a) {
   const Geo& g = a.g;
-  const int dir = blockIdx.z / 6, p = blockIdx.z % 6;
+  const int p = blockIdx.z;
   const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y;
-  const int ni = dir == 0 ? g.P + 1 : g.P, nj = dir == 0 ? g.P : g.P + 1;
-  if (j >= nj || i >= ni) return;
-  const int s = dir == 0 ? i : j;
-  if (s < g.lo || s > g.hi) return;
+  if (j > g.P || i >= g.P) return;
+  if (j < g.lo || j > g.hi) return;
   const double* c = a.coef + 8 * (*a.steps & a.cmask);
-  const double* const* B = dir == 0 ? a.bu : a.bv;
-  const long long st = dir == 0 ? g.ld : 1;
   const long long id = gidx(g, p, i, j);
   double u = 0.0, us0 = 0.0, usm = 0.0, usp = 0.0;
   for (int m = 0; m < a.nb; ++m) {
-    const double b0 = B[m][id];
+    const double b0 = a.bv[m][id];
     u = fma(c[m], b0, u);
     if (a.rk2) {
       us0 = fma(c[4 + m], b0, us0);
-      usm = fma(c[4 + m], B[m][id - st], usm);
-      usp = fma(c[4 + m], B[m][id + st], usp);
+      usm = fma(c[4 + m], a.bv[m][id - 1], usm);
+      usp = fma(c[4 + m], a.bv[m][id + 1], usp);
     }
   }
   double r = u;
   if (a.rk2) {
-    const double aa = u * a.dto2 / (dir == 0 ? g.dx : g.dy);
-    r = (u >= 0) ? fma(aa, usm - us0, us0) : fma(aa, us0 - usp, us0);     // (1-a) u*_i + a u*_{i-1} | -a u*_{i+1} + (1+a) u*_i
-    (dir == 0 ? a.um : a.vm)[id] = u;
+    const double aa = u * a.dto2 / g.dy;
+    r = (u >= 0) ? fma(aa, usm - us0, us0) : fma(aa, us0 - usp, us0);     // (1-a) u*_j + a u*_{j-1} | -a u*_{j+1} + (1+a) u*_j
+    a.vm[id] = u;
   }
-  (dir == 0 ? a.ua : a.va)[id] = r;
+  a.va[id] = r;
+}
+// dir = 0 (u on the x-edges): the neighbours along the direction are the rows above and below; a thread owns a
+// column and marches a chunk of rows with u* of three consecutive rows in registers, so that every basis
+// value is loaded once.  blockIdx.y = chunk of WB_ROWS edges, blockIdx.z = panel.
+constexpr int WB_ROWS = 32;
+__global__ void wind_basis_u_kernel(const __grid_constant__ WindBasisArgs a) {
+  const Geo& g = a.g;
+  const int p = blockIdx.z;
+  const int j = blockIdx.x * BX + threadIdx.x;
+  if (j >= g.P) return;
+  const int i0 = g.lo + blockIdx.y * WB_ROWS, i1 = min(i0 + WB_ROWS, g.hi + 1);      // edges lo .. hi
+  const double* c = a.coef + 8 * (*a.steps & a.cmask);
+  double cf[4], cg[4];
+  for (int m = 0; m < 4; ++m) { cf[m] = m < a.nb ? c[m] : 0.0; cg[m] = m < a.nb ? c[4 + m] : 0.0; }
+  const long long L = g.ld;
+  long long id = gidx(g, p, i0, j);
+  auto combo = [&](long long at, double& f, double& gs) {
+    f = 0.0; gs = 0.0;
+    for (int m = 0; m < a.nb; ++m) {
+      const double b = a.bu[m][at];
+      f = fma(cf[m], b, f);
+      gs = fma(cg[m], b, gs);
+    }
+  };
+  double fm, usm, f0, us0, fp, usp;
+  if (a.rk2) combo(id - L, fm, usm);
+  combo(id, f0, us0);
+  for (int i = i0; i < i1; ++i, id += L) {
+    double r = f0;
+    if (a.rk2) {
+      combo(id + L, fp, usp);
+      const double aa = f0 * a.dto2 / g.dx;
+      r = (f0 >= 0) ? fma(aa, usm - us0, us0) : fma(aa, us0 - usp, us0);
+      a.um[id] = f0;
+      usm = us0; us0 = usp; f0 = fp;
+      a.ua[id] = r;
+    } else {
+      a.ua[id] = r;
+      if (i + 1 < i1) combo(id + L, f0, us0);
+    }
+  }
 }
 __global__ void wind_coef_fill_kernel(double* tab, int cmask, long long s0, long long k0, int n, double dt, int vf) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -470,7 +509,9 @@ int k_wind_basis_combine(pycs_handle h, double* const* bu, double* const* bv, in
   a.nb = nb;
   a.rk2 = (h->prm.dp == 2) ? 1 : 0;
   a.dto2 = g.dt * 0.5;
-  wind_basis_kernel<<<dim3((g.P + 1 + BX - 1) / BX, g.P + 1, 12), BX, 0, h->stream>>>(a);
+  wind_basis_u_kernel<<<dim3((g.P + BX - 1) / BX, (g.N + 1 + WB_ROWS - 1) / WB_ROWS, 6), BX, 0, h->stream>>>(a);
+  CKL(h);
+  wind_basis_v_kernel<<<dim3((g.P + 1 + BX - 1) / BX, g.P, 6), BX, 0, h->stream>>>(a);
   CKL(h);
   return 0;
 }

@@ -53,6 +53,22 @@ def main():
             worst = max(worst, err, errf)
             print("rank %d/%d impl=%s N=%d vf=%d %s rows [%d,%d): slab err %.2e, gathered err %.2e"
                   % (rank, world, impl, N, vf, name, lo, hi, err, errf), flush=True)
+            if N <= 384:
+                # the host-buffer step on a sharded handle moves only the rank's slab (pycs_adv_time_step_host)
+                import ctypes as C
+                Qa = np.ascontiguousarray(qb.copy())
+                Qb = np.ascontiguousarray(qb.copy())
+                Qa[:lo] = np.nan                       # rows of other ranks are neither read nor written
+                Qa[hi:] = np.nan
+                dp = C.POINTER(C.c_double)
+                for kk in range(k + 1, k + 4):
+                    a.dev.call("pycs_adv_time_step_host", Qa.ctypes.data_as(dp), kk, kk * a.dt, 1)
+                    b.dev.call("pycs_adv_time_step_host", Qb.ctypes.data_as(dp), kk, kk * b.dt, 1)
+                errh = float(np.max(np.abs(Qa[lo:hi, 4:N + 4] - Qb[lo:hi, 4:N + 4])) / np.max(np.abs(Qb[4:N + 4, 4:N + 4])))
+                ok_nan = bool(np.all(np.isnan(Qa[:lo])) and np.all(np.isnan(Qa[hi:])))
+                worst = max(worst, errh, 0.0 if ok_nan else 1.0)
+                print("rank %d/%d impl=%s N=%d host-buffer steps: slab err %.2e, other rows untouched: %s"
+                      % (rank, world, impl, N, errh, ok_nan), flush=True)
             a.dev.call("pycs_synchronize")
             dist.barrier()
             a.dev.close()
