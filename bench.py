@@ -199,7 +199,7 @@ def run_gpu(args):
     # 5 and 20 steps of this workload; every rank checks the sample rows of its slab.
     parity = None
     gp = os.path.join(ROOT, "tests", "golden", "config_N1536_vf3.npz")
-    if N == 1536 and os.path.exists(gp):
+    if N == 1536 and os.path.exists(gp) and not args.quick:
         ref = np.load(gp)
         idx = ref["sample_index"]
         rows = [n for n, i in enumerate(idx) if slab[0] <= i < slab[1]]
@@ -246,6 +246,15 @@ def run_gpu(args):
     cells = 6.0 * N * N                      # whole sphere: the ranks share one problem
     own_cells = 6.0 * N * (slab[1] - slab[0])
     value = cells * args.steps / (ms_total * 1e-3)
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "n_gpus": world, "steps": args.steps, "ms_per_step": ms_total / args.steps,
+                              "value": value, "launches": int(launches), "clocks": clocks,
+                              "env": {k: v for k, v in os.environ.items() if k.startswith("PYCS_")}}))
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
 
     # ---- roofline: the step kernel alone, CUDA events around back-to-back launches.
     # kernel_ms: best of 3 bursts of 50 launches (the HBM peak it is compared with is a burst copy,
@@ -365,6 +374,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--host-grid", action="store_true", help="build the grid with host numpy like the reference")
+    ap.add_argument("--quick", action="store_true", help="tuning runs: only the device-resident timed steps (no roofline, "
+                    "e2e, CPU or parity legs); the line is not a bench record")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -368,15 +368,19 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
       const char* ei = getenv("PYCS_SPLIT_ROWS");
       const int nrows = h->row_hi - h->row_lo;
       fs.band = eb ? atoi(eb) : 12;
-      fs.edge_rows = ee ? atoi(ee) : 16;
       if (fs.band < 4) fs.band = 4;                // >= the 4-wide E / W strips and the 3 halo rows
+      // edge-strip chunks: short enough to be done well before the interior, long enough to keep the
+      // 6-row ramp of a chunk cheap
+      const int inner_rows = nrows - 2 * fs.band;
+      fs.edge_rows = ee ? atoi(ee) : (inner_rows / 6 < 12 ? 12 : (inner_rows / 6 > 32 ? 32 : inner_rows / 6));
       int irows = ei ? atoi(ei) : 0;
       if (irows <= 0) {
         std::vector<CtaDesc> tmp;
         const int nbnd = pycs_plan_split_ctas(h->row_lo, h->row_hi, fs.nstrips, fs.band, fs.edge_rows, nrows, &tmp);
         const int per_sm = pycs_fused2b_resident(h->prm.recon, h->prm.opsplit, (h->prm.dp == 2) ? 1 : 0);
-        int slots = h->sm_count * (per_sm > 0 ? per_sm : 4) - nbnd;      // the boundary CTAs are resident too
-        if (slots < h->sm_count) slots = h->sm_count;
+        // the boundary CTAs are short and retire early: the interior is sized for all CTA slots
+        (void)nbnd;
+        const int slots = h->sm_count * (per_sm > 0 ? per_sm : 4);
         const int icols = 6 * (fs.nstrips - 2), inrows = nrows - 2 * fs.band;
         int best = inrows > 0 ? inrows : 8;
         double best_cost = 1e30;
