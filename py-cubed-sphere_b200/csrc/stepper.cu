@@ -28,6 +28,7 @@
 // captured once per parity into a CUDA graph and replayed (PYCS_GRAPH=0 turns that off).
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <map>
 #include <vector>
 #include "pycs_common.cuh"
@@ -284,6 +285,29 @@ int k_fused_supported(pycs_handle h) {
   return (h->prm.et == 3 && h->prm.mf != 2) ? 1 : 0;
 }
 
+// Makespan (in marched rows) of a split step with the given boundary / interior shapes, by list scheduling of
+// its CTAs -- boundary CTAs first, as the high-priority stream dispatches them -- onto `slots` CTA slots.  A
+// CTA costs its rows + 6 (the ramp of a chunk), a boundary CTA 9 % more (ghost-cell projection term); the
+// exchange and the next ghost fill follow the last boundary CTA and cost ~20 rows' time.  Measured against
+// it at N = 1536 on 2 GPUs: 108 rows predicted, 112 us per step observed (a marched row takes ~1 us when the
+// SM is full).
+static double split_shape_cost(int row_lo, int row_hi, int nstrips, int slots, int band, int edge_rows, int rows) {
+  std::vector<CtaDesc> tab;
+  const int nb = pycs_plan_split_ctas(row_lo, row_hi, nstrips, band, edge_rows, rows, &tab);
+  std::vector<double> heap(slots, 0.0);            // min-heap of slot free times
+  auto cmp = [](double a, double b) { return a > b; };
+  double chain = 0.0, makespan = 0.0;
+  for (int k = 0; k < (int)tab.size(); ++k) {
+    std::pop_heap(heap.begin(), heap.end(), cmp);
+    const double f = heap.back() + (tab[k].r1 - tab[k].r0 + 6) * (k < nb ? 1.09 : 1.0);
+    heap.back() = f;
+    std::push_heap(heap.begin(), heap.end(), cmp);
+    if (k < nb && f > chain) chain = f;
+    if (f > makespan) makespan = f;
+  }
+  return makespan > chain + 20.0 ? makespan : chain + 20.0;
+}
+
 static int fused_setup(pycs_handle h, FusedState& fs) {
   const Geo& g = h->g;
   if (!fs.ctl) {
@@ -362,38 +386,38 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
     if (fs.split == 1) {
       // Boundary CTAs march few rows each, so that they are done early and the exchange + ghost fill of
       // the next step run beside the interior CTAs: bands of `band` rows at both ends of the slab, the
-      // first / last strip in chunks of `edge_rows`; the interior in chunks sized for the CTA slots left.
+      // first / last strip in chunks of `edge_rows`, the interior in chunks of `irows`.  The three sizes
+      // are chosen by simulating the launch (split_shape_cost); PYCS_SPLIT_BAND / _EDGE_ROWS / _ROWS override.
       const char* eb = getenv("PYCS_SPLIT_BAND");
       const char* ee = getenv("PYCS_SPLIT_EDGE_ROWS");
       const char* ei = getenv("PYCS_SPLIT_ROWS");
       const int nrows = h->row_hi - h->row_lo;
-      fs.band = eb ? atoi(eb) : 12;
-      if (fs.band < 4) fs.band = 4;                // >= the 4-wide E / W strips and the 3 halo rows
-      // edge-strip chunks: short enough to be done well before the interior, long enough to keep the
-      // 6-row ramp of a chunk cheap
-      const int inner_rows = nrows - 2 * fs.band;
-      fs.edge_rows = ee ? atoi(ee) : (inner_rows / 6 < 12 ? 12 : (inner_rows / 6 > 32 ? 32 : inner_rows / 6));
-      int irows = ei ? atoi(ei) : 0;
-      if (irows <= 0) {
-        std::vector<CtaDesc> tmp;
-        const int nbnd = pycs_plan_split_ctas(h->row_lo, h->row_hi, fs.nstrips, fs.band, fs.edge_rows, nrows, &tmp);
-        const int per_sm = pycs_fused2b_resident(h->prm.recon, h->prm.opsplit, (h->prm.dp == 2) ? 1 : 0);
-        // the boundary CTAs are short and retire early: the interior is sized for all CTA slots
-        (void)nbnd;
-        const int slots = h->sm_count * (per_sm > 0 ? per_sm : 4);
-        const int icols = 6 * (fs.nstrips - 2), inrows = nrows - 2 * fs.band;
-        int best = inrows > 0 ? inrows : 8;
-        double best_cost = 1e30;
-        for (int nch = 1; icols > 0 && nch <= inrows; ++nch) {
-          const int rr = (inrows + nch - 1) / nch;
-          if (rr < 8 && nch > 1) break;
-          const int waves = (icols * ((inrows + rr - 1) / rr) + slots - 1) / slots;
-          const double cost = (double)waves * (rr + 6);
-          if (cost < best_cost) { best_cost = cost; best = rr; }
+      const int per_sm = pycs_fused2b_resident(h->prm.recon, h->prm.opsplit, (h->prm.dp == 2) ? 1 : 0);
+      const int slots = h->sm_count * (per_sm > 0 ? per_sm : 4);
+      int band = 12, edge = 32, irows = nrows;
+      double best = 1e30;
+      const int bands[] = {8, 12, 16, 24}, edges[] = {12, 16, 20, 24, 28, 32, 40, 48, 64, 96};
+      for (int b : bands)
+        for (int e : edges) {
+          const int inner = nrows - 2 * b;
+          const int nmax = inner > 16 ? (inner / 8 < 64 ? inner / 8 : 64) : 1;
+          for (int n = 1; n <= nmax; ++n) {
+            const int ir = inner > 0 ? (inner + n - 1) / n : nrows;
+            const double c = split_shape_cost(h->row_lo, h->row_hi, fs.nstrips, slots, b, e, ir);
+            if (c < best) { best = c; band = b; edge = e; irows = ir; }
+          }
         }
-        irows = best;
-      }
+      if (eb) band = atoi(eb);
+      if (ee) edge = atoi(ee);
+      if (ei && atoi(ei) > 0) irows = atoi(ei);
+      if (band < 4) band = 4;                      // >= the 4-wide E / W strips and the 3 halo rows
+      fs.band = band;
+      fs.edge_rows = edge;
       fs.irows = irows;
+      if (getenv("PYCS_STEP_PROFILE"))
+        fprintf(stderr, "[pycs split shape] rows [%d,%d): band %d, edge chunks %d, interior chunks %d rows; predicted %.0f rows' time\n",
+                h->row_lo, h->row_hi, band, edge, irows,
+                split_shape_cost(h->row_lo, h->row_hi, fs.nstrips, slots, band, edge, irows));
       std::vector<CtaDesc> tab;
       fs.n_b = pycs_plan_split_ctas(h->row_lo, h->row_hi, fs.nstrips, fs.band, fs.edge_rows, irows, &tab);
       fs.n_i = (int)tab.size() - fs.n_b;
