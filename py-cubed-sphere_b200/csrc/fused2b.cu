@@ -312,6 +312,38 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
     if (!row(IC<5>{}, rb + 5)) break;
   }
 
+  // ---- several GPUs, boundary CTAs: ship what the peers read of this CTA's rows (see FusedArgs::xjobs)
+  if (GH && a.xjob_off) {
+    __syncthreads();                           // the CTA's output rows are visible to all its threads
+    const long long xc = *((const volatile long long*)&a.ctl->xcount);
+    const int jb0 = a.xjob_off[cta], jb1 = a.xjob_off[cta + 1];
+    for (int jb = jb0; jb < jb1; ++jb) {
+      const int4 x = a.xjobs[jb];
+      const int peer = x.x & 15, i0 = x.x >> 4, w = x.w - x.z, n = (x.y - i0) * w;
+      double* __restrict__ dst = a.xpeer_q[peer];
+      for (int t = tid; t < n; t += TB) {
+        const long long id = gidx(g, p, i0 + t / w, x.z + t % w);
+        dst[id] = __ldcg(a.qn + id);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence_system();                  // cumulative over the stores the barrier ordered before it
+      sF[41] = (atomicAdd(a.xcounter, 1u) == (unsigned)a.n_boundary - 1u) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (sF[41] != 0.0 && tid < 32) {           // last boundary CTA: every piece of this rank's exchange is out
+      if (tid == 0) {
+        *a.xcounter = 0u;
+        a.ctl->xcount = xc + 1;
+      }
+      if (tid < a.pub.world) {
+        __threadfence_system();
+        *((volatile long long*)&a.pub.peer_sync[tid]->dflag[a.pub.rank]) = xc + 1;
+      }
+    }
+  }
+
   // ---- per-CTA partial of sum(pxdF + pydF) over its outputs (MF-PR), fixed order; the last CTA of
   // the step (of both launches of a split step) totals them and closes the step
   __syncthreads();

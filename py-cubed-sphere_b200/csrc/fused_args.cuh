@@ -69,6 +69,15 @@ struct FusedArgs {
   int* mg_err;                // bounded wait: see mg_wait_flag (mgpu.cuh)
   unsigned long long mg_timeout_ns;
   FusedMgPub pub;
+  // several GPUs, boundary launch (GH = 1): the exchange is part of the kernel.  Each boundary CTA, once its
+  // rows are written, stores the pieces of them that peers read (xjobs[xjob_off[cta] .. xjob_off[cta+1]),
+  // rectangles of its own panel) straight into the peers' output arrays; the last of the n_boundary CTAs
+  // raises dflag on every rank.  No exchange kernel, no launch between the boundary CTAs and the peers.
+  const int* xjob_off;        // nullptr: no in-kernel exchange
+  const int4* xjobs;          // (peer | i0 << 4, i1, j0, j1)
+  double* xpeer_q[8];         // the peers' arrays that correspond to qn
+  unsigned* xcounter;
+  int n_boundary;
   int timing;                 // roofline timing launches: leave the control block alone
 };
 

@@ -293,6 +293,7 @@ int k_mg_replan(pycs_handle h) {
     CK(cudaMemcpy(mg->jobs_dev[idx], jobs.data(), sizeof(MgScatterJob) * jobs.size(), cudaMemcpyHostToDevice));
   }
   mg->njobs = n;
+  k_fused_replan_exchange(h);
   return 0;
 }
 

@@ -58,6 +58,7 @@ int k_mg_check(pycs_handle h);       // after a stream synchronisation: did a fl
 // after the boundary CTAs of a step wrote `qnext`: deliver the rectangles, then raise dflag on every peer
 int k_mg_exchange(pycs_handle h, const double* qnext, StepCtl* ctl, cudaStream_t st);
 void k_fused_reset_grid(pycs_handle h);
+void k_fused_replan_exchange(pycs_handle h);
 
 #ifdef __CUDACC__
 // Wait until *f >= epoch.  A peer that is merely late (host work between runs, a slow rank) is waited

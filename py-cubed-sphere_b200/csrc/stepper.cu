@@ -233,6 +233,8 @@ struct FusedState {
   long long ws_until = -1;     // ... and index < ws_until
   int prof = -1;               // PYCS_STEP_PROFILE: CUDA events around the kernels of every step
   std::vector<cudaEvent_t> ev; // 4 per profiled step
+  std::vector<cudaEvent_t> ev2; // split step: 6 per profiled step (boundary stream: start, after boundary CTAs, after
+                                // exchange kernel, after ghost fill; interior stream: start, end)
   int npart_cap = 0;
   double* bu = nullptr;        // separable wind: ucontra(t = 0) incl. ghost edges
   double* bv = nullptr;        //                 vcontra(t = 0)
@@ -255,6 +257,11 @@ struct FusedState {
   // split step
   int split = 0;               // 0 undecided, 1 on, -1 off
   int4* cta_tab = nullptr;     // CTA table of the split step: n_b boundary CTAs, then n_i interior CTAs
+  std::vector<CtaDesc> cta_host;
+  int* xjob_off = nullptr;     // several GPUs: per boundary CTA, the pieces of its rows that peers read
+  int4* xjobs = nullptr;
+  unsigned* xcounter = nullptr;
+  int xkernel = 0;             // PYCS_MG_XKERNEL=1: separate exchange kernel instead
   int n_i = 0, n_b = 0;
   int band = 0, edge_rows = 0, irows = 0;
   cudaStream_t s2 = nullptr;
@@ -424,6 +431,41 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
       static_assert(sizeof(CtaDesc) == sizeof(int4), "CTA table entries are int4");
       CK(cudaMalloc(&fs.cta_tab, sizeof(int4) * tab.size()));
       CK(cudaMemcpy(fs.cta_tab, tab.data(), sizeof(int4) * tab.size(), cudaMemcpyHostToDevice));
+      fs.cta_host = tab;
+      if (const char* ex = getenv("PYCS_MG_XKERNEL")) fs.xkernel = atoi(ex);
+      if (h->mg && h->mg->connected && !fs.xkernel) {
+        // in-kernel exchange: cut the send rectangles of the plan along the boundary CTAs that write them
+        std::vector<int> off(fs.n_b + 1, 0);
+        std::vector<int4> jobs;
+        for (int c = 0; c < fs.n_b; ++c) {
+          const CtaDesc& d = tab[c];
+          const int cj0 = g.lo + d.strip * fs.wcols, cj1 = cj0 + fs.wcols < g.hi ? cj0 + fs.wcols : g.hi;
+          for (const MgRect& r : *h->mg->rects) {
+            if (r.panel != d.panel) continue;
+            const int i0 = r.i0 > d.r0 ? r.i0 : d.r0, i1 = r.i1 < d.r1 ? r.i1 : d.r1;
+            const int j0 = r.j0 > cj0 ? r.j0 : cj0, j1 = r.j1 < cj1 ? r.j1 : cj1;
+            if (i0 < i1 && j0 < j1) jobs.push_back(make_int4(r.peer | (i0 << 4), i1, j0, j1));
+          }
+          off[c + 1] = (int)jobs.size();
+        }
+        // every cell of the plan must be shipped by some boundary CTA (tests/test_host_cpu.py checks the cover)
+        long long planned = 0, cut = 0;
+        for (const MgRect& r : *h->mg->rects) planned += (long long)(r.i1 - r.i0) * (r.j1 - r.j0);
+        for (const int4& x : jobs) cut += (long long)(x.y - (x.x >> 4)) * (x.w - x.z);
+        if (planned != cut) {
+          pycs_set_error("split step: the boundary CTAs do not cover the exchange plan");
+          return PYCS_ERR_STATE;
+        }
+        if (jobs.empty()) jobs.push_back(make_int4(0, 0, 0, 0));
+        CK(cudaMalloc(&fs.xjob_off, sizeof(int) * off.size()));
+        CK(cudaMemcpy(fs.xjob_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&fs.xjobs, sizeof(int4) * jobs.size()));
+        CK(cudaMemcpy(fs.xjobs, jobs.data(), sizeof(int4) * jobs.size(), cudaMemcpyHostToDevice));
+        if (!fs.xcounter) {
+          CK(cudaMalloc(&fs.xcounter, sizeof(unsigned)));
+          CK(cudaMemset(fs.xcounter, 0, sizeof(unsigned)));
+        }
+      }
       if (!fs.s2) {
         int lo_pri = 0, hi_pri = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
@@ -542,6 +584,23 @@ void k_fused_profile_report(pycs_handle h) {
           h->mg ? h->mg->rank : 0, ns - skip, 1e3 * t[0] / n, 1e3 * t[1] / n, 1e3 * t[2] / n, 1e3 * t[3] / n);
   for (auto e : fs.ev) cudaEventDestroy(e);
   fs.ev.clear();
+  if (fs.ev2.size() >= 12) {
+    const size_t n2 = fs.ev2.size() / 6, sk = n2 > 8 ? 4 : 0;
+    double u[4] = {0, 0, 0, 0};
+    for (size_t k = sk; k < n2; ++k) {
+      float ms;
+      cudaEventElapsedTime(&ms, fs.ev2[6 * k], fs.ev2[6 * k + 1]); u[0] += ms;
+      cudaEventElapsedTime(&ms, fs.ev2[6 * k + 1], fs.ev2[6 * k + 2]); u[1] += ms;
+      cudaEventElapsedTime(&ms, fs.ev2[6 * k + 2], fs.ev2[6 * k + 3]); u[2] += ms;
+      cudaEventElapsedTime(&ms, fs.ev2[6 * k + 4], fs.ev2[6 * k + 5]); u[3] += ms;
+    }
+    const double m = (double)(n2 - sk);
+    fprintf(stderr, "[pycs split profile] rank %d: boundary CTAs %.2f us, exchange kernel %.2f us, next ghost fill (+ wait "
+                    "for the peers' data) %.2f us | interior CTAs %.2f us\n",
+            h->mg ? h->mg->rank : 0, 1e3 * u[0] / m, 1e3 * u[1] / m, 1e3 * u[2] / m, 1e3 * u[3] / m);
+  }
+  for (auto e : fs.ev2) cudaEventDestroy(e);
+  fs.ev2.clear();
 }
 
 // A new Q was uploaded into PYCS_F_Q: whatever the fused path had pending belonged to the old state.
@@ -644,6 +703,9 @@ void k_fused_release(pycs_handle h) {
   for (double* p : {fs.wua, fs.wum, fs.wva, fs.wvm, fs.wcoef})
     if (p) cudaFree(p);
   if (fs.cta_tab) cudaFree(fs.cta_tab);
+  if (fs.xjob_off) cudaFree(fs.xjob_off);
+  if (fs.xjobs) cudaFree(fs.xjobs);
+  if (fs.xcounter) cudaFree(fs.xcounter);
   if (fs.e_fork) cudaEventDestroy(fs.e_fork);
   if (fs.e_join) cudaEventDestroy(fs.e_join);
   if (fs.s2) cudaStreamDestroy(fs.s2);
@@ -658,6 +720,10 @@ void k_fused_reset_grid(pycs_handle h) {
   fs.rows = 0;
   if (fs.cta_tab) cudaFree(fs.cta_tab);  // the CTA table of the split step belongs to the old grid
   fs.cta_tab = nullptr;
+  if (fs.xjob_off) cudaFree(fs.xjob_off);
+  if (fs.xjobs) cudaFree(fs.xjobs);
+  fs.xjob_off = nullptr;
+  fs.xjobs = nullptr;
   fs.n_i = fs.n_b = 0;
   fs.split = 0;                          // decided again by fused_setup
   fs.ghost_ready = 0;
@@ -669,6 +735,22 @@ void k_fused_reset_grid(pycs_handle h) {
     fs.ws_until = -1;
     fs.wc_until = -1;
   }
+}
+
+// the exchange plan changed (new Lagrange tables on a sharded handle): the split step's tables follow it
+void k_fused_replan_exchange(pycs_handle h) {
+  auto it = g_fused.find(h);
+  if (it == g_fused.end()) return;
+  FusedState& fs = it->second;
+  if (fs.cta_tab) cudaFree(fs.cta_tab);
+  if (fs.xjob_off) cudaFree(fs.xjob_off);
+  if (fs.xjobs) cudaFree(fs.xjobs);
+  fs.cta_tab = nullptr;
+  fs.xjob_off = nullptr;
+  fs.xjobs = nullptr;
+  fs.n_i = fs.n_b = 0;
+  fs.split = 0;
+  drop_graphs(fs);
 }
 
 // geometry was re-uploaded: 1/sqrtg and the t = 0 winds must be rebuilt
@@ -972,21 +1054,43 @@ static int enqueue_split(pycs_handle h, FusedState& fs, double* qcur, double* qn
   }
   CK(cudaEventRecord(fs.e_fork, h->stream));            // everything before this step
   CK(cudaStreamWaitEvent(fs.s2, fs.e_fork, 0));
+  auto mark2 = [&](cudaStream_t st) {
+    if (!profile || fs.ev2.size() >= 6 * 4096) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    fs.ev2.push_back(e);
+  };
+  mark2(fs.s2);
   FusedArgs b = a;
   b.cta_tab = fs.cta_tab;
   b.cta_off = 0;
+  const bool xin = h->mg && fs.xjob_off;                // the boundary CTAs ship their rows themselves
+  if (xin) {
+    b.xjob_off = fs.xjob_off;
+    b.xjobs = fs.xjobs;
+    b.xcounter = fs.xcounter;
+    b.n_boundary = fs.n_b;
+    const int idx = (qnext == h->mg->alloc[0]) ? 0 : 1;
+    for (int d = 0; d < 8; ++d) b.xpeer_q[d] = d < h->mg->world ? h->mg->peer_q[idx][d] : nullptr;
+  }
   TRY(launch_step(h, fs, b, mask, 1, fs.n_b, fs.s2));   // reads ghost cells, feeds the peers
-  if (h->mg) TRY(k_mg_exchange(h, qnext, fs.ctl, fs.s2));
+  mark2(fs.s2);
+  if (h->mg && !xin) TRY(k_mg_exchange(h, qnext, fs.ctl, fs.s2));
+  mark2(fs.s2);
   // the ghost cells the NEXT step reads: their sources are boundary cells of this step's output (own:
   // stream order; the peers': dflag), so the fill runs beside this step's interior CTAs
   TRY(launch_ghost_fill(h, qnext, fs.s2, nullptr, fs.ctl, 0, nullptr, nullptr, true));
+  mark2(fs.s2);
   CK(cudaEventRecord(fs.e_join, fs.s2));
+  mark2(h->stream);
   if (fs.n_i) {
     FusedArgs c = a;
     c.cta_tab = fs.cta_tab;
     c.cta_off = fs.n_b;
     TRY(launch_step(h, fs, c, mask, 0, fs.n_i, h->stream));   // reads no ghost cell
   }
+  mark2(h->stream);
   CK(cudaStreamWaitEvent(h->stream, fs.e_join, 0));
   mark();
   mark();

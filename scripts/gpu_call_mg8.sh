@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: gpu_call_mg8.sh NGPUS : parity worker (short) + driver-shaped bench + quick long run + profile
+# usage: gpu_call_mg8.sh NGPUS : parity worker (N=1536 only) + driver-shaped bench + profiles + quick long runs
 N=${1:-8}
 mkdir -p gpurun_out
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29641 tests/mgpu_worker.py 1536 > gpurun_out/mg${N}_worker.log 2>&1
@@ -7,6 +7,9 @@ echo "worker rc=$?" >> gpurun_out/mg${N}_worker.log
 tail -3 gpurun_out/mg${N}_worker.log
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29642 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/mg${N}_bench_20.json 2> gpurun_out/mg${N}_bench_20.err
 cut -c1-330 gpurun_out/mg${N}_bench_20.json
+q() { env "$@" timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29652 bench.py --gpus $N --steps 300 --warmup 5 --quick 2>gpurun_out/mg${N}_q.err | grep quick | cut -c1-100; }
+echo "default:"; q PYCS_X=0
+echo "xkernel:"; q PYCS_MG_XKERNEL=1
+echo "edge32:"; q PYCS_SPLIT_EDGE_ROWS=32 PYCS_SPLIT_ROWS=48
 PYCS_STEP_PROFILE=1 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29651 bench.py --gpus $N --steps 300 --warmup 5 --quick > gpurun_out/mg${N}_profile.log 2>&1
-grep "pycs" gpurun_out/mg${N}_profile.log | head -12
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29652 bench.py --gpus $N --steps 300 --warmup 5 --quick 2>/dev/null | grep quick | cut -c1-120
+grep "pycs" gpurun_out/mg${N}_profile.log | grep -v " 5 steps" | sort | uniq | head -14
