@@ -138,6 +138,13 @@ int pycs_halo_fill_scalar(pycs_handle h, int32_t fx, int32_t fy);
 /* edges_ghost_cell_treatment_vector (src/edges_treatment.py:296-347) on U_pu, U_pv, U_pc. */
 int pycs_halo_fill_vector(pycs_handle h);
 
+/* The two stages of the duo-grid wind ghost fill on their own: wind_edges2center_cubic_interpolation
+ * (src/interpolation.py:347-430: U_pu / U_pv -> U_pc on the boundary ring, lat-lon, Lagrange ghost fill) and
+ * wind_center2ghostedge_cubic_interpolation (src/interpolation.py:436-532: U_pc ghost centres -> ghost edges of
+ * U_pu / U_pv, contravariant). */
+int pycs_wind_edges2center(pycs_handle h);
+int pycs_wind_center2ghostedge(pycs_handle h);
+
 /* ---- operators (L2) ---------------------------------------------------------- */
 /* time_averaged_velocity (src/averaged_velocity.py:14-62). */
 int pycs_time_averaged_velocity(pycs_handle h);
@@ -145,6 +152,10 @@ int pycs_time_averaged_velocity(pycs_handle h);
 int pycs_cfl(pycs_handle h, int32_t dst, int32_t src, int32_t dir);
 /* ppm_reconstruction (src/reconstruction_1d.py:387-394) of (fx, fy) into px / py. */
 int pycs_ppm_reconstruction(pycs_handle h, int32_t fx, int32_t fy);
+/* edges_extrapolation (src/edges_treatment.py:82-206, with average_parabola_cube_edges :31-76): the ET-PL07
+ * one-sided edge values next to the cube edges of px / py reconstructed from (fx, fy), averaged across the
+ * edge and copied into the ghost parabolas.  pycs_ppm_reconstruction calls it itself when et == 2. */
+int pycs_edges_extrapolation(pycs_handle h, int32_t fx, int32_t fy);
 /* numerical_flux_ppm_x / _y (src/flux.py:20-128) after a reconstruction. */
 int pycs_numerical_flux(pycs_handle h, int32_t fx, int32_t fy);
 /* compute_fluxes (src/flux.py:9-15) = reconstruction + both fluxes. */

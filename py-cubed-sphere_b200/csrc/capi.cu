@@ -401,6 +401,19 @@ extern "C" int pycs_halo_fill_vector(pycs_handle h) {
   return k_wind_ghost_fill(h);
 }
 
+extern "C" int pycs_wind_edges2center(pycs_handle h) {
+  TRY(wind_sync(h));
+  if (!h->kminE) {
+    g_err = "wind_edges2center needs pycs_upload_lagrange first";
+    return PYCS_ERR_STATE;
+  }
+  return k_wind_edges2center(h);
+}
+extern "C" int pycs_wind_center2ghostedge(pycs_handle h) {
+  TRY(wind_sync(h));
+  return k_wind_center2ghostedge(h);
+}
+
 // --------------------------------------------------------------------------- operators
 extern "C" int pycs_time_averaged_velocity(pycs_handle h) {
   TRY(wind_sync(h));
@@ -423,6 +436,14 @@ extern "C" int pycs_ppm_reconstruction(pycs_handle h, int32_t fx, int32_t fy) {
   TRY(k_recon(h, x, y));
   if (h->prm.et == 2) TRY(k_edges_extrapolation(h, x, y));   // src/reconstruction_1d.py:392-394
   return 0;
+}
+
+extern "C" int pycs_edges_extrapolation(pycs_handle h, int32_t fx, int32_t fy) {
+  TRY(normalize_q(h));
+  double *x, *y;
+  TRY(pycs_field_ptr(h, fx, &x));
+  TRY(pycs_field_ptr(h, fy, &y));
+  return k_edges_extrapolation(h, x, y);
 }
 
 extern "C" int pycs_numerical_flux(pycs_handle h, int32_t fx, int32_t fy) {
@@ -540,6 +561,9 @@ extern "C" int pycs_run(pycs_handle h, int64_t k0, int64_t nsteps, int32_t fused
 extern "C" int pycs_run_timed(pycs_handle h, int64_t k0, int64_t nsteps, int32_t fused, float* ms) {
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
+  // several GPUs: the ranks enter the timed steps together -- a barrier on the device, in stream order, so
+  // that no rank's timed region contains the wait for a rank whose host got here later
+  if (h->mg) TRY(k_mg_device_barrier(h, h->stream));
   CK(cudaEventRecord(h->ev0, h->stream));
   int r = run_steps(h, k0, nsteps, fused);
   CK(cudaEventRecord(h->ev1, h->stream));

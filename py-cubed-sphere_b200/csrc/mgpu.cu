@@ -38,6 +38,14 @@ __global__ void mg_wait_steps_kernel(MgSync* sync, const StepCtl* ctl, int world
 
 struct PeerSync { MgSync* s[MG_MAX_WORLD]; };
 
+__global__ void mg_barrier_kernel(PeerSync peers, MgSync* sync, int world, int rank, long long value,
+                                  unsigned long long timeout_ns) {
+  if ((int)threadIdx.x >= world) return;
+  __threadfence_system();
+  *((volatile long long*)&peers.s[threadIdx.x]->bflag[rank]) = value;
+  mg_wait_flag(&sync->bflag[threadIdx.x], value, &sync->err, timeout_ns);
+  __threadfence_system();
+}
 __global__ void mg_quiesce_raise_kernel(PeerSync peers, int world, int rank, long long value) {
   if ((int)threadIdx.x >= world) return;
   __threadfence_system();
@@ -369,6 +377,16 @@ int k_mg_exchange(pycs_handle h, const double* qnext, StepCtl* ctl, cudaStream_t
   return 0;
 }
 
+int k_mg_device_barrier(pycs_handle h, cudaStream_t st) {
+  MgpuState* mg = h->mg;
+  if (!mg || !mg->connected) return 0;
+  PeerSync ps;
+  for (int d = 0; d < MG_MAX_WORLD; ++d) ps.s[d] = d < mg->world ? mg->peer_sync[d] : nullptr;
+  mg->bcount += 1;
+  mg_barrier_kernel<<<1, 32, 0, st>>>(ps, mg->sync, mg->world, mg->rank, mg->bcount, mg->timeout_ns);
+  CKL(h);
+  return 0;
+}
 int k_mg_quiesce_raise(pycs_handle h, cudaStream_t st) {
   MgpuState* mg = h->mg;
   if (!mg->connected) return 0;

@@ -13,6 +13,7 @@ struct MgSync {
   long long sflag[MG_MAX_WORLD];
   long long dflag[MG_MAX_WORLD];
   long long qflag[MG_MAX_WORLD];
+  long long bflag[MG_MAX_WORLD];     // device-side barrier (k_mg_device_barrier): rank d has reached barrier number bflag[d]
   double psum[2][MG_MAX_WORLD];
   int err;                           // != 0: a flag wait of this rank gave up (a peer is gone); the host turns it
                                      // into PYCS_ERR_STATE at the next synchronisation point (k_mg_check)
@@ -35,6 +36,7 @@ struct MgpuState {
   int njobs;
   int gf_lo, gf_hi;                  // rows whose ghost cells this rank needs: [row_lo - 3, row_hi + 3)
   long long qcount;                  // flushes of this rank (every rank runs the same call sequence)
+  long long bcount;                  // device-side barriers issued
 };
 
 // Host-side plan (no GPU needed: exercised by the CPU tests).
@@ -54,6 +56,9 @@ int k_mg_wait_steps(pycs_handle h, cudaStream_t st);  // until every rank has co
 // over: every flush ends with k_mg_quiesce_raise, and the writer waits with k_mg_quiesce_wait.
 int k_mg_quiesce_raise(pycs_handle h, cudaStream_t st);
 int k_mg_quiesce_wait(pycs_handle h, cudaStream_t st);
+// stream-ordered barrier over the ranks, on the device: what follows on the stream starts within a flag
+// latency of the slowest rank reaching this point (pycs_run_timed: the ranks enter the timed steps together)
+int k_mg_device_barrier(pycs_handle h, cudaStream_t st);
 int k_mg_check(pycs_handle h);       // after a stream synchronisation: did a flag wait time out?
 // after the boundary CTAs of a step wrote `qnext`: deliver the rectangles, then raise dflag on every peer
 int k_mg_exchange(pycs_handle h, const double* qnext, StepCtl* ctl, cudaStream_t st);

@@ -143,6 +143,8 @@ int k_rect_max(pycs_handle h, const double* f, int i0, int i1, int j0, int j1, d
 // wind.cu
 int k_time_averaged_velocity(pycs_handle h);
 int k_wind_ghost_fill(pycs_handle h);
+int k_wind_edges2center(pycs_handle h);
+int k_wind_center2ghostedge(pycs_handle h);
 int k_update_adv(pycs_handle h, double t);
 int k_wind_interior(pycs_handle h, double t, int convert_interior_only, int do_velocity, int basis = -1);
 int k_wind_basis_count(pycs_handle h);

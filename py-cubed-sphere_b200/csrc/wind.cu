@@ -392,29 +392,47 @@ int k_time_averaged_velocity(pycs_handle h) {
   return 0;
 }
 
-int k_wind_ghost_fill(pycs_handle h) {
+// wind_edges2center_cubic_interpolation (src/interpolation.py:347-430): C-grid winds -> centres on the boundary
+// ring, -> lat-lon, Lagrange ghost fill of both components
+int k_wind_edges2center(pycs_handle h) {
   const Geo& g = h->g;
   F(h, PYCS_F_PU_UCONTRA, u); F(h, PYCS_F_PV_VCONTRA, v);
+  F(h, PYCS_F_PC_UCONTRA, cu); F(h, PYCS_F_PC_VCONTRA, cv);
+  F(h, PYCS_F_PC_ULON, cul); F(h, PYCS_F_PC_VLAT, cvl);
+  F(h, PYCS_F_PC_EXLON, exlon); F(h, PYCS_F_PC_EXLAT, exlat);
+  F(h, PYCS_F_PC_EYLON, eylon); F(h, PYCS_F_PC_EYLAT, eylat);
+  ring_kernel<<<dim3(1, g.N, 6), BX, 0, h->stream>>>(g, u, v, cu, cv, cul, cvl, exlon, exlat, eylon, eylat);
+  CKL(h);
+  TRY(k_dg_fill_single(h, cul));
+  return k_dg_fill_single(h, cvl);
+}
+
+// wind_center2ghostedge_cubic_interpolation (src/interpolation.py:436-532): ghost centres -> ghost edges, -> contravariant
+int k_wind_center2ghostedge(pycs_handle h) {
+  const Geo& g = h->g;
+  F(h, PYCS_F_PU_UCONTRA, u); F(h, PYCS_F_PV_VCONTRA, v);
+  F(h, PYCS_F_PC_ULON, cul); F(h, PYCS_F_PC_VLAT, cvl);
+  F(h, PYCS_F_PU_ULON, uul); F(h, PYCS_F_PU_VLAT, uvl); F(h, PYCS_F_PU_VCONTRA, uvc);
+  F(h, PYCS_F_PV_ULON, vul); F(h, PYCS_F_PV_VLAT, vvl); F(h, PYCS_F_PV_UCONTRA, vuc);
+  Conv cpu, cpv;
+  TRY(get_conv(h, PYCS_F_PU_EXLON, &cpu));
+  TRY(get_conv(h, PYCS_F_PV_EXLON, &cpv));
+  ghost_edge_kernel<0><<<dim3(1, g.P + 1, 6), BX, 0, h->stream>>>(g, cul, cvl, uul, uvl, u, uvc, cpu);
+  CKL(h);
+  ghost_edge_kernel<1><<<dim3(1, g.P, 6), BX, 0, h->stream>>>(g, cul, cvl, vul, vvl, vuc, v, cpv);
+  CKL(h);
+  return 0;
+}
+
+// edges_ghost_cell_treatment_vector (src/edges_treatment.py:296-347)
+int k_wind_ghost_fill(pycs_handle h) {
+  const Geo& g = h->g;
   if (h->prm.et == 3) {
-    F(h, PYCS_F_PC_UCONTRA, cu); F(h, PYCS_F_PC_VCONTRA, cv);
-    F(h, PYCS_F_PC_ULON, cul); F(h, PYCS_F_PC_VLAT, cvl);
-    F(h, PYCS_F_PC_EXLON, exlon); F(h, PYCS_F_PC_EXLAT, exlat);
-    F(h, PYCS_F_PC_EYLON, eylon); F(h, PYCS_F_PC_EYLAT, eylat);
-    ring_kernel<<<dim3(1, g.N, 6), BX, 0, h->stream>>>(g, u, v, cu, cv, cul, cvl, exlon,
-                                                                         exlat, eylon, eylat);
-    CKL(h);
-    TRY(k_dg_fill_single(h, cul));
-    TRY(k_dg_fill_single(h, cvl));
-    F(h, PYCS_F_PU_ULON, uul); F(h, PYCS_F_PU_VLAT, uvl); F(h, PYCS_F_PU_VCONTRA, uvc);
-    F(h, PYCS_F_PV_ULON, vul); F(h, PYCS_F_PV_VLAT, vvl); F(h, PYCS_F_PV_UCONTRA, vuc);
-    Conv cpu, cpv;
-    TRY(get_conv(h, PYCS_F_PU_EXLON, &cpu));
-    TRY(get_conv(h, PYCS_F_PV_EXLON, &cpv));
-    ghost_edge_kernel<0><<<dim3(1, g.P + 1, 6), BX, 0, h->stream>>>(g, cul, cvl, uul, uvl, u, uvc, cpu);
-    CKL(h);
-    ghost_edge_kernel<1><<<dim3(1, g.P, 6), BX, 0, h->stream>>>(g, cul, cvl, vul, vvl, vuc, v, cpv);
-    CKL(h);
-  } else if (h->prm.dp == 2) {
+    TRY(k_wind_edges2center(h));
+    return k_wind_center2ghostedge(h);
+  }
+  if (h->prm.dp == 2) {
+    F(h, PYCS_F_PU_UCONTRA, u); F(h, PYCS_F_PV_VCONTRA, v);
     rk2_copy_kernel<<<dim3((g.N + BX - 1) / BX, 12), BX, 0, h->stream>>>(g, u, v);
     CKL(h);
   }

@@ -74,6 +74,9 @@ def load_library():
         "pycs_halo_fill_copy": [h, C.c_int32, C.c_int32],
         "pycs_halo_fill_scalar": [h, C.c_int32, C.c_int32],
         "pycs_halo_fill_vector": [h],
+        "pycs_wind_edges2center": [h],
+        "pycs_wind_center2ghostedge": [h],
+        "pycs_edges_extrapolation": [h, C.c_int32, C.c_int32],
         "pycs_time_averaged_velocity": [h],
         "pycs_cfl": [h, C.c_int32, C.c_int32, C.c_int32],
         "pycs_ppm_reconstruction": [h, C.c_int32, C.c_int32],

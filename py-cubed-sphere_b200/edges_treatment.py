@@ -25,6 +25,13 @@ def average_flux_cube_edges(px, py, cs_grid):
 
 
 def edges_extrapolation(Qx, Qy, px, py, cs_grid, simulation):
-    """ET-PL07 edge extrapolation (src/edges_treatment.py:82-206): runs inside
-    ppm_reconstruction on the device when et_name == 'ET-PL07'."""
-    raise NotImplementedError("runs as part of reconstruction_1d.ppm_reconstruction")
+    """ET-PL07 edge extrapolation and parabola averaging at the cube edges (src/edges_treatment.py:82-206,
+    :31-76) on the device-resident px / py; reconstruction_1d.ppm_reconstruction runs it itself when
+    et_name == 'ET-PL07'."""
+    dev = simulation.dev
+    with staged(dev, Qx, F["USER_A"], writeback=False) as fx:
+        if Qy is Qx:
+            dev.call("pycs_edges_extrapolation", fx, fx)
+        else:
+            with staged(dev, Qy, F["USER_B"], writeback=False) as fy:
+                dev.call("pycs_edges_extrapolation", fx, fy)

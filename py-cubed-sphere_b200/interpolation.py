@@ -59,9 +59,12 @@ def ghost_cells_adjacent_panels(Qx, Qy, cs_grid, simulation):
 
 
 def wind_edges2center_cubic_interpolation(U_pc, U_pu, U_pv, cs_grid, simulation):
-    """src/interpolation.py:347-430 -- fused with the next routine on the device;
-    call edges_treatment.edges_ghost_cell_treatment_vector."""
-    raise NotImplementedError("use edges_ghost_cell_treatment_vector (both stages run in one call)")
+    """C-grid winds to the cell centres of the boundary ring, to lat-lon, Lagrange ghost fill of both
+    components, on the device-resident U_pu / U_pv / U_pc (src/interpolation.py:347-430)."""
+    simulation.dev.call("pycs_wind_edges2center")
 
 
-wind_center2ghostedge_cubic_interpolation = wind_edges2center_cubic_interpolation
+def wind_center2ghostedge_cubic_interpolation(U_pc, U_pu, U_pv, cs_grid, simulation):
+    """Ghost centres to ghost edges and back to contravariant components, on the device-resident
+    U_pc / U_pu / U_pv (src/interpolation.py:436-532)."""
+    simulation.dev.call("pycs_wind_center2ghostedge")

@@ -540,3 +540,43 @@ def test_device_error_norms_match_host(mods, g16):
         for x, y in zip(got, want):
             assert abs(x - y) <= 1e-12 * abs(y) + 1e-15
     sim.dev.close()
+
+
+# ------------------------------------------------------------------ reference-named stages callable on their own
+def test_wind_ghost_fill_stages_callable_separately(mods, g16):
+    """wind_edges2center_cubic_interpolation + wind_center2ghostedge_cubic_interpolation (src/interpolation.py:347-532)
+    called one after the other equal edges_ghost_cell_treatment_vector (src/edges_treatment.py:296-304)."""
+    a = make_sim(mods, g16, 2, TUPLES["AVLT-RK2-DG-PR"])
+    b = make_sim(mods, g16, 2, TUPLES["AVLT-RK2-DG-PR"])
+    for s in (a, b):
+        mods.advection_timestep.update_adv(g16, s, 0.3)          # some other wind than the one of init
+    mods.edges_treatment.edges_ghost_cell_treatment_vector(a.U_pu, a.U_pv, a.U_pc, g16, a)
+    mods.interpolation.wind_edges2center_cubic_interpolation(b.U_pc, b.U_pu, b.U_pv, g16, b)
+    mid = np.asarray(b.U_pc.ulon).copy()
+    mods.interpolation.wind_center2ghostedge_cubic_interpolation(b.U_pc, b.U_pu, b.U_pv, g16, b)
+    assert np.array_equal(mid, np.asarray(a.U_pc.ulon))
+    for obj, names in (("U_pu", ("ucontra", "vcontra", "ulon", "vlat")), ("U_pv", ("ucontra", "vcontra", "ulon", "vlat")),
+                       ("U_pc", ("ulon", "vlat", "ucontra", "vcontra"))):
+        for nm in names:
+            assert np.array_equal(np.asarray(getattr(getattr(a, obj), nm)), np.asarray(getattr(getattr(b, obj), nm))), (obj, nm)
+    a.dev.close()
+    b.dev.close()
+
+
+def test_edges_extrapolation_callable_separately(mods, g16):
+    """edges_extrapolation (src/edges_treatment.py:82-206) on its own after a reconstruction equals the
+    reconstruction of an ET-PL07 simulation, which calls it itself (src/reconstruction_1d.py:392-394)."""
+    rng = np.random.default_rng(5)
+    Qx = rng.standard_normal((24, 24, 6))
+    Qy = rng.standard_normal((24, 24, 6))
+    a = make_sim(mods, g16, 1, TUPLES["PL07-RK1"])              # ET-PL07
+    b = make_sim(mods, g16, 1, (3, 1, 3, 1, 2, 1))              # same scheme with ET-S72: no extrapolation inside
+    mods.reconstruction_1d.ppm_reconstruction(Qx, Qy, a.px, a.py, g16, a)
+    mods.reconstruction_1d.ppm_reconstruction(Qx, Qy, b.px, b.py, g16, b)
+    assert not np.array_equal(np.asarray(a.px.q_L), np.asarray(b.px.q_L))
+    mods.edges_treatment.edges_extrapolation(Qx, Qy, b.px, b.py, g16, b)
+    for par in ("px", "py"):
+        for nm in ("q_L", "q_R"):
+            assert np.array_equal(np.asarray(getattr(getattr(a, par), nm)), np.asarray(getattr(getattr(b, par), nm))), (par, nm)
+    a.dev.close()
+    b.dev.close()
