@@ -139,9 +139,8 @@ def run_reference(args):
         t += cpu_steps(g, sim, ost, k, 1)
         k += 1
     value = 6.0 * N * N * args.steps / t
-    cfg = workload(args.n)
-    cfg["cpu_sample"] = "ran at N=%d (%d cells per step), same scheme, wind and dt rule" % (N, 6 * N * N)
-    line = {"impl": "reference", "metric": "cell-updates/s (fp64 advection step)", "value": value,
+    cfg = workload(args.n)            # the arm's config is the GPU arm's, key for key; what ran is in cpu_sample
+    line = {"impl": "reference", "cpu_sample": "ran at N=%d (%d cells per step), same scheme, wind and dt rule" % (N, 6 * N * N), "metric": "cell-updates/s (fp64 advection step)", "value": value,
             "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": cfg,

@@ -5,9 +5,20 @@
 #include <cstring>
 #include <new>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>
 #include "pycs_common.cuh"
 #include "fused_args.cuh"
 #include "mgpu.cuh"
+
+// NVTX range per reference-level operation (header-only NVTX 3: a no-op unless a tool is attached), so that
+// a timeline shows adv_time_step / divergence / ghost fills the way the reference's call stack names them
+namespace {
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
+#define PYCS_RANGE(name) NvtxRange nvtx_range__(name)
 
 static thread_local std::string g_err;
 void pycs_set_error(const std::string& msg) { g_err = msg; }
@@ -158,7 +169,11 @@ extern "C" int pycs_create(const pycs_params* prm, pycs_handle* out) {
   cudaDeviceProp dp;
   CK(cudaGetDeviceProperties(&dp, prm->device));
   h->sm_count = dp.multiProcessorCount;
-  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {   // highest priority: in a split step the boundary CTAs run on this stream, ahead of the interior CTAs
+    int lo_pri = 0, hi_pri = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+    CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, hi_pri));
+  }
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
   CK(cudaMalloc(&h->red_out, 16 * sizeof(double)));
@@ -239,6 +254,7 @@ static int upload_from(pycs_handle h, int field, const double* host, int i0 = 0,
 }
 
 extern "C" int pycs_upload_field(pycs_handle h, int32_t field, const double* host) {
+  PYCS_RANGE("upload_field");
   TRY(wind_sync(h));
   if (!host) return arg_fail("null host pointer");
   CK(cudaSetDevice(h->device));
@@ -267,6 +283,7 @@ static int download_to(pycs_handle h, int field, double* host, int i0 = 0, int i
 }
 
 extern "C" int pycs_download_field(pycs_handle h, int32_t field, double* host) {
+  PYCS_RANGE("download_field");
   TRY(state_sync(h));
   if (!host) return arg_fail("null host pointer");
   CK(cudaSetDevice(h->device));
@@ -325,6 +342,7 @@ extern "C" int pycs_upload_lagrange(pycs_handle h, int32_t degree, const int32_t
 
 // --------------------------------------------------------------------------- device-side set-up (f2 / f3)
 extern "C" int pycs_generate_geometry(pycs_handle h, const double* xc, const double* xe) {
+  PYCS_RANGE("generate_geometry");
   if (!xc || !xe) return arg_fail("null coordinate array");
   CK(cudaSetDevice(h->device));
   TRY(state_sync(h));
@@ -375,6 +393,7 @@ extern "C" int pycs_halo_gather(pycs_handle h, int32_t fx, int32_t fy, double* e
 }
 
 extern "C" int pycs_halo_fill_dg(pycs_handle h, int32_t field) {
+  PYCS_RANGE("ghost_cell_pc_lagrange_interpolation");
   TRY(normalize_q(h));
   double* q;
   TRY(pycs_field_ptr(h, field, &q));
@@ -383,6 +402,7 @@ extern "C" int pycs_halo_fill_dg(pycs_handle h, int32_t field) {
 }
 
 extern "C" int pycs_halo_fill_copy(pycs_handle h, int32_t fx, int32_t fy) {
+  PYCS_RANGE("ghost_cells_adjacent_panels");
   TRY(normalize_q(h));
   double *x, *y;
   TRY(pycs_field_ptr(h, fx, &x));
@@ -397,6 +417,7 @@ extern "C" int pycs_halo_fill_scalar(pycs_handle h, int32_t fx, int32_t fy) {
 }
 
 extern "C" int pycs_halo_fill_vector(pycs_handle h) {
+  PYCS_RANGE("edges_ghost_cell_treatment_vector");
   TRY(wind_sync(h));
   return k_wind_ghost_fill(h);
 }
@@ -416,6 +437,7 @@ extern "C" int pycs_wind_center2ghostedge(pycs_handle h) {
 
 // --------------------------------------------------------------------------- operators
 extern "C" int pycs_time_averaged_velocity(pycs_handle h) {
+  PYCS_RANGE("time_averaged_velocity");
   TRY(wind_sync(h));
   return k_time_averaged_velocity(h);
 }
@@ -455,6 +477,7 @@ extern "C" int pycs_numerical_flux(pycs_handle h, int32_t fx, int32_t fy) {
 }
 
 extern "C" int pycs_compute_fluxes(pycs_handle h, int32_t fx, int32_t fy) {
+  PYCS_RANGE("compute_fluxes");
   TRY(wind_sync(h));
   TRY(pycs_ppm_reconstruction(h, fx, fy));
   return pycs_numerical_flux(h, fx, fy);
@@ -466,6 +489,7 @@ extern "C" int pycs_average_flux_cube_edges(pycs_handle h) { return k_average_fl
 
 // divergence, operator by operator (src/discrete_operators.py:18-101)
 extern "C" int pycs_divergence(pycs_handle h) {
+  PYCS_RANGE("divergence");
   TRY(state_sync(h));
   double *Q, *gQ, *cx, *cy, *ua, *va;
   TRY(pycs_field_ptr(h, PYCS_F_Q, &Q));
@@ -490,6 +514,7 @@ extern "C" int pycs_divergence(pycs_handle h) {
 }
 
 extern "C" int pycs_adv_time_step(pycs_handle h, int64_t k, double t) {
+  PYCS_RANGE("adv_time_step");
   TRY(wind_sync(h));
   (void)k; (void)t;
   CK(cudaSetDevice(h->device));
@@ -504,6 +529,7 @@ extern "C" int pycs_adv_time_step(pycs_handle h, int64_t k, double t) {
 }
 
 extern "C" int pycs_update_adv(pycs_handle h, double t) {
+  PYCS_RANGE("update_adv");
   TRY(wind_sync(h));
   return k_update_adv(h, t);
 }
@@ -555,10 +581,12 @@ extern "C" int pycs_fused_supported(pycs_handle h, int32_t* yes) {
 }
 
 extern "C" int pycs_run(pycs_handle h, int64_t k0, int64_t nsteps, int32_t fused) {
+  PYCS_RANGE("pycs_run (adv_sphere time loop)");
   return run_steps(h, k0, nsteps, fused);
 }
 
 extern "C" int pycs_run_timed(pycs_handle h, int64_t k0, int64_t nsteps, int32_t fused, float* ms) {
+  PYCS_RANGE("pycs_run_timed");
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   // several GPUs: the ranks enter the timed steps together -- a barrier on the device, in stream order, so
@@ -595,6 +623,7 @@ extern "C" int pycs_step_kernel_name(pycs_handle h, char* name, int32_t name_len
 }
 
 extern "C" int pycs_adv_time_step_host(pycs_handle h, double* Q, int64_t k, double t, int32_t fused) {
+  PYCS_RANGE("adv_time_step (host buffers)");
   if (!Q) return arg_fail("null Q");
   CK(cudaSetDevice(h->device));
   if (h->mg && !fused) return arg_fail("multi-GPU handles run the fused step only");
@@ -690,6 +719,7 @@ static int whole_sphere_only(pycs_handle h, const char* what) {
 }
 
 extern "C" int pycs_errors(pycs_handle h, const double* qexact_interior, double* out3) {
+  PYCS_RANGE("compute_errors");
   TRY(whole_sphere_only(h, "pycs_errors"));
   // stage the (N,N,6) exact field into the interior of USER_B
   const Geo& g = h->g;
@@ -715,6 +745,7 @@ extern "C" int pycs_errors_exact(pycs_handle h, double t, double* out3) {
 }
 
 extern "C" int pycs_mass(pycs_handle h, double* mass) {
+  PYCS_RANGE("mass_computation");
   TRY(whole_sphere_only(h, "pycs_mass"));
   TRY(normalize_q(h));
   return k_mass(h, mass);

@@ -8,9 +8,9 @@
 //   serial (one GPU)       ghost fill (folds the pending MF-PR term into the ghost cells, hands the
 //                          coefficient to the step kernel) -> step kernel over the whole grid.
 //
-//   split (several GPUs,   stream B, high priority:  boundary CTAs (GH = 1) -> exchange -> ghost fill of
-//   PYCS_SPLIT=1 on one)                             the NEXT step (raw: no projection term)
-//                          stream A (the handle's):  interior CTAs (GH = 0)
+//   split (several GPUs,   the handle's stream (high priority):  boundary CTAs (GH = 1, they ship their rows to the
+//   PYCS_SPLIT=1 on one)                             peers themselves) -> ghost fill of the NEXT step (raw: no projection term)
+//                          second stream:            interior CTAs (GH = 0)
 //                          The boundary CTAs are everything a ghost cell or a peer reads: first / last
 //                          column strip of every panel, first / last chunk of the slab.  Exchange,
 //                          flag latency and ghost fill run beside the interior update; the two launches
@@ -469,7 +469,7 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
       if (!fs.s2) {
         int lo_pri = 0, hi_pri = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
-        CK(cudaStreamCreateWithPriority(&fs.s2, cudaStreamNonBlocking, hi_pri));
+        CK(cudaStreamCreateWithPriority(&fs.s2, cudaStreamNonBlocking, lo_pri));   // interior CTAs: behind the handle's stream
         CK(cudaEventCreateWithFlags(&fs.e_fork, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&fs.e_join, cudaEventDisableTiming));
       }
@@ -592,11 +592,11 @@ void k_fused_profile_report(pycs_handle h) {
       cudaEventElapsedTime(&ms, fs.ev2[6 * k], fs.ev2[6 * k + 1]); u[0] += ms;
       cudaEventElapsedTime(&ms, fs.ev2[6 * k + 1], fs.ev2[6 * k + 2]); u[1] += ms;
       cudaEventElapsedTime(&ms, fs.ev2[6 * k + 2], fs.ev2[6 * k + 3]); u[2] += ms;
-      cudaEventElapsedTime(&ms, fs.ev2[6 * k + 4], fs.ev2[6 * k + 5]); u[3] += ms;
+      cudaEventElapsedTime(&ms, fs.ev2[6 * k + 3], fs.ev2[6 * k + 4]); u[3] += ms;
     }
     const double m = (double)(n2 - sk);
     fprintf(stderr, "[pycs split profile] rank %d: boundary CTAs %.2f us, exchange kernel %.2f us, next ghost fill (+ wait "
-                    "for the peers' data) %.2f us | interior CTAs %.2f us\n",
+                    "for the peers' data) %.2f us, then %.2f us until the interior CTAs are done\n",
             h->mg ? h->mg->rank : 0, 1e3 * u[0] / m, 1e3 * u[1] / m, 1e3 * u[2] / m, 1e3 * u[3] / m);
   }
   for (auto e : fs.ev2) cudaEventDestroy(e);
@@ -1027,8 +1027,8 @@ static int enqueue_serial(pycs_handle h, FusedState& fs, double* qcur, double* q
   return 0;
 }
 
-// split: boundary CTAs -> exchange -> ghost fill of the next step on the high-priority stream, interior
-// CTAs on the handle's stream.  Precondition: the ghost cells of qcur are (raw) filled.
+// split: boundary CTAs (+ exchange) -> ghost fill of the next step on the handle's high-priority stream, interior
+// CTAs on the second stream.  Precondition: the ghost cells of qcur are (raw) filled.
 static int enqueue_split(pycs_handle h, FusedState& fs, double* qcur, double* qnext, int mask, bool winds,
                          bool profile, int wind_mode) {
   auto mark = [&]() {
@@ -1052,8 +1052,11 @@ static int enqueue_split(pycs_handle h, FusedState& fs, double* qcur, double* qn
     a.pub.rank = h->mg->rank;
     for (int d = 0; d < 8; ++d) a.pub.peer_sync[d] = d < h->mg->world ? h->mg->peer_sync[d] : nullptr;
   }
+  // The boundary CTAs go on the handle's stream (high priority, no cross-stream dependency to resolve before
+  // their launch): they take the CTA slots first.  The interior launch follows on the second stream.
+  // (The other way round, the interior launch won the slots and the boundary CTAs trickled in behind it:
+  // 92 us for the boundary launch at 4 GPUs instead of ~25, profiles/r2_mgpu_split_profile.md.)
   CK(cudaEventRecord(fs.e_fork, h->stream));            // everything before this step
-  CK(cudaStreamWaitEvent(fs.s2, fs.e_fork, 0));
   auto mark2 = [&](cudaStream_t st) {
     if (!profile || fs.ev2.size() >= 6 * 4096) return;
     cudaEvent_t e;
@@ -1061,7 +1064,7 @@ static int enqueue_split(pycs_handle h, FusedState& fs, double* qcur, double* qn
     cudaEventRecord(e, st);
     fs.ev2.push_back(e);
   };
-  mark2(fs.s2);
+  mark2(h->stream);
   FusedArgs b = a;
   b.cta_tab = fs.cta_tab;
   b.cta_off = 0;
@@ -1074,24 +1077,25 @@ static int enqueue_split(pycs_handle h, FusedState& fs, double* qcur, double* qn
     const int idx = (qnext == h->mg->alloc[0]) ? 0 : 1;
     for (int d = 0; d < 8; ++d) b.xpeer_q[d] = d < h->mg->world ? h->mg->peer_q[idx][d] : nullptr;
   }
-  TRY(launch_step(h, fs, b, mask, 1, fs.n_b, fs.s2));   // reads ghost cells, feeds the peers
-  mark2(fs.s2);
-  if (h->mg && !xin) TRY(k_mg_exchange(h, qnext, fs.ctl, fs.s2));
-  mark2(fs.s2);
-  // the ghost cells the NEXT step reads: their sources are boundary cells of this step's output (own:
-  // stream order; the peers': dflag), so the fill runs beside this step's interior CTAs
-  TRY(launch_ghost_fill(h, qnext, fs.s2, nullptr, fs.ctl, 0, nullptr, nullptr, true));
-  mark2(fs.s2);
-  CK(cudaEventRecord(fs.e_join, fs.s2));
+  TRY(launch_step(h, fs, b, mask, 1, fs.n_b, h->stream));   // reads ghost cells, feeds the peers
   mark2(h->stream);
   if (fs.n_i) {
+    CK(cudaStreamWaitEvent(fs.s2, fs.e_fork, 0));
     FusedArgs c = a;
     c.cta_tab = fs.cta_tab;
     c.cta_off = fs.n_b;
-    TRY(launch_step(h, fs, c, mask, 0, fs.n_i, h->stream));   // reads no ghost cell
+    TRY(launch_step(h, fs, c, mask, 0, fs.n_i, fs.s2));     // reads no ghost cell
+    CK(cudaEventRecord(fs.e_join, fs.s2));
   }
+  if (h->mg && !xin) TRY(k_mg_exchange(h, qnext, fs.ctl, h->stream));
   mark2(h->stream);
-  CK(cudaStreamWaitEvent(h->stream, fs.e_join, 0));
+  // the ghost cells the NEXT step reads: their sources are boundary cells of this step's output (own:
+  // stream order; the peers': dflag), so the fill runs beside this step's interior CTAs
+  TRY(launch_ghost_fill(h, qnext, h->stream, nullptr, fs.ctl, 0, nullptr, nullptr, true));
+  mark2(h->stream);
+  if (fs.n_i) CK(cudaStreamWaitEvent(h->stream, fs.e_join, 0));
+  mark2(h->stream);
+  mark2(h->stream);
   mark();
   mark();
   return 0;
