@@ -28,6 +28,7 @@
 //         split step);
 // GH = 1: boundary CTAs of a split step: the ghost fill ran early and raw, the projection term of
 //         the ghost cells (corr * ghost(sqrtg)) is added here as the rows are loaded.
+#include <cstdlib>
 #include "fused_args.cuh"
 #include "mgpu.cuh"
 // PPM-PL07 edge-value coefficients as constant-bank operands
@@ -42,6 +43,7 @@ __constant__ double f2b_ppm_coef[5] = {2.0 / 60.0, -13.0 / 60.0, 47.0 / 60.0, 27
 #define F2B_TB 160         // threads per CTA: 154 output columns; 96 registers, 49 KB -> 4 CTAs / SM
 #define F2B_PF 2           // rows in flight ahead of the march
 #define F2B_MINB 4         // register cap as CTAs per SM
+#define F2B_ISSUE_DEFAULT 0
 
 namespace {
 
@@ -71,7 +73,9 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-template <int TB, int RECON, int SPLIT, int MASK, int GH>
+// ISS: form of the TMA issue path of warp 0's elected lane (it sits between the two barriers of a row, the other
+// four warps wait for it): 0 = bases + byte offset, 1 = one running pointer per staged array
+template <int TB, int RECON, int SPLIT, int MASK, int GH, int ISS = 0>
 __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
   constexpr int PF = F2B_PF;
   constexpr int RW = TB + 6;                 // staged row: columns jbase-6 .. jbase+TB-1
@@ -194,44 +198,81 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
     return R;
   };
   const long long ld8 = (long long)g.ld * 8;
-  long long o0 = (long long)rfirst * ld8;    // byte offset of the next row to issue
+  // Source pointers of the next row to issue, one per staged array, each advanced by one row pitch per issue:
+  // the elected lane's path between the two barriers of a row is two uniform instructions per address (it was
+  // five with base + offset - constant: profiles/r2_fused_v2b_ncu.md, "issue path").  Q, v and the centre
+  // metrics are staged at the marched row R, sqrtg_pu one row late (R-1), u two rows late (R-2).
+  auto rowp = [&](const double* base, int row) {
+    return reinterpret_cast<const char*>(base) + (long long)row * ld8;
+  };
+  const char *pQ = rowp(gq, rfirst), *pV = rowp(gv, rfirst), *pSGC = rowp(gsgc, rfirst), *pSGV = rowp(gsgv, rfirst),
+             *pRGC = rowp(grgc, rfirst), *pSGU = rowp(gsgu, rfirst - 1), *pU = rowp(gu, max(rfirst - 2, 0)),
+             *pVM = rowp(gvm, rfirst), *pUM = rowp(gum, max(rfirst - 2, 0));
+  long long o0 = (long long)rfirst * ld8;    // ISS = 0: byte offset of the next row to issue
   auto at = [](const double* base, long long off) {
     return reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + off);
   };
   constexpr int NCOPY = NS + NL;
-  // the TMA copies of the row with phase k (elected lane of warp 0, after its fence.proxy.async); o0, o1, o2:
-  // byte offsets of that row and of the rows staged one (sqrtg_pu) and two (u) rows late
-  auto issue_k = [&](auto kc, long long o1, long long o2) {
+  // the TMA copies of the row with phase k (elected lane of warp 0, after its fence.proxy.async)
+  auto issue_k = [&](auto kc, bool first) {
     constexpr int k = decltype(kc)::value;
     const uint32_t dS = ringS_a + 8u * (uint32_t)((k % DS) * SSLOT), dL = ringL_a + 8u * (uint32_t)(k * LSLOT),
                    bar = full_a + 8u * (uint32_t)k;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * NCOPY)
                  : "memory");
-    tma(dS + 8u * S_Q * RW, at(gq, o0), bar);
-    tma(dL + 8u * L_V * RW, at(gv, o0), bar);
-    tma(dL + 8u * L_SGC * RW, at(gsgc, o0), bar);
-    tma(dL + 8u * L_SGV * RW, at(gsgv, o0), bar);
-    tma(dL + 8u * L_RGC * RW, at(grgc, o0), bar);
-    tma(dS + 8u * S_SGU * RW, at(gsgu, o1), bar);
-    tma(dS + 8u * S_U * RW, at(gu, o2), bar);
-    if (MASK & 1) {
-      tma(dL + 8u * L_VM * RW, at(gvm, o0), bar);
-      tma(dS + 8u * S_UM * RW, at(gum, o2), bar);
+    if (ISS == 1) {
+      auto P = [](const char* p) { return reinterpret_cast<const double*>(p); };
+      tma(dS + 8u * S_Q * RW, P(pQ), bar);
+      tma(dL + 8u * L_V * RW, P(pV), bar);
+      tma(dL + 8u * L_SGC * RW, P(pSGC), bar);
+      tma(dL + 8u * L_SGV * RW, P(pSGV), bar);
+      tma(dL + 8u * L_RGC * RW, P(pRGC), bar);
+      tma(dS + 8u * S_SGU * RW, P(pSGU), bar);
+      tma(dS + 8u * S_U * RW, P(pU), bar);
+      if (MASK & 1) {
+        tma(dL + 8u * L_VM * RW, P(pVM), bar);
+        tma(dS + 8u * S_UM * RW, P(pUM), bar);
+      }
+    } else {
+      const long long o1 = o0 - ld8, o2 = first ? (long long)max(rfirst - 2, 0) * ld8 : o0 - 2 * ld8;
+      tma(dS + 8u * S_Q * RW, at(gq, o0), bar);
+      tma(dL + 8u * L_V * RW, at(gv, o0), bar);
+      tma(dL + 8u * L_SGC * RW, at(gsgc, o0), bar);
+      tma(dL + 8u * L_SGV * RW, at(gsgv, o0), bar);
+      tma(dL + 8u * L_RGC * RW, at(grgc, o0), bar);
+      tma(dS + 8u * S_SGU * RW, at(gsgu, o1), bar);
+      tma(dS + 8u * S_U * RW, at(gu, o2), bar);
+      if (MASK & 1) {
+        tma(dL + 8u * L_VM * RW, at(gvm, o0), bar);
+        tma(dS + 8u * S_UM * RW, at(gum, o2), bar);
+      }
+    }
+  };
+  auto advance = [&]() {                     // warp-uniform
+    if (ISS == 1) {
+      pQ += ld8; pV += ld8; pSGC += ld8; pSGV += ld8; pRGC += ld8; pSGU += ld8; pU += ld8;
+      if (MASK & 1) { pVM += ld8; pUM += ld8; }
+    } else {
+      o0 += ld8;
     }
   };
 
   if (warp_u == 0) {                         // rows rfirst, rfirst + 1 (rfirst >= 1: only row -1 is clamped)
     if (elect_one()) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue_k(IC<0>{}, o0 - ld8, (long long)max(rfirst - 2, 0) * ld8);
+      issue_k(IC<0>{}, true);
     }
-    o0 += ld8;
+    advance();
+    if (ISS == 1) {                          // the clamp of the first row does not carry over
+      pU = rowp(gu, rfirst - 1);
+      pUM = rowp(gum, rfirst - 1);
+    }
     if (rfirst + 1 <= rlast) {
       if (elect_one()) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue_k(IC<1>{}, o0 - ld8, o0 - 2 * ld8);
+        issue_k(IC<1>{}, false);
       }
-      o0 += ld8;
+      advance();
     }
   }
   double* __restrict__ QN = a.qn + (long long)p * g.ps + PYCS_JOFF + min(j, g.P - 1) + (long long)r0 * g.ld;
@@ -276,9 +317,9 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
     if (warp_u == 0 && r + PF <= rlast) {              // warp 0 issues the TMA copies of row r+PF
       if (elect_one()) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue_k(IC<(k + PF) % DL>{}, o0 - ld8, o0 - 2 * ld8);
+        issue_k(IC<(k + PF) % DL>{}, false);
       }
-      o0 += ld8;
+      advance();
     }
     // ---------------- phase 2: y-fluxes at edge j: inner on Q row r, outer on Qx row r-3
     double F[1], G[1], CF[1] = {0.0}, CG[1];
@@ -357,7 +398,9 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
     double t = 0.0;
     for (int w = 0; w < TB / 32; ++w) t += sF[w];
     a.part[cta] = t;
-    sF[40] = fused_last_writer(a.counter, (unsigned)ntot, mgw > 1) ? 1.0 : 0.0;
+    // device scope suffices here: the ticket orders the partial sums; peer stores (in-kernel exchange) were
+    // fenced at system scope before their own ticket, and the publication below fences its own stores
+    sF[40] = fused_last_writer(a.counter, (unsigned)ntot, false) ? 1.0 : 0.0;
   }
   __syncthreads();
   if (sF[40] != 0.0 && tid < 32) {
@@ -389,11 +432,11 @@ constexpr size_t smem_bytes() {
          sizeof(uint64_t) * DL + 16;
 }
 
-template <int TB, int RECON, int SPLIT, int MASK, int GH>
-cudaError_t launch_one(const FusedArgs& a, int nblocks, cudaStream_t st, int* resident) {
+template <int TB, int RECON, int SPLIT, int MASK, int GH, int ISS>
+cudaError_t launch_iss(const FusedArgs& a, int nblocks, cudaStream_t st, int* resident) {
   static bool configured = false;
   const size_t smem = smem_bytes<TB, MASK>();
-  auto kern = fused2b_kernel<TB, RECON, SPLIT, MASK, GH>;
+  auto kern = fused2b_kernel<TB, RECON, SPLIT, MASK, GH, ISS>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -402,6 +445,24 @@ cudaError_t launch_one(const FusedArgs& a, int nblocks, cudaStream_t st, int* re
   if (resident) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(resident, kern, TB, smem);
   kern<<<nblocks, TB, smem, st>>>(a);
   return cudaSuccess;
+}
+
+// PYCS_ISSUE selects the issue-path form of the par-default scheme's kernels (experiment knob)
+static int issue_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PYCS_ISSUE");
+    v = e ? atoi(e) : F2B_ISSUE_DEFAULT;
+  }
+  return v;
+}
+template <int TB, int RECON, int SPLIT, int MASK, int GH>
+cudaError_t launch_one(const FusedArgs& a, int nblocks, cudaStream_t st, int* resident) {
+  if constexpr (RECON == 3 && SPLIT == 1) {
+    if (issue_variant() != F2B_ISSUE_DEFAULT)
+      return launch_iss<TB, RECON, SPLIT, MASK, GH, 1 - F2B_ISSUE_DEFAULT>(a, nblocks, st, resident);
+  }
+  return launch_iss<TB, RECON, SPLIT, MASK, GH, F2B_ISSUE_DEFAULT>(a, nblocks, st, resident);
 }
 
 template <int RECON, int SPLIT>

@@ -294,8 +294,8 @@ int k_fused_supported(pycs_handle h) {
 
 // Makespan (in marched rows) of a split step with the given boundary / interior shapes, by list scheduling of
 // its CTAs -- boundary CTAs first, as the high-priority stream dispatches them -- onto `slots` CTA slots.  A
-// CTA costs its rows + 6 (the ramp of a chunk), a boundary CTA 9 % more (ghost-cell projection term); the
-// exchange and the next ghost fill follow the last boundary CTA and cost ~20 rows' time.  Measured against
+// CTA costs its rows + 6 (the ramp of a chunk) + 6 (prologue, first staged rows, closing ticket), a boundary CTA
+// 9 % more (ghost-cell projection term); the next ghost fill follows the last boundary CTA, ~20 rows' time.  Measured against
 // it at N = 1536 on 2 GPUs: 108 rows predicted, 112 us per step observed (a marched row takes ~1 us when the
 // SM is full).
 static double split_shape_cost(int row_lo, int row_hi, int nstrips, int slots, int band, int edge_rows, int rows) {
@@ -306,7 +306,7 @@ static double split_shape_cost(int row_lo, int row_hi, int nstrips, int slots, i
   double chain = 0.0, makespan = 0.0;
   for (int k = 0; k < (int)tab.size(); ++k) {
     std::pop_heap(heap.begin(), heap.end(), cmp);
-    const double f = heap.back() + (tab[k].r1 - tab[k].r0 + 6) * (k < nb ? 1.09 : 1.0);
+    const double f = heap.back() + (tab[k].r1 - tab[k].r0 + 6) * (k < nb ? 1.09 : 1.0) + 6.0;   // + a CTA's fixed cost
     heap.back() = f;
     std::push_heap(heap.begin(), heap.end(), cmp);
     if (k < nb && f > chain) chain = f;

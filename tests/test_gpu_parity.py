@@ -326,6 +326,26 @@ def test_config3_n768_lean_grid(mods):
     _check_big(mods, "config_N768_vf2.npz", True, lean=True)
 
 
+@pytest.mark.parametrize("N,nsteps", [(768, 20), (1536, 2)])
+def test_config4_full_field_vs_oracle(mods, N, nsteps):
+    """The whole field (every interior cell and the ghost ring) of the config-4 scheme against the numpy oracle
+    run on this host: 20 steps at N = 768 and the first steps at the full size N = 1536 (the fixtures only
+    hold a 51 x 51 x 6 sample of N = 1536)."""
+    og, osim, ost = oracle_sim(N, 3, TUPLES["default"])
+    ost.run(og, osim, nsteps, 0)
+    g = mods.cs_datastruct.cubed_sphere(N, lean=True)
+    sim = make_sim(mods, g, 3, TUPLES["default"])
+    mods.advection_timestep.run_steps(g, sim, 0, nsteps, fused=True)
+    Q = np.asarray(sim.Q)
+    I = np.s_[4:N + 4, 4:N + 4, :]
+    assert relerr(Q[I], osim.Q[I]) <= TOL
+    assert relerr(Q, osim.Q) <= TOL                       # ghost ring as the reference leaves it
+    for a, b in zip(ost.compute_errors(Q[I], ost.qexact_adv(og.pc.lon[I], og.pc.lat[I], nsteps * osim.dt, osim)),
+                    ost.compute_errors(osim.Q[I], ost.qexact_adv(og.pc.lon[I], og.pc.lat[I], nsteps * osim.dt, osim))):
+        assert abs(a - b) <= TOL * abs(b) + 4 * np.finfo(float).eps
+    sim.dev.close()
+
+
 # ------------------------------------------------------------------ fused vs operator path
 @pytest.mark.parametrize("N", [16, 20, 50, 130])
 @pytest.mark.parametrize("vf,name", [(1, "default"), (3, "default"), (2, "AVLT-RK2-DG-PR"),
