@@ -133,8 +133,7 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
   const long long step = *((const volatile long long*)&a.ctl->steps);
   if (a.wait_flags) {           // several GPUs: every rank has finished step - 1 (its sum is here, and
     if (tid < a.wait_world) {   // nobody reads the buffers this step's exchange will write any more)
-      mg_wait_flag(a.wait_flags + tid, step, a.mg_err, a.mg_timeout_ns);
-      __threadfence_system();
+      mg_wait_flag(a.wait_flags + tid, step, a.mg_err, a.mg_timeout_ns);     // acquire: see mgpu.cuh
     }
     __syncthreads();
   }
@@ -341,6 +340,14 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
         L.psum += sdiv[0];
       }
       QN += g.ld;
+    }
+    if (GH && a.edge_flux) {
+      // MF-AF: the outer fluxes (times dt/dx, as the kernel carries them) on the panel's edge lines, interior extent
+      const int ex = r - 2, ry = r - 3;                 // x-edge just completed; row of the outer y-fluxes
+      if ((ex == g.lo || ex == g.hi) && out_lane)
+        a.edge_flux[((long long)p * 4 + (ex == g.lo ? 0 : 1)) * g.N + (j - g.lo)] = L.fout_prev[0];
+      if ((j == g.lo || j == g.hi) && ry >= r0 && ry < r1)
+        a.edge_flux[((long long)p * 4 + (j == g.lo ? 2 : 3)) * g.N + (ry - g.lo)] = G[0];
     }
     return true;
   };

@@ -78,6 +78,9 @@ struct FusedArgs {
   double* xpeer_q[8];         // the peers' arrays that correspond to qn
   unsigned* xcounter;
   int n_boundary;
+  // MF-AF (GH = 1 flavour): the outer fluxes on the four edge lines of every panel are recorded here,
+  // [panel][W, E, S, N][N], for the cube-edge averaging that follows the launch (stepper.cu: mf_af_patch_kernel)
+  double* edge_flux;
   int timing;                 // roofline timing launches: leave the control block alone
 };
 

@@ -76,13 +76,21 @@ __device__ __forceinline__ unsigned long long mg_now_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ bool mg_wait_flag(const volatile long long* f, long long epoch, int* err,
+// The flag is read with acquire semantics at system scope: what the peer stored before raising it (its rows,
+// its MF-PR sum) is visible to the loads that follow, without a separate fence in every waiting CTA.
+__device__ __forceinline__ long long mg_ld_acquire(const long long* f) {
+  long long v;
+  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool mg_wait_flag(const volatile long long* fv, long long epoch, int* err,
                                              unsigned long long timeout_ns) {
-  if (*f >= epoch) return true;
+  const long long* f = const_cast<const long long*>(fv);
+  if (mg_ld_acquire(f) >= epoch) return true;
   if (*(volatile int*)err) return false;
   const unsigned long long t0 = mg_now_ns();
   for (;;) {
-    if (*f >= epoch) return true;
+    if (mg_ld_acquire(f) >= epoch) return true;
     __nanosleep(32);
     if (mg_now_ns() - t0 > timeout_ns) {
       atomicExch(err, 1);

@@ -35,6 +35,7 @@
 #include "fused_args.cuh"
 #include "mgpu.cuh"
 #include "ghost_core.cuh"
+#include "cube_edges.cuh"
 
 namespace {
 
@@ -94,8 +95,7 @@ __global__ void dg_fill_kernel(const __grid_constant__ GhostFillArgs a) {
   if (a.flags) {
     if ((int)threadIdx.x < a.world) {
       const long long xc = *((const volatile long long*)&a.ctl->xcount);
-      mg_wait_flag(a.flags + threadIdx.x, xc, a.mg_err, a.mg_timeout_ns);
-      __threadfence_system();
+      mg_wait_flag(a.flags + threadIdx.x, xc, a.mg_err, a.mg_timeout_ns);     // acquire: see mgpu.cuh
     }
     __syncthreads();
   }
@@ -189,6 +189,35 @@ __global__ void copy_ring_kernel(Geo g, double* __restrict__ dst, const double* 
   dst[id] = v;
 }
 
+// MF-AF (src/edges_treatment.py:231-278): the outer fluxes on the 12 cube edges are replaced by the average of
+// the two panels' values (with the sign / flip of the edge pair) before the flux differences are taken.  The step
+// kernel has already formed Q + (pxdF + pydF) / sqrtg with each panel's own edge flux and recorded those fluxes;
+// the update is linear in them, so the averaging is a correction of the cells next to the cube edges:
+//   side lo: Q[lo]     += (f_avg - f_own) / sqrtg,     side hi: Q[hi - 1] -= (f_avg - f_own) / sqrtg.
+// pass = 0 corrects the ends that are x-edges, pass = 1 the y-edges: within a pass no two ends touch the same
+// cell (a corner cell belongs to one x- and one y-edge), so the result does not depend on thread order.
+__global__ void mf_af_patch_kernel(Geo g, const double* __restrict__ ef, const double* __restrict__ rgc,
+                                   double* __restrict__ q, int pass) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.N) return;
+  const CubeEdge ce = cube_edge(blockIdx.y);
+  const int tb = ce.flip ? g.N - 1 - t : t;
+  const double sg = ce.a.side == ce.b.side ? -1.0 : 1.0;
+  auto rec = [&](const EdgeEnd& e, int pos) { return ef[((long long)e.panel * 4 + 2 * e.dir + e.side) * g.N + pos]; };
+  const double fa = rec(ce.a, t), fb = rec(ce.b, tb);
+  const double v = 0.5 * fa + sg * (0.5 * fb);           // :242-278, a = b = 1/2
+  auto fix = [&](const EdgeEnd& e, int pos, double delta) {
+    if (e.dir != pass) return;
+    const int c = e.side == 0 ? g.lo : g.hi - 1;         // the cell next to the edge
+    const int i = e.dir == 0 ? c : g.lo + pos, j = e.dir == 0 ? g.lo + pos : c;
+    const long long id = gidx(g, e.panel, i, j);
+    const double d = e.side == 0 ? delta : -delta;
+    q[id] = fma(d, rgc[gidx(g, 0, i, j)], q[id]);
+  };
+  fix(ce.a, t, v - fa);
+  fix(ce.b, tb, sg * v - fb);
+}
+
 __global__ void recip_kernel(Geo g, const double* __restrict__ s, double* __restrict__ d) {
   int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
   if (j > g.P) return;
@@ -262,6 +291,7 @@ struct FusedState {
   int4* xjobs = nullptr;
   unsigned* xcounter = nullptr;
   int xkernel = 0;             // PYCS_MG_XKERNEL=1: separate exchange kernel instead
+  double* edge_flux = nullptr; // MF-AF: recorded outer fluxes on the panels' edge lines [6][4][N]
   int n_i = 0, n_b = 0;
   int band = 0, edge_rows = 0, irows = 0;
   cudaStream_t s2 = nullptr;
@@ -287,9 +317,12 @@ static void drop_graphs(FusedState& fs) {
 }
 
 int k_fused_supported(pycs_handle h) {
-  // duo-grid ghost cells only (ET-S72/PL07 refill ghosts between the two stages and
-  // ET-PL07 couples parabolas across panels); MF-AF couples fluxes across panels.
-  return (h->prm.et == 3 && h->prm.mf != 2) ? 1 : 0;
+  // duo-grid ghost cells only (ET-S72/PL07 refill ghosts between the two stages and ET-PL07 couples
+  // parabolas across panels).  MF-AF couples the outer fluxes across the cube edges: handled by recording
+  // them in the step kernel and a correction pass (mf_af_patch_kernel) -- production kernel, one GPU.
+  if (h->prm.et != 3) return 0;
+  if (h->prm.mf == 2) return (pycs_fused2b_has(h->prm.recon, h->prm.opsplit) && !h->mg) ? 1 : 0;
+  return 1;
 }
 
 // Makespan (in marched rows) of a split step with the given boundary / interior shapes, by list scheduling of
@@ -389,7 +422,7 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
   if (fs.split == 0) {
     const char* es = getenv("PYCS_SPLIT");
     const bool want = h->mg || (es && atoi(es));   // several GPUs always run the split step
-    fs.split = (want && fs.impl == 4) ? 1 : -1;
+    fs.split = (want && fs.impl == 4 && h->prm.mf != 2) ? 1 : -1;   // (MF-AF runs the serial step)
     if (fs.split == 1) {
       // Boundary CTAs march few rows each, so that they are done early and the exchange + ghost fill of
       // the next step run beside the interior CTAs: bands of `band` rows at both ends of the slab, the
@@ -483,6 +516,10 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
     fs.npart_cap = nb;
   }
   fs.npart = nb;
+  if (h->prm.mf == 2 && !fs.edge_flux) {
+    CK(cudaMalloc(&fs.edge_flux, sizeof(double) * 24 * g.N));
+    CK(cudaMemsetAsync(fs.edge_flux, 0, sizeof(double) * 24 * g.N, h->stream));
+  }
   if (!fs.counter) {
     CK(cudaMalloc(&fs.counter, sizeof(unsigned)));
     CK(cudaMemsetAsync(fs.counter, 0, sizeof(unsigned), h->stream));
@@ -706,6 +743,7 @@ void k_fused_release(pycs_handle h) {
   if (fs.xjob_off) cudaFree(fs.xjob_off);
   if (fs.xjobs) cudaFree(fs.xjobs);
   if (fs.xcounter) cudaFree(fs.xcounter);
+  if (fs.edge_flux) cudaFree(fs.edge_flux);
   if (fs.e_fork) cudaEventDestroy(fs.e_fork);
   if (fs.e_join) cudaEventDestroy(fs.e_join);
   if (fs.s2) cudaStreamDestroy(fs.s2);
@@ -1021,7 +1059,17 @@ static int enqueue_serial(pycs_handle h, FusedState& fs, double* qcur, double* q
   FusedArgs a;
   TRY(step_args(h, fs, qcur, qnext, mask, &a, wind_mode));
   a.corr_ptr = (h->prm.mf == 3) ? h->red_out + 8 : nullptr;
-  TRY(launch_step(h, fs, a, mask, 0, fs.npart, h->stream));
+  if (h->prm.mf == 2) {          // MF-AF: record the outer edge fluxes (GH = 1 flavour), then average them
+    a.edge_flux = fs.edge_flux;
+    TRY(launch_step(h, fs, a, mask, 1, fs.npart, h->stream));
+    const Geo& g = h->g;
+    for (int pass = 0; pass < 2; ++pass) {
+      mf_af_patch_kernel<<<dim3((g.N + 127) / 128, 12), 128, 0, h->stream>>>(g, fs.edge_flux, fs.rgc, qnext, pass);
+      CKL(h);
+    }
+  } else {
+    TRY(launch_step(h, fs, a, mask, 0, fs.npart, h->stream));
+  }
   mark();
   mark();
   return 0;
@@ -1162,7 +1210,7 @@ int k_fused_step(pycs_handle h, long long k, double t, int wind_mode) {
     FusedArgs warm;
     TRY(step_args(h, fs, qcur, qnext, mask, &warm, wind_mode));
     if (fs.impl == 4 && (pycs_fused2b_resident(h->prm.recon, h->prm.opsplit, mask, 0) < 1 ||
-                         pycs_fused2b_resident(h->prm.recon, h->prm.opsplit, mask, split ? 1 : 0) < 1)) {
+                         pycs_fused2b_resident(h->prm.recon, h->prm.opsplit, mask, (split || h->prm.mf == 2) ? 1 : 0) < 1)) {
       pycs_set_error("fused2b kernel: occupancy query failed");
       return PYCS_ERR_CUDA;
     }
