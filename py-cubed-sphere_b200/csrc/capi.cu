@@ -124,6 +124,14 @@ static int state_sync(pycs_handle h) {
   TRY(wind_sync(h));
   return normalize_q(h);
 }
+// the same, but only for what an access to `field` can observe: Q / Q_NEXT need the projection flush, the wind
+// arrays (and cx / cy, which are formed from them) the lazy wind catch-up; everything else neither
+static bool is_wind_field(int f) { return (f >= PYCS_F_PU_ULON && f <= PYCS_F_PC_VCONTRA) || f == PYCS_F_CX || f == PYCS_F_CY; }
+static int field_sync(pycs_handle h, int field) {
+  if (field == PYCS_F_Q || field == PYCS_F_Q_NEXT) return normalize_q(h);
+  if (is_wind_field(field)) return wind_sync(h);
+  return 0;
+}
 
 // --------------------------------------------------------------------------- lifetime
 extern "C" const char* pycs_last_error(void) { return g_err.c_str(); }
@@ -255,7 +263,8 @@ static int upload_from(pycs_handle h, int field, const double* host, int i0 = 0,
 
 extern "C" int pycs_upload_field(pycs_handle h, int32_t field, const double* host) {
   PYCS_RANGE("upload_field");
-  TRY(wind_sync(h));
+  // wind arrays, and the geometry the wind catch-up is computed from, must not be overwritten under a pending catch-up
+  if (is_wind_field(field) || (field >= PYCS_F_SQRTG_PC && field <= PYCS_F_PV_LAT)) TRY(wind_sync(h));
   if (!host) return arg_fail("null host pointer");
   CK(cudaSetDevice(h->device));
   if (field == PYCS_F_Q) TRY(k_fused_discard(h));   // a new state: nothing of the old one is pending
@@ -284,7 +293,7 @@ static int download_to(pycs_handle h, int field, double* host, int i0 = 0, int i
 
 extern "C" int pycs_download_field(pycs_handle h, int32_t field, double* host) {
   PYCS_RANGE("download_field");
-  TRY(state_sync(h));
+  TRY(field_sync(h, field));
   if (!host) return arg_fail("null host pointer");
   CK(cudaSetDevice(h->device));
   TRY(download_to(h, field, host));
@@ -293,7 +302,8 @@ extern "C" int pycs_download_field(pycs_handle h, int32_t field, double* host) {
 }
 
 extern "C" int pycs_copy_field(pycs_handle h, int32_t dst, int32_t src) {
-  TRY(state_sync(h));
+  TRY(field_sync(h, dst));
+  TRY(field_sync(h, src));
   double *d, *s;
   TRY(pycs_field_ptr(h, dst, &d));
   TRY(pycs_field_ptr(h, src, &s));
@@ -304,7 +314,7 @@ extern "C" int pycs_copy_field(pycs_handle h, int32_t dst, int32_t src) {
 }
 
 extern "C" int pycs_fill_field(pycs_handle h, int32_t field, double value) {
-  TRY(state_sync(h));
+  TRY(field_sync(h, field));
   double* d;
   TRY(pycs_field_ptr(h, field, &d));
   long long n = (long long)(pycs_field_single_panel(field) ? 1 : 6) * h->g.ps;

@@ -43,17 +43,18 @@ constexpr int WS_CAP = 4096;        // entries of the separable-wind time-factor
 constexpr int WS_BATCH = 1024;      // entries filled per refill
 
 // sum of n partials in a fixed order (every CTA gets the same bits)
-__device__ double reduce_partials(const volatile double* part, int n) {
+__device__ double reduce_partials(const double* part, int n) {
   double v = 0.0;
   for (int k = 0; k < n; ++k) v += part[k];
   return v;
 }
 
-// projection coefficient of the step that ended last: -sum / a2, the expression of the step kernel
+// projection coefficient of the step that ended last: -sum / a2, the expression of the step kernel.  Plain
+// (cached, broadcast) loads: the kernels that call this run after the step that wrote the control block and
+// nothing changes it while they run (volatile loads from every thread cost 300 us at N = 1536).
 __device__ __forceinline__ double pending_corr(const StepCtl* ctl, const MgSync* sync, int world, double inv_a2) {
-  if (!*((const volatile int*)&ctl->pend)) return 0.0;
-  const long long steps = *((const volatile long long*)&ctl->steps);
-  const double sm = world > 1 ? reduce_partials(sync->psum[steps & 1], world) : *((const volatile double*)&ctl->sum);
+  if (!ctl->pend) return 0.0;
+  const double sm = world > 1 ? reduce_partials(sync->psum[ctl->steps & 1], world) : ctl->sum;
   return -sm * inv_a2;
 }
 
