@@ -23,13 +23,25 @@ import numpy as np  # noqa: E402
 
 TUPLE = (3, 1, 1, 3, 1, 3)      # recon, dp, opsplit, et, mt, mf  (par/advection.par defaults)
 VF, IC = 3, 2
+DT16 = 0.00625                  # canonical dt(N) = DT16 * 16 / N (src/advection_error.py:43-58)
+GOLDEN, GOLDEN_KS = "config_N1536_vf3.npz", (5, 20)
+NAME = "config4: N=%d vf=3 divergent flow, Gaussian hill, PPM-PL07/RK1/SP-AVLT/ET-DG/MT-0/MF-PR"
 BYTES_PER_CELL = 40.0           # Q r/w, two winds, sqrt(g)
 
 
+def select_config(c):
+    """--config 4 (default, the headline): BASELINE.json config 4.  --config 3: config 3 -- N=768, Nair-Lauritzen
+    non-divergent flow (time-dependent wind), RK2 departure points, AVLT-RK2-DG-PR; recorded, not the headline."""
+    global TUPLE, VF, DT16, GOLDEN, GOLDEN_KS, NAME
+    if c == 3:
+        TUPLE, VF, DT16 = (3, 2, 1, 3, 1, 3), 2, 0.0125
+        GOLDEN, GOLDEN_KS = "config_N768_vf2.npz", (10, 50)
+        NAME = "config3: N=%d vf=2 Nair-Lauritzen non-divergent flow, Gaussian hill, PPM-PL07/RK2/SP-AVLT/ET-DG/MT-0/MF-PR"
+
+
 def workload(N):
-    return {"workload": "config4: N=%d vf=3 divergent flow, Gaussian hill, PPM-PL07/RK1/SP-AVLT/ET-DG/MT-0/MF-PR" % N,
-            "N": N, "cells": 6 * N * N, "dt": 0.00625 * 16 / N,
-            "l2": "inputs (566 MB/step at N=1536) exceed the 126 MB L2"}
+    return {"workload": NAME % N, "N": N, "cells": 6 * N * N, "dt": DT16 * 16 / N,
+            "l2": "inputs (%d MB/step) exceed the 126 MB L2" % round(BYTES_PER_CELL * 6 * N * N / 1e6)}
 
 
 class ClockSampler:
@@ -104,7 +116,7 @@ def measured_peak():
 # --------------------------------------------------------------------------- CPU arm
 def oracle_state(g, N):
     from oracle import step as ost
-    sim = ost.Simulation(g, 0.00625 * 16 / N, 5, IC, VF, 1, *TUPLE)
+    sim = ost.Simulation(g, DT16 * 16 / N, 5, IC, VF, 1, *TUPLE)
     ost.init_vars_adv(g, sim)
     return sim, ost
 
@@ -197,13 +209,13 @@ def run_gpu(args):
     # tests/golden/config_N1536_vf3.npz holds Q of the unmodified reference on a 51 x 51 x 6 sample after
     # 5 and 20 steps of this workload; every rank checks the sample rows of its slab.
     parity = None
-    gp = os.path.join(ROOT, "tests", "golden", "config_N1536_vf3.npz")
-    if N == 1536 and os.path.exists(gp) and not args.quick:
+    gp = os.path.join(ROOT, "tests", "golden", GOLDEN)
+    if os.path.exists(gp) and not args.quick and int(np.load(gp)["N"]) == N:
         ref = np.load(gp)
         idx = ref["sample_index"]
         rows = [n for n, i in enumerate(idx) if slab[0] <= i < slab[1]]
         worst, kdone = 0.0, 0
-        for kk in (5, 20):
+        for kk in GOLDEN_KS:
             dev.call("pycs_run", kdone, kk - kdone, 1)
             kdone = kk
             Qs = np.asarray(sim.Q)[np.ix_(idx[rows], idx, np.arange(6))]
@@ -214,8 +226,8 @@ def run_gpu(args):
             tt = torch.tensor([worst], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             worst = float(tt.item())
-        parity = {"relerr": worst, "against": "tests/golden/config_N1536_vf3.npz (unmodified reference, Q on a "
-                  "51x51x6 sample at k = 5 and 20)", "tolerance": 1e-12, "ok": bool(worst <= 1e-12)}
+        parity = {"relerr": worst, "against": "tests/golden/%s (unmodified reference, Q on a 51x51x6 sample at "
+                  "k = %d and %d)" % ((GOLDEN,) + GOLDEN_KS), "tolerance": 1e-12, "ok": bool(worst <= 1e-12)}
         sim.Q[...] = Q0                   # back to the initial state for the timed run
         barrier()
 
@@ -259,14 +271,15 @@ def run_gpu(args):
     # kernel_ms: best of 3 bursts of 50 launches (the HBM peak it is compared with is a burst copy,
     # best of 10); kernel_ms_sustained: average over a long run (the 1 kW power cap shows there).
     kms = C.c_float()
-    dev.call("pycs_time_step_kernel", 5, 1, C.byref(kms))
+    sep = 1 if (VF == 3 and TUPLE[1] == 1) else 0      # the flavour the timed steps launch
+    dev.call("pycs_time_step_kernel", 5, sep, C.byref(kms))
     bursts = []
     for _ in range(3):
-        dev.call("pycs_time_step_kernel", 50, 1, C.byref(kms))
+        dev.call("pycs_time_step_kernel", 50, sep, C.byref(kms))
         bursts.append(float(kms.value) / 50)
     k_ms = min(bursts)
     reps = max(20, args.steps)
-    dev.call("pycs_time_step_kernel", reps, 1, C.byref(kms))
+    dev.call("pycs_time_step_kernel", reps, sep, C.byref(kms))
     k_ms_sustained = float(kms.value) / reps
     if world > 1:
         import torch.distributed as dist
@@ -353,8 +366,9 @@ def run_gpu(args):
                 "setup_s": setup_s, "grid": "host numpy" if args.host_grid else "device-generated (lean)",
                 "parallelism": "single GPU" if world == 1 else
                 "%d row slabs per panel, peer-mapped halo stores over NVLink (csrc/mgpu.cu)" % world,
-                "wind_path": "separable (U(t)=U(0)cos(pi t/T) scaled in-kernel; the exposed wind arrays are "
-                             "caught up lazily when something reads them)"}
+                "wind_path": ("separable (U(t)=U(0)cos(pi t/T) scaled in-kernel" if sep else
+                              "basis winds (the wind of a step combined from static basis fields by one kernel per direction") +
+                             "; the exposed wind arrays are caught up lazily when something reads them)"}
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
@@ -367,7 +381,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--n", type=int, default=1536)
+    ap.add_argument("--n", type=int, default=0, help="cells per panel edge (0: the configuration's own, 1536 / 768)")
+    ap.add_argument("--config", type=int, default=4, choices=(3, 4), help="BASELINE.json configuration (4 = headline)")
     ap.add_argument("--cpu-n", type=int, default=0,
                     help="N of the CPU sample (0: reference arm 1536 if steps + warmup <= 8 else 768; cpu_baseline leg 768)")
     ap.add_argument("--cpu-steps", type=int, default=3)
@@ -376,6 +391,9 @@ def main():
     ap.add_argument("--quick", action="store_true", help="tuning runs: only the device-resident timed steps (no roofline, "
                     "e2e, CPU or parity legs); the line is not a bench record")
     args = ap.parse_args()
+    select_config(args.config)
+    if not args.n:
+        args.n = 1536 if args.config == 4 else 768
     if args.impl == "reference":
         run_reference(args)
     else:
