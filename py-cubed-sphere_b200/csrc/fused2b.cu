@@ -43,7 +43,20 @@ __constant__ double f2b_ppm_coef[5] = {2.0 / 60.0, -13.0 / 60.0, 47.0 / 60.0, 27
 #define F2B_TB 160         // threads per CTA: 154 output columns; 96 registers, 49 KB -> 4 CTAs / SM
 #define F2B_PF 2           // rows in flight ahead of the march
 #define F2B_MINB 4         // register cap as CTAs per SM
-#define F2B_ISSUE_DEFAULT 1  // running pointers: 0.1641 ms against 0.1659 ms per launch (profiles/r2_issue_variants.log)
+// Variant bits of the march (template parameter VAR; PYCS_VARIANT selects among the instantiated ones, experiment knob):
+//   1  the TMA copies of row r+3 are issued after barrier B of row r (default form: row r+2 after barrier A) -- the
+//      ring slots are free at that point already, so the copies get ~0.7 row times more lead at no shared memory
+//   2  L2 prefetch (cp.async.bulk.prefetch.L2) of the HBM-sourced rows (Q, u, v) 4 rows beyond the row being issued
+//   4  the same, 8 rows beyond
+//   8  y-stencils take the thread's own cell from its register (4 LDS per flux instead of 5)
+//  16  x-edge weights: one dynamically addressed load of sqrtg at the upwind centre instead of both candidates
+//  32  the CFL numbers of the two y-fluxes (wind row x dt/dy) are formed before barrier A
+// Measured at N=1536 (profiles/r2_march_variants.log): default 0.1640 ms; 1: 0.1659; 2 / 4 (+1): 0.1659-0.1664;
+// 8: 0.1680; 16: 0.1660; 32: 0.1637 (the default since).  A probe with barrier B left out (wrong results) ran at
+// 0.1603 ms: the barriers cost 2 %, and the longer lead of the copies / the L2 prefetch buy nothing -- the march is
+// bound by per-warp dependency stalls at 20 warps per SM, not by the staging.
+// To time a variant: -DF2B_VARIANTS="F2B_V(1); F2B_V(8);" instantiates it for the par-default scheme.
+#define F2B_VAR_DEFAULT 32
 
 namespace {
 
@@ -73,9 +86,7 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// ISS: form of the TMA issue path of warp 0's elected lane (it sits between the two barriers of a row, the other
-// four warps wait for it): 0 = bases + byte offset, 1 = one running pointer per staged array
-template <int TB, int RECON, int SPLIT, int MASK, int GH, int ISS = 0>
+template <int TB, int RECON, int SPLIT, int MASK, int GH, int VAR = 0>
 __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
   constexpr int PF = F2B_PF;
   constexpr int RW = TB + 6;                 // staged row: columns jbase-6 .. jbase+TB-1
@@ -207,71 +218,70 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
   const char *pQ = rowp(gq, rfirst), *pV = rowp(gv, rfirst), *pSGC = rowp(gsgc, rfirst), *pSGV = rowp(gsgv, rfirst),
              *pRGC = rowp(grgc, rfirst), *pSGU = rowp(gsgu, rfirst - 1), *pU = rowp(gu, max(rfirst - 2, 0)),
              *pVM = rowp(gvm, rfirst), *pUM = rowp(gum, max(rfirst - 2, 0));
-  long long o0 = (long long)rfirst * ld8;    // ISS = 0: byte offset of the next row to issue
-  auto at = [](const double* base, long long off) {
-    return reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + off);
+  constexpr int AHEAD = (VAR & 1) ? 3 : PF;                     // rows between the marched row and the row issued
+  constexpr int PFD = (VAR & 2) ? 4 : ((VAR & 4) ? 8 : 0);       // L2 prefetch distance beyond the issued row
+  auto l2pf = [&](const char* src) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(row_bytes) : "memory");
   };
   constexpr int NCOPY = NS + NL;
   // the TMA copies of the row with phase k (elected lane of warp 0, after its fence.proxy.async)
-  auto issue_k = [&](auto kc, bool first) {
+  auto issue_k = [&](auto kc) {
     constexpr int k = decltype(kc)::value;
     const uint32_t dS = ringS_a + 8u * (uint32_t)((k % DS) * SSLOT), dL = ringL_a + 8u * (uint32_t)(k * LSLOT),
                    bar = full_a + 8u * (uint32_t)k;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * NCOPY)
                  : "memory");
-    if (ISS == 1) {
-      auto P = [](const char* p) { return reinterpret_cast<const double*>(p); };
-      tma(dS + 8u * S_Q * RW, P(pQ), bar);
-      tma(dL + 8u * L_V * RW, P(pV), bar);
-      tma(dL + 8u * L_SGC * RW, P(pSGC), bar);
-      tma(dL + 8u * L_SGV * RW, P(pSGV), bar);
-      tma(dL + 8u * L_RGC * RW, P(pRGC), bar);
-      tma(dS + 8u * S_SGU * RW, P(pSGU), bar);
-      tma(dS + 8u * S_U * RW, P(pU), bar);
-      if (MASK & 1) {
-        tma(dL + 8u * L_VM * RW, P(pVM), bar);
-        tma(dS + 8u * S_UM * RW, P(pUM), bar);
-      }
-    } else {
-      const long long o1 = o0 - ld8, o2 = first ? (long long)max(rfirst - 2, 0) * ld8 : o0 - 2 * ld8;
-      tma(dS + 8u * S_Q * RW, at(gq, o0), bar);
-      tma(dL + 8u * L_V * RW, at(gv, o0), bar);
-      tma(dL + 8u * L_SGC * RW, at(gsgc, o0), bar);
-      tma(dL + 8u * L_SGV * RW, at(gsgv, o0), bar);
-      tma(dL + 8u * L_RGC * RW, at(grgc, o0), bar);
-      tma(dS + 8u * S_SGU * RW, at(gsgu, o1), bar);
-      tma(dS + 8u * S_U * RW, at(gu, o2), bar);
-      if (MASK & 1) {
-        tma(dL + 8u * L_VM * RW, at(gvm, o0), bar);
-        tma(dS + 8u * S_UM * RW, at(gum, o2), bar);
-      }
+    auto P = [](const char* p) { return reinterpret_cast<const double*>(p); };
+    tma(dS + 8u * S_Q * RW, P(pQ), bar);
+    tma(dL + 8u * L_V * RW, P(pV), bar);
+    tma(dL + 8u * L_SGC * RW, P(pSGC), bar);
+    tma(dL + 8u * L_SGV * RW, P(pSGV), bar);
+    tma(dL + 8u * L_RGC * RW, P(pRGC), bar);
+    tma(dS + 8u * S_SGU * RW, P(pSGU), bar);
+    tma(dS + 8u * S_U * RW, P(pU), bar);
+    if (MASK & 1) {
+      tma(dL + 8u * L_VM * RW, P(pVM), bar);
+      tma(dS + 8u * S_UM * RW, P(pUM), bar);
+    }
+  };
+  // L2 prefetch of the HBM-sourced rows PFD rows beyond the row whose copies were just issued (row `ri`)
+  auto prefetch_k = [&](int ri) {
+    if (PFD > 0 && ri + PFD <= rlast) {
+      l2pf(pQ + PFD * ld8);
+      l2pf(pV + PFD * ld8);
+      l2pf(pU + PFD * ld8);
+      if (MASK & 1) { l2pf(pVM + PFD * ld8); l2pf(pUM + PFD * ld8); }
     }
   };
   auto advance = [&]() {                     // warp-uniform
-    if (ISS == 1) {
-      pQ += ld8; pV += ld8; pSGC += ld8; pSGV += ld8; pRGC += ld8; pSGU += ld8; pU += ld8;
-      if (MASK & 1) { pVM += ld8; pUM += ld8; }
-    } else {
-      o0 += ld8;
-    }
+    pQ += ld8; pV += ld8; pSGC += ld8; pSGV += ld8; pRGC += ld8; pSGU += ld8; pU += ld8;
+    if (MASK & 1) { pVM += ld8; pUM += ld8; }
   };
 
-  if (warp_u == 0) {                         // rows rfirst, rfirst + 1 (rfirst >= 1: only row -1 is clamped)
+  if (warp_u == 0) {                         // rows rfirst .. rfirst + AHEAD - 1 (rfirst >= 1: only row -1 is clamped)
     if (elect_one()) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue_k(IC<0>{}, true);
+      issue_k(IC<0>{});
     }
     advance();
-    if (ISS == 1) {                          // the clamp of the first row does not carry over
-      pU = rowp(gu, rfirst - 1);
-      pUM = rowp(gum, rfirst - 1);
-    }
+    pU = rowp(gu, rfirst - 1);               // the clamp of the first row does not carry over
+    pUM = rowp(gum, rfirst - 1);
     if (rfirst + 1 <= rlast) {
-      if (elect_one()) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue_k(IC<1>{}, false);
-      }
+      if (elect_one()) issue_k(IC<1>{});
       advance();
+    }
+    if (AHEAD == 3 && rfirst + 2 <= rlast) {
+      if (elect_one()) issue_k(IC<2>{});
+      advance();
+    }
+    if (PFD > 0 && elect_one()) {            // the pointers stand at row rfirst + AHEAD: rows up to PFD - 1 beyond it
+      for (int d = 0; d < PFD; ++d)
+        if (rfirst + AHEAD + d <= rlast) {
+          l2pf(pQ + d * ld8);
+          l2pf(pV + d * ld8);
+          l2pf(pU + d * ld8);
+          if (MASK & 1) { l2pf(pVM + d * ld8); l2pf(pUM + d * ld8); }
+        }
     }
   }
   double* __restrict__ QN = a.qn + (long long)p * g.ps + PYCS_JOFF + min(j, g.P - 1) + (long long)r0 * g.ld;
@@ -286,6 +296,19 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
   Lane L;
   lane_init(L);
   uint32_t parb = 0;
+  // warp 0: TMA copies of row r + AHEAD (the generic-proxy reads of the slots it overwrites were ordered before this
+  // point by the barrier the caller has just passed)
+  auto issue_ahead = [&](auto kc, int r) {
+    constexpr int k = decltype(kc)::value;
+    if (warp_u == 0 && r + AHEAD <= rlast) {
+      if (elect_one()) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue_k(IC<(k + AHEAD) % DL>{});
+        prefetch_k(r + AHEAD);
+      }
+      advance();
+    }
+  };
   // one marched row; false once the chunk is finished
   auto row = [&](auto kc, int r) -> bool {
     constexpr int k = decltype(kc)::value;
@@ -310,24 +333,21 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
     // ---------------- phase 1: own column
     XEdge X;
     double qx[1];
-    phase_x_inner<RECON, SPLIT, MASK, k>(L, X, R, qnew, cdx, qx);
+    phase_x_inner<RECON, SPLIT, MASK, k, WLEN, (VAR & 16) != 0>(L, X, R, qnew, cdx, qx);
     sX[e] = qx[0];
+    double cch0[1], cch3[1];
+    if (VAR & 32) { cch0[0] = R.v0[0] * cdy; cch3[0] = R.v3[0] * cdy; }
     __syncthreads();                                   // barrier A
-    if (warp_u == 0 && r + PF <= rlast) {              // warp 0 issues the TMA copies of row r+PF
-      if (elect_one()) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue_k(IC<(k + PF) % DL>{}, false);
-      }
-      advance();
-    }
+    if (!(VAR & 1)) issue_ahead(IC<k>{}, r);           // warp 0 issues the TMA copies of row r+PF
     // ---------------- phase 2: y-fluxes at edge j: inner on Q row r, outer on Qx row r-3
     double F[1], G[1], CF[1] = {0.0}, CG[1];
-    yflux_pair<RECON, SPLIT, MASK, k>(R.v0, R.vm0, R.sgv0, R.sgc0, R.q, cdy, F, CF);
-    yflux_pair<RECON, SPLIT, MASK, k>(R.v3, R.vm3, R.sgv3, R.sgc3, sX + e, cdy, G, CG);
+    yflux_pair<RECON, SPLIT, MASK, k, (VAR & 8) != 0, (VAR & 32) != 0>(R.v0, R.vm0, R.sgv0, R.sgc0, R.q, cdy, F, CF, qnew, cch0);
+    yflux_pair<RECON, SPLIT, MASK, k, (VAR & 8) != 0, (VAR & 32) != 0>(R.v3, R.vm3, R.sgv3, R.sgc3, sX + e, cdy, G, CG, qx, cch3);
     sF[e] = F[0];
     sG[e] = G[0];
     if (SPLIT != 1) sC[e] = CF[0];
     __syncthreads();                                   // barrier B
+    if (VAR & 1) issue_ahead(IC<k>{}, r);              // rows r (short ring) and r-3 (long ring) are dead: row r+3
     // ---------------- phase 3: Qy row r, outer x-flux on Qy, output row r-3
     double Fn[1], Gn[1], CFn[1] = {0.0}, out[1], sdiv[1];
     Fn[0] = sF[e + 1];
@@ -439,11 +459,11 @@ constexpr size_t smem_bytes() {
          sizeof(uint64_t) * DL + 16;
 }
 
-template <int TB, int RECON, int SPLIT, int MASK, int GH, int ISS>
-cudaError_t launch_iss(const FusedArgs& a, int nblocks, cudaStream_t st, int* resident) {
+template <int TB, int RECON, int SPLIT, int MASK, int GH, int VAR>
+cudaError_t launch_var(const FusedArgs& a, int nblocks, cudaStream_t st, int* resident) {
   static bool configured = false;
   const size_t smem = smem_bytes<TB, MASK>();
-  auto kern = fused2b_kernel<TB, RECON, SPLIT, MASK, GH, ISS>;
+  auto kern = fused2b_kernel<TB, RECON, SPLIT, MASK, GH, VAR>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -454,22 +474,27 @@ cudaError_t launch_iss(const FusedArgs& a, int nblocks, cudaStream_t st, int* re
   return cudaSuccess;
 }
 
-// PYCS_ISSUE selects the issue-path form of the par-default scheme's kernels (experiment knob)
-static int issue_variant() {
+// PYCS_VARIANT selects among the instantiated march variants of the par-default scheme's serial-step kernels
+// (experiment knob; anything not instantiated falls back to the default)
+static int march_variant() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("PYCS_ISSUE");
-    v = e ? atoi(e) : F2B_ISSUE_DEFAULT;
+    const char* e = getenv("PYCS_VARIANT");
+    v = e ? atoi(e) : F2B_VAR_DEFAULT;
   }
   return v;
 }
 template <int TB, int RECON, int SPLIT, int MASK, int GH>
 cudaError_t launch_one(const FusedArgs& a, int nblocks, cudaStream_t st, int* resident) {
-  if constexpr (RECON == 3 && SPLIT == 1) {
-    if (issue_variant() != F2B_ISSUE_DEFAULT)
-      return launch_iss<TB, RECON, SPLIT, MASK, GH, 1 - F2B_ISSUE_DEFAULT>(a, nblocks, st, resident);
+#ifdef F2B_VARIANTS
+  if constexpr (RECON == 3 && SPLIT == 1 && GH == 0 && MASK != 1) {
+    const int v = march_variant();
+#define F2B_V(V) if (v == V && V != F2B_VAR_DEFAULT) return launch_var<TB, RECON, SPLIT, MASK, GH, V>(a, nblocks, st, resident)
+    F2B_VARIANTS
+#undef F2B_V
   }
-  return launch_iss<TB, RECON, SPLIT, MASK, GH, F2B_ISSUE_DEFAULT>(a, nblocks, st, resident);
+#endif
+  return launch_var<TB, RECON, SPLIT, MASK, GH, F2B_VAR_DEFAULT>(a, nblocks, st, resident);
 }
 
 template <int RECON, int SPLIT>

@@ -163,7 +163,9 @@ PYCS_HD void lane_init(Lane& L) {
 // qnew[c]: Q of row r in the lane's columns (the caller loads it, and patches it when a
 // projection term is pending).
 // cdxw = dt/dx times the time factor of a separable wind (1 otherwise).
-template <int RECON, int SPLIT, int MASK, int K = -1, int W = WLEN>
+// DYNGC: sqrtg at the upwind centre through one dynamically addressed load (behind the wind-sign compare) instead
+// of loading both candidates
+template <int RECON, int SPLIT, int MASK, int K = -1, int W = WLEN, bool DYNGC = false>
 PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, const double qnew[NC], double cdxw, double qx[NC]) {
   constexpr int MT = (SPLIT == 3) ? 2 : 1;
 #pragma unroll
@@ -179,8 +181,9 @@ PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, const double qne
     const double su1c = R.su1[o];
     const double gE = L.su2[c];
     const double gO = up ? L.su3[c] : su1c;
-    const double gC = up ? R.sgc3[o] : R.sgc2[o];   // both loads are issued early; a pointer select
-                                                    // would put the LDS behind the wind-sign compare
+    const double gC = DYNGC ? (up ? R.sgc3 : R.sgc2)[o]
+                            : (up ? R.sgc3[o] : R.sgc2[o]);   // both loads are issued early; a pointer select
+                                                              // puts the LDS behind the wind-sign compare
     const double rg = R.rg3[o];
     double WE, WO, WG;
     edge_weights<MT, !(MASK & 1)>(cc, up, gE, gO, gC, WE, WO, WG);
@@ -204,14 +207,20 @@ PYCS_HD void phase_x_inner(Lane& L, XEdge& X, const RowPtrs& R, const double qne
 // ---- phase 2: y-fluxes at the lane's NC edges of one row ------------------------------------
 // v, vm, sgv, sgc: staged rows of that row (lane-offset); src: the advected row (Q or Qx),
 // lane-offset as well, so that src[k] is the value k columns right of the lane's first column.
-template <int RECON, int SPLIT, int MASK, int K = -1>
+// OWN (const-slot march only): own[c] = src[c * CSTEP], the lane's own cell, which it holds in a register.  The
+// stencil is then read mirrored about the edge -- x1..x5 run from the far upwind cell towards the downwind one,
+// so that E = r(x) and O = l(x) whichever way the wind blows -- and costs four loads instead of five.
+// HCC: cch[c] = v[c * CSTEP] * cdyw was formed by the caller already (before the barrier in front of this phase: the
+// wind row is TMA-staged, not thread-written, so the head of the dependency chain need not wait for the barrier).
+template <int RECON, int SPLIT, int MASK, int K = -1, bool OWN = false, bool HCC = false>
 PYCS_HD void yflux_pair(const double* v, const double* vm, const double* sgv, const double* sgc,
-                        const double* src, double cdyw, double f[NC], double cmy[NC]) {
+                        const double* src, double cdyw, double f[NC], double cmy[NC], const double* own = nullptr,
+                        const double* cch = nullptr) {
   constexpr int MT = (SPLIT == 3) ? 2 : 1;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const int o = c * CSTEP;
-    const double cc = v[o] * cdyw;
+    const double cc = HCC ? cch[c] : v[o] * cdyw;
     const bool vp = ((MASK & 1) ? vm[o] : cc) >= 0.0;
     const int up1 = vp ? -1 : 0;                     // upwind cell relative to the edge
     const double gE = sgv[o];
@@ -222,13 +231,24 @@ PYCS_HD void yflux_pair(const double* v, const double* vm, const double* sgv, co
       //   f = c [ m (m E' - b O') + b (3 - 2b) G' ],  E' = E gE, O' = O gO, G' = q gC  (MT-0)
       // is two FP64 operations shorter than forming the three weights (const-slot march only:
       // the shifting-window kernels keep the arithmetic they were measured with)
-      const double* s = src + o + up1;
-      double l, r;
-      edge_values<RECON, true>(s[-2], s[-1], s[0], s[1], s[2], l, r);
-      const double E = vp ? r : l, O = vp ? l : r;
+      double E, O, qc;
+      if (OWN) {
+        const double* s0 = src + o;
+        const double xa = s0[-2], xb = s0[-1], xc = s0[1], x1 = s0[vp ? -3 : 2], xo = own[c];
+        const double x2 = vp ? xa : xc, x5 = vp ? xc : xa, x3 = vp ? xb : xo, x4 = vp ? xo : xb;
+        edge_values<RECON, true>(x1, x2, x3, x4, x5, O, E);
+        qc = x3;
+      } else {
+        const double* s = src + o + up1;
+        double l, r;
+        edge_values<RECON, true>(s[-2], s[-1], s[0], s[1], s[2], l, r);
+        E = vp ? r : l;
+        O = vp ? l : r;
+        qc = s[0];
+      }
       const double b = !(MASK & 1) ? fabs(cc) : (vp ? cc : -cc);
       const double m = 1.0 - b, bt = b * fma(2.0, m, 1.0);
-      const double Eg = (MT == 1) ? E * gE : E, Og = (MT == 1) ? O * gO : O, Gg = (MT == 1) ? s[0] * gC : s[0];
+      const double Eg = (MT == 1) ? E * gE : E, Og = (MT == 1) ? O * gO : O, Gg = (MT == 1) ? qc * gC : qc;
       const double cs = (MT == 2) ? cc * gE : cc;
       f[c] = cs * fma(m, fma(m, Eg, -(b * Og)), bt * Gg);
     } else {

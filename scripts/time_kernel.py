@@ -1,5 +1,5 @@
 """ms per launch of the step kernel alone at the bench size (pycs_time_step_kernel: CUDA events around back-to-back
-launches over the whole grid), for the environment it is started with.  Usage: [PYCS_ISSUE=1] python scripts/time_kernel.py [N]"""
+launches over the whole grid), for the environment it is started with.  Usage: [PYCS_VARIANT=v] python scripts/time_kernel.py [N]"""
 import ctypes as C
 import os
 import sys

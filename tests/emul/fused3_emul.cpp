@@ -148,9 +148,24 @@ void run(const Args& a) {
 static const int* g_blk_list = nullptr;
 static int g_blk_count = 0;
 // compile-time row phase k = (r - first row) % 6 of the circular-window march
+// march variant of the const-slot emulation (bits as F2B_VAR in csrc/fused2b.cu: 1 = copies of row r+3 issued after
+// barrier B, 8 = own cell from the register in the y-stencils, 16 = single dynamically addressed sqrtg load)
+static int g_var = 0;
+extern "C" void f3_emul_set_variant(int v) { g_var = v; }
 template <int RECON, int SPLIT, int MASK, int W = f1::WLEN>
 void x_inner_k(int k, f1::Lane& L, f1::XEdge& X, const f1::RowPtrs& R, const double* qnew, double cdxw, double* qx) {
   using namespace f1;
+  if (k >= 0 && k < 6 && (g_var & 16)) {
+    switch (k) {
+      case 0: phase_x_inner<RECON, SPLIT, MASK, 0, W, true>(L, X, R, qnew, cdxw, qx); break;
+      case 1: phase_x_inner<RECON, SPLIT, MASK, 1, W, true>(L, X, R, qnew, cdxw, qx); break;
+      case 2: phase_x_inner<RECON, SPLIT, MASK, 2, W, true>(L, X, R, qnew, cdxw, qx); break;
+      case 3: phase_x_inner<RECON, SPLIT, MASK, 3, W, true>(L, X, R, qnew, cdxw, qx); break;
+      case 4: phase_x_inner<RECON, SPLIT, MASK, 4, W, true>(L, X, R, qnew, cdxw, qx); break;
+      default: phase_x_inner<RECON, SPLIT, MASK, 5, W, true>(L, X, R, qnew, cdxw, qx); break;
+    }
+    return;
+  }
   switch (k) {
     case 0: phase_x_inner<RECON, SPLIT, MASK, 0, W>(L, X, R, qnew, cdxw, qx); break;
     case 1: phase_x_inner<RECON, SPLIT, MASK, 1, W>(L, X, R, qnew, cdxw, qx); break;
@@ -235,7 +250,10 @@ void run_block(const Args& a, int TB) {
       cp(dS + S_U * RW, a.ua + colb + rm2);
       if (MASK & 1) { cp(dL + L_VM * RW, a.vm + colb + rr); cp(dS + S_UM * RW, a.um + colb + rm2); }
     };
-    for (int r = rfirst; r < rfirst + PF && r <= rlast; ++r) issue(r);
+    const bool lateB = a.circ && (g_var & 1);      // copies of row r+3 after barrier B instead of row r+PF after barrier A
+    const int ahead = lateB ? 3 : PF;
+    std::vector<double> QXo(TB), QNo(TB);          // the threads' registers qx, qnew (variant 8)
+    for (int r = rfirst; r < rfirst + ahead && r <= rlast; ++r) issue(r);
     for (int r = rfirst; r <= rlast; ++r) {
       const int kc = a.circ ? (r - rfirst) % WLEN : -1;
       for (int t = 0; t < TB; ++t) {               // patch + phase 1
@@ -257,12 +275,16 @@ void run_block(const Args& a, int TB) {
         double qx[1];
         x_inner_k<RECON, SPLIT, MASK>(kc, L[t], X[t], P, qnew, cdxw, qx);
         sX[e] = qx[0];
+        QXo[t] = qx[0]; QNo[t] = qnew[0];
       }
-      if (r + PF <= rlast) issue(r + PF);          // barrier A passed: warp 0 issues the copies of row r+PF
+      if (!lateB && r + PF <= rlast) issue(r + PF);   // barrier A passed: warp 0 issues the copies of row r+PF
       for (int t = 0; t < TB; ++t) {               // barrier A; phase 2
         const int e = t + 3;
         double f[1], g[1], cf[1] = {0.0}, cg[1];
-        if (a.circ) {   // K >= 0 selects the factored y-flux of the const-slot march (any phase: K is only a flag here)
+        if (a.circ && (g_var & 8)) {
+          yflux_pair<RECON, SPLIT, MASK, 0, true>(R[t].v0, R[t].vm0, R[t].sgv0, R[t].sgc0, R[t].q, cdyw, f, cf, &QNo[t]);
+          yflux_pair<RECON, SPLIT, MASK, 0, true>(R[t].v3, R[t].vm3, R[t].sgv3, R[t].sgc3, sX + e, cdyw, g, cg, &QXo[t]);
+        } else if (a.circ) {   // K >= 0 selects the factored y-flux of the const-slot march (any phase: K is only a flag here)
           yflux_pair<RECON, SPLIT, MASK, 0>(R[t].v0, R[t].vm0, R[t].sgv0, R[t].sgc0, R[t].q, cdyw, f, cf);
           yflux_pair<RECON, SPLIT, MASK, 0>(R[t].v3, R[t].vm3, R[t].sgv3, R[t].sgc3, sX + e, cdyw, g, cg);
         } else {
@@ -272,6 +294,7 @@ void run_block(const Args& a, int TB) {
         F[t] = f[0]; G[t] = g[0]; CF[t] = cf[0];
       }
       for (int t = 0; t < TB; ++t) { sF[t + 3] = F[t]; sG[t + 3] = G[t]; sC[t + 3] = CF[t]; }
+      if (lateB && r + 3 <= rlast) issue(r + 3);   // barrier B passed: the copies of row r+3 land while phase 3 runs
       for (int t = 0; t < TB; ++t) {               // barrier B; phase 3
         const int e = t + 3, j = jbase - 3 + t;
         double f[1] = {F[t]}, g[1] = {G[t]}, cf[1] = {CF[t]};

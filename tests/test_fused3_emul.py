@@ -37,6 +37,8 @@ def emul():
     lib.f3_emul_step_block_circ.restype = C.c_int
     lib.f3_emul_step_block_pair.argtypes = lib.f3_emul_step.argtypes
     lib.f3_emul_step_block_pair.restype = C.c_int
+    lib.f3_emul_set_variant.argtypes = [C.c_int]
+    lib.f3_emul_set_variant.restype = None
     lib.f3_emul_set_block_list.argtypes = [C.POINTER(C.c_int), C.c_int]
     lib.f3_emul_set_block_list.restype = None
     lib.f3_emul_block_grid.argtypes = [C.c_int] * 3
@@ -221,6 +223,37 @@ def test_emulated_v2b_circular_windows_against_shifting(emul):
     a, _ = one_step(emul, 50, 3, TUPLES["default"], 3, depth=2, rows=11, block_tb=64, circ=True)
     b, _ = one_step(emul, 50, 3, TUPLES["default"], 3, depth=2, rows=11, block_tb=64, circ=False)
     assert 0 < np.max(np.abs(a - b)) <= 1e-14 * np.max(np.abs(b))
+
+
+# ---- march variants of the const-slot kernel (F2B_VAR bits in csrc/fused2b.cu) ---------------------------------
+@pytest.mark.parametrize("var", [1, 8, 16, 25])
+@pytest.mark.parametrize("tb,rows,kw", [(32, 7, {}), (64, 16, {"pending": True}), (160, 50, {"separable": True}),
+                                        (160, 6, {}), (64, 12, {})])
+def test_emulated_v2b_march_variants(emul, var, tb, rows, kw):
+    """copies of row r+3 issued after barrier B (1), own cell from the register in the y-stencils (8), single
+    sqrtg load at the upwind centre (16): same result as the default march (bit for bit unless the mirrored
+    stencil of variant 8 reorders the sums) and as the oracle."""
+    base, want = one_step(emul, 50, 3, TUPLES["default"], 3, depth=2, rows=rows, block_tb=tb, circ=True, **kw)
+    emul.f3_emul_set_variant(var)
+    try:
+        got, _ = one_step(emul, 50, 3, TUPLES["default"], 3, depth=2, rows=rows, block_tb=tb, circ=True, **kw)
+    finally:
+        emul.f3_emul_set_variant(0)
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+    if var & 8:
+        assert np.max(np.abs(got - base)) <= 1e-14 * np.max(np.abs(base))
+    else:
+        assert np.array_equal(got, base)
+
+
+@pytest.mark.parametrize("tup", [(1, 1, 1, 3, 1, 3), (3, 2, 2, 3, 1, 3), (1, 1, 3, 3, 2, 1)])
+def test_emulated_v2b_march_variants_other_schemes(emul, tup):
+    emul.f3_emul_set_variant(25)
+    try:
+        got, want = one_step(emul, 20, 2, tup, 2, depth=2, block_tb=32, circ=True)
+    finally:
+        emul.f3_emul_set_variant(0)
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
 
 
 # ---- v2b, two rows per pair of barriers (MINB >= 50): rings of 4 / 8 slots, windows of 8 registers --

@@ -14,7 +14,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "py-cubed-sphere_b200", "build", "fused2b.o")
 LOG = os.path.join(ROOT, "py-cubed-sphere_b200", "build", "fused2b.cu.ptxas.log")
-DEFAULT = "Li160ELi3ELi1ELi%dELi0ELi1EEEv"      # fused2b_kernel<160, 3, 1, MASK, GH = 0, ISS = 1>
+DEFAULT = "Li160ELi3ELi1ELi%dELi0ELi32EEEv"     # fused2b_kernel<160, 3, 1, MASK, GH = 0, VAR = 32 (F2B_VAR_DEFAULT)>
 
 pytestmark = pytest.mark.skipif(not (os.path.exists(OBJ) and os.path.exists(LOG) and shutil.which("cuobjdump")),
                                 reason="needs the in-tree build (python __graft_entry__.py) and cuobjdump")
@@ -31,7 +31,7 @@ def test_no_step_kernel_spills_and_default_fits_four_ctas():
         assert int(regs) * 160 * 4 <= 65536, (name, regs)
     for mask in (0, 1, 2):
         for gh in (0, 1):
-            hit = [(int(a), int(b), int(c)) for n, a, b, c, _ in entries if (DEFAULT % mask).replace("ELi0ELi1EEEv", "ELi%dELi1EEEv" % gh) in n]
+            hit = [(int(a), int(b), int(c)) for n, a, b, c, _ in entries if (DEFAULT % mask).replace("ELi0ELi32EEEv", "ELi%dELi32EEEv" % gh) in n]
             # the interior / single-GPU flavour (GH = 0) must not spill at all; the boundary flavour of the
             # multi-GPU split step (GH = 1, in-kernel exchange) may keep one 8-byte slot
             assert hit and (hit[0] == (0, 0, 0) if gh == 0 else max(hit[0]) <= 8), (mask, gh, hit)
