@@ -133,12 +133,14 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
   const int len = min(RW, g.ld - PYCS_JOFF - c0) & ~1;
   const uint32_t row_bytes = (uint32_t)len * 8u;
 
+  pdl_trigger();                             // the next kernel of the stream may be scheduled behind this grid's last CTAs
   for (int k = tid; k < DS * SSLOT + DL * LSLOT + NWORK * RW; k += TB) ringS[k] = 0.0;
   if (tid == 0) {
     for (int s = 0; s < DL; ++s) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();                                // everything above overlaps the predecessor (ghost fill / wind kernels)
 
   // ---- per-step state from the control block ------------------------------------------------
   const long long step = *((const volatile long long*)&a.ctl->steps);
@@ -470,6 +472,7 @@ cudaError_t launch_var(const FusedArgs& a, int nblocks, cudaStream_t st, int* re
     configured = true;
   }
   if (resident) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(resident, kern, TB, smem);
+  if (a.pdl) return pycs_launch_pdl(kern, dim3(nblocks), dim3(TB), smem, st, true, a);
   kern<<<nblocks, TB, smem, st>>>(a);
   return cudaSuccess;
 }

@@ -82,6 +82,7 @@ struct FusedArgs {
   // [panel][W, E, S, N][N], for the cube-edge averaging that follows the launch (stepper.cu: mf_af_patch_kernel)
   double* edge_flux;
   int timing;                 // roofline timing launches: leave the control block alone
+  int pdl;                    // launch with the programmatic-dependent-launch attribute (pycs_common.cuh)
 };
 
 // CTA table of a split step over the rows [row_lo, row_hi) of a panel of N x N cells cut into nstrips column

@@ -84,6 +84,34 @@ struct pycs_handle_s {
 // error plumbing ------------------------------------------------------------
 void pycs_set_error(const std::string& msg);
 int pycs_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// The kernels of a serial step (ghost fill -> [basis winds] -> step kernel -> next ghost fill ...) are chained in
+// one stream.  Launched with the programmatic-stream-serialization attribute, a kernel's CTAs may become resident
+// while its predecessor drains -- launch latency, CTA prologue (shared-memory set-up) and the predecessor's tail
+// overlap -- and every such kernel calls pdl_wait() before its first global access: it returns once the
+// predecessor grid has completed and flushed (transitively everything before it).  pdl_trigger() at the top of a
+// kernel lets its own successor be scheduled as soon as all of this kernel's CTAs have started.  Without the
+// attribute both calls are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t pycs_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                   Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 #define CK(call)                                                                 \
   do {                                                                           \
     cudaError_t e__ = (call);                                                    \
@@ -150,7 +178,7 @@ int k_wind_interior(pycs_handle h, double t, int convert_interior_only, int do_v
 int k_wind_basis_count(pycs_handle h);
 int k_wind_basis_build(pycs_handle h, int m);
 int k_wind_basis_combine(pycs_handle h, double* const* bu, double* const* bv, int nb, double* ua, double* um, double* va,
-                         double* vm, const double* coef, int cmask, const long long* steps);
+                         double* vm, const double* coef, int cmask, const long long* steps, int pdl = 0);
 int k_wind_coef_fill(pycs_handle h, double* tab, int cmask, long long s0, long long k0, int n);
 // stepper.cu
 int k_fused_supported(pycs_handle h);

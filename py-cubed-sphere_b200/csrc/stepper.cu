@@ -93,6 +93,8 @@ struct GhostFillArgs {
 
 __global__ void dg_fill_kernel(const __grid_constant__ GhostFillArgs a) {
   const Geo& g = a.g;
+  pdl_trigger();               // PDL (pycs_common.cuh): no-ops unless launched with the attribute
+  pdl_wait();
   if (a.flags) {
     if ((int)threadIdx.x < a.world) {
       const long long xc = *((const volatile long long*)&a.ctl->xcount);
@@ -299,6 +301,7 @@ struct FusedState {
   cudaEvent_t e_fork = nullptr, e_join = nullptr;
   // graphs: one per ping-pong parity and wind mask
   int use_graph = -1;
+  int use_pdl = -1;
   cudaGraphExec_t gexec[2][5] = {};
   const double* gq[2][5] = {};
   int gnodes[2][5] = {};
@@ -531,6 +534,10 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
     const char* eg = getenv("PYCS_GRAPH");
     fs.use_graph = eg ? (atoi(eg) ? 1 : 0) : (fs.split == 1 ? 0 : 1);
   }
+  if (fs.use_pdl < 0) {
+    const char* ep = getenv("PYCS_PDL");
+    fs.use_pdl = ep ? (atoi(ep) ? 1 : 0) : 1;
+  }
   if (fs.prof < 0) fs.prof = getenv("PYCS_STEP_PROFILE") ? 1 : 0;
   return 0;
 }
@@ -540,7 +547,7 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
 // cells of rows [mg->gf_lo, mg->gf_hi) only -- what this rank's step reads, and what the exchange
 // plan delivers the sources of.
 static int launch_ghost_fill(pycs_handle h, double* q, cudaStream_t st, const double* gs, const StepCtl* ctl, int fold,
-                             double* corr_out, const double* corr_in, bool wait_peers) {
+                             double* corr_out, const double* corr_in, bool wait_peers, bool pdl = false) {
   const Geo& g = h->g;
   GhostFillArgs a;
   a.g = g;
@@ -576,7 +583,8 @@ static int launch_ghost_fill(pycs_handle h, double* q, cudaStream_t st, const do
   a.nbx_sn = (a.k1 - a.k0 + 127) / 128;
   a.nbx_ew = a.ew_mask ? (g.N + 127) / 128 : 0;
   const int nblk = a.nbx_sn * 4 * 12 + a.nbx_ew * 4 * 12 + 3;
-  dg_fill_kernel<<<nblk, 128, 0, st>>>(a);
+  if (pdl) CK(pycs_launch_pdl(dg_fill_kernel, dim3(nblk), dim3(128), 0, st, true, a));
+  else dg_fill_kernel<<<nblk, 128, 0, st>>>(a);
   CKL(h);
   return 0;
 }
@@ -1030,13 +1038,13 @@ int k_fused_grid_info(pycs_handle h, int* tb, int* rows, int* nblocks) {
 
 // ---- one step, enqueued (or captured) on the handle's stream ----------------------------------------
 // serial: ghost fill with the projection term folded in, (wind kernels), step kernel over the whole grid
-static int step_winds(pycs_handle h, FusedState& fs, bool winds, int wind_mode) {
+static int step_winds(pycs_handle h, FusedState& fs, bool winds, int wind_mode, bool pdl = false) {
   if (winds) {                    // the reference's wind kernels (src/advection_timestep.py:31-37)
     TRY(k_wind_ghost_fill(h));
     TRY(k_time_averaged_velocity(h));
   } else if (wind_mode == 2) {    // the same winds combined from the basis fields, one launch
     TRY(k_wind_basis_combine(h, fs.basis_u, fs.basis_v, fs.nbasis, fs.wua, fs.wum, fs.wva, fs.wvm, fs.wcoef,
-                             WS_CAP - 1, &fs.ctl->steps));
+                             WS_CAP - 1, &fs.ctl->steps, pdl ? 1 : 0));
   }
   return 0;
 }
@@ -1051,15 +1059,22 @@ static int enqueue_serial(pycs_handle h, FusedState& fs, double* qcur, double* q
     fs.ev.push_back(e);
   };
   mark();
+  // The kernels of a serial step on one GPU are chained by programmatic dependent launches (pycs_common.cuh):
+  // each may be scheduled while its predecessor drains and waits on the device for it to complete.
+  // Measured (profiles/r2_pdl.log, N=1536): 0.1738 -> 0.1725 ms per step replayed from the graph, N=48: 18.4 -> 17.4 us,
+  // N=384: 30.7 -> 28.7 us; launched directly the chain got slower (0.1749 -> 0.1770), and so did the basis-wind
+  // step (two more kernels in the chain: 0.1538 -> 0.1568) -- PDL is used where it paid.
+  const bool pdl = fs.use_pdl && fs.use_graph && !h->mg && !profile && !winds && wind_mode != 2;
   // 1. ghost cells of Q (src/advection_timestep.py:28), folding in the pending MF-PR term
-  TRY(launch_ghost_fill(h, qcur, h->stream, fs.gs, fs.ctl, h->prm.mf == 3 ? 1 : 0, h->red_out + 8, nullptr, false));
+  TRY(launch_ghost_fill(h, qcur, h->stream, fs.gs, fs.ctl, h->prm.mf == 3 ? 1 : 0, h->red_out + 8, nullptr, false, pdl));
   // 2. winds (src/advection_timestep.py:31-37)
-  TRY(step_winds(h, fs, winds, wind_mode));
+  TRY(step_winds(h, fs, winds, wind_mode, pdl));
   mark();
   // 3. divergence + Q update
   FusedArgs a;
   TRY(step_args(h, fs, qcur, qnext, mask, &a, wind_mode));
   a.corr_ptr = (h->prm.mf == 3) ? h->red_out + 8 : nullptr;
+  a.pdl = (pdl && fs.impl == 4) ? 1 : 0;
   if (h->prm.mf == 2) {          // MF-AF: record the outer edge fluxes (GH = 1 flavour), then average them
     a.edge_flux = fs.edge_flux;
     TRY(launch_step(h, fs, a, mask, 1, fs.npart, h->stream));

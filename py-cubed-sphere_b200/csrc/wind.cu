@@ -126,6 +126,8 @@ struct WindBasisArgs {
 // same cache lines -- plain loads.  blockIdx.z = panel.
 __global__ void wind_basis_v_kernel(const __grid_constant__ WindBasisArgs a) {
   const Geo& g = a.g;
+  pdl_trigger();               // PDL (pycs_common.cuh): no-ops unless launched with the attribute
+  pdl_wait();
   const int p = blockIdx.z;
   const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y;
   if (j > g.P || i >= g.P) return;
@@ -156,6 +158,8 @@ __global__ void wind_basis_v_kernel(const __grid_constant__ WindBasisArgs a) {
 constexpr int WB_ROWS = 32;
 __global__ void wind_basis_u_kernel(const __grid_constant__ WindBasisArgs a) {
   const Geo& g = a.g;
+  pdl_trigger();
+  pdl_wait();
   const int p = blockIdx.z;
   const int j = blockIdx.x * BX + threadIdx.x;
   if (j >= g.P) return;
@@ -512,7 +516,7 @@ int k_wind_basis_build(pycs_handle h, int m) {
 }
 
 int k_wind_basis_combine(pycs_handle h, double* const* bu, double* const* bv, int nb, double* ua, double* um, double* va,
-                         double* vm, const double* coef, int cmask, const long long* steps) {
+                         double* vm, const double* coef, int cmask, const long long* steps, int pdl) {
   const Geo& g = h->g;
   WindBasisArgs a;
   a.g = g;
@@ -527,9 +531,12 @@ int k_wind_basis_combine(pycs_handle h, double* const* bu, double* const* bv, in
   a.nb = nb;
   a.rk2 = (h->prm.dp == 2) ? 1 : 0;
   a.dto2 = g.dt * 0.5;
-  wind_basis_u_kernel<<<dim3((g.P + BX - 1) / BX, (g.N + 1 + WB_ROWS - 1) / WB_ROWS, 6), BX, 0, h->stream>>>(a);
+  const dim3 gu((g.P + BX - 1) / BX, (g.N + 1 + WB_ROWS - 1) / WB_ROWS, 6), gv((g.P + 1 + BX - 1) / BX, g.P, 6);
+  if (pdl) CK(pycs_launch_pdl(wind_basis_u_kernel, gu, dim3(BX), 0, h->stream, true, a));
+  else wind_basis_u_kernel<<<gu, BX, 0, h->stream>>>(a);
   CKL(h);
-  wind_basis_v_kernel<<<dim3((g.P + 1 + BX - 1) / BX, g.P, 6), BX, 0, h->stream>>>(a);
+  if (pdl) CK(pycs_launch_pdl(wind_basis_v_kernel, gv, dim3(BX), 0, h->stream, true, a));
+  else wind_basis_v_kernel<<<gv, BX, 0, h->stream>>>(a);
   CKL(h);
   return 0;
 }
