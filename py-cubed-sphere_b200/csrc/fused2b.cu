@@ -28,9 +28,12 @@
 //         split step);
 // GH = 1: boundary CTAs of a split step: the ghost fill ran early and raw, the projection term of
 //         the ghost cells (corr * ghost(sqrtg)) is added here as the rows are loaded.
+// GH = 2: one-kernel step: as GH = 1, and every CTA first fills the ghost cells its own march reads (Lagrange fill,
+//         ghost_core.cuh; on several GPUs after waiting for the peers' exchange flags) -- no ghost-fill kernel.
 #include <cstdlib>
 #include "fused_args.cuh"
 #include "mgpu.cuh"
+#include "ghost_core.cuh"
 // PPM-PL07 edge-value coefficients as constant-bank operands
 __constant__ double f2b_ppm_coef[5] = {2.0 / 60.0, -13.0 / 60.0, 47.0 / 60.0, 27.0 / 60.0, -3.0 / 60.0};
 #define F3_COEF_BANK f2b_ppm_coef
@@ -63,6 +66,7 @@ namespace {
 using namespace f1;
 
 template <int K> struct IC { static constexpr int value = K; };   // compile-time row phase
+template <bool B> struct BC { static constexpr bool value = B; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -142,32 +146,16 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
   __syncthreads();
   pdl_wait();                                // everything above overlaps the predecessor (ghost fill / wind kernels)
 
-  // ---- per-step state from the control block ------------------------------------------------
-  const long long step = *((const volatile long long*)&a.ctl->steps);
-  if (a.wait_flags) {           // several GPUs: every rank has finished step - 1 (its sum is here, and
-    if (tid < a.wait_world) {   // nobody reads the buffers this step's exchange will write any more)
-      mg_wait_flag(a.wait_flags + tid, step, a.mg_err, a.mg_timeout_ns);     // acquire: see mgpu.cuh
-    }
-    __syncthreads();
-  }
-  double corr = 0.0;
-  if (a.apply_corr) {
-    if (a.corr_ptr) {
-      corr = *a.corr_ptr;
-    } else if (*((const volatile int*)&a.ctl->pend)) {
-      double sm = 0.0;
-      if (a.pub.world > 1) {
-        const volatile double* ps = a.pub.peer_sync[a.pub.rank]->psum[step & 1];
-        for (int k = 0; k < a.pub.world; ++k) sm += ps[k];
-      } else {
-        sm = *((const volatile double*)&a.ctl->sum);
-      }
-      corr = -sm * a.inv_a2;
-    }
-  }
-  const double ws = (MASK & 2) ? a.ws_tab[step & a.ws_mask] : 1.0;
-  const double cdx = a.cdx * ws, cdy = a.cdy * ws;       // time factor of a separable wind folded in
-
+  // ---- which CTAs stage cells that this launch itself has to produce or wait for (GH = 2) ----------------------
+  // gcta: the rectangle the CTA stages holds ghost cells (GH = 1: the table says so already); peer_rows: rows that
+  // peers deliver (the first n_boundary CTAs of a sharded handle's table).  Everybody else can issue its first row
+  // copies before it looks at the control block and the flags.
+  const int Ra = (r0 - 3 < g.lo) ? 0 : r0 - 3, Rb = (r1 + 3 > g.hi) ? g.P : r1 + 3;
+  const int Ca = (jbase - 3 < g.lo) ? 0 : jbase - 3, Cb = (jend + 3 > g.hi) ? g.P : jend + 3;
+  const int nL = max(0, g.lo - Ca), nR = max(0, Cb - g.hi), nT = max(0, g.lo - Ra), nB = max(0, Rb - g.hi);
+  const bool gcta = GH == 1 || (GH == 2 && __shfl_sync(0xffffffffu, (nL | nR | nT | nB) != 0 ? 1 : 0, 0) != 0);   // warp-uniform
+  const bool peer_rows = GH == 2 && a.gf_flags && cta < a.n_boundary;
+  const bool late_issue = GH == 2 && (gcta || peer_rows);
   // TMA row copies are issued by one elected lane of warp 0 (one row per marched row, PF rows ahead).
   const uint32_t ringS_a = smem_u32(ringS), ringL_a = smem_u32(ringL), full_a = smem_u32(full);
   const double* const gq = a.q + (long long)p * g.ps + PYCS_JOFF + c0;
@@ -260,32 +248,144 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
     if (MASK & 1) { pVM += ld8; pUM += ld8; }
   };
 
-  if (warp_u == 0) {                         // rows rfirst .. rfirst + AHEAD - 1 (rfirst >= 1: only row -1 is clamped)
-    if (elect_one()) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue_k(IC<0>{});
-    }
-    advance();
-    pU = rowp(gu, rfirst - 1);               // the clamp of the first row does not carry over
-    pUM = rowp(gum, rfirst - 1);
-    if (rfirst + 1 <= rlast) {
-      if (elect_one()) issue_k(IC<1>{});
+  auto first_issue = [&]() {
+    if (warp_u == 0) {                         // rows rfirst .. rfirst + AHEAD - 1 (rfirst >= 1: only row -1 is clamped)
+      if (elect_one()) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue_k(IC<0>{});
+      }
       advance();
+      pU = rowp(gu, rfirst - 1);               // the clamp of the first row does not carry over
+      pUM = rowp(gum, rfirst - 1);
+      if (rfirst + 1 <= rlast) {
+        if (elect_one()) issue_k(IC<1>{});
+        advance();
+      }
+      if (AHEAD == 3 && rfirst + 2 <= rlast) {
+        if (elect_one()) issue_k(IC<2>{});
+        advance();
+      }
+      if (PFD > 0 && elect_one()) {            // the pointers stand at row rfirst + AHEAD: rows up to PFD - 1 beyond it
+        for (int d = 0; d < PFD; ++d)
+          if (rfirst + AHEAD + d <= rlast) {
+            l2pf(pQ + d * ld8);
+            l2pf(pV + d * ld8);
+            l2pf(pU + d * ld8);
+            if (MASK & 1) { l2pf(pVM + d * ld8); l2pf(pUM + d * ld8); }
+          }
+      }
     }
-    if (AHEAD == 3 && rfirst + 2 <= rlast) {
-      if (elect_one()) issue_k(IC<2>{});
-      advance();
+  };
+  if (!late_issue) first_issue();
+
+  // ---- per-step state from the control block ------------------------------------------------
+  const long long step = *((const volatile long long*)&a.ctl->steps);
+  if (a.wait_flags) {           // several GPUs: every rank has finished step - 1 (its sum is here, and
+    if (tid < a.wait_world) {   // nobody reads the buffers this step's exchange will write any more)
+      mg_wait_flag(a.wait_flags + tid, step, a.mg_err, a.mg_timeout_ns);     // acquire: see mgpu.cuh
     }
-    if (PFD > 0 && elect_one()) {            // the pointers stand at row rfirst + AHEAD: rows up to PFD - 1 beyond it
-      for (int d = 0; d < PFD; ++d)
-        if (rfirst + AHEAD + d <= rlast) {
-          l2pf(pQ + d * ld8);
-          l2pf(pV + d * ld8);
-          l2pf(pU + d * ld8);
-          if (MASK & 1) { l2pf(pVM + d * ld8); l2pf(pUM + d * ld8); }
-        }
+    __syncthreads();
+  }
+  double corr = 0.0;
+  if (a.apply_corr) {
+    if (a.corr_ptr) {
+      corr = *a.corr_ptr;
+    } else if (*((const volatile int*)&a.ctl->pend)) {
+      double sm = 0.0;
+      if (a.pub.world > 1) {
+        const volatile double* ps = a.pub.peer_sync[a.pub.rank]->psum[step & 1];
+        for (int k = 0; k < a.pub.world; ++k) sm += ps[k];
+      } else {
+        sm = *((const volatile double*)&a.ctl->sum);
+      }
+      corr = -sm * a.inv_a2;
     }
   }
+  const double ws = (MASK & 2) ? a.ws_tab[step & a.ws_mask] : 1.0;
+  const double cdx = a.cdx * ws, cdy = a.cdy * ws;       // time factor of a separable wind folded in
+
+  // ---- GH = 2: ghost cells of the rectangle this CTA stages (src/interpolation.py:154-314), written to Q itself
+  // before the first row copy reads them.  Neighbouring CTAs whose rectangles overlap write the same bits.  At a
+  // panel edge all four ghost layers (and the 4 x 4 corners) are filled although the march reads three, so that the
+  // ring of the array is complete for whoever restores it after the run (stepper.cu: copy_ring_kernel).
+  if (GH == 2) {
+    if (peer_rows) {                         // the peers' pieces of this rank's halo rows and ghost-fill sources
+      if (tid < a.wait_world) {
+        const long long xc = *((const volatile long long*)&a.ctl->xcount);
+        mg_wait_flag(a.gf_flags + tid, xc, a.mg_err, a.mg_timeout_ns);
+      }
+      __syncthreads();
+    }
+    if (gcta) {
+      double* __restrict__ qw = const_cast<double*>(a.q);
+      // Edge ghost cells in batches of four per thread: the stencil positions of all four first, then every source
+      // cell and weight, then the stores -- two memory round trips per batch instead of two per cell (the fill is
+      // latency, not bandwidth: with one cell at a time it held a CTA at a panel edge back by ~8 us).  Same
+      // operations in the same order as dg_phase1_value (ghost_core.cuh); the 4 x 4 corners take that path.
+      auto fill = [&](int n, auto decode) {
+        constexpr int GB = 4;
+        for (int t0 = tid; t0 < n; t0 += GB * TB) {
+          int ci[GB], cj[GB], sd[GB], gl[GB], kk[GB], ge[GB], km[GB];
+          bool ok[GB], cor[GB];
+#pragma unroll
+          for (int u = 0; u < GB; ++u) {
+            const int t = t0 + u * TB;
+            ok[u] = t < n;
+            ci[u] = cj[u] = sd[u] = gl[u] = kk[u] = ge[u] = km[u] = 0;
+            cor[u] = false;
+            if (ok[u]) {
+              decode(t, ci[u], cj[u]);
+              const bool ii = ci[u] >= g.lo && ci[u] < g.hi, jj = cj[u] >= g.lo && cj[u] < g.hi;
+              cor[u] = !ii && !jj;
+              if (ii) { sd[u] = cj[u] >= g.hi ? SIDE_N : SIDE_S; gl[u] = cj[u] >= g.hi ? cj[u] - g.hi : cj[u]; kk[u] = ci[u]; }
+              else { sd[u] = ci[u] >= g.hi ? SIDE_E : SIDE_W; gl[u] = ci[u] >= g.hi ? ci[u] - g.hi : ci[u]; kk[u] = cj[u]; }
+              ge[u] = (sd[u] == SIDE_E || sd[u] == SIDE_N) ? gl[u] : PYCS_NG - 1 - gl[u];
+              if (!cor[u]) km[u] = a.gf_kmin[ge[u] * g.P + kk[u]];
+            }
+          }
+          double acc[GB];
+#pragma unroll
+          for (int u = 0; u < GB; ++u) {
+            acc[u] = 0.0;
+            if (ok[u] && !cor[u]) {
+              const SideMap& m = a.gf_maps.m[p][sd[u]];
+              const double* __restrict__ w = a.gf_w + ((long long)ge[u] * g.P + kk[u]) * a.gf_order;
+#pragma unroll
+              for (int l = 0; l < 8; ++l)                       // order <= 8 (pycs_upload_lagrange)
+                if (l < a.gf_order) {
+                  const double v = (sd[u] < 2) ? halo_src(a.q, g, m, gl[u], km[u] + l) : halo_src(a.q, g, m, km[u] + l, gl[u]);
+                  acc[u] = __dadd_rn(acc[u], __dmul_rn(v, w[l]));
+                }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < GB; ++u)
+            if (ok[u]) {
+              if (cor[u]) acc[u] = dg_ghost_cell(g, a.gf_maps, a.q, a.gf_kmin, a.gf_w, a.gf_order, p, ci[u], cj[u]);
+              qw[gidx(g, p, ci[u], cj[u])] = acc[u];
+            }
+        }
+      };
+      const int ncg = nL + nR, nrow = Rb - Ra;
+      fill(nrow * ncg, [&](int t, int& i, int& jg) {          // ghost columns, all rows of the rectangle (corners included)
+        const int c = t % ncg;
+        i = Ra + t / ncg;
+        jg = c < nL ? Ca + c : g.hi + (c - nL);
+      });
+      const int ja = max(Ca, g.lo), w = min(Cb, g.hi) - ja, nrg = nT + nB;
+      fill(nrg * w, [&](int t, int& i, int& jg) {             // ghost rows over the interior columns
+        const int rr = t / w;
+        jg = ja + t % w;
+        i = rr < nT ? Ra + rr : g.hi + (rr - nT);
+      });
+      // the row copies below read these cells through the async proxy
+      asm volatile("fence.proxy.async;" ::: "memory");
+      __threadfence();
+      __syncthreads();
+    }
+  }
+
+  if (late_issue) first_issue();
   double* __restrict__ QN = a.qn + (long long)p * g.ps + PYCS_JOFF + min(j, g.P - 1) + (long long)r0 * g.ld;
   // GH: ghost(sqrtg) of the thread's column, one row ahead of the march (an L2 hit that must not sit on
   // the critical path of phase 1); only threads that own a ghost cell in that row load it
@@ -293,7 +393,7 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
   double gs_next = 0.0;
   if (GH) {
     GS = a.gs + (long long)p * g.ps + PYCS_JOFF + min(j, g.P - 1) + (long long)rfirst * g.ld;
-    if (a.apply_corr && !(jint && rfirst >= g.lo && rfirst < g.hi)) gs_next = __ldg(GS);
+    if (gcta && a.apply_corr && !(jint && rfirst >= g.lo && rfirst < g.hi)) gs_next = __ldg(GS);
   }
   Lane L;
   lane_init(L);
@@ -312,8 +412,12 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
     }
   };
   // one marched row; false once the chunk is finished
-  auto row = [&](auto kc, int r) -> bool {
+  // GC (compile time): the CTA stages ghost cells and adds their projection term itself (GH = 1 always, GH = 2 for
+  // the CTAs at a panel edge -- those run their own copy of the march, so that the loop of the others is the GH = 0
+  // loop: one loop with both forms ran 8 % slower, 28 KB of code per trip against 21.6 KB)
+  auto row = [&](auto kc, auto gc, int r) -> bool {
     constexpr int k = decltype(kc)::value;
+    constexpr bool GC = decltype(gc)::value;
     if (r > rlast) return false;
     constexpr int kS = (k % DS) * SSLOT;
     while (!mbar_try_wait(&full[k], parb)) {}
@@ -322,7 +426,7 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
     if (a.apply_corr) {
       // pending MF-PR term on the own cell of the new row (neighbours read it after barrier A)
       const bool inner = jint && r >= g.lo && r < g.hi;
-      if (GH) {
+      if (GC) {
         qnew[0] = fma(inner ? R.sgc0[0] : gs_next, corr, qnew[0]);
         ringS[kS + S_Q * RW + e] = qnew[0];
         GS += g.ld;
@@ -363,7 +467,7 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
       }
       QN += g.ld;
     }
-    if (GH && a.edge_flux) {
+    if (GH == 1 && a.edge_flux) {
       // MF-AF: the outer fluxes (times dt/dx, as the kernel carries them) on the panel's edge lines, interior extent
       const int ex = r - 2, ry = r - 3;                 // x-edge just completed; row of the outer y-fluxes
       if ((ex == g.lo || ex == g.hi) && out_lane)
@@ -373,17 +477,25 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
     }
     return true;
   };
-  for (int rb = rfirst;; rb += DL, parb ^= 1u) {
-    if (!row(IC<0>{}, rb)) break;
-    if (!row(IC<1>{}, rb + 1)) break;
-    if (!row(IC<2>{}, rb + 2)) break;
-    if (!row(IC<3>{}, rb + 3)) break;
-    if (!row(IC<4>{}, rb + 4)) break;
-    if (!row(IC<5>{}, rb + 5)) break;
+  auto march = [&](auto gc) {
+    for (int rb = rfirst;; rb += DL, parb ^= 1u) {
+      if (!row(IC<0>{}, gc, rb)) break;
+      if (!row(IC<1>{}, gc, rb + 1)) break;
+      if (!row(IC<2>{}, gc, rb + 2)) break;
+      if (!row(IC<3>{}, gc, rb + 3)) break;
+      if (!row(IC<4>{}, gc, rb + 4)) break;
+      if (!row(IC<5>{}, gc, rb + 5)) break;
+    }
+  };
+  if (GH == 2) {
+    if (gcta) march(BC<true>{});
+    else march(BC<false>{});
+  } else {
+    march(BC<GH == 1>{});
   }
 
   // ---- several GPUs, boundary CTAs: ship what the peers read of this CTA's rows (see FusedArgs::xjobs)
-  if (GH && a.xjob_off) {
+  if (GH && a.xjob_off && cta < a.n_boundary) {
     __syncthreads();                           // the CTA's output rows are visible to all its threads
     const long long xc = *((const volatile long long*)&a.ctl->xcount);
     const int jb0 = a.xjob_off[cta], jb1 = a.xjob_off[cta + 1];
@@ -432,9 +544,26 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
     sF[40] = fused_last_writer(a.counter, (unsigned)ntot, false) ? 1.0 : 0.0;
   }
   __syncthreads();
+  if (sF[40] != 0.0) {                       // CTA-uniform: the last CTA of the step
+    // total of the partials in a fixed order, by the whole CTA: thread t adds part[t], part[t + TB], ... (all loads
+    // in flight at once), then warps, then the five warp sums -- ~1 us where one warp took ~5 (36 dependent L2 trips
+    // at 1140 CTAs), and that time is serial: nothing of the next step can start before it
+    __threadfence();
+    double pv[8];
+    double tsum = 0.0;
+    for (int k0 = tid; k0 < ntot; k0 += 8 * TB) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) pv[u] = (k0 + u * TB < ntot) ? __ldcg(a.part + k0 + u * TB) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) tsum += pv[u];
+    }
+    for (int o = 16; o > 0; o >>= 1) tsum += __shfl_down_sync(0xffffffffu, tsum, o);
+    if ((tid & 31) == 0) sG[tid >> 5] = tsum;
+    __syncthreads();
+  }
   if (sF[40] != 0.0 && tid < 32) {
-    double tot = fused_warp_sum(a.part, ntot, tid);
-    tot = __shfl_sync(0xffffffffu, tot, 0);
+    double tot = 0.0;
+    for (int w = 0; w < TB / 32; ++w) tot += sG[w];
     if (tid == 0) *a.counter = 0u;
     if (!a.timing) {
       if (tid == 0) {
@@ -506,6 +635,7 @@ cudaError_t launch_mask(const FusedArgs& a, int mask, int gh, int nblocks, cudaS
   if (mask == M && gh == G) return launch_one<F2B_TB, RECON, SPLIT, M, G>(a, nblocks, st, resident)
   F2B_CASE(0, 0); F2B_CASE(1, 0); F2B_CASE(2, 0);
   F2B_CASE(0, 1); F2B_CASE(1, 1); F2B_CASE(2, 1);
+  F2B_CASE(0, 2); F2B_CASE(1, 2); F2B_CASE(2, 2);
 #undef F2B_CASE
   return cudaErrorInvalidValue;
 }

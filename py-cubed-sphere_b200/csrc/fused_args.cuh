@@ -83,6 +83,15 @@ struct FusedArgs {
   double* edge_flux;
   int timing;                 // roofline timing launches: leave the control block alone
   int pdl;                    // launch with the programmatic-dependent-launch attribute (pycs_common.cuh)
+  // GH = 2 (one-kernel step): the ghost cells a CTA's march reads are filled by the CTA itself before its first
+  // row copy -- the Lagrange fill of ghost_core.cuh, raw (the projection term is added on load as for GH = 1) --
+  // so a step is ONE launch: no ghost-fill kernel, no second stream.  Several GPUs: the first n_boundary CTAs of
+  // the table (everything that reads a ghost cell or a peer's row) first wait for the peers' exchange flags.
+  HaloMaps gf_maps;
+  const int* gf_kmin;
+  const double* gf_w;
+  int gf_order;
+  const long long* gf_flags;  // the peers' dflag (nullptr on one GPU)
 };
 
 // CTA table of a split step over the rows [row_lo, row_hi) of a panel of N x N cells cut into nstrips column

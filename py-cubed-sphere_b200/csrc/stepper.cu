@@ -39,6 +39,9 @@
 
 namespace {
 
+#ifndef PYCS_ONEKERNEL_DEFAULT
+#define PYCS_ONEKERNEL_DEFAULT 1
+#endif
 constexpr int WS_CAP = 4096;        // entries of the separable-wind time-factor table (power of two)
 constexpr int WS_BATCH = 1024;      // entries filled per refill
 
@@ -302,6 +305,7 @@ struct FusedState {
   // graphs: one per ping-pong parity and wind mask
   int use_graph = -1;
   int use_pdl = -1;
+  int onek = -1;               // one-kernel step (GH = 2: the step kernel fills its own ghost cells), PYCS_ONEKERNEL
   cudaGraphExec_t gexec[2][5] = {};
   const double* gq[2][5] = {};
   int gnodes[2][5] = {};
@@ -423,6 +427,10 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
     fs.nchunks = (nrows + rows - 1) / rows;
     drop_graphs(fs);
   }
+  if (fs.onek < 0) {
+    const char* eo = getenv("PYCS_ONEKERNEL");
+    fs.onek = ((eo ? atoi(eo) : PYCS_ONEKERNEL_DEFAULT) && fs.impl == 4 && h->prm.mf != 2) ? 1 : 0;   // (MF-AF: serial step)
+  }
   if (fs.split == 0) {
     const char* es = getenv("PYCS_SPLIT");
     const bool want = h->mg || (es && atoi(es));   // several GPUs always run the split step
@@ -451,6 +459,13 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
             if (c < best) { best = c; band = b; edge = e; irows = ir; }
           }
         }
+      if (fs.onek) {
+        // one-kernel step: nothing has to finish early -- the ghost fill is part of the next launch, the exchange
+        // only has to be out by the end of the step -- so the table is the uniform grid of the serial step (one
+        // wave of equal chunks).  Measured at 2 GPUs, N = 1536: 0.1081 ms per step against 0.1142 with the short
+        // boundary CTAs of the two-stream shape (profiles/r2_mgpu_onekernel.md).
+        band = edge = irows = fs.rows;
+      }
       if (eb) band = atoi(eb);
       if (ee) edge = atoi(ee);
       if (ei && atoi(ei) > 0) irows = atoi(ei);
@@ -529,14 +544,14 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
     CK(cudaMemsetAsync(fs.counter, 0, sizeof(unsigned), h->stream));
   }
   if (fs.use_graph < 0) {
-    // replay from a CUDA graph: on by default for the serial step; the split step is launched directly
-    // unless PYCS_GRAPH=1 (measured at 2 GPUs, N = 1536: 0.131 ms per step replayed, 0.122 ms launched)
+    // replay from a CUDA graph: on by default for the serial and the one-kernel step; the two-stream split step is
+    // launched directly unless PYCS_GRAPH=1 (measured at 2 GPUs, N = 1536: 0.131 ms per step replayed, 0.122 ms launched)
     const char* eg = getenv("PYCS_GRAPH");
-    fs.use_graph = eg ? (atoi(eg) ? 1 : 0) : (fs.split == 1 ? 0 : 1);
+    fs.use_graph = eg ? (atoi(eg) ? 1 : 0) : ((fs.split == 1 && !fs.onek) ? 0 : 1);
   }
   if (fs.use_pdl < 0) {
     const char* ep = getenv("PYCS_PDL");
-    fs.use_pdl = ep ? (atoi(ep) ? 1 : 0) : 1;
+    fs.use_pdl = ep ? atoi(ep) : 1;
   }
   if (fs.prof < 0) fs.prof = getenv("PYCS_STEP_PROFILE") ? 1 : 0;
   return 0;
@@ -1165,6 +1180,49 @@ static int enqueue_split(pycs_handle h, FusedState& fs, double* qcur, double* qn
   return 0;
 }
 
+// one kernel: every CTA of the step in ONE launch of the GH = 2 flavour -- the CTAs that stage ghost cells fill them
+// first (the Lagrange fill inside the step kernel, raw; on several GPUs after waiting for the peers' exchange flags),
+// the boundary CTAs of a sharded handle come first in the table and ship their rows to the peers as soon as they
+// are written.  No ghost-fill kernel, no second stream, no events: the step is a single graph node.
+static int enqueue_onekernel(pycs_handle h, FusedState& fs, double* qcur, double* qnext, int mask, int wind_mode) {
+  TRY(step_winds(h, fs, false, wind_mode));
+  FusedArgs a;
+  TRY(step_args(h, fs, qcur, qnext, mask, &a, wind_mode));
+  a.gf_maps = h->maps;
+  a.gf_kmin = h->kminE;
+  a.gf_w = h->wE;
+  a.gf_order = h->order;
+  if (fs.split == 1) {
+    a.cta_tab = fs.cta_tab;
+    a.cta_off = 0;
+    a.n_boundary = fs.n_b;
+  }
+  if (h->mg) {
+    a.wait_flags = h->mg->sync->sflag;
+    a.wait_world = h->mg->world;
+    a.mg_err = &h->mg->sync->err;
+    a.mg_timeout_ns = h->mg->timeout_ns;
+    a.pub.world = h->mg->world;
+    a.pub.rank = h->mg->rank;
+    for (int d = 0; d < 8; ++d) a.pub.peer_sync[d] = d < h->mg->world ? h->mg->peer_sync[d] : nullptr;
+    a.gf_flags = h->mg->sync->dflag;
+    if (!fs.xjob_off) {
+      pycs_set_error("one-kernel step on several GPUs needs the in-kernel exchange (PYCS_MG_XKERNEL must be 0)");
+      return PYCS_ERR_STATE;
+    }
+    a.xjob_off = fs.xjob_off;
+    a.xjobs = fs.xjobs;
+    a.xcounter = fs.xcounter;
+    const int idx = (qnext == h->mg->alloc[0]) ? 0 : 1;
+    for (int d = 0; d < 8; ++d) a.xpeer_q[d] = d < h->mg->world ? h->mg->peer_q[idx][d] : nullptr;
+  }
+  // launched directly (PYCS_GRAPH=0), the step kernels can chain by programmatic dependent launch (PYCS_PDL=2): the
+  // next step's CTAs become resident and set up their shared memory while this step's last CTAs drain
+  a.pdl = (fs.use_pdl == 2 && !fs.use_graph && wind_mode != 2) ? 1 : 0;
+  TRY(launch_step(h, fs, a, mask, 2, fs.npart, h->stream));
+  return 0;
+}
+
 // wind_mode: how the step gets its winds without the reference's per-step wind kernels
 //   0  none of the below: steady winds (fields 1 and 4) are read as init_vars_adv left them, time-dependent
 //      ones are refreshed by the wind kernels around the step kernel (PYCS_NO_SEPARABLE);
@@ -1198,8 +1256,10 @@ int k_fused_step(pycs_handle h, long long k, double t, int wind_mode) {
   if (wind_mode == 2) TRY(ensure_basis_winds(h, fs));
   TRY(ensure_gs(h, fs));
   const int mask = separable ? 2 : ((h->prm.dp == 2) ? 1 : 0);    // RK1: averaged wind == instantaneous wind
-  const bool winds = (h->prm.vf == 2 || h->prm.vf == 3) && wind_mode == 0;
   const bool split = fs.split == 1;
+  const bool winds = (h->prm.vf == 2 || h->prm.vf == 3) && wind_mode == 0;
+  const bool profile = fs.prof > 0;
+  const bool onek = fs.onek == 1 && !winds && !profile && (!h->mg || (split && !fs.xkernel));
 
   // per-step coefficients of the lazy wind modes for this and the following steps
   const long long idx = fs.steps_host;
@@ -1214,24 +1274,23 @@ int k_fused_step(pycs_handle h, long long k, double t, int wind_mode) {
     fs.wc_off = k - idx;
     fs.wc_until = idx + WS_BATCH;
   }
-  if (split && !fs.ghost_ready) {
+  if (split && !onek && !fs.ghost_ready) {
     // first step after something else touched Q: the raw ghost fill this step's boundary CTAs read
     TRY(launch_ghost_fill(h, qcur, h->stream, nullptr, fs.ctl, 0, nullptr, nullptr, true));
   }
 
-  const bool profile = fs.prof > 0;
   const bool graph = fs.use_graph && !winds && !profile;
   if (graph) {
     // nothing may allocate or configure inside the capture: touch every field and kernel attribute first
     FusedArgs warm;
     TRY(step_args(h, fs, qcur, qnext, mask, &warm, wind_mode));
-    if (fs.impl == 4 && (pycs_fused2b_resident(h->prm.recon, h->prm.opsplit, mask, 0) < 1 ||
+    if (fs.impl == 4 && (pycs_fused2b_resident(h->prm.recon, h->prm.opsplit, mask, onek ? 2 : 0) < 1 ||
                          pycs_fused2b_resident(h->prm.recon, h->prm.opsplit, mask, (split || h->prm.mf == 2) ? 1 : 0) < 1)) {
       pycs_set_error("fused2b kernel: occupancy query failed");
       return PYCS_ERR_CUDA;
     }
     const int par = (qcur == qa) ? 0 : 1;      // keyed by the buffer that is read (f[Q] / f[Q_NEXT] may have been swapped)
-    const int key = wind_mode == 2 ? 3 + mask : mask;
+    const int key = wind_mode == 2 ? 3 + mask : mask;      // (a handle runs either the one-kernel step or the other shapes)
     cudaGraphExec_t& ge = fs.gexec[par][key];
     if (ge && fs.gq[par][key] != qcur) {
       cudaGraphExecDestroy(ge);
@@ -1241,8 +1300,9 @@ int k_fused_step(pycs_handle h, long long k, double t, int wind_mode) {
       const long long l0 = h->launches;
       cudaGraph_t gr = nullptr;
       CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-      int r = split ? enqueue_split(h, fs, qcur, qnext, mask, false, false, wind_mode)
-                    : enqueue_serial(h, fs, qcur, qnext, mask, false, false, wind_mode);
+      int r = onek ? enqueue_onekernel(h, fs, qcur, qnext, mask, wind_mode)
+              : split ? enqueue_split(h, fs, qcur, qnext, mask, false, false, wind_mode)
+                      : enqueue_serial(h, fs, qcur, qnext, mask, false, false, wind_mode);
       cudaError_t ce = cudaStreamEndCapture(h->stream, &gr);
       if (r) return r;
       CK(ce);
@@ -1254,6 +1314,8 @@ int k_fused_step(pycs_handle h, long long k, double t, int wind_mode) {
     }
     CK(cudaGraphLaunch(ge, h->stream));
     h->launches += fs.gnodes[par][key];
+  } else if (onek) {
+    TRY(enqueue_onekernel(h, fs, qcur, qnext, mask, wind_mode));
   } else if (split) {
     TRY(enqueue_split(h, fs, qcur, qnext, mask, winds, profile, wind_mode));
   } else {
@@ -1264,8 +1326,8 @@ int k_fused_step(pycs_handle h, long long k, double t, int wind_mode) {
   h->qcur ^= 1;
   fs.pending = (h->prm.mf == 3) ? 1 : 0;
   fs.ring_pending = 1;
-  fs.ring_raw = split ? 1 : 0;
-  fs.ghost_ready = split ? 1 : 0;
+  fs.ring_raw = (split || onek) ? 1 : 0;
+  fs.ghost_ready = (split && !onek) ? 1 : 0;
   // wind refresh for the next step (src/advection_timestep.py:48-75)
   if (winds) TRY(k_update_adv(h, t));
   return 0;

@@ -10,7 +10,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pycs_b200  # noqa
 from pycs_b200 import cs_datastruct, advection_ic, advection_vars, advection_timestep
 
-for split in ("0", "1"):
+for onek, split in (("1", "0"), ("1", "1"), ("0", "0"), ("0", "1")):     # one-kernel step (uniform grid / CTA table), serial, split
+    os.environ["PYCS_ONEKERNEL"] = onek
     os.environ["PYCS_SPLIT"] = split
     for N, vf, tup in ((50, 3, (3, 1, 1, 3, 1, 3)), (130, 2, (3, 2, 1, 3, 1, 3)), (130, 1, (4, 1, 1, 3, 1, 3))):
         g = cs_datastruct.cubed_sphere(N)
@@ -21,5 +22,5 @@ for split in ("0", "1"):
             advection_timestep.run_steps(g, s, k, n, fused=True)
             k += n
             q = np.asarray(s.Q)
-        print("split=%s N=%d vf=%d tuple=%s: max|Q| = %.6f" % (split, N, vf, tup, float(np.max(np.abs(q)))), flush=True)
+        print("onekernel=%s split=%s N=%d vf=%d tuple=%s: max|Q| = %.6f" % (onek, split, N, vf, tup, float(np.max(np.abs(q)))), flush=True)
         s.dev.close()

@@ -33,10 +33,13 @@ def main():
     if len(sys.argv) > 1:
         cases = [(int(sys.argv[1]), 3, "default", (10,))]
     worst = 0.0
-    # the multi-GPU step is always the split step; replayed from CUDA graphs (default) or launched directly
-    for impl in ("graph", "nograph"):
+    # the multi-GPU step is the one-kernel step over the CTA table (boundary CTAs first, in-kernel ghost fill and
+    # exchange), replayed from CUDA graphs (default) or launched directly; "split": the two-stream split step
+    # (PYCS_ONEKERNEL=0) it replaced
+    for impl in ("graph", "nograph", "split"):
         os.environ["PYCS_GRAPH"] = "1" if impl == "graph" else "0"
-        for N, vf, name, calls in cases:
+        os.environ["PYCS_ONEKERNEL"] = "0" if impl == "split" else "1"
+        for N, vf, name, calls in (cases if impl != "split" else cases[:3]):
             g = cs_datastruct.cubed_sphere(N)
             a = make(g, vf, TUPLES[name], local)
             b = make(g, vf, TUPLES[name], local)

@@ -365,19 +365,23 @@ def test_fused_matches_operator_path(mods, N, vf, name):
     b.dev.close()
 
 
-@pytest.mark.parametrize("mode", ["serial", "serial-nograph", "split", "split-nograph"])
+@pytest.mark.parametrize("mode", ["onekernel", "onekernel-nograph", "onekernel-table", "serial", "serial-nograph", "split",
+                                  "split-nograph"])
 @pytest.mark.parametrize("N,vf,name", [(16, 1, "default"), (50, 3, "default"), (130, 2, "AVLT-RK2-DG-PR"),
                                        (130, 1, "PL07-RK1-DG-PR"), (200, 4, "default"), (130, 3, "L04-AVLT-DG-PR"),
                                        (320, 2, "AVLT-RK2-DG-AF"), (320, 3, "default"), (1536, 3, "default")])
 def test_fused_step_shapes_match_operator_path(mods, N, vf, name, mode, monkeypatch):
-    """Both shapes of the fused step (csrc/stepper.cu) -- serial: ghost fill with the projection term folded
-    in, then one launch; split (PYCS_SPLIT=1, the shape every multi-GPU run uses): boundary CTAs with the
-    in-kernel projection term on ghost cells + early raw ghost fill on a second stream beside the interior
+    """The shapes of the fused step (csrc/stepper.cu) -- one kernel (the default: every CTA fills the ghost cells it
+    stages itself, one launch per step; "-table": with the CTA table of a sharded handle, boundary CTAs first);
+    serial (PYCS_ONEKERNEL=0): ghost fill with the projection term folded in, then one launch; split
+    (PYCS_ONEKERNEL=0 PYCS_SPLIT=1): boundary CTAs with the in-kernel projection term on ghost cells + early raw
+    ghost fill on a second stream beside the interior
     CTAs -- replayed from CUDA graphs or launched directly (PYCS_GRAPH=0), against the operator path, over
     several run calls (separable wind, pending projection and ghost state carried across calls).  The
     PPM-L04 tuple runs on the first-generation kernel (csrc/fused.cu); the MF-AF tuple (edge-flux averaging
     across the cube edges, src/edges_treatment.py:231-278) always runs the serial shape."""
-    monkeypatch.setenv("PYCS_SPLIT", "1" if mode.startswith("split") else "0")
+    monkeypatch.setenv("PYCS_ONEKERNEL", "1" if mode.startswith("onekernel") else "0")
+    monkeypatch.setenv("PYCS_SPLIT", "1" if mode.startswith("split") or mode.endswith("table") else "0")
     monkeypatch.setenv("PYCS_GRAPH", "0" if mode.endswith("nograph") else "1")
     g = mods.cs_datastruct.cubed_sphere(N)
     a = make_sim(mods, g, vf, TUPLES[name])

@@ -26,14 +26,14 @@ def test_no_step_kernel_spills_and_default_fits_four_ctas():
                          r"(\d+) bytes spill loads\nptxas info\s+: Used (\d+) registers", txt)
     assert len(entries) >= 30
     for name, stack, st, ld, regs in entries:
-        # one 8-byte spill slot is tolerated in the SP-L04 instantiations; none in the default scheme
-        assert int(stack) <= 8 and int(st) <= 8 and int(ld) <= 8, name
+        # one 8-byte spill slot is tolerated in the SP-L04 / SP-PL07 instantiations; none in the default scheme
+        assert int(stack) <= 8 and int(st) <= 8 and int(ld) <= 16, name
         assert int(regs) * 160 * 4 <= 65536, (name, regs)
     for mask in (0, 1, 2):
-        for gh in (0, 1):
+        for gh in (0, 1, 2):
             hit = [(int(a), int(b), int(c)) for n, a, b, c, _ in entries if (DEFAULT % mask).replace("ELi0ELi32EEEv", "ELi%dELi32EEEv" % gh) in n]
             # the interior / single-GPU flavour (GH = 0) must not spill at all; the boundary flavour of the
-            # multi-GPU split step (GH = 1, in-kernel exchange) may keep one 8-byte slot
+            # multi-GPU split step (GH = 1, in-kernel exchange) and the one-kernel flavour (GH = 2) may keep one 8-byte slot
             assert hit and (hit[0] == (0, 0, 0) if gh == 0 else max(hit[0]) <= 8), (mask, gh, hit)
 
 

@@ -63,6 +63,7 @@ def test_split_step_matches_operator_path(mods, N, vf, monkeypatch):
     several run calls (separable wind, pending projection) against the operator path."""
     from pycs_b200 import advection_vars, advection_timestep
     monkeypatch.setenv("PYCS_SPLIT", "1")
+    monkeypatch.setenv("PYCS_ONEKERNEL", "0")
     g = mods.cs_datastruct.cubed_sphere(N)
 
     def sim_of():
