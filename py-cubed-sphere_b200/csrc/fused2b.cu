@@ -90,8 +90,90 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+
+// ---- GH = 2: the ghost cells of the rectangle rows [Ra, Rb) x columns [Ca, Cb) of panel p, written to Q (raw
+// Lagrange fill, same operations in the same order as ghost_core.cuh).  This runs once per CTA at a panel edge and
+// is pure latency, so it is written for memory-level parallelism in little code: ONE loop over the CTA's ghost
+// cells, two cells per trip, and per cell the stencil position first, then all source cells and weights at once
+// (up to eight, predicated), then the sum.  History (N = 1536, one GPU, one-kernel step against the serial step's
+// 0.170 ms): dg_ghost_cell inlined in two loops -- a dependent load per stencil point, 2 600 instructions: 0.180;
+// four cells per trip with the corner path inlined four times -- 14 500 instructions: 0.192; the plain loop in a
+// non-inlined function that reads its arguments through a generic pointer: 0.190 (profiles/r2_mgpu_onekernel.md).
+__device__ __noinline__ double ghost_corner_nl(Geo g, const HaloMaps* maps, const double* q, const int* kmin,
+                                               const double* wE, int order, int p, int i, int j) {
+  return dg_corner_value(g, *maps, q, kmin, wE, order, p, i >= g.hi ? SIDE_E : SIDE_W, i >= g.hi ? i - g.hi : i, j);
+}
+struct GhostCell { int i, j, s, gl, k, ge, km; bool ok, corner; };
+__device__ __forceinline__ void ghost_prologue(const FusedArgs& a, int p, int Ra, int Rb, int Ca, int Cb, int tid, int tb) {
+  const Geo& g = a.g;
+  double* __restrict__ qw = const_cast<double*>(a.q);
+  const int nL = max(0, g.lo - Ca), nR = max(0, Cb - g.hi), nT = max(0, g.lo - Ra), nB = max(0, Rb - g.hi);
+  const int ncg = nL + nR, ncol = ncg * (Rb - Ra);       // ghost columns over all rows of the rectangle (corners included)
+  const int ja = max(Ca, g.lo), w = min(Cb, g.hi) - ja, nrg = nT + nB;   // ghost rows over the interior columns
+  const int n = ncol + nrg * w;
+  auto locate = [&](int t) {
+    GhostCell c;
+    c.ok = t < n;
+    c.i = c.j = c.s = c.gl = c.k = c.ge = c.km = 0;
+    c.corner = false;
+    if (c.ok) {
+      if (t < ncol) {
+        const int cc = t % ncg;
+        c.i = Ra + t / ncg;
+        c.j = cc < nL ? Ca + cc : g.hi + (cc - nL);
+      } else {
+        const int u = t - ncol, rr = u / w;
+        c.j = ja + u % w;
+        c.i = rr < nT ? Ra + rr : g.hi + (rr - nT);
+      }
+      const bool ii = c.i >= g.lo && c.i < g.hi, jj = c.j >= g.lo && c.j < g.hi;
+      c.corner = !ii && !jj;
+      if (ii) { c.s = c.j >= g.hi ? SIDE_N : SIDE_S; c.gl = c.j >= g.hi ? c.j - g.hi : c.j; c.k = c.i; }
+      else { c.s = c.i >= g.hi ? SIDE_E : SIDE_W; c.gl = c.i >= g.hi ? c.i - g.hi : c.i; c.k = c.j; }
+      c.ge = (c.s == SIDE_E || c.s == SIDE_N) ? c.gl : PYCS_NG - 1 - c.gl;
+      if (!c.corner) c.km = a.gf_kmin[c.ge * g.P + c.k];
+    }
+    return c;
+  };
+  auto gather = [&](const GhostCell& c, double (&v)[8], double (&wt)[8]) {
+    const SideMap& m = a.gf_maps.m[p][c.s];
+    // source cell of stencil point l: halo_src(gl, km + l) on the E / W sides, (km + l, gl) on N / S: affine in l
+    const int a0 = c.s < 2 ? c.gl : c.km, b0 = c.s < 2 ? c.km : c.gl, da = c.s < 2 ? 0 : 1, db = 1 - da;
+    const long long base = gidx(g, m.nb, m.ci + m.ai * a0 + m.bi * b0, m.cj + m.aj * a0 + m.bj * b0);
+    const long long step = (long long)(m.ai * da + m.bi * db) * g.ld + (m.aj * da + m.bj * db);
+    const double* __restrict__ wp = a.gf_w + ((long long)c.ge * g.P + c.k) * a.gf_order;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      const bool on = c.ok && !c.corner && l < a.gf_order;
+      v[l] = on ? a.q[base + l * step] : 0.0;
+      wt[l] = on ? wp[l] : 0.0;
+    }
+  };
+  auto finish = [&](const GhostCell& c, const double (&v)[8], const double (&wt)[8]) {
+    if (!c.ok) return;
+    double acc = 0.0;
+    if (c.corner) {
+      acc = ghost_corner_nl(g, &a.gf_maps, a.q, a.gf_kmin, a.gf_w, a.gf_order, p, c.i, c.j);
+    } else {
+#pragma unroll
+      for (int l = 0; l < 8; ++l)
+        if (l < a.gf_order) acc = __dadd_rn(acc, __dmul_rn(v[l], wt[l]));
+    }
+    qw[gidx(g, p, c.i, c.j)] = acc;
+  };
+#pragma unroll 1
+  for (int t = tid; t < n; t += 2 * tb) {
+    const GhostCell c0 = locate(t), c1 = locate(t + tb);
+    double v0[8], w0[8], v1[8], w1[8];
+    gather(c0, v0, w0);
+    gather(c1, v1, w1);
+    finish(c0, v0, w0);
+    finish(c1, v1, w1);
+  }
+}
+
 template <int TB, int RECON, int SPLIT, int MASK, int GH, int VAR = 0>
-__global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
+__global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(const __grid_constant__ FusedArgs a) {
   constexpr int PF = F2B_PF;
   constexpr int RW = TB + 6;                 // staged row: columns jbase-6 .. jbase+TB-1
   constexpr int NS = (MASK & 1) ? 4 : 3, NL = (MASK & 1) ? 5 : 4;
@@ -317,67 +399,7 @@ __global__ void __launch_bounds__(TB, F2B_MINB) fused2b_kernel(FusedArgs a) {
       __syncthreads();
     }
     if (gcta) {
-      double* __restrict__ qw = const_cast<double*>(a.q);
-      // Edge ghost cells in batches of four per thread: the stencil positions of all four first, then every source
-      // cell and weight, then the stores -- two memory round trips per batch instead of two per cell (the fill is
-      // latency, not bandwidth: with one cell at a time it held a CTA at a panel edge back by ~8 us).  Same
-      // operations in the same order as dg_phase1_value (ghost_core.cuh); the 4 x 4 corners take that path.
-      auto fill = [&](int n, auto decode) {
-        constexpr int GB = 4;
-        for (int t0 = tid; t0 < n; t0 += GB * TB) {
-          int ci[GB], cj[GB], sd[GB], gl[GB], kk[GB], ge[GB], km[GB];
-          bool ok[GB], cor[GB];
-#pragma unroll
-          for (int u = 0; u < GB; ++u) {
-            const int t = t0 + u * TB;
-            ok[u] = t < n;
-            ci[u] = cj[u] = sd[u] = gl[u] = kk[u] = ge[u] = km[u] = 0;
-            cor[u] = false;
-            if (ok[u]) {
-              decode(t, ci[u], cj[u]);
-              const bool ii = ci[u] >= g.lo && ci[u] < g.hi, jj = cj[u] >= g.lo && cj[u] < g.hi;
-              cor[u] = !ii && !jj;
-              if (ii) { sd[u] = cj[u] >= g.hi ? SIDE_N : SIDE_S; gl[u] = cj[u] >= g.hi ? cj[u] - g.hi : cj[u]; kk[u] = ci[u]; }
-              else { sd[u] = ci[u] >= g.hi ? SIDE_E : SIDE_W; gl[u] = ci[u] >= g.hi ? ci[u] - g.hi : ci[u]; kk[u] = cj[u]; }
-              ge[u] = (sd[u] == SIDE_E || sd[u] == SIDE_N) ? gl[u] : PYCS_NG - 1 - gl[u];
-              if (!cor[u]) km[u] = a.gf_kmin[ge[u] * g.P + kk[u]];
-            }
-          }
-          double acc[GB];
-#pragma unroll
-          for (int u = 0; u < GB; ++u) {
-            acc[u] = 0.0;
-            if (ok[u] && !cor[u]) {
-              const SideMap& m = a.gf_maps.m[p][sd[u]];
-              const double* __restrict__ w = a.gf_w + ((long long)ge[u] * g.P + kk[u]) * a.gf_order;
-#pragma unroll
-              for (int l = 0; l < 8; ++l)                       // order <= 8 (pycs_upload_lagrange)
-                if (l < a.gf_order) {
-                  const double v = (sd[u] < 2) ? halo_src(a.q, g, m, gl[u], km[u] + l) : halo_src(a.q, g, m, km[u] + l, gl[u]);
-                  acc[u] = __dadd_rn(acc[u], __dmul_rn(v, w[l]));
-                }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < GB; ++u)
-            if (ok[u]) {
-              if (cor[u]) acc[u] = dg_ghost_cell(g, a.gf_maps, a.q, a.gf_kmin, a.gf_w, a.gf_order, p, ci[u], cj[u]);
-              qw[gidx(g, p, ci[u], cj[u])] = acc[u];
-            }
-        }
-      };
-      const int ncg = nL + nR, nrow = Rb - Ra;
-      fill(nrow * ncg, [&](int t, int& i, int& jg) {          // ghost columns, all rows of the rectangle (corners included)
-        const int c = t % ncg;
-        i = Ra + t / ncg;
-        jg = c < nL ? Ca + c : g.hi + (c - nL);
-      });
-      const int ja = max(Ca, g.lo), w = min(Cb, g.hi) - ja, nrg = nT + nB;
-      fill(nrg * w, [&](int t, int& i, int& jg) {             // ghost rows over the interior columns
-        const int rr = t / w;
-        jg = ja + t % w;
-        i = rr < nT ? Ra + rr : g.hi + (rr - nT);
-      });
+      ghost_prologue(a, p, Ra, Rb, Ca, Cb, tid, TB);
       // the row copies below read these cells through the async proxy
       asm volatile("fence.proxy.async;" ::: "memory");
       __threadfence();

@@ -39,9 +39,6 @@
 
 namespace {
 
-#ifndef PYCS_ONEKERNEL_DEFAULT
-#define PYCS_ONEKERNEL_DEFAULT 1
-#endif
 constexpr int WS_CAP = 4096;        // entries of the separable-wind time-factor table (power of two)
 constexpr int WS_BATCH = 1024;      // entries filled per refill
 
@@ -429,7 +426,11 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
   }
   if (fs.onek < 0) {
     const char* eo = getenv("PYCS_ONEKERNEL");
-    fs.onek = ((eo ? atoi(eo) : PYCS_ONEKERNEL_DEFAULT) && fs.impl == 4 && h->prm.mf != 2) ? 1 : 0;   // (MF-AF: serial step)
+    // default: on for sharded handles (one launch per step instead of three on two streams); off on one GPU, where
+    // the serial step with its separate 9 us ghost fill is faster -- the CTAs at a panel edge pay ~8 us for their
+    // own fill and the first row copies behind it, and with two such CTAs in a slot the launch ends 15 us later
+    // (0.185 against 0.170 ms per step at N = 1536, profiles/r2_mgpu_onekernel.md)
+    fs.onek = ((eo ? atoi(eo) : (h->mg ? 1 : 0)) && fs.impl == 4 && h->prm.mf != 2) ? 1 : 0;   // (MF-AF: serial step)
   }
   if (fs.split == 0) {
     const char* es = getenv("PYCS_SPLIT");
