@@ -426,11 +426,14 @@ static int fused_setup(pycs_handle h, FusedState& fs) {
   }
   if (fs.onek < 0) {
     const char* eo = getenv("PYCS_ONEKERNEL");
-    // default: on for sharded handles (one launch per step instead of three on two streams); off on one GPU, where
-    // the serial step with its separate 9 us ghost fill is faster -- the CTAs at a panel edge pay ~8 us for their
-    // own fill and the first row copies behind it, and with two such CTAs in a slot the launch ends 15 us later
-    // (0.185 against 0.170 ms per step at N = 1536, profiles/r2_mgpu_onekernel.md)
-    fs.onek = ((eo ? atoi(eo) : (h->mg ? 1 : 0)) && fs.impl == 4 && h->prm.mf != 2) ? 1 : 0;   // (MF-AF: serial step)
+    // Default: on for a handle sharded over two GPUs, off otherwise -- measured at N = 1536 (profiles/r2_mgpu_onekernel.md):
+    //   1 GPU   0.185 ms per step against 0.170 for the serial step: the CTAs at a panel edge pay ~8 us for their own
+    //           fill and the late first row copies, and with two such CTAs in a slot the launch ends 15 us later;
+    //   2 GPUs  0.108 against 0.113 for the two-stream split step (one launch and no events instead of three launches);
+    //   8 GPUs  0.055 against 0.049: with 22-row chunks the fill of the edge CTAs is a quarter of their march, and
+    //           the split step hides it behind the interior CTAs.
+    const int dflt = (h->mg && h->mg->world == 2) ? 1 : 0;
+    fs.onek = ((eo ? atoi(eo) : dflt) && fs.impl == 4 && h->prm.mf != 2) ? 1 : 0;   // (MF-AF: serial step)
   }
   if (fs.split == 0) {
     const char* es = getenv("PYCS_SPLIT");
