@@ -365,11 +365,15 @@ def test_fused_matches_operator_path(mods, N, vf, name):
     b.dev.close()
 
 
-@pytest.mark.parametrize("mode", ["onekernel", "onekernel-nograph", "onekernel-table", "serial", "serial-nograph", "split",
-                                  "split-nograph"])
-@pytest.mark.parametrize("N,vf,name", [(16, 1, "default"), (50, 3, "default"), (130, 2, "AVLT-RK2-DG-PR"),
-                                       (130, 1, "PL07-RK1-DG-PR"), (200, 4, "default"), (130, 3, "L04-AVLT-DG-PR"),
-                                       (320, 2, "AVLT-RK2-DG-AF"), (320, 3, "default"), (1536, 3, "default")])
+_SHAPE_MODES = ["onekernel", "onekernel-nograph", "onekernel-table", "serial", "serial-nograph", "split", "split-nograph"]
+_SHAPE_CASES = [(16, 1, "default"), (50, 3, "default"), (130, 2, "AVLT-RK2-DG-PR"), (130, 1, "PL07-RK1-DG-PR"),
+                (200, 4, "default"), (130, 3, "L04-AVLT-DG-PR"), (320, 2, "AVLT-RK2-DG-AF"), (320, 3, "default"),
+                (1536, 3, "default")]
+
+
+# the bench size runs the three replayed shapes only (its host-side grid takes ~10 s per case)
+@pytest.mark.parametrize("N,vf,name,mode", [c + (m,) for c in _SHAPE_CASES for m in _SHAPE_MODES
+                                            if c[0] < 1000 or m in ("onekernel", "serial", "split")])
 def test_fused_step_shapes_match_operator_path(mods, N, vf, name, mode, monkeypatch):
     """The shapes of the fused step (csrc/stepper.cu) -- one kernel (the default: every CTA fills the ghost cells it
     stages itself, one launch per step; "-table": with the CTA table of a sharded handle, boundary CTAs first);

@@ -220,7 +220,11 @@ def _split_plan(row_lo, row_hi, ns, band, edge_rows, rows):
 @pytest.mark.parametrize("N,world,rank,band,edge_rows,rows", [(1536, 1, 0, 12, 16, 81), (1536, 8, 0, 12, 16, 28),
                                                               (1536, 8, 3, 12, 12, 40), (1536, 2, 1, 8, 24, 90),
                                                               (320, 1, 0, 12, 16, 60), (48, 1, 0, 12, 16, 48),
-                                                              (130, 8, 7, 4, 8, 8), (384, 4, 2, 12, 16, 30)])
+                                                              (130, 8, 7, 4, 8, 8), (384, 4, 2, 12, 16, 30),
+                                                              # uniform tables of the one-kernel step (band = edge = rows)
+                                                              (1536, 2, 0, 86, 86, 86), (1536, 2, 1, 86, 86, 86),
+                                                              (1536, 4, 1, 43, 43, 43), (1536, 8, 7, 22, 22, 22),
+                                                              (48, 2, 1, 24, 24, 24), (130, 2, 0, 33, 33, 33)])
 def test_split_step_cta_table(N, world, rank, band, edge_rows, rows):
     """The CTA table of the split step: (1) the CTAs tile the slab exactly once per panel; (2) an interior
     CTA stages no ghost cell and no row outside the slab (rows r0-3 .. r1+2, columns of its strip -3 .. +2);
@@ -261,6 +265,71 @@ def test_split_step_cta_table(N, world, rank, band, edge_rows, rows):
         km = ohalo.lagrange_tables(LeanGrid.centres_only(N), 3)[0][0][0]
         for peer, panel, i0, i1, j0, j1 in mgpu_plan(N, world, rank, km, 3)[2]:
             assert np.all(bnd[panel, i0:i1, j0:j1]), (peer, panel, i0, i1, j0, j1)
+
+
+def _ghost_cells_of_cta(N, r0, r1, j0, j1):
+    """Python mirror of the cell enumeration of ghost_prologue (csrc/fused2b.cu, GH = 2): the ghost cells a CTA
+    that updates rows [r0, r1) x columns [j0, j1) fills before its first row copy."""
+    lo, hi, P = 4, N + 4, N + 8
+    Ra, Rb = (0 if r0 - 3 < lo else r0 - 3), (P if r1 + 3 > hi else r1 + 3)
+    Ca, Cb = (0 if j0 - 3 < lo else j0 - 3), (P if j1 + 3 > hi else j1 + 3)
+    nL, nR, nT, nB = max(0, lo - Ca), max(0, Cb - hi), max(0, lo - Ra), max(0, Rb - hi)
+    ncg, ncol = nL + nR, (nL + nR) * (Rb - Ra)
+    ja, w, nrg = max(Ca, lo), min(Cb, hi) - max(Ca, lo), nT + nB
+    cells = []
+    for t in range(ncol + nrg * w):
+        if t < ncol:
+            c, i = t % ncg, Ra + t // ncg
+            j = Ca + c if c < nL else hi + (c - nL)
+        else:
+            u = t - ncol
+            rr, j = u // w, ja + u % w
+            i = Ra + rr if rr < nT else hi + (rr - nT)
+        cells.append((i, j))
+    return cells
+
+
+@pytest.mark.parametrize("N,world,rank,rows", [(1536, 1, 0, 81), (1536, 2, 1, 86), (1536, 8, 0, 22), (1536, 8, 3, 22),
+                                               (320, 1, 0, 60), (48, 1, 0, 48), (16, 1, 0, 16), (130, 2, 0, 33)])
+def test_one_kernel_step_ghost_rectangles(N, world, rank, rows):
+    """One-kernel step: every CTA fills the ghost cells of the rectangle it stages before it reads them.  Per CTA:
+    no cell twice, no interior cell, every ghost cell of the staged rows r0-3 .. r1+2 x columns j0-3 .. j1+2 is in
+    the list.  Over a rank's CTAs: all four ghost layers of the rows it reads (slab +- 3) on the S / N sides, the
+    whole W / E rows where the slab touches them, and the 4 x 4 corners there -- what the stand-alone ghost fill
+    covers for that rank (stepper.cu: launch_ghost_fill), so the ring restore after a run finds a complete ring."""
+    lo, hi, P = 4, N + 4, N + 8
+    base, rem = divmod(N, world)
+    a = lo + rank * base + min(rank, rem)
+    b = a + base + (1 if rank < rem else 0)
+    wmax = 154
+    ns = (N + wmax - 1) // wmax
+    wcols = (N + ns - 1) // ns
+    wcols += wcols & 1
+    tab, _ = _split_plan(a, b, ns, rows, rows, rows)
+    filled = np.zeros((P, P), bool)
+    for r0, r1, strip, panel in tab:
+        if panel:
+            continue
+        j0, j1 = lo + strip * wcols, min(lo + (strip + 1) * wcols, hi)
+        cells = _ghost_cells_of_cta(N, r0, r1, j0, j1)
+        assert len(set(cells)) == len(cells)
+        got = np.zeros((P, P), bool)
+        for i, j in cells:
+            assert 0 <= i < P and 0 <= j < P and not (lo <= i < hi and lo <= j < hi), (i, j)
+            got[i, j] = True
+        staged = np.zeros((P, P), bool)
+        staged[max(r0 - 3, 0):min(r1 + 3, P), max(j0 - 3, 0):min(j1 + 3, P)] = True
+        staged[lo:hi, lo:hi] = False
+        assert np.all(got[staged]), (r0, r1, strip)
+        filled |= got
+    want = np.zeros((P, P), bool)
+    ra, rb = max(a - 3, lo), min(b + 3, hi)
+    want[ra:rb, :lo] = want[ra:rb, hi:] = True            # S / N ghost columns of the rows the rank reads
+    if a == lo:
+        want[:lo, :] = True                               # W ghost rows incl. corners
+    if b == hi:
+        want[hi:, :] = True                               # E ghost rows incl. corners
+    assert np.array_equal(filled, want)
 
 
 @pytest.mark.parametrize("vf", [1, 2, 3, 4])
