@@ -67,7 +67,7 @@ def ptr(a):
 
 
 def one_step(emul, N, vf, tup, pre_steps, nw=3, depth=3, rows=None, pending=False, separable=False, block_tb=0,
-             circ=False, split_sets=None):
+             circ=False, split_sets=None, own_ghosts=None):
     from oracle.grid import LeanGrid
     from oracle import step as ost, wind as owind
     recon, dp, split, et, mt, mf = tup
@@ -111,7 +111,23 @@ def one_step(emul, N, vf, tup, pre_steps, nw=3, depth=3, rows=None, pending=Fals
         part = np.zeros(emul.f3_emul_block_grid(N, block_tb, rows))
         fn = {False: emul.f3_emul_step_block, True: emul.f3_emul_step_block_circ,
               "pair": emul.f3_emul_step_block_pair}[circ]
-        if split_sets is None:
+        if own_ghosts is not None:
+            # one-kernel step (GH = 2): every CTA runs on an input whose ghost cells are NaN except the ones its own
+            # prologue fills -- own_ghosts(block) lists them as (i, j) of the block's panel
+            for blk in range(len(part)):
+                qb = q.copy()
+                qb[:, :4, :] = qb[:, N + 4:, :] = np.nan
+                qb[:, :, :JOFF + 4] = qb[:, :, JOFF + N + 4:] = np.nan
+                pnl = blk % 6
+                for i, j in own_ghosts(blk):
+                    qb[pnl, i, JOFF + j] = q[pnl, i, JOFF + j]
+                lst = np.array([blk], dtype=np.int32)
+                emul.f3_emul_set_block_list(lst.ctypes.data_as(C.POINTER(C.c_int)), 1)
+                rc = fn(N, recon, split, mask, block_tb, depth, rows, ptr(qb), ptr(qn),
+                        *[ptr(a) for a in arrs], ptr(part), corr, 1 if pending else 0, dt / g.dx, dt / g.dy, ws)
+                emul.f3_emul_set_block_list(None, 0)
+                assert rc == 0
+        elif split_sets is None:
             rc = fn(N, recon, split, mask, block_tb, depth, rows, ptr(q), ptr(qn),
                     *[ptr(a) for a in arrs], ptr(part), corr, 1 if pending else 0, dt / g.dx, dt / g.dy, ws)
         else:
@@ -253,6 +269,34 @@ def test_emulated_v2b_march_variants_other_schemes(emul, tup):
         got, want = one_step(emul, 20, 2, tup, 2, depth=2, block_tb=32, circ=True)
     finally:
         emul.f3_emul_set_variant(0)
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+
+
+# ---- one-kernel step (GH = 2): a CTA reads no ghost cell that its own prologue has not filled -------------------
+@pytest.mark.parametrize("N,tb,rows,kw", [(50, 32, 11, {}), (50, 64, 50, {"pending": True}), (20, 32, 7, {}),
+                                          (130, 160, 40, {"separable": True})])
+def test_emulated_one_kernel_step_ghost_rectangles(emul, N, tb, rows, kw):
+    """Every CTA of the uniform grid marched alone on an input whose ghost ring is NaN except for the cells the
+    prologue of THAT CTA fills (tests/test_host_cpu.py::_ghost_cells_of_cta mirrors the enumeration of
+    csrc/fused2b.cu: ghost_prologue): the step must come out as with the complete ring."""
+    from test_host_cpu import _ghost_cells_of_cta
+    wmax = tb - 6
+    ns = (N + wmax - 1) // wmax
+    wcols = (N + ns - 1) // ns
+    wcols += wcols & 1
+
+    def own(blk):
+        b = blk // 6
+        strip, chunk = b % ns, b // ns
+        r0 = 4 + chunk * rows
+        r1 = min(r0 + rows, N + 4)
+        j0 = 4 + strip * wcols
+        j1 = min(j0 + wcols, N + 4)
+        return _ghost_cells_of_cta(N, r0, r1, j0, j1)
+
+    vf = 3 if kw.get("separable") else 1
+    got, want = one_step(emul, N, vf, TUPLES["default"], 2, depth=2, rows=rows, block_tb=tb, circ=True, own_ghosts=own, **kw)
+    assert np.all(np.isfinite(got))
     assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
 
 
