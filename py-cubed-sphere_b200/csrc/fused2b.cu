@@ -13,7 +13,7 @@
 //   phase 1 (own column: new row, inner x-flux, Qx) | barrier A | phase 2 (y-fluxes of Q row r and
 //   of Qx row r-3 at the thread's edge) | barrier B | phase 3 (Qy, outer x-flux, output row r-3).
 // Rows are staged by one elected lane of warp 0 with cp.async.bulk (TMA 1-D row copies,
-// mbarrier complete_tx), two rows ahead, into a two-level ring: Q, u, sqrtg_pu are needed by one
+// mbarrier complete_tx), two rows ahead (the first two before the CTA looks at the control block), into a two-level ring: Q, u, sqrtg_pu are needed by one
 // march step (3 slots); v, sqrtg_pv, sqrtg_pc, 1/sqrtg_pc by steps r..r+3 (6 slots).  The march
 // runs in groups of six rows -- the common period of both rings and of the register windows --
 // so that every ring slot and every window register is a compile-time constant

@@ -3,12 +3,18 @@
 // wind; CUDA-graph replay; and the small kernels around the step kernel (Lagrange ghost fill,
 // projection flush, ring restore).
 //
-// Two shapes of a step:
+// Three shapes of a step:
 //
 //   serial (one GPU)       ghost fill (folds the pending MF-PR term into the ghost cells, hands the
-//                          coefficient to the step kernel) -> step kernel over the whole grid.
+//                          coefficient to the step kernel) -> step kernel over the whole grid; the two are
+//                          chained by a programmatic dependent launch inside the replayed graph.
 //
-//   split (several GPUs,   the handle's stream (high priority):  boundary CTAs (GH = 1, they ship their rows to the
+//   one kernel (2 GPUs;    ONE launch of the GH = 2 flavour: a CTA whose staged rectangle touches a panel edge
+//   PYCS_ONEKERNEL=1)      fills those ghost cells itself first (on a sharded handle after the peers' dflags),
+//                          the boundary CTAs ship their rows to the peers at the end of their march.  Uniform
+//                          CTA table, a single graph node per step.
+//
+//   split (4 / 8 GPUs,     the handle's stream (high priority):  boundary CTAs (GH = 1, they ship their rows to the
 //   PYCS_SPLIT=1 on one)                             peers themselves) -> ghost fill of the NEXT step (raw: no projection term)
 //                          second stream:            interior CTAs (GH = 0)
 //                          The boundary CTAs are everything a ghost cell or a peer reads: first / last
