@@ -628,6 +628,7 @@ cudaError_t launch_var(const FusedArgs& a, int nblocks, cudaStream_t st, int* re
   return cudaSuccess;
 }
 
+#ifdef F2B_VARIANTS
 // PYCS_VARIANT selects among the instantiated march variants of the par-default scheme's serial-step kernels
 // (experiment knob; anything not instantiated falls back to the default)
 static int march_variant() {
@@ -638,6 +639,7 @@ static int march_variant() {
   }
   return v;
 }
+#endif
 template <int TB, int RECON, int SPLIT, int MASK, int GH>
 cudaError_t launch_one(const FusedArgs& a, int nblocks, cudaStream_t st, int* resident) {
 #ifdef F2B_VARIANTS
