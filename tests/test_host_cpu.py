@@ -350,3 +350,26 @@ def test_host_exact_contravariant_wind_matches_oracle_bits(vf):
         opts = getattr(og, pos)
         ou, ov = owind.ll2contra(*owind.velocity_adv(opts.lon, opts.lat, 0.0, vf), og, pos)
         assert np.array_equal(u, ou) and np.array_equal(v, ov), pos
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference runs without a GPU: one JSON line with the keys the driver reads, the reference
+    arm's own cpu_baseline and an e2e that repeats the line's value with zero copied bytes."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-n", "32"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "impl"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["unit"] == "cell-updates/s" and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 0
+    assert d["config"]["N"] == 1536 and "workload" in d["config"]          # the arm's config is the GPU arm's
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
