@@ -385,7 +385,7 @@ def main():
     ap.add_argument("--config", type=int, default=4, choices=(3, 4), help="BASELINE.json configuration (4 = headline)")
     ap.add_argument("--cpu-n", type=int, default=0,
                     help="N of the CPU sample (0: reference arm 1536 if steps + warmup <= 8 else 768; cpu_baseline leg 768)")
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=6, help="steps of the cpu_baseline sample (N=768: ~1.7 s each on one core)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--host-grid", action="store_true", help="build the grid with host numpy like the reference")
     ap.add_argument("--quick", action="store_true", help="tuning runs: only the device-resident timed steps (no roofline, "
